@@ -1,0 +1,137 @@
+/* omniquant_b200 -- C ABI of the B200 (sm_100a) calibration hot path.
+ *
+ * Drop-in boundary.  The reference (SuperVan-Young/OmniQuant) is
+ * pure PyTorch and has no FFI of its own: its operator API is the nn.Module
+ * surface.  These entry points are what that surface binds to here -- each
+ * comment cites the reference code the call replaces (paths relative to the
+ * reference repo).  The Python mirror of the modules lives in
+ * omniquant_b200/{quantize,models}/ and calls only these functions for device
+ * compute (ctypes; see INTEGRATION.md for the binding a maintainer would add).
+ *
+ * Conventions
+ *   - every function returns int: 0 ok, <0 invalid argument, >0 a cudaError_t;
+ *     oq_last_error() returns a thread-local message for the last failure;
+ *   - the caller owns all memory; every pointer is a DEVICE pointer unless
+ *     named *_host; the library never allocates, frees or synchronises;
+ *   - all work is enqueued on the explicit `stream` (last argument);
+ *   - tensors are row-major; "ld" arguments are leading dimensions in ELEMENTS;
+ *   - dtypes are fixed per argument: `void*` activations / operands are bf16,
+ *     `float*` are fp32 master weights, parameters, statistics and reductions;
+ *   - no C++ exceptions, no torch types.
+ */
+#ifndef OMNIQUANT_B200_H_
+#define OMNIQUANT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* oq_stream_t; /* == cudaStream_t */
+
+int oq_version(void);
+const char* oq_last_error(void);
+int oq_sm_count(void);
+
+/* ---- K0: weight path -----------------------------------------------------
+ * LET fold + LWC clip + per-channel / per-group fake-quant of one weight.
+ *   W' = (W * col_scale[k]) {row_op: 0 none | 1 * row_scale[n] | 2 / row_scale[n]}
+ *        models/transformation.py:41 (smooth_ln_fcs), :51,:60 (smooth_fc_fc), :66,:68 (smooth_q_k)
+ *   matvec_out[n] = sum_k W[n,k]*shift[k]   (raw W; transformation.py:38-40,:57-59)
+ *   group extrema -> sigmoid(up/low) clip -> scale, rounded zero point
+ *        quantize/quantizer.py:122-147 (UniformAffineQuantizer.per_token_dynamic_calibration)
+ *   codes = clamp(round(W'/s)+z, 0, 2^n-1); W_q = (codes-z)*s   quantizer.py:84-105 (fake_quant)
+ * group_size 0 = per output channel.  up/low: LWC factors [N*ceil(K/group)] or both NULL.
+ * recip_div: 0 = CPU ATen semantics for `range / (2^n-1)` (true division), 1 = CUDA ATen
+ * semantics (multiply by the fp32 reciprocal).  Any of the outputs may be NULL.
+ * Replaces models/int_llama_layer.py:285-304 (smooth_and_quant_temporary) per weight. */
+int oq_weight_quant_fwd(const float* W, int N, int K, const float* col_scale, const float* row_scale, int row_op,
+                        const float* shift, float* matvec_out, int n_bits, int symmetric, int group_size,
+                        const float* up, const float* low, int recip_div, void* wq_bf16, long ld_bf16, float* wq_f32,
+                        uint8_t* codes, float* scale_out, float* zp_out, float* xmin_out, float* xmax_out,
+                        oq_stream_t stream);
+
+/* Backward of the above (autograd of quantizer.py:84-147 + transformation.py folds).
+ * grad_wq: dL/dW_q [N,K] (bf16, or fp32 when grad_is_f32).  xmin/xmax: raw group extrema saved by the
+ * forward.  Writes d_up/d_low [N*G]; writes drow[n] = sum_k dW'[n,k]*(W*col)[n,k]; atomically ADDS
+ * dcol_acc[k] += sum_n dW'[n,k]*rowfac[n]*W[n,k] and dshift_acc[k] += sum_n W[n,k]*e_row[n]
+ * (caller zeroes them once per step); optionally writes the full dL/dW' (fp32 [N,K]). */
+int oq_weight_quant_bwd(const float* W, int N, int K, const float* col_scale, const float* row_scale, int row_op,
+                        int n_bits, int symmetric, int group_size, const float* up, const float* low, int recip_div,
+                        const float* xmin, const float* xmax, const void* grad_wq, int grad_is_f32, long ld_grad,
+                        const float* e_row, float* d_up, float* d_low, float* dcol_acc, float* drow, float* dshift_acc,
+                        float* dW_full, oq_stream_t stream);
+
+/* ---- K4: per-token dynamic activation fake-quant ---------------------------
+ * UniformAffineQuantizer(dynamic_method="per_token") forward, quantizer.py:108-147,:84-105, as called by
+ * QuantLinear.forward (quantize/int_linear.py:59-60) and QuantMatMul.quant_x1/x2 (quantize/int_matmul.py:31-39).
+ * Row r lives at x + (r / rows_inner)*ld_outer + (r % rows_inner)*ld_inner, C contiguous bf16 elements.
+ * rope_cos/sin ([seq_len, C] fp32, or NULL): rotary embedding applied before quantisation
+ * (models/int_llama_layer.py:124-125), position = (r / rows_inner) % seq_len; needs C in {64,128}.
+ * n_bits >= 16 with rope = rotary only. */
+int oq_act_quant_fwd(const void* x, long rows, int C, int rows_inner, long ld_outer, long ld_inner, int n_bits,
+                     int symmetric, int recip_div, const float* rope_cos, const float* rope_sin, int seq_len, void* y,
+                     long ldy_outer, long ldy_inner, float* scale_out, float* zp_out, oq_stream_t stream);
+/* Backward: gx = d/dx [ fake_quant(rope(x)) ] . gy   (x is the forward INPUT, re-quantised on the fly). */
+int oq_act_quant_bwd(const void* x, long rows, int C, int rows_inner, long ld_outer, long ld_inner, int n_bits,
+                     int symmetric, int recip_div, const float* rope_cos, const float* rope_sin, int seq_len,
+                     const void* gy, long ldg_outer, long ldg_inner, void* gx, long ldgx_outer, long ldgx_inner,
+                     oq_stream_t stream);
+
+/* ---- K7: norms with temporary (folded) weight / bias ------------------------
+ * kind 0: OmniLlamaRMSNorm.forward quantize/omni_norm.py:52-63; kind 1: OmniLayerNorm.forward :26-33.
+ * w/b are the temp_weight/temp_bias of the step (b may be NULL). */
+int oq_norm_fwd(const void* x, long rows, int C, long ldx, const float* w, const float* b, float eps, int kind, void* y,
+                long ldy, float* mean_out, float* rstd_out, oq_stream_t stream);
+/* dx = norm'(x).dy (+ dx_add);  dw_acc[c] += sum_r dy*xhat, db_acc[c] += sum_r dy (atomic adds; NULL to skip). */
+int oq_norm_bwd(const void* x, long rows, int C, long ldx, const float* w, int kind, const float* mean,
+                const float* rstd, const void* dy, long lddy, void* dx, long lddx, const void* dx_add, long ldadd,
+                float* dw_acc, float* db_acc, oq_stream_t stream);
+
+/* ---- K1/K2/K3/K5: tcgen05 bf16 GEMM ----------------------------------------
+ * C[b] = alpha * A[b] * B[b]^T (+ bias[n]) (+ residual[b]),  fp32 accumulation in TMEM.
+ *   a_mn=0: A[m,k] at A + b*strideA + m*lda + k     a_mn=1: A[m,k] at A + b*strideA + k*lda + m
+ *   b_mn=0: B[n,k] at B + b*strideB + n*ldb + k     b_mn=1: B[n,k] at B + b*strideB + k*ldb + n
+ * C bf16 or fp32 (c_is_f32).  causal: 0 none; 1 skip output tiles strictly above the diagonal (QK^T, dP);
+ * 2 reduce only k < m0+128 (P.V, dS.K); 3 reduce only k >= m0 (P^T.dO, dS^T.Q).  tile_n 0 = auto.
+ * Replaces F.linear in QuantLinear.forward (quantize/int_linear.py:62) + its autograd dgrad/wgrad, and
+ * torch.matmul/bmm in QuantMatMul.forward (quantize/int_matmul.py:41-43). */
+int oq_gemm_bf16(const void* A, int a_mn, long lda, long strideA, const void* B, int b_mn, long ldb, long strideB,
+                 void* C, int c_is_f32, long ldc, long strideC, int M, int N, int K, int batch, const float* bias,
+                 const void* residual, long ldr, long strideR, float alpha, int causal, int tile_n, int max_ctas,
+                 oq_stream_t stream);
+
+/* ---- elementwise / reductions ----------------------------------------------
+ * SwiGLU of QuantLlamaMLP.forward (models/int_llama_layer.py:44-45): gu = [gate | up] [rows, 2F]. */
+int oq_swiglu_fwd(const void* gu, long ldgu, void* m, long ldm, long rows, int F, oq_stream_t stream);
+int oq_swiglu_bwd(const void* gu, long ldgu, const void* dm, long lddm, void* dgu, long lddgu, long rows, int F,
+                  oq_stream_t stream);
+/* ReLU of QuantOPTDecoderLayer.forward (models/int_opt_layer.py:318). */
+int oq_relu_fwd(const void* x, void* y, long n, oq_stream_t stream);
+int oq_relu_bwd(const void* x, const void* dy, void* dx, long n, oq_stream_t stream);
+/* P = softmax_fp32(max(S + mask, finfo.min)) -> bf16 (models/int_llama_layer.py:156-160). S fp32 [batch,Tq,Tk]. */
+int oq_softmax_fwd(const float* S, void* P, const float* mask, long mask_bstride, long batch, int Tq, int Tk,
+                   int causal, oq_stream_t stream);
+/* dS = P * (dP - rowsum(P*dP)) -> bf16 (dS may alias P); causal rows only read/write j <= i. */
+int oq_softmax_bwd(const void* P, const float* dP, void* dS, long batch, int Tq, int Tk, int causal,
+                   oq_stream_t stream);
+/* loss_acc += mean((out-target)^2) [+ mean((out-target2)^2)]; dout = d loss / d out
+ * (torch.nn.MSELoss at quantize/omniquant.py:142,220-222 and its backward). */
+int oq_mse_fwd_bwd(const void* out, const void* target, const void* target2, long n, float inv_numel, float* loss_acc,
+                   void* dout, oq_stream_t stream);
+/* torch.optim.AdamW step on a flat fp32 segment (quantize/omniquant.py:207-208, utils.py:32-46);
+ * g is multiplied by grad_scale first (1/world after the NCCL sum); *step_dev is the 1-based step. */
+int oq_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
+             float weight_decay, float grad_scale, const int* step_dev, oq_stream_t stream);
+int oq_step_inc(int* step_dev, oq_stream_t stream);
+/* truncate_number on .data (models/transformation.py:5-20; models/int_llama_layer.py:281-284). */
+int oq_truncate(float* p, long n, float threshold, oq_stream_t stream);
+/* out[c] (+)= sum_r X[r,c]  (bias gradients feeding the LET shift/scale gradients). */
+int oq_colsum(const void* X, long ld, long rows, int C, float* out, int accumulate, oq_stream_t stream);
+int oq_transpose_bf16(const void* in, long ldi, void* out, long ldo, int R, int C, oq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMNIQUANT_B200_H_ */

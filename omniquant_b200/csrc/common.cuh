@@ -1,0 +1,103 @@
+// Shared device helpers for the omniquant_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "oq_math.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (C ABI: 0 ok, <0 bad argument, >0 cudaError_t) ----------
+void oq_set_error(const char* fmt, ...);
+int oq_check_launch(const char* what);
+#define OQ_REQUIRE(cond, ...)        \
+  do {                               \
+    if (!(cond)) {                   \
+      oq_set_error(__VA_ARGS__);     \
+      return -1;                     \
+    }                                \
+  } while (0)
+
+int oq_num_sms();
+
+// ---- warp / block reductions -------------------------------------------------
+template <typename T, typename Op>
+__device__ __forceinline__ T warp_reduce(T v, Op op) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+struct OpSum {
+  __device__ __forceinline__ float operator()(float a, float b) const { return a + b; }
+};
+struct OpMax {
+  __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); }
+};
+struct OpMin {
+  __device__ __forceinline__ float operator()(float a, float b) const { return fminf(a, b); }
+};
+
+// Block-wide reduction of NV values at once; result broadcast to all threads.
+// `scratch` must hold NV*32 floats.  Safe to call repeatedly (trailing barrier).
+template <int NV, typename Op>
+__device__ __forceinline__ void block_reduce(float (&v)[NV], float* scratch, Op op, float identity) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_reduce(v[i], op);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) scratch[i * 32 + warp] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float x = lane < nwarps ? scratch[i * 32 + lane] : identity;
+    v[i] = warp_reduce(x, op);
+  }
+  __syncthreads();
+}
+
+// ---- bf16 pack / unpack ---------------------------------------------------------
+__device__ __forceinline__ float bf2f(bf16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ bf16 f2bf(float x) { return __float2bfloat16_rn(x); }
+
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void unpack_bf2(uint32_t u, float& a, float& b) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
+  a = __low2float(t);
+  b = __high2float(t);
+}
+// 4 bf16 <-> 4 floats through one 8-byte access
+__device__ __forceinline__ void load_bf4(const bf16* p, float (&v)[4]) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  unpack_bf2(u.x, v[0], v[1]);
+  unpack_bf2(u.y, v[2], v[3]);
+}
+__device__ __forceinline__ void store_bf4(bf16* p, const float (&v)[4]) {
+  uint2 u;
+  u.x = pack_bf2(v[0], v[1]);
+  u.y = pack_bf2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+// 8 bf16 <-> 8 floats through one 16-byte access
+__device__ __forceinline__ void load_bf8(const bf16* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  unpack_bf2(u.x, v[0], v[1]);
+  unpack_bf2(u.y, v[2], v[3]);
+  unpack_bf2(u.z, v[4], v[5]);
+  unpack_bf2(u.w, v[6], v[7]);
+}
+__device__ __forceinline__ void store_bf8(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf2(v[0], v[1]);
+  u.y = pack_bf2(v[2], v[3]);
+  u.z = pack_bf2(v[4], v[5]);
+  u.w = pack_bf2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+static inline int ceil_div_i(long a, long b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,302 @@
+// Coalesced, vectorised elementwise / reduction kernels of the calibration step:
+// SwiGLU / ReLU (models/int_llama_layer.py:44-45, models/int_opt_layer.py:318),
+// masked fp32 softmax of QuantMatMul scores (models/int_llama_layer.py:156-160),
+// the block-output MSE loss forward+backward (quantize/omniquant.py:142,220-222),
+// AdamW on the flat LWC/LET parameter buffer (quantize/omniquant.py:207-208 +
+// utils.py:32-46), bias-gradient column sums, truncate_number
+// (models/transformation.py:5-20) and a bf16 transpose.  All HBM-bound.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// ---------------------------------------------------------------- SwiGLU
+// gu: [rows, 2F] = [gate | up];  m = silu(gate) * up
+__global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* gu, long ldgu, bf16* m, long ldm, long rows, int F) {
+  const long n8 = (long)rows * (F / 8);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / (F / 8);
+    const int c = (int)(i % (F / 8)) * 8;
+    float g[8], u[8];
+    load_bf8(gu + r * ldgu + c, g);
+    load_bf8(gu + r * ldgu + F + c, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = g[j] * sigmoid_fast(g[j]) * u[j];
+    store_bf8(m + r * ldm + c, g);
+  }
+}
+__global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* gu, long ldgu, const bf16* dm, long lddm, bf16* dgu,
+                                                         long lddgu, long rows, int F) {
+  const long n8 = (long)rows * (F / 8);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / (F / 8);
+    const int c = (int)(i % (F / 8)) * 8;
+    float g[8], u[8], d[8];
+    load_bf8(gu + r * ldgu + c, g);
+    load_bf8(gu + r * ldgu + F + c, u);
+    load_bf8(dm + r * lddm + c, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = sigmoid_fast(g[j]);
+      const float dg = d[j] * u[j] * s * (1.0f + g[j] * (1.0f - s));
+      const float du = d[j] * g[j] * s;
+      g[j] = dg;
+      u[j] = du;
+    }
+    store_bf8(dgu + r * lddgu + c, g);
+    store_bf8(dgu + r * lddgu + F + c, u);
+  }
+}
+
+// ---------------------------------------------------------------- ReLU (OPT)
+__global__ void __launch_bounds__(256) relu_fwd_kernel(const bf16* x, bf16* y, long n8) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    float v[8];
+    load_bf8(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+    store_bf8(y + i * 8, v);
+  }
+}
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const bf16* x, const bf16* dy, bf16* dx, long n8) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    float v[8], g[8];
+    load_bf8(x + i * 8, v);
+    load_bf8(dy + i * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = v[j] > 0.0f ? g[j] : 0.0f;
+    store_bf8(dx + i * 8, g);
+  }
+}
+
+// ---------------------------------------------------------------- softmax
+// S: fp32 scores [B, Tq, Tk] (already scaled by 1/sqrt(d) in the GEMM epilogue);
+// P = softmax(max(S + mask, -FLT_MAX)) in fp32, stored bf16.  causal != 0 masks j > i + (Tk - Tq).
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* S, bf16* P, const float* mask, long mask_bstride,
+                                                          int Tq, int Tk, int causal) {
+  __shared__ float scratch[32];
+  const long row = blockIdx.x;  // over B*Tq
+  const int i = (int)(row % Tq);
+  const long b = row / Tq;
+  const float* s = S + row * (long)Tk;
+  bf16* p = P + row * (long)Tk;
+  const float* mk = mask ? mask + b * mask_bstride + (long)i * Tk : nullptr;
+  const int lim = causal ? min(Tk, i + (Tk - Tq) + 1) : Tk;
+  float mx[1] = {-INFINITY};
+  for (int j = threadIdx.x; j < lim; j += blockDim.x) {
+    float v = s[j];
+    if (mk) v = fmaxf(v + mk[j], -3.4028234663852886e38f);
+    mx[0] = fmaxf(mx[0], v);
+  }
+  block_reduce<1>(mx, scratch, OpMax(), -INFINITY);
+  float sm[1] = {0.f};
+  for (int j = threadIdx.x; j < lim; j += blockDim.x) {
+    float v = s[j];
+    if (mk) v = fmaxf(v + mk[j], -3.4028234663852886e38f);
+    sm[0] += __expf(v - mx[0]);
+  }
+  block_reduce<1>(sm, scratch, OpSum(), 0.0f);
+  const float inv = 1.0f / sm[0];
+  for (int j = threadIdx.x; j < Tk; j += blockDim.x) {
+    float o = 0.0f;
+    if (j < lim) {
+      float v = s[j];
+      if (mk) v = fmaxf(v + mk[j], -3.4028234663852886e38f);
+      o = __expf(v - mx[0]) * inv;
+    }
+    p[j] = f2bf(o);
+  }
+}
+// dS = P * (dP - sum_j P*dP), stored bf16 (may alias P).  causal: row i only holds j <= i + (Tk - Tq);
+// the rest of dP was never written by the tile-skipping GEMM and dS is zero there.
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const bf16* P, const float* dP, bf16* dS, int Tq, int Tk, int causal) {
+  __shared__ float scratch[32];
+  const long row = blockIdx.x;
+  const int i = (int)(row % Tq);
+  const int lim = causal ? min(Tk, i + (Tk - Tq) + 1) : Tk;
+  const bf16* p = P + row * (long)Tk;
+  const float* dp = dP + row * (long)Tk;
+  bf16* ds = dS + row * (long)Tk;
+  float acc[1] = {0.f};
+  for (int j = threadIdx.x; j < lim; j += blockDim.x) acc[0] += bf2f(p[j]) * dp[j];
+  block_reduce<1>(acc, scratch, OpSum(), 0.0f);
+  for (int j = threadIdx.x; j < Tk; j += blockDim.x) {
+    float o = 0.0f;
+    if (j < lim) o = bf2f(p[j]) * (dp[j] - acc[0]);
+    ds[j] = f2bf(o);
+  }
+}
+
+// ---------------------------------------------------------------- MSE
+// loss += inv_numel * sum((out-target)^2 [+ (out-target2)^2]);  dout = 2*inv_numel*((out-target) [+ (out-target2)])
+__global__ void __launch_bounds__(256) mse_kernel(const bf16* out, const bf16* tgt, const bf16* tgt2, long n8,
+                                                  float inv_numel, float* loss_acc, bf16* dout) {
+  __shared__ float scratch[32];
+  float acc[1] = {0.f};
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    float o[8], t[8], t2[8];
+    load_bf8(out + i * 8, o);
+    load_bf8(tgt + i * 8, t);
+    if (tgt2) load_bf8(tgt2 + i * 8, t2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float d = o[j] - t[j];
+      acc[0] += d * d;
+      if (tgt2) {
+        const float d2 = o[j] - t2[j];
+        acc[0] += d2 * d2;
+        d += d2;
+      }
+      o[j] = 2.0f * inv_numel * d;
+    }
+    if (dout) store_bf8(dout + i * 8, o);
+  }
+  block_reduce<1>(acc, scratch, OpSum(), 0.0f);
+  if (threadIdx.x == 0 && loss_acc) atomicAdd(loss_acc, acc[0] * inv_numel);
+}
+
+// ---------------------------------------------------------------- AdamW
+// torch.optim.AdamW (amsgrad=False, maximize=False) on a flat fp32 segment.
+__global__ void __launch_bounds__(256) adamw_kernel(float* p, const float* g, float* m, float* v, long n, float lr,
+                                                    float b1, float b2, float eps, float wd, float grad_scale,
+                                                    const int* step_ptr) {
+  const int step = *step_ptr;
+  const float bc1 = 1.0f - powf(b1, (float)step);
+  const float bc2 = 1.0f - powf(b2, (float)step);
+  const float step_size = lr / bc1;
+  const float bc2_sqrt = sqrtf(bc2);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i];
+    pi *= (1.0f - lr * wd);
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+__global__ void step_inc_kernel(int* step) { *step += 1; }
+
+__global__ void __launch_bounds__(256) truncate_kernel(float* p, long n, float thr) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    p[i] = oq_truncate(p[i], thr);
+}
+
+// ---------------------------------------------------------------- column sums
+// out[c] (+)= sum_r X[r, c]; X bf16 [rows, C].  grid (C/256 tiles, row chunks).
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* X, long ld, long rows, int C, float* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long r0 = (long)blockIdx.y * rows / gridDim.y, r1 = (long)(blockIdx.y + 1) * rows / gridDim.y;
+  float acc = 0.f;
+  for (long r = r0; r < r1; ++r) acc += bf2f(X[r * ld + c]);
+  atomicAdd(out + c, acc);
+}
+
+// ---------------------------------------------------------------- transpose
+__global__ void transpose_kernel(const bf16* in, long ldi, bf16* out, long ldo, int R, int C) {
+  __shared__ bf16 tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < C) tile[j][threadIdx.x] = in[(long)r * ldi + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < C) out[(long)c * ldo + r] = tile[threadIdx.x][j];
+  }
+}
+
+int grid_for(long n, int per_thread = 1) {
+  long blocks = (n + 256L * per_thread - 1) / (256L * per_thread);
+  long cap = (long)oq_num_sms() * 8;
+  return (int)std::max<long>(1, std::min(blocks, cap));
+}
+bool al16(const void* p) { return ((uintptr_t)p % 16) == 0; }
+
+}  // namespace
+
+extern "C" int oq_swiglu_fwd(const void* gu, long ldgu, void* m, long ldm, long rows, int F, cudaStream_t stream) {
+  OQ_REQUIRE(gu && m && rows > 0 && F > 0 && F % 8 == 0 && ldgu % 8 == 0 && ldm % 8 == 0 && al16(gu) && al16(m),
+             "oq_swiglu_fwd: need F, strides multiples of 8 and 16-byte aligned pointers");
+  swiglu_fwd_kernel<<<grid_for(rows * (F / 8)), 256, 0, stream>>>((const bf16*)gu, ldgu, (bf16*)m, ldm, rows, F);
+  return oq_check_launch("oq_swiglu_fwd");
+}
+extern "C" int oq_swiglu_bwd(const void* gu, long ldgu, const void* dm, long lddm, void* dgu, long lddgu, long rows,
+                             int F, cudaStream_t stream) {
+  OQ_REQUIRE(gu && dm && dgu && rows > 0 && F > 0 && F % 8 == 0 && ldgu % 8 == 0 && lddm % 8 == 0 && lddgu % 8 == 0 &&
+                 al16(gu) && al16(dm) && al16(dgu),
+             "oq_swiglu_bwd: need F, strides multiples of 8 and 16-byte aligned pointers");
+  swiglu_bwd_kernel<<<grid_for(rows * (F / 8)), 256, 0, stream>>>((const bf16*)gu, ldgu, (const bf16*)dm, lddm,
+                                                                  (bf16*)dgu, lddgu, rows, F);
+  return oq_check_launch("oq_swiglu_bwd");
+}
+extern "C" int oq_relu_fwd(const void* x, void* y, long n, cudaStream_t stream) {
+  OQ_REQUIRE(x && y && n > 0 && n % 8 == 0 && al16(x) && al16(y), "oq_relu_fwd: n %% 8 and 16-byte alignment required");
+  relu_fwd_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const bf16*)x, (bf16*)y, n / 8);
+  return oq_check_launch("oq_relu_fwd");
+}
+extern "C" int oq_relu_bwd(const void* x, const void* dy, void* dx, long n, cudaStream_t stream) {
+  OQ_REQUIRE(x && dy && dx && n > 0 && n % 8 == 0 && al16(x) && al16(dy) && al16(dx),
+             "oq_relu_bwd: n %% 8 and 16-byte alignment required");
+  relu_bwd_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, n / 8);
+  return oq_check_launch("oq_relu_bwd");
+}
+extern "C" int oq_softmax_fwd(const float* S, void* P, const float* mask, long mask_bstride, long batch, int Tq, int Tk,
+                              int causal, cudaStream_t stream) {
+  OQ_REQUIRE(S && P && batch > 0 && Tq > 0 && Tk > 0 && batch * Tq < (1L << 31), "oq_softmax_fwd: bad arguments");
+  softmax_fwd_kernel<<<(unsigned)(batch * Tq), 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);
+  return oq_check_launch("oq_softmax_fwd");
+}
+extern "C" int oq_softmax_bwd(const void* P, const float* dP, void* dS, long batch, int Tq, int Tk, int causal,
+                              cudaStream_t stream) {
+  OQ_REQUIRE(P && dP && dS && batch > 0 && Tq > 0 && Tk > 0 && batch * Tq < (1L << 31), "oq_softmax_bwd: bad arguments");
+  softmax_bwd_kernel<<<(unsigned)(batch * Tq), 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal);
+  return oq_check_launch("oq_softmax_bwd");
+}
+extern "C" int oq_mse_fwd_bwd(const void* out, const void* target, const void* target2, long n, float inv_numel,
+                              float* loss_acc, void* dout, cudaStream_t stream) {
+  OQ_REQUIRE(out && target && n > 0 && n % 8 == 0 && al16(out) && al16(target) && al16(target2) && al16(dout),
+             "oq_mse_fwd_bwd: n %% 8 and 16-byte alignment required");
+  mse_kernel<<<grid_for(n / 8, 2), 256, 0, stream>>>((const bf16*)out, (const bf16*)target, (const bf16*)target2, n / 8,
+                                                     inv_numel, loss_acc, (bf16*)dout);
+  return oq_check_launch("oq_mse_fwd_bwd");
+}
+extern "C" int oq_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, float grad_scale, const int* step_dev, cudaStream_t stream) {
+  OQ_REQUIRE(p && g && m && v && step_dev && n > 0, "oq_adamw: null pointer or empty segment");
+  adamw_kernel<<<grid_for(n), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step_dev);
+  return oq_check_launch("oq_adamw");
+}
+extern "C" int oq_step_inc(int* step_dev, cudaStream_t stream) {
+  OQ_REQUIRE(step_dev, "oq_step_inc: null pointer");
+  step_inc_kernel<<<1, 1, 0, stream>>>(step_dev);
+  return oq_check_launch("oq_step_inc");
+}
+extern "C" int oq_truncate(float* p, long n, float threshold, cudaStream_t stream) {
+  OQ_REQUIRE(p && n > 0, "oq_truncate: null pointer or empty");
+  truncate_kernel<<<grid_for(n), 256, 0, stream>>>(p, n, threshold);
+  return oq_check_launch("oq_truncate");
+}
+extern "C" int oq_colsum(const void* X, long ld, long rows, int C, float* out, int accumulate, cudaStream_t stream) {
+  OQ_REQUIRE(X && out && rows > 0 && C > 0, "oq_colsum: bad arguments");
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * C, stream);
+    if (e != cudaSuccess) return (int)e;
+  }
+  dim3 grid((C + 255) / 256, (unsigned)std::max<long>(1, std::min<long>(rows / 32, 64)));
+  colsum_kernel<<<grid, 256, 0, stream>>>((const bf16*)X, ld, rows, C, out);
+  return oq_check_launch("oq_colsum");
+}
+extern "C" int oq_transpose_bf16(const void* in, long ldi, void* out, long ldo, int R, int C, cudaStream_t stream) {
+  OQ_REQUIRE(in && out && R > 0 && C > 0, "oq_transpose_bf16: bad arguments");
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, stream>>>((const bf16*)in, ldi, (bf16*)out, ldo, R, C);
+  return oq_check_launch("oq_transpose_bf16");
+}

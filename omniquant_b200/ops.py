@@ -1,0 +1,223 @@
+"""Thin tensor-level wrappers over the C ABI (include/omniquant_b200.h).
+
+Every function takes torch CUDA tensors (device memory + the current stream
+are the only things torch contributes), checks dtypes / layouts, and enqueues
+exactly one library call.  No computation happens in Python.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from ._lib import lib, OqError
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: Optional[torch.Tensor], dtype, name: str):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise OqError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise OqError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def _rowmajor(t: torch.Tensor, name: str):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise OqError(f"{name} must be 2-D with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t.stride(0)
+
+
+# ------------------------------------------------------------------ weight path
+def weight_quant_fwd(W, *, n_bits, symmetric=False, group_size=0, up=None, low=None, col_scale=None, row_scale=None,
+                     row_op=0, shift=None, matvec_out=None, recip_div=True, wq_bf16=None, wq_f32=None, codes=None,
+                     scale_out=None, zp_out=None, xmin_out=None, xmax_out=None):
+    _chk(W, F32, "W")
+    for n, t in (("up", up), ("low", low), ("col_scale", col_scale), ("row_scale", row_scale), ("shift", shift),
+                 ("matvec_out", matvec_out), ("wq_f32", wq_f32), ("scale_out", scale_out), ("zp_out", zp_out),
+                 ("xmin_out", xmin_out), ("xmax_out", xmax_out)):
+        _chk(t, F32, n)
+    _chk(wq_bf16, BF16, "wq_bf16")
+    _chk(codes, torch.uint8, "codes")
+    if not W.is_contiguous():
+        raise OqError("W must be contiguous [N, K]")
+    N, K = W.shape
+    ld = _rowmajor(wq_bf16, "wq_bf16") if wq_bf16 is not None else 0
+    lib().call("oq_weight_quant_fwd", _p(W), N, K, _p(col_scale), _p(row_scale), row_op, _p(shift), _p(matvec_out),
+               n_bits, int(symmetric), int(group_size or 0), _p(up), _p(low), int(recip_div), _p(wq_bf16), ld,
+               _p(wq_f32), _p(codes), _p(scale_out), _p(zp_out), _p(xmin_out), _p(xmax_out), _stream())
+
+
+def weight_quant_bwd(W, grad_wq, xmin, xmax, *, n_bits, symmetric=False, group_size=0, up=None, low=None,
+                     col_scale=None, row_scale=None, row_op=0, recip_div=True, e_row=None, d_up=None, d_low=None,
+                     dcol_acc=None, drow=None, dshift_acc=None, dW_full=None):
+    _chk(W, F32, "W")
+    if grad_wq.dtype not in (BF16, F32):
+        raise OqError("grad_wq must be bf16 or fp32")
+    N, K = W.shape
+    ldg = _rowmajor(grad_wq, "grad_wq")
+    lib().call("oq_weight_quant_bwd", _p(W), N, K, _p(col_scale), _p(row_scale), row_op, n_bits, int(symmetric),
+               int(group_size or 0), _p(up), _p(low), int(recip_div), _p(xmin), _p(xmax), _p(grad_wq),
+               int(grad_wq.dtype == F32), ldg, _p(e_row), _p(d_up), _p(d_low), _p(dcol_acc), _p(drow), _p(dshift_acc),
+               _p(dW_full), _stream())
+
+
+# ------------------------------------------------------------------ activations
+def _rows2(x: torch.Tensor, name: str):
+    """(rows, C, rows_inner, ld_outer, ld_inner) for a 2-D [rows, C] or 3-D [outer, inner, C] bf16 view."""
+    _chk(x, BF16, name)
+    if x.stride(-1) != 1:
+        raise OqError(f"{name}: last dim must be contiguous")
+    if x.dim() == 2:
+        return x.shape[0], x.shape[1], 1, x.stride(0), 0
+    if x.dim() == 3:
+        return x.shape[0] * x.shape[1], x.shape[2], x.shape[1], x.stride(0), x.stride(1)
+    raise OqError(f"{name}: expected 2-D or 3-D view, got {tuple(x.shape)}")
+
+
+def act_quant_fwd(x, y, *, n_bits, symmetric=False, recip_div=True, cos=None, sin=None, seq_len=0, scale_out=None,
+                  zp_out=None):
+    rows, C, ri, lo, li = _rows2(x, "x")
+    rows2, C2, ri2, lo2, li2 = _rows2(y, "y")
+    if (rows, C, ri) != (rows2, C2, ri2):
+        raise OqError("act_quant_fwd: x / y shape mismatch")
+    lib().call("oq_act_quant_fwd", _p(x), rows, C, ri, lo, li, n_bits, int(symmetric), int(recip_div), _p(cos), _p(sin),
+               seq_len, _p(y), lo2, li2, _p(scale_out), _p(zp_out), _stream())
+
+
+def act_quant_bwd(x, gy, gx, *, n_bits, symmetric=False, recip_div=True, cos=None, sin=None, seq_len=0):
+    rows, C, ri, lo, li = _rows2(x, "x")
+    r2, c2, ri2, glo, gli = _rows2(gy, "gy")
+    r3, c3, ri3, xlo, xli = _rows2(gx, "gx")
+    if (rows, C, ri) != (r2, c2, ri2) or (rows, C, ri) != (r3, c3, ri3):
+        raise OqError("act_quant_bwd: shape mismatch")
+    lib().call("oq_act_quant_bwd", _p(x), rows, C, ri, lo, li, n_bits, int(symmetric), int(recip_div), _p(cos), _p(sin),
+               seq_len, _p(gy), glo, gli, _p(gx), xlo, xli, _stream())
+
+
+# ------------------------------------------------------------------ norms
+def norm_fwd(x, w, b, eps, kind, y, mean_out=None, rstd_out=None):
+    _chk(x, BF16, "x"); _chk(y, BF16, "y"); _chk(w, F32, "w"); _chk(b, F32, "b")
+    lib().call("oq_norm_fwd", _p(x), x.shape[0], x.shape[1], _rowmajor(x, "x"), _p(w), _p(b), float(eps), kind, _p(y),
+               _rowmajor(y, "y"), _p(mean_out), _p(rstd_out), _stream())
+
+
+def norm_bwd(x, w, kind, mean, rstd, dy, dx=None, dx_add=None, dw_acc=None, db_acc=None):
+    _chk(x, BF16, "x"); _chk(dy, BF16, "dy"); _chk(dx, BF16, "dx"); _chk(dx_add, BF16, "dx_add")
+    lib().call("oq_norm_bwd", _p(x), x.shape[0], x.shape[1], _rowmajor(x, "x"), _p(w), kind, _p(mean), _p(rstd), _p(dy),
+               _rowmajor(dy, "dy"), _p(dx), _rowmajor(dx, "dx") if dx is not None else 0, _p(dx_add),
+               _rowmajor(dx_add, "dx_add") if dx_add is not None else 0, _p(dw_acc), _p(db_acc), _stream())
+
+
+# ------------------------------------------------------------------ GEMM
+def gemm(A, B, C, *, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=None, batch=1, strideA=0, strideB=0,
+         strideC=0, bias=None, residual=None, ldr=0, strideR=0, alpha=1.0, causal=0, tile_n=0, max_ctas=0):
+    """C[b] = alpha * A[b] @ B[b]^T (+bias) (+residual); raw strided form (see the header)."""
+    _chk(A, BF16, "A"); _chk(B, BF16, "B"); _chk(bias, F32, "bias"); _chk(residual, BF16, "residual")
+    if C.dtype not in (BF16, F32):
+        raise OqError("C must be bf16 or fp32")
+    lib().call("oq_gemm_bf16", _p(A), int(a_mn), lda, strideA, _p(B), int(b_mn), ldb, strideB, _p(C),
+               int(C.dtype == F32), ldc, strideC, M, N, K, batch, _p(bias), _p(residual), ldr, strideR, float(alpha),
+               causal, tile_n, max_ctas, _stream())
+
+
+def linear_fwd(x, wq, out, bias=None, residual=None):
+    """out[M,N] = x[M,K] @ wq[N,K]^T + bias + residual   (QuantLinear forward GEMM)."""
+    M, K = x.shape
+    N = wq.shape[0]
+    gemm(x, wq, out, M=M, N=N, K=K, lda=_rowmajor(x, "x"), ldb=_rowmajor(wq, "wq"), ldc=_rowmajor(out, "out"), bias=bias,
+         residual=residual, ldr=_rowmajor(residual, "residual") if residual is not None else 0)
+
+
+def linear_dgrad(dy, wq, dx, residual=None):
+    """dx[M,K] = dy[M,N] @ wq[N,K]   (B operand read N-major, no transpose copy)."""
+    M, N = dy.shape
+    K = wq.shape[1]
+    gemm(dy, wq, dx, M=M, N=K, K=N, lda=_rowmajor(dy, "dy"), b_mn=True, ldb=_rowmajor(wq, "wq"), ldc=_rowmajor(dx, "dx"),
+         residual=residual, ldr=_rowmajor(residual, "residual") if residual is not None else 0)
+
+
+def linear_wgrad(dy, x, dw):
+    """dw[N,K] = dy[M,N]^T @ x[M,K]   (both operands read MN-major)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    gemm(dy, x, dw, M=N, N=K, K=M, a_mn=True, lda=_rowmajor(dy, "dy"), b_mn=True, ldb=_rowmajor(x, "x"),
+         ldc=_rowmajor(dw, "dw"))
+
+
+# ------------------------------------------------------------------ elementwise
+def swiglu_fwd(gu, m):
+    lib().call("oq_swiglu_fwd", _p(gu), _rowmajor(gu, "gu"), _p(m), _rowmajor(m, "m"), m.shape[0], m.shape[1], _stream())
+
+
+def swiglu_bwd(gu, dm, dgu):
+    lib().call("oq_swiglu_bwd", _p(gu), _rowmajor(gu, "gu"), _p(dm), _rowmajor(dm, "dm"), _p(dgu), _rowmajor(dgu, "dgu"),
+               dm.shape[0], dm.shape[1], _stream())
+
+
+def relu_fwd(x, y):
+    lib().call("oq_relu_fwd", _p(x), _p(y), x.numel(), _stream())
+
+
+def relu_bwd(x, dy, dx):
+    lib().call("oq_relu_bwd", _p(x), _p(dy), _p(dx), x.numel(), _stream())
+
+
+def softmax_fwd(S, P, mask=None, causal=False):
+    """S fp32 [B,Tq,Tk] contiguous -> P bf16."""
+    _chk(S, F32, "S"); _chk(P, BF16, "P"); _chk(mask, F32, "mask")
+    B, Tq, Tk = S.shape
+    mbs = 0
+    if mask is not None:
+        mask = mask.reshape(-1, Tq, Tk)
+        mbs = 0 if mask.shape[0] == 1 else Tq * Tk
+    lib().call("oq_softmax_fwd", _p(S), _p(P), _p(mask), mbs, B, Tq, Tk, int(causal), _stream())
+
+
+def softmax_bwd(P, dP, dS, causal=False):
+    _chk(P, BF16, "P"); _chk(dP, F32, "dP"); _chk(dS, BF16, "dS")
+    B, Tq, Tk = P.shape
+    lib().call("oq_softmax_bwd", _p(P), _p(dP), _p(dS), B, Tq, Tk, int(causal), _stream())
+
+
+def mse_fwd_bwd(out, target, loss_acc, dout=None, target2=None):
+    _chk(out, BF16, "out"); _chk(target, BF16, "target"); _chk(target2, BF16, "target2"); _chk(loss_acc, F32, "loss_acc")
+    n = out.numel()
+    lib().call("oq_mse_fwd_bwd", _p(out), _p(target), _p(target2), n, 1.0 / n, _p(loss_acc), _p(dout), _stream())
+
+
+def adamw(p, g, m, v, step_dev, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    for n, t in (("p", p), ("g", g), ("m", m), ("v", v)):
+        _chk(t, F32, n)
+    lib().call("oq_adamw", _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, grad_scale,
+               _p(step_dev), _stream())
+
+
+def step_inc(step_dev):
+    lib().call("oq_step_inc", _p(step_dev), _stream())
+
+
+def truncate_(p, threshold=1e-2):
+    _chk(p, F32, "p")
+    lib().call("oq_truncate", _p(p), p.numel(), threshold, _stream())
+
+
+def colsum(X, out, accumulate=False):
+    _chk(X, BF16, "X"); _chk(out, F32, "out")
+    lib().call("oq_colsum", _p(X), _rowmajor(X, "X"), X.shape[0], X.shape[1], _p(out), int(accumulate), _stream())
+
+
+def transpose(x, out):
+    lib().call("oq_transpose_bf16", _p(x), _rowmajor(x, "x"), _p(out), _rowmajor(out, "out"), x.shape[0], x.shape[1],
+               _stream())

@@ -45,7 +45,7 @@ def _group_view(x: torch.Tensor, group_size: Optional[int]):
         return x, 0
     deficiency = (-x.shape[-1]) % group_size
     if deficiency:
-        x = torch.cat((x, torch.zeros((x.shape[0], deficiency), dtype=x.dtype)), dim=1)
+        x = torch.cat((x, torch.zeros((x.shape[0], deficiency), dtype=x.dtype, device=x.device)), dim=1)
     return x.reshape(-1, group_size), deficiency
 
 
@@ -69,7 +69,7 @@ def qparams(x: torch.Tensor, n_bits: int, symmetric: bool = False,
 
     def sdiv(t, d):
         if recip_div:
-            return t * torch.tensor(1.0 / d, dtype=torch.float32).to(t.dtype)
+            return t * torch.tensor(1.0 / d, dtype=torch.float32, device=t.device).to(t.dtype)
         return t / d
 
     if symmetric:
@@ -349,7 +349,7 @@ def llama_forward(x, T, n_heads, cos, sin, mask, cfg: QCfg, act_quant=True, eps=
     s = torch.matmul(q, k.transpose(2, 3)) / math.sqrt(d)
     if mask is not None:
         s = s + mask
-        s = torch.max(s, torch.tensor(torch.finfo(s.dtype).min))
+        s = torch.max(s, torch.tensor(torch.finfo(s.dtype).min, device=s.device))
     p = F.softmax(s, dim=-1, dtype=torch.float32).to(q.dtype)
     v = aq(v, cfg, act_quant)
     o = torch.matmul(p, v).transpose(1, 2).reshape(b, L, H)
@@ -409,7 +409,7 @@ def opt_forward(x, T, n_heads, mask, cfg: QCfg, act_quant=True, eps=1e-5):
     s = torch.bmm(sh(q), sh(k).transpose(1, 2))
     if mask is not None:
         s = s.view(b, n_heads, L, L) + mask
-        s = torch.max(s, torch.tensor(torch.finfo(s.dtype).min)).view(b * n_heads, L, L)
+        s = torch.max(s, torch.tensor(torch.finfo(s.dtype).min, device=s.device)).view(b * n_heads, L, L)
     p = F.softmax(s, dim=-1)
     o = torch.bmm(p, sh(v)).view(b, n_heads, L, d).transpose(1, 2).reshape(b, L, H)
     h1 = x + lin(o, "o")

@@ -1,0 +1,483 @@
+"""Parity of every CUDA kernel (called through the C ABI) against the CPU oracle
+(oracle/oq_oracle.py), the golden fixtures generated from the live reference,
+and -- for the floating-point GEMM / norm / softmax -- a torch fp32 reference.
+
+Bit-exactness bar (BASELINE.json north_star): integer codes, scales and zero
+points of the weight quantiser are compared bit for bit.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import load, t
+from oracle import oq_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+KAT = load("quantizer_kat.npz")
+W_CASES = sorted({k.split("/")[0] for k in KAT.files if k.startswith("w")})
+A_CASES = sorted({k.split("/")[0] for k in KAT.files if k.startswith("a")})
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from omniquant_b200 import ops as o
+    return o
+
+
+def cu(x, dtype=None):
+    x = torch.as_tensor(np.asarray(x)) if not isinstance(x, torch.Tensor) else x
+    x = x.cuda()
+    return x.to(dtype) if dtype is not None else x
+
+
+def bits_equal(a, b):
+    a = np.ascontiguousarray(np.asarray(a, np.float32)).ravel()
+    b = np.ascontiguousarray(np.asarray(b, np.float32)).ravel()
+    assert a.shape == b.shape
+    return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b)) | ((a == 0) & (b == 0))
+
+
+def run_wq(ops, W, nb, sym, grp, up, low, recip, **kw):
+    N, K = W.shape
+    G = math.ceil(K / grp) if grp else 1
+    out = dict(wq_f32=torch.empty(N, K, device="cuda"), wq_bf16=torch.empty(N, K, device="cuda", dtype=torch.bfloat16),
+               codes=torch.empty(N, K, device="cuda", dtype=torch.uint8),
+               scale_out=torch.empty(N * G, device="cuda"), zp_out=torch.empty(N * G, device="cuda"),
+               xmin_out=torch.empty(N * G, device="cuda"), xmax_out=torch.empty(N * G, device="cuda"))
+    ops.weight_quant_fwd(W, n_bits=nb, symmetric=sym, group_size=grp, up=up, low=low, recip_div=recip, **out, **kw)
+    torch.cuda.synchronize()
+    return out
+
+
+# ---------------------------------------------------------------- weight quantiser: bit-exact
+@pytest.mark.parametrize("case", W_CASES)
+def test_weight_quant_bit_exact_vs_golden(ops, case):
+    """recip_div=0 (CPU ATen division semantics) against fixtures made by the reference on CPU.
+    The kernel evaluates sigmoid() itself (CUDA expf) while the fixture used ATen's CPU sigmoid, so
+    first check with the numpy oracle fed the *device* sigmoid (must be bit-exact everywhere), then
+    against the fixture directly (bit-exact wherever the two sigmoids agree bit for bit)."""
+    g = lambda k: KAT[f"{case}/{k}"]
+    nb, sym, grp, lwc = [int(v) for v in g("meta")]
+    W = cu(g("W"))
+    up = cu(g("up")).reshape(-1) if lwc else None
+    low = cu(g("low")).reshape(-1) if lwc else None
+    out = run_wq(ops, W, nb, bool(sym), grp, up, low, False)
+    sig_up = torch.sigmoid(up).cpu().numpy() if lwc else None
+    sig_low = torch.sigmoid(low).cpu().numpy() if lwc else None
+    deq, s, z, codes = orc.fake_quant_numpy(g("W"), nb, bool(sym), grp or None, sig_up, sig_low)
+    N, K = g("W").shape
+    assert bits_equal(out["scale_out"].cpu().numpy(), s).all()
+    assert bits_equal(out["zp_out"].cpu().numpy(), z).all()
+    assert bits_equal(out["wq_f32"].cpu().numpy(), deq).all()
+    cg = codes.reshape(N, -1)[:, :K]
+    ok = np.isnan(cg) | (cg == out["codes"].cpu().numpy().astype(np.float32))
+    assert ok.all()
+    # bf16 operand = round-to-nearest-even of the fp32 dequantised value
+    ref_bf = torch.from_numpy(deq).to(torch.bfloat16)
+    got_bf = out["wq_bf16"].cpu()
+    assert (torch.isnan(ref_bf) | (ref_bf == got_bf)).all()
+    # straight against the reference's fixture
+    same_sig = np.ones(s.size, bool)
+    if lwc and f"{case}/sig_up" in KAT.files:
+        same_sig = bits_equal(sig_up, g("sig_up")) & bits_equal(sig_low, g("sig_low"))
+    se = bits_equal(out["scale_out"].cpu().numpy(), g("scale"))
+    assert se[same_sig].all()
+    assert bits_equal(out["zp_out"].cpu().numpy(), g("zp"))[same_sig].all()
+    frac = 1.0 - bits_equal(out["wq_f32"].cpu().numpy(), g("deq")).mean()
+    assert frac <= (1.0 - same_sig.mean()) + 1e-12, f"dequant mismatch fraction {frac}"
+
+
+@pytest.mark.parametrize("case", W_CASES)
+def test_weight_quant_bit_exact_vs_cuda_aten(ops, case):
+    """recip_div=1: the reference's own arithmetic executed by ATen on this GPU (the oracle's torch
+    functions run on CUDA tensors) -- scales, zero points, codes bit-exact."""
+    g = lambda k: KAT[f"{case}/{k}"]
+    nb, sym, grp, lwc = [int(v) for v in g("meta")]
+    W = cu(g("W"))
+    up = cu(g("up")) if lwc else None
+    low = cu(g("low")) if lwc else None
+    deq, s, z, codes = orc.fake_quant(W, nb, bool(sym), grp or None, up, low, return_all=True)
+    out = run_wq(ops, W, nb, bool(sym), grp, up.reshape(-1) if lwc else None, low.reshape(-1) if lwc else None, True)
+    assert bits_equal(out["scale_out"].cpu().numpy(), s.cpu().numpy()).all()
+    assert bits_equal(out["zp_out"].cpu().numpy(), z.cpu().numpy()).all()
+    assert bits_equal(out["wq_f32"].cpu().numpy(), deq.cpu().numpy()).all()
+
+
+def test_weight_quant_large_bit_exact(ops):
+    """LLaMA-7B sized rows (K=4096 and 11008, per-channel and g128), random LWC factors."""
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    for (N, K, grp, nb) in [(512, 4096, 0, 4), (256, 11008, 0, 4), (256, 4096, 128, 3), (128, 11008, 64, 2)]:
+        W = (torch.randn(N, K, device="cuda", generator=gen) * 0.02).half().float()
+        G = K // grp if grp else 1
+        up = torch.randn(N * G, 1, device="cuda", generator=gen) * 1.5 + 3
+        low = torch.randn(N * G, 1, device="cuda", generator=gen) * 1.5 + 3
+        deq, s, z, _ = orc.fake_quant(W, nb, False, grp or None, up, low, return_all=True)
+        out = run_wq(ops, W, nb, False, grp, up.reshape(-1), low.reshape(-1), True)
+        assert torch.equal(out["scale_out"], s.reshape(-1))
+        assert torch.equal(out["zp_out"], z.reshape(-1))
+        assert torch.equal(out["wq_f32"], deq)
+
+
+def test_weight_quant_let_fold_and_matvec(ops):
+    """fold (W*col)/row and (W*col)*row in the reference's op order + W@shift."""
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    N, K = 192, 320
+    W = (torch.randn(N, K, device="cuda", generator=gen) * 0.05).half().float()
+    col = torch.rand(K, device="cuda", generator=gen) + 0.5
+    row = torch.rand(N, device="cuda", generator=gen) + 0.5
+    shift = torch.randn(K, device="cuda", generator=gen) * 0.1
+    up = torch.full((N, 1), 4.0, device="cuda")
+    for grp in (0, 64):
+        G = K // grp if grp else 1
+        upg = torch.full((N * G, 1), 4.0, device="cuda")
+        for row_op, fold in ((2, lambda w: (w * col.view(1, -1)) / row.view(-1, 1)),
+                             (1, lambda w: (w * col.view(1, -1)) * row.view(-1, 1)), (0, lambda w: w * col.view(1, -1))):
+            mv = torch.empty(N, device="cuda")
+            out = run_wq(ops, W, 4, False, grp, upg.reshape(-1), upg.reshape(-1), True, col_scale=col,
+                         row_scale=row if row_op else None, row_op=row_op, shift=shift, matvec_out=mv)
+            deq, s, z, _ = orc.fake_quant(fold(W), 4, False, grp or None, upg, upg, return_all=True)
+            assert torch.equal(out["wq_f32"], deq)
+            torch.testing.assert_close(mv, W @ shift, rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------- weight quantiser backward
+@pytest.mark.parametrize("case", [c for c in W_CASES if f"{c}/dW" in KAT.files and c != "w4_pc_asym"])
+def test_weight_quant_bwd_vs_golden(ops, case):
+    g = lambda k: KAT[f"{case}/{k}"]
+    nb, sym, grp, lwc = [int(v) for v in g("meta")]
+    W = cu(g("W"))
+    N, K = W.shape
+    up = cu(g("up")).reshape(-1) if lwc else None
+    low = cu(g("low")).reshape(-1) if lwc else None
+    out = run_wq(ops, W, nb, bool(sym), grp, up, low, False)
+    G = out["scale_out"].numel()
+    d_up, d_low = torch.zeros(G, device="cuda"), torch.zeros(G, device="cuda")
+    dW = torch.zeros(N, K, device="cuda")
+    ops.weight_quant_bwd(W, cu(g("gy")), out["xmin_out"], out["xmax_out"], n_bits=nb, symmetric=bool(sym),
+                         group_size=grp, up=up, low=low, recip_div=False, d_up=d_up, d_low=d_low, dW_full=dW)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(dW.cpu().numpy(), g("dW"), rtol=1e-4, atol=1e-5)
+    if lwc:
+        np.testing.assert_allclose(d_up.cpu().numpy(), g("d_up").ravel(), rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(d_low.cpu().numpy(), g("d_low").ravel(), rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("grp,row_op", [(0, 2), (0, 1), (64, 2), (0, 0)])
+def test_weight_quant_bwd_let_reductions(ops, grp, row_op):
+    """dcol / drow / dshift / d_up / d_low against oracle autograd through fold + fake-quant."""
+    gen = torch.Generator().manual_seed(11)
+    N, K = 96, 256
+    W = (torch.randn(N, K, generator=gen) * 0.05).half().float()
+    col = (torch.rand(K, generator=gen) + 0.5).requires_grad_(True)
+    row = (torch.rand(N, generator=gen) + 0.5).requires_grad_(True)
+    shift = (torch.randn(K, generator=gen) * 0.1).requires_grad_(True)
+    G = K // grp if grp else 1
+    up = (torch.randn(N * G, 1, generator=gen) + 3).requires_grad_(True)
+    low = (torch.randn(N * G, 1, generator=gen) + 3).requires_grad_(True)
+    gy = torch.randn(N, K, generator=gen)
+    e = torch.randn(N, generator=gen)
+    W1 = W * col.view(1, -1)
+    W2 = W1 / row.view(-1, 1) if row_op == 2 else (W1 * row.view(-1, 1) if row_op == 1 else W1)
+    y = orc.fake_quant(W2, 4, False, grp or None, up, low)
+    ((y * gy).sum() + ((W @ shift) * e).sum()).backward()
+    Wc = W.cuda()
+    out = run_wq(ops, Wc, 4, False, grp, up.detach().cuda().reshape(-1), low.detach().cuda().reshape(-1), False,
+                 col_scale=col.detach().cuda(), row_scale=row.detach().cuda() if row_op else None, row_op=row_op)
+    d_up, d_low = torch.zeros(N * G, device="cuda"), torch.zeros(N * G, device="cuda")
+    dcol, dshift, drow = torch.zeros(K, device="cuda"), torch.zeros(K, device="cuda"), torch.zeros(N, device="cuda")
+    for gdt in (torch.float32, torch.bfloat16):
+        dcol.zero_(); dshift.zero_()
+        ops.weight_quant_bwd(Wc, gy.cuda().to(gdt), out["xmin_out"], out["xmax_out"], n_bits=4, group_size=grp,
+                             up=up.detach().cuda().reshape(-1), low=low.detach().cuda().reshape(-1), recip_div=False,
+                             col_scale=col.detach().cuda(), row_scale=row.detach().cuda() if row_op else None,
+                             row_op=row_op, e_row=e.cuda(), d_up=d_up, d_low=d_low, dcol_acc=dcol, drow=drow,
+                             dshift_acc=dshift)
+        torch.cuda.synchronize()
+        tol = dict(rtol=2e-3, atol=2e-3) if gdt == torch.float32 else dict(rtol=3e-2, atol=5e-2)
+        torch.testing.assert_close(dcol.cpu(), col.grad, **tol)
+        torch.testing.assert_close(dshift.cpu(), shift.grad, rtol=1e-3, atol=1e-4)
+        torch.testing.assert_close(d_up.cpu(), up.grad.reshape(-1), **tol)
+        torch.testing.assert_close(d_low.cpu(), low.grad.reshape(-1), **tol)
+        if row_op:
+            # drow holds sum_k dW2*W1; apply the op's own factor
+            r = row.detach()
+            ref = drow.cpu() * (1.0 if row_op == 1 else -1.0) / (1.0 if row_op == 1 else r * r)
+            torch.testing.assert_close(ref, row.grad, **tol)
+
+
+# ---------------------------------------------------------------- activation quantiser
+@pytest.mark.parametrize("case", A_CASES)
+def test_act_quant_vs_golden(ops, case):
+    """bf16-representable inputs: fixtures hold fp16 values, so re-run the oracle on the bf16-rounded
+    input (fp32 arithmetic, CPU division semantics) and compare dequantised values exactly."""
+    g = lambda k: KAT[f"{case}/{k}"]
+    nb = int(g("meta")[0])
+    X = t(g("X")).to(torch.bfloat16)
+    C = X.shape[-1]
+    Xf = X.float().reshape(-1, C).requires_grad_(True)
+    deq, s, z, _ = orc.fake_quant(Xf, nb, return_all=True)
+    gy = t(g("gy")).to(torch.bfloat16).reshape(-1, C)
+    deq.backward(gy.float())
+    x = X.reshape(-1, C).cuda()
+    y = torch.empty_like(x)
+    sc, zp = torch.empty(x.shape[0], device="cuda"), torch.empty(x.shape[0], device="cuda")
+    ops.act_quant_fwd(x, y, n_bits=nb, recip_div=False, scale_out=sc, zp_out=zp)
+    gx = torch.empty_like(x)
+    ops.act_quant_bwd(x, gy.cuda(), gx, n_bits=nb, recip_div=False)
+    torch.cuda.synchronize()
+    assert torch.equal(sc.cpu(), s.detach().reshape(-1))
+    assert torch.equal(zp.cpu(), z.detach().reshape(-1))
+    assert torch.equal(y.cpu(), deq.detach().to(torch.bfloat16))
+    torch.testing.assert_close(gx.cpu().float(), Xf.grad, rtol=1e-2, atol=1e-2)
+
+
+def test_act_quant_rope_heads(ops):
+    """fused rotary + per-(token, head) quant on the strided [T, 3H] QKV buffer (d=128 and d=64)."""
+    gen = torch.Generator().manual_seed(5)
+    for d, h, T in ((128, 4, 48), (64, 6, 40)):
+        H = h * d
+        qkv = torch.randn(T, 3 * H, generator=gen).to(torch.bfloat16)
+        cos, sin = orc.rope_tables(d, T)
+        q = qkv[:, :H].float().view(T, h, d).requires_grad_(True)
+        qr, _ = orc.apply_rope(q.transpose(0, 1)[None], q.transpose(0, 1)[None], cos, sin)
+        ref = orc.fake_quant(qr, 4)                      # [1,h,T,d]
+        gy = torch.randn(T, h, d, generator=gen).to(torch.bfloat16)
+        ref.backward(gy.float().transpose(0, 1)[None])
+        dq = qkv.cuda()
+        x = dq[:, :H].view(T, h, d)
+        y = torch.empty(T, h, d, device="cuda", dtype=torch.bfloat16)
+        ops.act_quant_fwd(x, y, n_bits=4, recip_div=False, cos=cos.cuda(), sin=sin.cuda(), seq_len=T)
+        gx = torch.empty(T, h, d, device="cuda", dtype=torch.bfloat16)
+        ops.act_quant_bwd(x, gy.cuda(), gx, n_bits=4, recip_div=False, cos=cos.cuda(), sin=sin.cuda(), seq_len=T)
+        torch.cuda.synchronize()
+        refy = ref.detach()[0].transpose(0, 1)
+        # codes can flip where the fused fp32 rope differs in the last ulp from the unfused one
+        mism = (y.cpu().float() - refy).abs() > 1e-2 * refy.abs().max()
+        assert mism.float().mean() < 2e-3
+        torch.testing.assert_close(gx.cpu().float(), q.grad, rtol=5e-2, atol=5e-2)
+        # rope only
+        y2 = torch.empty_like(y)
+        ops.act_quant_fwd(x, y2, n_bits=16, cos=cos.cuda(), sin=sin.cuda(), seq_len=T)
+        torch.testing.assert_close(y2.cpu().float(), qr.detach()[0].transpose(0, 1), rtol=1e-2, atol=1e-2)
+
+
+def test_act_quant_large_rows(ops):
+    gen = torch.Generator().manual_seed(9)
+    for C in (4096, 11008, 768, 100):
+        X = (torch.randn(64, C, generator=gen) * 2).to(torch.bfloat16)
+        X[:, 7] *= 20
+        ref, s, z, _ = orc.fake_quant(X.float(), 4, return_all=True)
+        x = X.cuda()
+        y = torch.empty_like(x)
+        sc = torch.empty(64, device="cuda")
+        ops.act_quant_fwd(x, y, n_bits=4, recip_div=False, scale_out=sc)
+        torch.cuda.synchronize()
+        assert torch.equal(sc.cpu(), s.reshape(-1))
+        assert torch.equal(y.cpu(), ref.to(torch.bfloat16))
+
+
+# ---------------------------------------------------------------- norms
+@pytest.mark.parametrize("kind,C", [(0, 4096), (0, 256), (1, 768), (1, 100)])
+def test_norm_fwd_bwd(ops, kind, C):
+    gen = torch.Generator().manual_seed(2)
+    R = 96
+    X = torch.randn(R, C, generator=gen).to(torch.bfloat16)
+    w = (1 + 0.1 * torch.randn(C, generator=gen)).requires_grad_(True)
+    b = (0.1 * torch.randn(C, generator=gen)).requires_grad_(True)
+    xf = X.float().requires_grad_(True)
+    eps = 1e-6 if kind == 0 else 1e-5
+    ref = orc.rms_norm(xf, w, b, eps) if kind == 0 else orc.layer_norm(xf, w, b, eps)
+    gy = torch.randn(R, C, generator=gen).to(torch.bfloat16)
+    add = torch.randn(R, C, generator=gen).to(torch.bfloat16)
+    ref.backward(gy.float())
+    x = X.cuda()
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(R, device="cuda"), torch.empty(R, device="cuda")
+    ops.norm_fwd(x, w.detach().cuda(), b.detach().cuda(), eps, kind, y, mean, rstd)
+    dx = torch.empty_like(x)
+    dw, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    ops.norm_bwd(x, w.detach().cuda(), kind, mean, rstd, gy.cuda(), dx=dx, dx_add=add.cuda(), dw_acc=dw, db_acc=db)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(y.cpu().float(), ref.detach(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(dx.cpu().float(), xf.grad + add.float(), rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(dw.cpu(), w.grad, rtol=1e-3, atol=1e-2)
+    torch.testing.assert_close(db.cpu(), b.grad, rtol=1e-3, atol=1e-2)
+
+
+# ---------------------------------------------------------------- GEMM (tcgen05)
+def _gemm_ref(A, B, alpha=1.0, bias=None, res=None):
+    out = alpha * (A.float() @ B.float().transpose(-1, -2))
+    if bias is not None:
+        out = out + bias
+    if res is not None:
+        out = out + res.float()
+    return out
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K,tile_n", [(256, 512, 256, 256), (200, 344, 136, 0), (128, 128, 64, 128), (384, 264, 1032, 256)])
+def test_gemm_layouts(ops, a_mn, b_mn, M, N, K, tile_n):
+    gen = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=gen).to(torch.bfloat16)
+    B = torch.randn(N, K, device="cuda", generator=gen).to(torch.bfloat16)
+    As = A.t().contiguous() if a_mn else A
+    Bs = B.t().contiguous() if b_mn else B
+    bias = torch.randn(N, device="cuda", generator=gen)
+    res = torch.randn(M, N, device="cuda", generator=gen).to(torch.bfloat16)
+    for cdt in (torch.float32, torch.bfloat16):
+        C = torch.full((M, N), float("nan"), device="cuda", dtype=cdt)
+        ops.gemm(As, Bs, C, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, lda=As.stride(0), ldb=Bs.stride(0), ldc=N, bias=bias,
+                 residual=res, ldr=N, alpha=0.5, tile_n=tile_n)
+        torch.cuda.synchronize()
+        ref = _gemm_ref(A, B, 0.5, bias, res)
+        tol = dict(rtol=1e-3, atol=1e-2) if cdt == torch.float32 else dict(rtol=2e-2, atol=1e-1)
+        torch.testing.assert_close(C.float(), ref, **tol)
+
+
+def test_gemm_llama_shapes_and_linear_helpers(ops):
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    M, K, N = 2048, 4096, 4096
+    x = torch.randn(M, K, device="cuda", generator=gen).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=gen) * 0.02).to(torch.bfloat16)
+    dy = torch.randn(M, N, device="cuda", generator=gen).to(torch.bfloat16)
+    y = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.linear_fwd(x, w, y)
+    dx = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
+    ops.linear_dgrad(dy, w, dx)
+    dw = torch.empty(N, K, device="cuda", dtype=torch.float32)
+    ops.linear_wgrad(dy, x, dw)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(y.float(), x.float() @ w.float().t(), rtol=2e-2, atol=5e-2)
+    torch.testing.assert_close(dx.float(), dy.float() @ w.float(), rtol=2e-2, atol=5e-2)
+    torch.testing.assert_close(dw, dy.float().t() @ x.float(), rtol=1e-3, atol=5e-2)
+
+
+def test_gemm_batched_heads_and_causal(ops):
+    """QuantMatMul shapes: per-head operands are strided slices of [T, H] buffers."""
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    T, h, d = 384, 3, 128
+    H = h * d
+    Q = torch.randn(T, H, device="cuda", generator=gen).to(torch.bfloat16)
+    Kt = torch.randn(T, H, device="cuda", generator=gen).to(torch.bfloat16)
+    V = torch.randn(T, H, device="cuda", generator=gen).to(torch.bfloat16)
+    qh = Q.view(T, h, d).transpose(0, 1).float()
+    kh = Kt.view(T, h, d).transpose(0, 1).float()
+    vh = V.view(T, h, d).transpose(0, 1).float()
+    tri = torch.tril(torch.ones(T, T, device="cuda", dtype=torch.bool))
+    for causal in (0, 1):
+        S = torch.zeros(h, T, T, device="cuda")
+        ops.gemm(Q, Kt, S, M=T, N=T, K=d, lda=H, ldb=H, ldc=T, batch=h, strideA=d, strideB=d, strideC=T * T,
+                 alpha=1 / math.sqrt(d), causal=causal)
+        torch.cuda.synchronize()
+        ref = qh @ kh.transpose(1, 2) / math.sqrt(d)
+        if causal:
+            torch.testing.assert_close(S[:, tri], ref[:, tri], rtol=1e-3, atol=1e-2)
+        else:
+            torch.testing.assert_close(S, ref, rtol=1e-3, atol=1e-2)
+    P = torch.softmax(ref.masked_fill(~tri, float("-inf")), -1).to(torch.bfloat16)
+    # O = P V  (B operand N-major), k-limited
+    for causal in (0, 2):
+        O = torch.empty(T, H, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(P, V, O, M=T, N=d, K=T, lda=T, ldb=H, b_mn=True, ldc=H, batch=h, strideA=T * T, strideB=d, strideC=d,
+                 causal=causal)
+        torch.cuda.synchronize()
+        refO = (P.float() @ vh).transpose(0, 1).reshape(T, H)
+        torch.testing.assert_close(O.float(), refO, rtol=2e-2, atol=2e-2)
+    # dV = P^T dO (both MN-major), k-start limited
+    dO = torch.randn(T, H, device="cuda", generator=gen).to(torch.bfloat16)
+    for causal in (0, 3):
+        dV = torch.empty(T, H, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(P, dO, dV, M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=H, ldc=H, batch=h, strideA=T * T, strideB=d,
+                 strideC=d, causal=causal)
+        torch.cuda.synchronize()
+        refdV = (P.float().transpose(1, 2) @ dO.view(T, h, d).transpose(0, 1).float()).transpose(0, 1).reshape(T, H)
+        torch.testing.assert_close(dV.float(), refdV, rtol=2e-2, atol=5e-2)
+
+
+# ---------------------------------------------------------------- elementwise
+def test_swiglu_relu(ops):
+    gen = torch.Generator().manual_seed(6)
+    R, Fd = 40, 704
+    gu = torch.randn(R, 2 * Fd, generator=gen).to(torch.bfloat16)
+    g = gu[:, :Fd].float().requires_grad_(True)
+    u = gu[:, Fd:].float().requires_grad_(True)
+    ref = torch.nn.functional.silu(g) * u
+    dm = torch.randn(R, Fd, generator=gen).to(torch.bfloat16)
+    ref.backward(dm.float())
+    m = torch.empty(R, Fd, device="cuda", dtype=torch.bfloat16)
+    ops.swiglu_fwd(gu.cuda(), m)
+    dgu = torch.empty(R, 2 * Fd, device="cuda", dtype=torch.bfloat16)
+    ops.swiglu_bwd(gu.cuda(), dm.cuda(), dgu)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(m.cpu().float(), ref.detach(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(dgu.cpu().float(), torch.cat([g.grad, u.grad], 1), rtol=2e-2, atol=2e-2)
+    x = torch.randn(R, Fd, generator=gen).to(torch.bfloat16).cuda()
+    y, dx = torch.empty_like(x), torch.empty_like(x)
+    ops.relu_fwd(x, y)
+    ops.relu_bwd(x, dm.cuda(), dx)
+    torch.cuda.synchronize()
+    assert torch.equal(y, torch.relu(x))
+    assert torch.equal(dx, torch.where(x > 0, dm.cuda(), torch.zeros_like(x)))
+
+
+def test_softmax_fwd_bwd(ops):
+    gen = torch.Generator().manual_seed(8)
+    B, T = 3, 200
+    S = (torch.randn(B, T, T, generator=gen) * 3).requires_grad_(True)
+    mask = orc.causal_mask(T)[0]
+    ref = torch.softmax(torch.max(S + mask, torch.tensor(torch.finfo(torch.float32).min)), -1)
+    dP = torch.randn(B, T, T, generator=gen)
+    ref.backward(dP)
+    for kw in (dict(causal=True), dict(mask=mask.cuda())):
+        P = torch.empty(B, T, T, device="cuda", dtype=torch.bfloat16)
+        ops.softmax_fwd(S.detach().cuda(), P, **kw)
+        dS = torch.empty_like(P)
+        ops.softmax_bwd(P, dP.cuda(), dS, causal=kw.get("causal", False))
+        torch.cuda.synchronize()
+        torch.testing.assert_close(P.cpu().float(), ref.detach(), rtol=1e-2, atol=4e-3)
+        torch.testing.assert_close(dS.cpu().float(), S.grad, rtol=5e-2, atol=1e-2)
+
+
+def test_mse_adamw_colsum_truncate_transpose(ops):
+    gen = torch.Generator().manual_seed(10)
+    n = 64 * 256
+    out = torch.randn(64, 256, generator=gen).to(torch.bfloat16)
+    tgt = torch.randn(64, 256, generator=gen).to(torch.bfloat16)
+    tg2 = torch.randn(64, 256, generator=gen).to(torch.bfloat16)
+    o = out.float().requires_grad_(True)
+    ref = torch.nn.functional.mse_loss(tgt.float(), o) + torch.nn.functional.mse_loss(tg2.float(), o)
+    ref.backward()
+    loss = torch.zeros(1, device="cuda")
+    dout = torch.empty(64, 256, device="cuda", dtype=torch.bfloat16)
+    ops.mse_fwd_bwd(out.cuda(), tgt.cuda(), loss, dout, target2=tg2.cuda())
+    torch.cuda.synchronize()
+    torch.testing.assert_close(loss.cpu()[0], ref.detach(), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(dout.cpu().float(), o.grad, rtol=1e-2, atol=1e-7)
+    # AdamW: 5 steps against torch.optim.AdamW
+    p0 = torch.randn(1000, generator=gen)
+    pt = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pt], lr=1e-2, weight_decay=0.1)
+    p = p0.cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.zeros(1, device="cuda", dtype=torch.int32)
+    for _ in range(5):
+        g = torch.randn(1000, generator=gen)
+        pt.grad = g.clone()
+        opt.step()
+        ops.step_inc(step)
+        ops.adamw(p, (g * 4).cuda(), m, v, step, lr=1e-2, weight_decay=0.1, grad_scale=0.25)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(p.cpu(), pt.detach(), rtol=1e-5, atol=1e-6)
+    X = torch.randn(300, 520, generator=gen).to(torch.bfloat16)
+    cs = torch.empty(520, device="cuda")
+    ops.colsum(X.cuda(), cs)
+    torch.testing.assert_close(cs.cpu(), X.float().sum(0), rtol=1e-4, atol=1e-3)
+    q = torch.tensor([0.5, 0.005, -0.003, 0.0, -2.0, 0.01], device="cuda")
+    ops.truncate_(q, 1e-2)
+    assert q.cpu().tolist() == pytest.approx([0.5, 0.01, -0.01, 0.0, -2.0, 0.01])
+    Xt = torch.empty(520, 300, device="cuda", dtype=torch.bfloat16)
+    ops.transpose(X.cuda(), Xt)
+    assert torch.equal(Xt.cpu(), X.t())
