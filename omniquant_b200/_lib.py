@@ -94,6 +94,7 @@ class _Lib:
         self.cdll = ctypes.CDLL(path)
         self.cdll.oq_last_error.restype = ctypes.c_char_p
         self.fns = {}
+        self.launches = 0      # library calls issued (each enqueues one kernel; a few add a memset)
         for name, (ret, params) in declared_functions().items():
             fn = getattr(self.cdll, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = ctypes.c_char_p if "char" in ret else ctypes.c_int
@@ -101,6 +102,7 @@ class _Lib:
             self.fns[name] = fn
 
     def call(self, name: str, *args):
+        self.launches += 1
         rc = self.fns[name](*args)
         if rc != 0:
             msg = self.cdll.oq_last_error()

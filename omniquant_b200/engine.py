@@ -1,0 +1,608 @@
+"""Block calibration engine: one decoder block's LWC/LET training step as an explicit,
+hand-scheduled sequence of sm_100a kernels (forward, backward, optimiser), no autograd.
+
+This is the B200-native replacement for the body of the reference's per-block loop
+(quantize/omniquant.py:157-250): ``smooth_and_quant_temporary`` -> block forward -> MSE ->
+backward -> AdamW, plus the FP pass (:165-172), the in-place fold/quantise (:239) and the
+re-quantised forward pass (:242-245).  The reference's module API (omniquant_b200/quantize,
+omniquant_b200/models) drives this engine; all device compute is the C-ABI library.
+
+Data layout in HBM (M = batch*T token rows, bf16 activations, fp32 masters):
+  weights   fp32 masters, concatenated by consumer:  Wqkv [3H,H], Wo [H,H], Wgu [2F,H] (gate|up) or
+            Wfc1 [F,H], Wd [H,F];  fake-quantised bf16 copies of the same shapes feed the GEMMs
+  params    one flat fp32 buffer  [LET scales | LET shifts | LWC up/low per weight]  (+ flat grad, m, v)
+  acts      a1,a1q [M,H]  qkv,qkvq [M,3H]  S/dP fp32 [h,T,T] (scratch)  P [b,h,T,T]  O,Oq,h1,a2,a2q [M,H]
+            gu [M,2F]  m,mq [M,F]  out [M,H]   and the matching gradient buffers
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+@dataclass
+class QuantConfig:
+    """The quantiser parameter dicts of main.py:268-303, flattened."""
+    wbits: int = 4
+    abits: int = 4
+    group_size: int = 0
+    symmetric: bool = False
+    lwc: bool = True
+    let: bool = True
+    recip_div: bool = True   # ATen-CUDA semantics of `x / (2**n - 1)`; False = ATen-CPU (true division)
+
+    @property
+    def act_quant(self):
+        return self.abits < 16
+
+
+class _Unit:
+    """One weight-quant launch: a row range of a concatenated master weight."""
+
+    def __init__(self, name, group, r0, r1, K, col=None, row=None, row_op=0, shift=None):
+        self.name, self.group, self.r0, self.r1, self.K = name, group, r0, r1, K
+        self.col, self.row, self.row_op, self.shift = col, row, row_op, shift
+        self.N = r1 - r0
+
+
+class BlockEngine:
+    LET_SCALES = ("qkv_s", "out_s", "fc1_s", "qkt_s")
+    LET_SHIFTS = ("qkv_d", "out_d", "fc1_d")
+
+    def __init__(self, family: str, weights: Dict[str, torch.Tensor], *, n_heads: int, seq_len: int, qcfg: QuantConfig,
+                 eps: float, device="cuda", batch: int = 1, let_init: Optional[Dict[str, torch.Tensor]] = None,
+                 let_lr=5e-3, lwc_lr=1e-2, wd=0.0, world_size=1, causal=True, mask: Optional[torch.Tensor] = None):
+        assert family in ("llama", "opt")
+        self.family, self.q, self.eps, self.dev = family, qcfg, float(eps), torch.device(device)
+        self.h, self.T, self.b = n_heads, seq_len, batch
+        self.let_lr, self.lwc_lr, self.wd, self.world = let_lr, lwc_lr, wd, world_size
+        self.causal = causal and mask is None
+        self.mask = None if mask is None else mask.to(self.dev, F32).contiguous()
+        f = lambda t: t.detach().to(self.dev, F32).contiguous()
+        H = weights["q"].shape[1]
+        self.H, self.d = H, H // n_heads
+        self.M = batch * seq_len
+        glu = family == "llama"
+        self.glu = glu
+        # ---- fp32 masters, concatenated by consumer
+        self.W = {}
+        self.W["qkv"] = torch.cat([f(weights["q"]), f(weights["k"]), f(weights["v"])], 0)
+        self.W["o"] = f(weights["o"])
+        if glu:
+            self.W["fc1"] = torch.cat([f(weights["gate"]), f(weights["up"])], 0)
+            self.W["fc2"] = f(weights["down"])
+            self.F = weights["gate"].shape[0]
+        else:
+            self.W["fc1"] = f(weights["fc1"])
+            self.W["fc2"] = f(weights["fc2"])
+            self.F = weights["fc1"].shape[0]
+        F_ = self.F
+        self.norm_kind = 0 if family == "llama" else 1
+        self.ln = {"ln1w": f(weights["ln1"]), "ln2w": f(weights["ln2"]),
+                   "ln1b": f(weights["ln1.bias"]) if "ln1.bias" in weights else None,
+                   "ln2b": f(weights["ln2.bias"]) if "ln2.bias" in weights else None}
+        # raw linear biases (OPT), concatenated like the weights
+        def rawb(names):
+            if all(f"{n}.bias" in weights for n in names):
+                return torch.cat([f(weights[f"{n}.bias"]) for n in names], 0)
+            return None
+        self.rawb = {"qkv": rawb(["q", "k", "v"]), "o": rawb(["o"]),
+                     "fc1": rawb(["gate", "up"]) if glu else rawb(["fc1"]), "fc2": rawb(["down"] if glu else ["fc2"])}
+        let = qcfg.let
+        U = [
+            _Unit("q", "qkv", 0, H, H, "qkv_s", "qkt_s", 2, "qkv_d"),
+            _Unit("k", "qkv", H, 2 * H, H, "qkv_s", "qkt_s", 1, "qkv_d"),
+            _Unit("v", "qkv", 2 * H, 3 * H, H, "qkv_s", "out_s", 2, "qkv_d"),
+            _Unit("o", "o", 0, H, H, "out_s", None, 0, "out_d"),
+            _Unit("fc1", "fc1", 0, self.W["fc1"].shape[0], H, "fc1_s", None, 0, "fc1_d"),
+            _Unit("fc2", "fc2", 0, H, F_, None, None, 0, None),
+        ]
+        if not let:
+            for u in U:
+                u.col = u.row = u.shift = None
+                u.row_op = 0
+        self.units = U
+        # ---- flat parameter buffer: [LET scales | LET shifts | LWC]
+        G = lambda K: (K + qcfg.group_size - 1) // qcfg.group_size if qcfg.group_size else 1
+        layout, off = {}, 0
+        if let:
+            for n in self.LET_SCALES + self.LET_SHIFTS:
+                layout[n] = (off, H)
+                off += H
+        self.n_let = off
+        if qcfg.lwc:
+            for u in U:
+                n = u.N * G(u.K)
+                layout[f"{u.name}.up"] = (off, n)
+                layout[f"{u.name}.low"] = (off + n, n)
+                off += 2 * n
+        self.n_params = off
+        self.layout = layout
+        z = lambda n, dt=F32: torch.zeros(n, device=self.dev, dtype=dt)
+        self.params, self.grads, self.adam_m, self.adam_v = z(max(off, 1)), z(max(off, 1)), z(max(off, 1)), z(max(off, 1))
+        self.step_dev = torch.zeros(1, device=self.dev, dtype=torch.int32)
+        self.p = {n: self.params[o:o + c] for n, (o, c) in layout.items()}
+        self.g = {n: self.grads[o:o + c] for n, (o, c) in layout.items()}
+        if qcfg.lwc:
+            for u in U:
+                self.p[f"{u.name}.up"].fill_(4.0)     # quantizer.py:62
+                self.p[f"{u.name}.low"].fill_(4.0)
+        if let:
+            for n in self.LET_SCALES:
+                self.p[n].fill_(1.0)
+            if let_init:
+                for n, v in let_init.items():
+                    self.p[n].copy_(v.to(self.dev, F32))
+        # ---- per-unit quantiser state + bf16 operands
+        self.Wq = {g: torch.empty_like(w, dtype=BF16) for g, w in self.W.items()}
+        self.Wfp = None
+        self.qstat = {u.name: dict(xmin=z(u.N * G(u.K)), xmax=z(u.N * G(u.K)), mv=z(u.N)) for u in U}
+        self.tmp = {}     # folded vectors of the current step
+        self.bufs = {}
+        self.loss_slot = z(1)
+        self._acc = {k: z(H) for k in ("dcol_qkv", "dcol_out", "dcol_fc1", "dsh_qkv", "dsh_out", "dsh_fc1", "dw1", "db1",
+                                       "dw2", "db2")}
+        self._drow = {k: z(H) for k in ("q", "k", "v")}
+
+    # ------------------------------------------------------------------ helpers
+    def buf(self, name, shape, dtype=BF16):
+        t = self.bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, device=self.dev, dtype=dtype)
+            self.bufs[name] = t
+        return t
+
+    def wview(self, u: _Unit, store):
+        return store[u.group][u.r0:u.r1]
+
+    def lwc(self, u: _Unit):
+        if not self.q.lwc:
+            return None, None
+        return self.p[f"{u.name}.up"], self.p[f"{u.name}.low"]
+
+    # ------------------------------------------------------------------ step preparation (smooth_and_quant_temporary)
+    def prepare(self, final: bool = False):
+        """LET folds + weight fake-quant for this step (models/int_llama_layer.py:279-307 /
+        models/int_opt_layer.py:385-413).  With ``final`` also returns fp32 fake-quantised weights,
+        scales and zero points (smooth_and_quant_inplace + register_scales_and_zeros)."""
+        q, p = self.q, self.p
+        if q.let:
+            ops.truncate_(self.params[:4 * self.H], 1e-2)   # the four *_smooth_scale vectors are contiguous
+        extra = {}
+        for u in self.units:
+            up, low = self.lwc(u)
+            st = self.qstat[u.name]
+            kw = {}
+            if final:
+                G = st["xmin"].numel()
+                extra[u.name] = dict(weight=torch.empty(u.N, u.K, device=self.dev), scales=torch.empty(G, device=self.dev),
+                                     zeros=torch.empty(G, device=self.dev))
+                kw = dict(wq_f32=extra[u.name]["weight"], scale_out=extra[u.name]["scales"], zp_out=extra[u.name]["zeros"])
+            if q.wbits >= 16:
+                self.wview(u, self.Wq).copy_(self.wview(u, self.W))     # weights left un-quantised
+                continue
+            ops.weight_quant_fwd(self.wview(u, self.W), n_bits=q.wbits, symmetric=q.symmetric, group_size=q.group_size,
+                                 up=up, low=low, col_scale=p.get(u.col) if u.col else None,
+                                 row_scale=p.get(u.row) if u.row else None, row_op=u.row_op,
+                                 shift=p.get(u.shift) if u.shift else None, matvec_out=st["mv"] if u.shift else None,
+                                 recip_div=q.recip_div, wq_bf16=self.wview(u, self.Wq), xmin_out=st["xmin"],
+                                 xmax_out=st["xmax"], **kw)
+        t = self.tmp
+        H = self.H
+        if q.let:
+            s1, d1, s2, d2 = p["qkv_s"], p["qkv_d"], p["fc1_s"], p["fc1_d"]
+            so, do, sk = p["out_s"], p["out_d"], p["qkt_s"]
+            ln = self.ln
+            # transformation.py:28-33
+            t["ln1b"] = (ln["ln1b"] - d1) / s1 if ln["ln1b"] is not None else (-1 * d1) / s1
+            t["ln1w"] = ln["ln1w"] / s1
+            t["ln2b"] = (ln["ln2b"] - d2) / s2 if ln["ln2b"] is not None else (-1 * d2) / s2
+            t["ln2w"] = ln["ln2w"] / s2
+            mv = {u.name: self.qstat[u.name]["mv"] for u in self.units}
+            rb = self.rawb["qkv"]
+            beta = lambda name, i: mv[name] if rb is None else rb[i * H:(i + 1) * H] + mv[name]   # transformation.py:37-40
+            bq = beta("q", 0) / sk                      # :67
+            bk = beta("k", 1) * sk                      # :69
+            bv = (beta("v", 2) - do) / so               # :49-50
+            t["bqkv"] = torch.cat([bq, bk, bv])
+            t["bo"] = mv["o"] if self.rawb["o"] is None else self.rawb["o"] + mv["o"]          # :56-59
+            t["bfc1"] = mv["fc1"] if self.rawb["fc1"] is None else self.rawb["fc1"] + mv["fc1"]
+            t["bfc2"] = self.rawb["fc2"]
+        else:
+            t.update(ln1w=self.ln["ln1w"], ln1b=self.ln["ln1b"], ln2w=self.ln["ln2w"], ln2b=self.ln["ln2b"],
+                     bqkv=self.rawb["qkv"], bo=self.rawb["o"], bfc1=self.rawb["fc1"], bfc2=self.rawb["fc2"])
+        if self.family == "opt":
+            # q = (x W^T + b) * d^-0.5 is folded into the q GEMM epilogue (models/int_opt_layer.py:96)
+            t["bq_scaled"] = None if t["bqkv"] is None else t["bqkv"][:H] * self.d ** -0.5
+        t["W"] = self.Wq
+        return extra
+
+    def fp_weights(self):
+        """bf16 copies of the raw weights for the full-precision pass (quantize/omniquant.py:165-172)."""
+        if self.Wfp is None:
+            self.Wfp = {g: w.to(BF16) for g, w in self.W.items()}
+        fp = dict(W=self.Wfp, ln1w=self.ln["ln1w"], ln1b=self.ln["ln1b"], ln2w=self.ln["ln2w"], ln2b=self.ln["ln2b"],
+                  bqkv=self.rawb["qkv"], bo=self.rawb["o"], bfc1=self.rawb["fc1"], bfc2=self.rawb["fc2"])
+        if self.family == "opt":
+            fp["bq_scaled"] = None if fp["bqkv"] is None else fp["bqkv"][:self.H] * self.d ** -0.5
+        return fp
+
+    # ------------------------------------------------------------------ forward
+    def _aq(self, x, name):
+        """per-token fake-quant over the last dim (QuantLinear.act_quantizer)."""
+        if not self._act_quant:
+            return x
+        y = self.buf(name, x.shape)
+        ops.act_quant_fwd(x, y, n_bits=self.q.abits, recip_div=self.q.recip_div)
+        return y
+
+    def forward(self, x: torch.Tensor, ws: dict, act_quant: bool, out: Optional[torch.Tensor] = None):
+        """Block forward on x [M,H] bf16 (models/int_llama_layer.py:213-267 / int_opt_layer.py:268-346)."""
+        M, H, F_, h, d, T = x.shape[0], self.H, self.F, self.h, self.d, self.T
+        nb = M // T
+        self._act_quant = act_quant and self.q.act_quant
+        B = self.buf
+        self.x = x
+        a1 = B("a1", (M, H))
+        self.st1 = (B("mean1", (M,), F32), B("rstd1", (M,), F32))
+        ops.norm_fwd(x, ws["ln1w"], ws["ln1b"], self.eps, self.norm_kind, a1, *self.st1)
+        a1q = self._aq(a1, "a1q")
+        qkv = B("qkv", (M, 3 * H))
+        W = ws["W"]
+        if self.family == "llama":
+            ops.linear_fwd(a1q, W["qkv"], qkv, bias=ws["bqkv"])
+        else:
+            sc = d ** -0.5
+            ops.gemm(a1q, W["qkv"], qkv, M=M, N=H, K=H, lda=H, ldb=H, ldc=3 * H, bias=ws["bq_scaled"], alpha=sc)
+            ops.gemm(a1q, W["qkv"][H:], qkv[:, H:], M=M, N=2 * H, K=H, lda=H, ldb=H, ldc=3 * H,
+                     bias=None if ws["bqkv"] is None else ws["bqkv"][H:])
+        # ---- Q/K/V operands of QuantMatMul
+        abits = self.q.abits if self._act_quant else 16
+        if self.family == "llama":
+            qkvq = B("qkvq", (M, 3 * H))
+            cos, sin = self.rope()
+            for i in range(2):      # rotary + per-(token, head) quant of q and k (int_llama_layer.py:124-125,141-142)
+                ops.act_quant_fwd(qkv[:, i * H:(i + 1) * H].view(M, h, d), qkvq[:, i * H:(i + 1) * H].view(M, h, d),
+                                  n_bits=abits, recip_div=self.q.recip_div, cos=cos, sin=sin, seq_len=T)
+            if abits < 16:          # v quantised per (token, head) (:162)
+                ops.act_quant_fwd(qkv[:, 2 * H:].view(M, h, d), qkvq[:, 2 * H:].view(M, h, d), n_bits=abits,
+                                  recip_div=self.q.recip_div)
+            else:
+                qkvq[:, 2 * H:].copy_(qkv[:, 2 * H:])
+            alpha = 1.0 / math.sqrt(d)
+        else:
+            if abits < 16:          # per token over the full hidden dim, before the head split (int_opt_layer.py:97,125,129)
+                qkvq = B("qkvq", (M, 3 * H))
+                for i in range(3):
+                    ops.act_quant_fwd(qkv[:, i * H:(i + 1) * H], qkvq[:, i * H:(i + 1) * H], n_bits=abits,
+                                      recip_div=self.q.recip_div)
+            else:
+                qkvq = qkv
+            alpha = 1.0
+        self.qkv, self.qkvq, self.att_alpha = qkv, qkvq, alpha
+        P = B("P", (nb, h, T, T))
+        S = B("S", (h, T, T), F32)
+        O = B("O", (M, H))
+        cz = 1 if self.causal else 0
+        for s in range(nb):
+            r = slice(s * T, (s + 1) * T)
+            ops.gemm(qkvq[r, :H], qkvq[r, H:2 * H], S, M=T, N=T, K=d, lda=3 * H, ldb=3 * H, ldc=T, batch=h, strideA=d,
+                     strideB=d, strideC=T * T, alpha=alpha, causal=cz)
+            ops.softmax_fwd(S, P[s], mask=self.mask, causal=self.causal)
+            ops.gemm(P[s], qkvq[r, 2 * H:], O[r], M=T, N=d, K=T, lda=T, ldb=3 * H, b_mn=True, ldc=H, batch=h,
+                     strideA=T * T, strideB=d, strideC=d, causal=2 * cz)
+        Oq = self._aq(O, "Oq")
+        h1 = B("h1", (M, H))
+        ops.linear_fwd(Oq, W["o"], h1, bias=ws["bo"], residual=x)
+        a2 = B("a2", (M, H))
+        self.st2 = (B("mean2", (M,), F32), B("rstd2", (M,), F32))
+        ops.norm_fwd(h1, ws["ln2w"], ws["ln2b"], self.eps, self.norm_kind, a2, *self.st2)
+        a2q = self._aq(a2, "a2q")
+        f1 = B("f1", (M, W["fc1"].shape[0]))
+        ops.linear_fwd(a2q, W["fc1"], f1, bias=ws["bfc1"])
+        m = B("m", (M, F_))
+        if self.glu:
+            ops.swiglu_fwd(f1, m)
+        else:
+            ops.relu_fwd(f1, m)
+        mq = self._aq(m, "mq")
+        if out is None:
+            out = B("out", (M, H))
+        ops.linear_fwd(mq, W["fc2"], out, bias=ws["bfc2"], residual=h1)
+        self.saved = dict(a1=a1, a1q=a1q, O=O, Oq=Oq, h1=h1, a2=a2, a2q=a2q, f1=f1, m=m, mq=mq, P=P, ws=ws)
+        return out
+
+    def rope(self):
+        if not hasattr(self, "_rope"):
+            inv = 1.0 / (10000.0 ** (torch.arange(0, self.d, 2, dtype=F32) / self.d))
+            emb = torch.outer(torch.arange(self.T, dtype=F32), inv)
+            emb = torch.cat((emb, emb), -1)
+            self._rope = (emb.cos().to(self.dev).contiguous(), emb.sin().to(self.dev).contiguous())
+        return self._rope
+
+    # ------------------------------------------------------------------ backward
+    def _aq_bwd(self, x, gy, name):
+        if not self._act_quant:
+            return gy
+        gx = self.buf(name, x.shape)
+        ops.act_quant_bwd(x, gy, gx, n_bits=self.q.abits, recip_div=self.q.recip_div)
+        return gx
+
+    def backward(self, dout: torch.Tensor):
+        """Hand-derived backward of forward() down to the LWC / LET gradients."""
+        sv, q, B = self.saved, self.q, self.buf
+        ws, W = sv["ws"], sv["ws"]["W"]
+        M, H, F_, h, d, T = dout.shape[0], self.H, self.F, self.h, self.d, self.T
+        nb = M // T
+        let = q.let
+        gdt = BF16
+        dW = {g: B(f"dW_{g}", w.shape, gdt) for g, w in self.W.items()}
+        if let:
+            for a in self._acc.values():
+                a.zero_()
+        # fc2 / down_proj
+        dmq = B("dmq", (M, F_))
+        ops.linear_dgrad(dout, W["fc2"], dmq)
+        ops.linear_wgrad(dout, sv["mq"], dW["fc2"])
+        dm = self._aq_bwd(sv["m"], dmq, "dm")
+        df1 = B("df1", sv["f1"].shape)
+        if self.glu:
+            ops.swiglu_bwd(sv["f1"], dm, df1)
+        else:
+            ops.relu_bwd(sv["f1"], dm, df1)
+        da2q = B("da2q", (M, H))
+        ops.linear_dgrad(df1, W["fc1"], da2q)
+        ops.linear_wgrad(df1, sv["a2q"], dW["fc1"])
+        da2 = self._aq_bwd(sv["a2"], da2q, "da2")
+        dh1 = B("dh1", (M, H))
+        ops.norm_bwd(sv["h1"], ws["ln2w"], self.norm_kind, self.st2[0], self.st2[1], da2, dx=dh1, dx_add=dout,
+                     dw_acc=self._acc["dw2"] if let else None, db_acc=self._acc["db2"] if let else None)
+        # out projection
+        dOq = B("dOq", (M, H))
+        ops.linear_dgrad(dh1, W["o"], dOq)
+        ops.linear_wgrad(dh1, sv["Oq"], dW["o"])
+        dO = self._aq_bwd(sv["O"], dOq, "dO")
+        # attention
+        qkv, qkvq, alpha = self.qkv, self.qkvq, self.att_alpha
+        dqkvq = B("dqkvq", (M, 3 * H))
+        dP = B("S", (h, T, T), F32)
+        cz = 1 if self.causal else 0
+        for s in range(nb):
+            r = slice(s * T, (s + 1) * T)
+            P = sv["P"][s]
+            ops.gemm(dO[r], qkvq[r, 2 * H:], dP, M=T, N=T, K=d, lda=H, ldb=3 * H, ldc=T, batch=h, strideA=d, strideB=d,
+                     strideC=T * T, causal=cz)
+            ops.gemm(P, dO[r], dqkvq[r, 2 * H:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=H, ldc=3 * H, batch=h,
+                     strideA=T * T, strideB=d, strideC=d, causal=3 * cz)
+            ops.softmax_bwd(P, dP, P, causal=self.causal)      # dS overwrites P
+            ops.gemm(P, qkvq[r, H:2 * H], dqkvq[r, :H], M=T, N=d, K=T, lda=T, b_mn=True, ldb=3 * H, ldc=3 * H, batch=h,
+                     strideA=T * T, strideB=d, strideC=d, alpha=alpha, causal=2 * cz)
+            ops.gemm(P, qkvq[r, :H], dqkvq[r, H:2 * H], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=3 * H,
+                     ldc=3 * H, batch=h, strideA=T * T, strideB=d, strideC=d, alpha=alpha, causal=3 * cz)
+        abits = q.abits if self._act_quant else 16
+        if self.family == "llama":
+            dqkv = B("dqkv", (M, 3 * H))
+            cos, sin = self.rope()
+            for i in range(2):
+                ops.act_quant_bwd(qkv[:, i * H:(i + 1) * H].view(M, h, d), dqkvq[:, i * H:(i + 1) * H].view(M, h, d),
+                                  dqkv[:, i * H:(i + 1) * H].view(M, h, d), n_bits=abits, recip_div=q.recip_div, cos=cos,
+                                  sin=sin, seq_len=T)
+            if abits < 16:
+                ops.act_quant_bwd(qkv[:, 2 * H:].view(M, h, d), dqkvq[:, 2 * H:].view(M, h, d),
+                                  dqkv[:, 2 * H:].view(M, h, d), n_bits=abits, recip_div=q.recip_div)
+            else:
+                dqkv[:, 2 * H:].copy_(dqkvq[:, 2 * H:])
+        else:
+            if abits < 16:
+                dqkv = B("dqkv", (M, 3 * H))
+                for i in range(3):
+                    ops.act_quant_bwd(qkv[:, i * H:(i + 1) * H], dqkvq[:, i * H:(i + 1) * H], dqkv[:, i * H:(i + 1) * H],
+                                      n_bits=abits, recip_div=q.recip_div)
+            else:
+                dqkv = dqkvq
+        # qkv projections
+        if self.family == "llama":
+            ops.linear_wgrad(dqkv, sv["a1q"], dW["qkv"])
+        else:
+            sc = d ** -0.5   # q = sc * (x W^T + b)
+            ops.gemm(dqkv, sv["a1q"], dW["qkv"], M=H, N=H, K=M, a_mn=True, lda=3 * H, b_mn=True, ldb=H, ldc=H, alpha=sc)
+            ops.gemm(dqkv[:, H:], sv["a1q"], dW["qkv"][H:], M=2 * H, N=H, K=M, a_mn=True, lda=3 * H, b_mn=True, ldb=H, ldc=H)
+        if let:
+            da1q = B("da1q", (M, H))
+            if self.family == "llama":
+                ops.linear_dgrad(dqkv, W["qkv"], da1q)
+            else:
+                ops.gemm(dqkv[:, H:], W["qkv"][H:], da1q, M=M, N=H, K=2 * H, lda=3 * H, b_mn=True, ldb=H, ldc=H)
+                ops.gemm(dqkv, W["qkv"], da1q, M=M, N=H, K=H, lda=3 * H, b_mn=True, ldb=H, ldc=H, alpha=d ** -0.5,
+                         residual=da1q, ldr=H)
+            da1 = self._aq_bwd(sv["a1"], da1q, "da1")
+            ops.norm_bwd(self.x, ws["ln1w"], self.norm_kind, self.st1[0], self.st1[1], da1, dw_acc=self._acc["dw1"],
+                         db_acc=self._acc["db1"])
+        self._weight_backward(dW, dqkv, dh1, df1)
+
+    def _weight_backward(self, dW, dqkv, dh1, df1):
+        """Quantiser + fold backward per weight, then the LET gradient assembly."""
+        q, p, g, H = self.q, self.p, self.g, self.H
+        let = q.let
+        e = {}
+        if let:
+            so, sk = p["out_s"], p["qkt_s"]
+            dbqkv = self.buf("dbqkv", (3 * H,), F32)
+            ops.colsum(dqkv, dbqkv)
+            dbo = self.buf("dbo", (H,), F32)
+            ops.colsum(dh1, dbo)
+            dbf = self.buf("dbf", (df1.shape[1],), F32)
+            ops.colsum(df1, dbf)
+            dbq, dbk, dbv = dbqkv[:H], dbqkv[H:2 * H], dbqkv[2 * H:]
+            if self.family == "opt":
+                dbq = dbq * self.d ** -0.5      # bias enters q before the d^-0.5 scaling
+            e = {"q": dbq / sk, "k": dbk * sk, "v": dbv / so, "o": dbo, "fc1": dbf}
+        acc = self._acc
+        colacc = {"qkv_s": acc["dcol_qkv"], "out_s": acc["dcol_out"], "fc1_s": acc["dcol_fc1"]}
+        shacc = {"qkv_d": acc["dsh_qkv"], "out_d": acc["dsh_out"], "fc1_d": acc["dsh_fc1"]}
+        for u in self.units:
+            if q.wbits >= 16:
+                continue
+            up, low = self.lwc(u)
+            st = self.qstat[u.name]
+            er = e.get(u.name)
+            ops.weight_quant_bwd(self.wview(u, self.W), self.wview(u, dW), st["xmin"], st["xmax"], n_bits=q.wbits,
+                                 symmetric=q.symmetric, group_size=q.group_size, up=up, low=low,
+                                 col_scale=p.get(u.col) if u.col else None, row_scale=p.get(u.row) if u.row else None,
+                                 row_op=u.row_op, recip_div=q.recip_div,
+                                 e_row=er.contiguous() if (er is not None and u.shift) else None,
+                                 d_up=g.get(f"{u.name}.up"), d_low=g.get(f"{u.name}.low"),
+                                 dcol_acc=colacc[u.col] if u.col else None, drow=self._drow[u.name] if u.row else None,
+                                 dshift_acc=shacc[u.shift] if u.shift else None)
+        if not let:
+            return
+        t = self.tmp
+        s1, s2 = p["qkv_s"], p["fc1_s"]
+        bq, bk, bv = t["bqkv"][:H], t["bqkv"][H:2 * H], t["bqkv"][2 * H:]
+        # norm side: w' = w/s, b' = (b - delta)/s
+        torch.sub(acc["dcol_qkv"], (acc["dw1"] * t["ln1w"] + acc["db1"] * t["ln1b"]) / s1, out=g["qkv_s"])
+        torch.sub(acc["dsh_qkv"], acc["db1"] / s1, out=g["qkv_d"])
+        torch.sub(acc["dcol_fc1"], (acc["dw2"] * t["ln2w"] + acc["db2"] * t["ln2b"]) / s2, out=g["fc1_s"])
+        torch.sub(acc["dsh_fc1"], acc["db2"] / s2, out=g["fc1_d"])
+        # q/k row scale: Wq' = W1/s, bq' = beta/s ; Wk' = W1*s, bk' = beta*s
+        torch.add((-self._drow["q"] / sk - dbq * bq) / sk, self._drow["k"] + dbk * bk / sk, out=g["qkt_s"])
+        # v row scale + out_proj column scale: Wv' = W1/s_out, bv' = (beta - d_out)/s_out
+        torch.sub(acc["dcol_out"], (self._drow["v"] / so + dbv * bv) / so, out=g["out_s"])
+        torch.sub(acc["dsh_out"], dbv / so, out=g["out_d"])
+
+    # ------------------------------------------------------------------ one optimiser step
+    def loss_and_grad(self, out, target, target2=None):
+        self.loss_slot.zero_()
+        dout = self.buf("dout", out.shape)
+        ops.mse_fwd_bwd(out, target, self.loss_slot, dout, target2=target2)
+        return dout
+
+    def train_step(self, x, target, target2=None, allreduce=None):
+        """smooth_and_quant_temporary + forward + MSE + backward + AdamW  (quantize/omniquant.py:217-229)."""
+        self.prepare()
+        out = self.forward(x, self.tmp, act_quant=True)
+        dout = self.loss_and_grad(out, target, target2)
+        self.backward(dout)
+        if allreduce is not None:
+            allreduce(self.grads)
+            allreduce(self.loss_slot)
+        self.optimizer_step()
+        return self.loss_slot
+
+    def optimizer_step(self):
+        ops.step_inc(self.step_dev)
+        gs = 1.0 / self.world
+        if self.n_let:
+            ops.adamw(self.params[:self.n_let], self.grads[:self.n_let], self.adam_m[:self.n_let], self.adam_v[:self.n_let],
+                      self.step_dev, lr=self.let_lr, weight_decay=self.wd, grad_scale=gs)
+        if self.n_params > self.n_let:
+            sl = slice(self.n_let, self.n_params)
+            ops.adamw(self.params[sl], self.grads[sl], self.adam_m[sl], self.adam_v[sl], self.step_dev, lr=self.lwc_lr,
+                      weight_decay=self.wd, grad_scale=gs)
+
+
+# ---------------------------------------------------------------------- per-block calibration loop
+def fp_pass(eng: BlockEngine, fp_inps: torch.Tensor, quant_inps: Optional[torch.Tensor] = None, aug_loss: bool = False):
+    """Full-precision targets (quantize/omniquant.py:165-172): fp_inps <- block(fp_inps) in place; with
+    ``aug_loss`` also returns block_fp(quant_inps) (the reference's fp_inps_2)."""
+    n, T, H = fp_inps.shape
+    b = eng.b
+    fpw = eng.fp_weights()
+    fp2 = None
+    with torch.no_grad():
+        if aug_loss:
+            fp2 = torch.empty_like(quant_inps)
+            for j in range(0, n, b):
+                eng.forward(quant_inps[j:j + b].view(b * T, H), fpw, act_quant=False, out=fp2[j:j + b].view(b * T, H))
+        tmp = torch.empty(b * T, H, device=eng.dev, dtype=BF16)
+        for j in range(0, n, b):
+            eng.forward(fp_inps[j:j + b].view(b * T, H), fpw, act_quant=False, out=tmp)
+            fp_inps[j:j + b].view(b * T, H).copy_(tmp)
+    return fp2
+
+
+def train(eng: BlockEngine, fp_inps, quant_inps, *, epochs: int, fp_inps_2=None, allreduce=None, record_grads=False,
+          log=None, use_graph: bool = False):
+    """The AdamW loop (quantize/omniquant.py:211-234) on this rank's samples; eng.b samples per step.
+    Losses stay on the device (no per-step host sync, unlike omniquant.py:223)."""
+    n, T, H = quant_inps.shape
+    b = eng.b
+    spe = n // b
+    steps = epochs * spe
+    losses = torch.zeros(max(steps, 1), device=eng.dev)
+    grads0 = None
+    k = 0
+    graph = None
+    if use_graph and steps > 3 and allreduce is None:
+        sx = torch.empty(b * T, H, device=eng.dev, dtype=BF16)
+        st = torch.empty_like(sx)
+        st2 = torch.empty_like(sx) if fp_inps_2 is not None else None
+    with torch.no_grad():
+        for ep in range(epochs):
+            for j in range(0, n, b):
+                x = quant_inps[j:j + b].view(b * T, H)
+                tgt = fp_inps[j:j + b].view(b * T, H)
+                tgt2 = fp_inps_2[j:j + b].view(b * T, H) if fp_inps_2 is not None else None
+                if record_grads and k == 0:
+                    eng.prepare()
+                    out = eng.forward(x, eng.tmp, act_quant=True)
+                    eng.backward(eng.loss_and_grad(out, tgt, tgt2))
+                    grads0 = eng.grads.clone()
+                if use_graph and steps > 3 and allreduce is None:
+                    sx.copy_(x)
+                    st.copy_(tgt)
+                    if st2 is not None:
+                        st2.copy_(tgt2)
+                    if graph is None and k >= 2:      # two eager steps warm every buffer, then capture
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph):
+                            eng.train_step(sx, st, st2)
+                    elif graph is not None:
+                        graph.replay()
+                    else:
+                        eng.train_step(sx, st, st2)
+                    loss = eng.loss_slot
+                else:
+                    loss = eng.train_step(x, tgt, tgt2, allreduce=allreduce)
+                losses[k:k + 1].copy_(loss)
+                k += 1
+            if log is not None:
+                log(ep, losses[ep * spe:(ep + 1) * spe])
+    if allreduce is not None and eng.world > 1:
+        losses = losses / eng.world
+    return losses, grads0
+
+
+def requant_pass(eng: BlockEngine, quant_inps: torch.Tensor):
+    """quant_inps <- quantised block(quant_inps) in place (quantize/omniquant.py:242-245); expects
+    eng.prepare(final=True) to have produced the folded, fake-quantised operands."""
+    n, T, H = quant_inps.shape
+    b = eng.b
+    with torch.no_grad():
+        tmp = torch.empty(b * T, H, device=eng.dev, dtype=BF16)
+        for j in range(0, n, b):
+            eng.forward(quant_inps[j:j + b].view(b * T, H), eng.tmp, act_quant=True, out=tmp)
+            quant_inps[j:j + b].view(b * T, H).copy_(tmp)
+
+
+def calibrate_block(eng: BlockEngine, fp_inps: torch.Tensor, quant_inps: torch.Tensor, *, epochs: int,
+                    aug_loss: bool = False, allreduce=None, record_grads: bool = False, log=None, use_graph=False):
+    """One decoder block of the reference loop (quantize/omniquant.py:157-250) on this rank's samples:
+    FP pass, AdamW loop, in-place fold + quantise, re-quantised forward.  fp_inps / quant_inps
+    ([n, T, H] bf16, resident in HBM) are overwritten with the block outputs like the reference's."""
+    n, T, H = quant_inps.shape
+    assert n % eng.b == 0 and T == eng.T and H == eng.H
+    fp2 = fp_pass(eng, fp_inps, quant_inps, aug_loss)
+    losses, grads0 = train(eng, fp_inps, quant_inps, epochs=epochs, fp_inps_2=fp2, allreduce=allreduce,
+                           record_grads=record_grads, log=log, use_graph=use_graph)
+    with torch.no_grad():
+        final = eng.prepare(final=True)          # smooth_and_quant_inplace (omniquant.py:239)
+    requant_pass(eng, quant_inps)
+    return dict(losses=losses, grads0=grads0, final=final)

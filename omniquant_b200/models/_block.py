@@ -1,0 +1,298 @@
+"""Shared implementation of the Quant*DecoderLayer block wrappers.
+
+Keeps the reference's block-wrapper surface (reference models/int_llama_layer.py:191-368,
+models/int_opt_layer.py:225-451): ``set_quant_state``, ``smooth_and_quant_temporary``,
+``clear_temp_variable``, ``smooth_and_quant_inplace``, ``let_parameters`` / ``lwc_parameters`` /
+``omni_parameters`` / ``omni_state_dict``, ``register_scales_and_zeros`` and a ``forward`` with the
+HF decoder-layer signature -- and runs all of it on the B200 block engine (omniquant_b200/engine.py).
+The sub-modules (QuantLinear, Omni*Norm, QuantMatMul) carry the reference's buffers, parameters
+and checkpoint key names; the wrapper synchronises them with the engine's flat buffers.
+"""
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from ..engine import BlockEngine, QuantConfig
+from ..quantize.int_linear import QuantLinear
+from ..quantize.int_matmul import QuantMatMul
+
+LET_NAMES = {"qkv_s": "qkv_smooth_scale", "qkv_d": "qkv_smooth_shift", "out_s": "out_smooth_scale",
+             "out_d": "out_smooth_shift", "fc1_s": "fc1_smooth_scale", "fc1_d": "fc1_smooth_shift",
+             "qkt_s": "qkt_smooth_scale"}
+
+
+class _BlockFn(torch.autograd.Function):
+    """Block forward/backward on the engine, exposed to autograd so the reference's training loop
+    (loss.backward(); optimizer.step()) works unchanged on the module parameters."""
+
+    @staticmethod
+    def forward(ctx, x, layer, ws, act_quant, *params):
+        eng = layer._eng
+        x2 = x.reshape(-1, x.shape[-1]).to(torch.bfloat16).contiguous()
+        out = eng.forward(x2, ws, act_quant=act_quant).clone()
+        ctx.layer, ctx.n = layer, len(params)
+        ctx.trainable = ws is eng.tmp
+        return out.view(x.shape).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, gout):
+        layer, eng = ctx.layer, ctx.layer._eng
+        if not ctx.trainable:
+            raise RuntimeError("backward through a block forward that did not use smooth_and_quant_temporary()")
+        g2 = gout.reshape(-1, gout.shape[-1]).to(torch.bfloat16).contiguous()
+        eng.backward(g2)
+        grads = layer._pull_grads()
+        return (None, None, None, None) + tuple(grads)
+
+
+class QuantDecoderLayerBase(nn.Module):
+    family = None          # "llama" | "opt"
+    linear_names = {}      # engine short name -> attribute path of the QuantLinear
+    norm_names = ()        # (first norm attr, second norm attr)
+
+    # ------------------------------------------------------------------ plumbing
+    def _init_common(self, args, n_heads, eps):
+        self._args, self._n_heads, self._eps = args, n_heads, eps
+        self._eng = None
+        self._final_ws = None
+        self.use_weight_quant = False
+        self.use_act_quant = False
+        self.let = False
+
+    def _mod(self, path):
+        m = self
+        for p in path.split("."):
+            m = getattr(m, p)
+        return m
+
+    def _linears(self):
+        return OrderedDict((k, self._mod(p)) for k, p in self.linear_names.items())
+
+    def _qcfg(self):
+        a = self._args
+        wq = a.weight_quant_params
+        return QuantConfig(wbits=wq["n_bits"], abits=a.act_quant_params["n_bits"], group_size=wq.get("group_size") or 0,
+                           symmetric=wq.get("symmetric", False), lwc=wq.get("lwc", False), let=bool(self.let),
+                           recip_div=getattr(a, "recip_div", True))
+
+    def _raw_weights(self):
+        W = {}
+        for k, m in self._linears().items():
+            W[k] = m.weight
+            if getattr(m, "bias", None) is not None:
+                W[f"{k}.bias"] = m.bias
+        n1, n2 = (self._mod(n) for n in self.norm_names)
+        W["ln1"], W["ln2"] = n1.weight, n2.weight
+        if getattr(n1, "bias", None) is not None:
+            W["ln1.bias"], W["ln2.bias"] = n1.bias, n2.bias
+        return W
+
+    def _ensure_engine(self, seq_len, batch, mask=None):
+        e = self._eng
+        q = self._qcfg()
+        if e is None or e.T != seq_len or e.b != batch or e.q != q:
+            dev = next(iter(self._linears().values())).weight.device
+            a = self._args
+            self._eng = BlockEngine(self.family, self._raw_weights(), n_heads=self._n_heads, seq_len=seq_len, qcfg=q,
+                                    eps=self._eps, device=dev, batch=batch, let_lr=getattr(a, "let_lr", 5e-3),
+                                    lwc_lr=getattr(a, "lwc_lr", 1e-2), wd=getattr(a, "wd", 0.0), mask=mask)
+            self._push_params()
+        return self._eng
+
+    def _param_map(self):
+        """[(engine name, [module parameters concatenated in engine order])]."""
+        out = []
+        eng = self._eng
+        if eng.q.let:
+            for k, long in LET_NAMES.items():
+                out.append((k, [getattr(self, long)]))
+        if eng.q.lwc:
+            lin = self._linears()
+            fc1 = ["gate", "up"] if self.family == "llama" else ["fc1"]
+            fc2 = "down" if self.family == "llama" else "fc2"
+            groups = [("q", ["q"]), ("k", ["k"]), ("v", ["v"]), ("o", ["o"]), ("fc1", fc1), ("fc2", [fc2])]
+            for unit, members in groups:
+                for s, attr in (("up", "upbound_factor"), ("low", "lowbound_factor")):
+                    out.append((f"{unit}.{s}", [getattr(lin[m].weight_quantizer, attr) for m in members]))
+        return out
+
+    def _push_params(self):
+        with torch.no_grad():
+            for name, plist in self._param_map():
+                dst, o = self._eng.p[name], 0
+                for p in plist:
+                    n = p.numel()
+                    dst[o:o + n].copy_(p.detach().reshape(-1).to(dst.dtype))
+                    o += n
+
+    def _pull_params(self):
+        with torch.no_grad():
+            for name, plist in self._param_map():
+                src, o = self._eng.p[name], 0
+                for p in plist:
+                    n = p.numel()
+                    p.copy_(src[o:o + n].view(p.shape).to(p.dtype))
+                    o += n
+
+    def _pull_grads(self):
+        grads = []
+        for name, plist in self._param_map():
+            src, o = self._eng.g[name], 0
+            for p in plist:
+                n = p.numel()
+                grads.append(src[o:o + n].view(p.shape).to(p.dtype).clone())
+                o += n
+        return grads
+
+    def _params_flat(self):
+        return [p for _, plist in self._param_map() for p in plist]
+
+    # ------------------------------------------------------------------ reference surface
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        # setting weight quantization here does not affect actual forward pass
+        self.use_weight_quant = weight_quant
+        self.use_act_quant = act_quant
+        for m in self.modules():
+            if isinstance(m, (QuantLinear, QuantMatMul)):
+                m.set_quant_state(weight_quant, act_quant)
+
+    def smooth_and_quant_temporary(self, seq_len=None, batch=None):
+        """LET fold + weight fake-quant for the coming forward (int_llama_layer.py:279-307)."""
+        e = self._eng
+        T = seq_len or (e.T if e is not None else 2048)
+        b = batch or (e.b if e is not None else 1)
+        eng = self._ensure_engine(T, b)
+        self._push_params()
+        eng.prepare()
+        self._publish_temp(eng)
+
+    def _publish_temp(self, eng):
+        H = eng.H
+        lin = self._linears()
+        t = eng.tmp
+        slices = {"q": ("qkv", 0, H), "k": ("qkv", H, 2 * H), "v": ("qkv", 2 * H, 3 * H), "o": ("o", 0, H)}
+        if self.family == "llama":
+            slices.update(gate=("fc1", 0, eng.F), up=("fc1", eng.F, 2 * eng.F), down=("fc2", 0, H))
+        else:
+            slices.update(fc1=("fc1", 0, eng.F), fc2=("fc2", 0, H))
+        bias_of = {"qkv": "bqkv", "o": "bo", "fc1": "bfc1", "fc2": "bfc2"}
+        for k, (g, r0, r1) in slices.items():
+            m = lin[k]
+            m.temp_weight = eng.Wq[g][r0:r1]
+            bb = t[bias_of[g]]
+            m.temp_bias = None if bb is None else bb[r0:r1]
+            m.use_temporary_parameter = True
+        for n, (w, b) in zip(self.norm_names, (("ln1w", "ln1b"), ("ln2w", "ln2b"))):
+            nm = self._mod(n)
+            nm.temp_weight, nm.temp_bias = t[w], t[b]
+            nm.use_temporary_parameter = eng.q.let
+
+    def clear_temp_variable(self):
+        for m in self._linears().values():
+            for a in ("temp_weight", "temp_bias"):
+                if hasattr(m, a):
+                    delattr(m, a)
+
+    @torch.no_grad()
+    def smooth_and_quant_inplace(self, seq_len=None, batch=None):
+        """Fold LET into the buffers and overwrite the weights by their fake-quantised values
+        (int_llama_layer.py:315-332)."""
+        e = self._eng
+        eng = self._ensure_engine(seq_len or (e.T if e is not None else 2048), batch or (e.b if e is not None else 1))
+        self._push_params()
+        extra = eng.prepare(final=True)
+        self._pull_params()       # truncate_number acted on the smooth scales
+        H = eng.H
+        lin = self._linears()
+        t = eng.tmp
+        fc1 = ["gate", "up"] if self.family == "llama" else ["fc1"]
+        fc2 = "down" if self.family == "llama" else "fc2"
+        parts = {"q": ("q", 0, "bqkv", 0), "k": ("k", 0, "bqkv", H), "v": ("v", 0, "bqkv", 2 * H), "o": ("o", 0, "bo", 0),
+                 fc2: ("fc2", 0, "bfc2", 0)}
+        r = 0
+        for nme in fc1:
+            parts[nme] = ("fc1", r, "bfc1", r)
+            r += lin[nme].out_features
+        for k, (unit, r0, bkey, b0) in parts.items():
+            m = lin[k]
+            N = m.out_features
+            if unit in extra:
+                G = extra[unit]["scales"].numel() // extra[unit]["weight"].shape[0]
+                m.weight = extra[unit]["weight"][r0:r0 + N].to(m.weight.dtype)
+                m.weight_quantizer.scale = extra[unit]["scales"][r0 * G:(r0 + N) * G].view(-1, 1)
+                m.weight_quantizer.round_zero_point = extra[unit]["zeros"][r0 * G:(r0 + N) * G].view(-1, 1)
+            bb = t[bkey]
+            if bb is not None:
+                val = bb[b0:b0 + N].clone()
+                if getattr(m, "bias", None) is not None:
+                    m.bias = val.to(m.bias.dtype)
+                else:
+                    if hasattr(m, "bias"):
+                        del m.bias
+                    m.register_buffer("bias", val)
+            m.use_temporary_parameter = False
+        for n, (w, b) in zip(self.norm_names, (("ln1w", "ln1b"), ("ln2w", "ln2b"))):
+            nm = self._mod(n)
+            nm.weight = t[w].clone().to(nm.weight.dtype)
+            if t[b] is not None:
+                if getattr(nm, "bias", None) is not None:
+                    nm.bias = t[b].clone().to(nm.bias.dtype)
+                else:
+                    if hasattr(nm, "bias"):
+                        del nm.bias
+                    nm.register_buffer("bias", t[b].clone())
+            nm.use_temporary_parameter = False
+        # operands of the post-calibration forward (raw-weight branch of QuantLinear.forward, int_linear.py:56-58)
+        self._final_ws = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in t.items() if k != "W"}
+        self._final_ws["W"] = {g: w.clone() for g, w in eng.Wq.items()}
+
+    def _named_omni(self, use_shift=True):
+        template = "smooth" if use_shift else "smooth_scale"
+        for n, p in self.named_parameters():
+            yield n, p, (n.find("bound_factor") > -1), (n.find(template) > -1)
+
+    def let_parameters(self, use_shift=True):
+        return iter([p for _, p, _, is_let in self._named_omni(use_shift) if is_let])
+
+    def lwc_parameters(self):
+        return iter([p for _, p, is_lwc, _ in self._named_omni() if is_lwc])
+
+    def omni_parameters(self, use_shift=True):
+        return iter([p for _, p, is_lwc, is_let in self._named_omni(use_shift) if is_lwc or is_let])
+
+    def omni_state_dict(self, destination=None, prefix="", keep_vars=False):
+        if destination is None:
+            destination = OrderedDict()
+        for name, param in self.named_parameters():
+            if name.find("smooth") > -1 or name.find("bound_factor") > -1:
+                destination[prefix + name] = param if keep_vars else param.detach()
+        return destination
+
+    def register_scales_and_zeros(self):
+        for m in self._linears().values():
+            m.weight_quantizer.register_scales_and_zeros()
+
+    # ------------------------------------------------------------------ forward
+    def _run(self, hidden_states, attention_mask):
+        b, T, H = hidden_states.shape
+        mask = None
+        if attention_mask is not None:
+            am = attention_mask.reshape(-1, T, T)[0]
+            causal = torch.triu(torch.full((T, T), torch.finfo(torch.float32).min, device=am.device), diagonal=1)
+            is_causal = bool(((am.float() < -1e4) == (causal < -1e4)).all())
+            if not is_causal:
+                mask = attention_mask.float()
+        eng = self._ensure_engine(T, b, mask=mask)
+        lin = next(iter(self._linears().values()))
+        if lin.use_temporary_parameter:
+            ws = eng.tmp
+        elif self._final_ws is not None:
+            ws = self._final_ws
+        elif self.use_weight_quant:
+            self._push_params()
+            eng.prepare()
+            ws = eng.tmp
+        else:
+            ws = eng.fp_weights()
+        return _BlockFn.apply(hidden_states, self, ws, bool(self.use_act_quant), *self._params_flat())

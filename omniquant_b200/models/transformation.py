@@ -1,0 +1,138 @@
+"""LET folding with the reference's function names and argument meaning (reference
+models/transformation.py:5-114).
+
+The six public entry points (``smooth_{ln_fcs,fc_fc,q_k}_{temporary,inplace}``) keep the
+reference's side effects on the module attributes -- ``temp_weight`` / ``temp_bias`` /
+``use_temporary_parameter`` for the differentiable per-step variant, in-place buffer updates (and
+newly registered ``bias`` buffers) for the once-per-block variant -- but share one implementation
+of the algebra.  Inside the calibration step the same algebra is fused into the weight fake-quant
+kernel (csrc/weight_quant.cu: column scale, row scale / divide, W@shift) and never materialises
+the folded fp32 weights.
+"""
+import torch
+
+from .. import ops
+
+__all__ = ["truncate_number", "smooth_ln_fcs_temporary", "smooth_fc_fc_temporary", "smooth_q_k_temporary",
+           "smooth_ln_fcs_inplace", "smooth_fc_fc_inplace", "smooth_q_k_inplace", "TruncateFunction"]
+
+
+class TruncateFunction(torch.autograd.Function):
+    """|x| < thr -> sign(x) * thr with identity backward (transformation.py:5-16)."""
+
+    @staticmethod
+    def forward(ctx, input, threshold):
+        clipped = input.detach().clone()
+        if clipped.is_cuda and clipped.dtype == torch.float32:
+            ops.truncate_(clipped.view(-1), threshold)
+        else:
+            tiny = clipped.abs() < threshold
+            clipped[tiny] = clipped[tiny].sign() * threshold
+        return clipped
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output.clone(), None
+
+
+def truncate_number(number, threshold=1e-2):
+    return TruncateFunction.apply(number, threshold)
+
+
+# ---------------------------------------------------------------------------- shared algebra
+def _bias_of(m):
+    b = getattr(m, "bias", None)
+    return b
+
+
+def _set_bias_inplace(m, value):
+    """in-place variants create the buffer when the module had no bias (transformation.py:79-80,88-89,104-105)."""
+    if _bias_of(m) is not None:
+        m.bias.copy_(value)
+    else:
+        if hasattr(m, "bias"):
+            del m.bias
+        m.register_buffer("bias", value)
+
+
+def _norm_fold(ln, scales, shifts):
+    b = _bias_of(ln)
+    new_b = (b - shifts) / scales if b is not None else (-1 * shifts) / scales      # :28-31
+    return ln.weight / scales, new_b                                                  # :33
+
+
+def _fc_in_fold(fc, scales, shifts):
+    """input-channel fold of a linear: W * s[col], b + W @ delta (raw W)  (:37-41, :56-60)."""
+    b = _bias_of(fc)
+    mv = fc.weight @ shifts
+    return fc.weight * scales.view(1, -1), (b + mv) if b is not None else mv
+
+
+def _apply(m, weight, bias, inplace):
+    m.use_temporary_parameter = not inplace
+    if inplace:
+        m.weight.copy_(weight)
+        if bias is not None:
+            _set_bias_inplace(m, bias)
+    else:
+        m.temp_weight, m.temp_bias = weight, bias
+
+
+def _ln_fcs(ln, fcs, scales, shifts, inplace):
+    fcs = fcs if isinstance(fcs, list) else [fcs]
+    folded = [_fc_in_fold(fc, scales, shifts) for fc in fcs]       # all from the un-modified weights
+    w, b = _norm_fold(ln, scales, shifts)
+    _apply(ln, w, b, inplace)
+    for fc, (fw, fb) in zip(fcs, folded):
+        _apply(fc, fw, fb, inplace)
+
+
+def _fc_fc(fc1, fc2, scales, shifts, inplace):
+    """v_proj -> out_proj (:44-60, :93-106): output-channel fold of fc1 on top of whatever it already
+    carries, input-channel fold of fc2."""
+    if inplace:
+        w1, b1 = fc1.weight, fc1.bias
+    elif hasattr(fc1, "temp_weight"):
+        w1, b1 = fc1.temp_weight, fc1.temp_bias - shifts
+    else:
+        w1, b1 = fc1.weight, fc1.bias
+    if inplace:
+        b1 = b1 - shifts
+    w2, b2 = _fc_in_fold(fc2, scales, shifts)
+    _apply(fc1, w1 / scales.view(-1, 1), b1 / scales.view(-1), inplace)
+    _apply(fc2, w2, b2, inplace)
+
+
+def _q_k(q_proj, k_proj, scales, inplace):
+    src = (lambda m: (m.weight, m.bias)) if inplace else (lambda m: (m.temp_weight, m.temp_bias))
+    (wq, bq), (wk, bk) = src(q_proj), src(k_proj)
+    _apply(q_proj, wq / scales.view(-1, 1), bq / scales.view(-1), inplace)      # :66-67
+    _apply(k_proj, wk * scales.view(-1, 1), bk * scales.view(-1), inplace)      # :68-69
+
+
+# ---------------------------------------------------------------------------- reference entry points
+def smooth_ln_fcs_temporary(ln, fcs, scales, shifts):
+    _ln_fcs(ln, fcs, scales, shifts, inplace=False)
+
+
+def smooth_fc_fc_temporary(fc1, fc2, scales, shifts=None):
+    _fc_fc(fc1, fc2, scales, shifts, inplace=False)
+
+
+def smooth_q_k_temporary(q_proj, k_proj, scales):
+    _q_k(q_proj, k_proj, scales, inplace=False)
+
+
+@torch.no_grad()
+def smooth_ln_fcs_inplace(ln, fcs, scales, shifts):
+    _ln_fcs(ln, fcs, scales, shifts, inplace=True)
+
+
+@torch.no_grad()
+def smooth_fc_fc_inplace(fc1, fc2, scales, shifts=None):
+    _fc_fc(fc1, fc2, scales, shifts, inplace=True)
+
+
+@torch.no_grad()
+def smooth_q_k_inplace(q_proj, k_proj, scales):
+    _q_k(q_proj, k_proj, scales, inplace=True)

@@ -247,10 +247,21 @@ class QCfg:
     """The six quantiser-parameter dicts main.py:268-303 builds, flattened."""
 
     def __init__(self, wbits=4, abits=4, group_size=None, symmetric=False, lwc=True, let=True,
-                 recip_div=False):
+                 recip_div=False, emu16=None):
         self.wbits, self.abits, self.group_size = wbits, abits, group_size
         self.symmetric, self.lwc, self.let = symmetric, lwc, let
         self.recip_div = recip_div
+        # emu16 (e.g. torch.bfloat16): round every tensor the CUDA engine stores in 16 bits (activations,
+        # GEMM operands) at the same points, with identity gradient -- SURVEY.md §7 hard part 2b.  None = the
+        # reference's fp32 (--deactive_amp) arithmetic.
+        self.emu16 = emu16
+
+
+def st(t, cfg):
+    """storage rounding of the 16-bit engine (straight-through)."""
+    if t is None or cfg.emu16 is None:
+        return t
+    return t + (t.to(cfg.emu16).to(t.dtype) - t).detach()
 
 
 LLAMA_LINEARS = ("q", "k", "v", "o", "gate", "up", "down")
@@ -334,8 +345,10 @@ def llama_forward(x, T, n_heads, cos, sin, mask, cfg: QCfg, act_quant=True, eps=
     b, L, H = x.shape
     d = H // n_heads
     n_kv = n_kv_heads or n_heads
-    lin = lambda t, n: F.linear(aq(t, cfg, act_quant), T[f"{n}.w"], T[f"{n}.b"])
-    a1 = rms_norm(x, T["ln1w"], T["ln1b"], eps)
+    S = lambda t: st(t, cfg)
+    lin = lambda t, n, res=None: S((F.linear(S(aq(t, cfg, act_quant)), S(T[f"{n}.w"]), T[f"{n}.b"])) if res is None else
+                                   (res + F.linear(S(aq(t, cfg, act_quant)), S(T[f"{n}.w"]), T[f"{n}.b"])))
+    a1 = S(rms_norm(x, T["ln1w"], T["ln1b"], eps))
     q = lin(a1, "q").view(b, L, n_heads, d).transpose(1, 2)
     k = lin(a1, "k").view(b, L, n_kv, d).transpose(1, 2)
     v = lin(a1, "v").view(b, L, n_kv, d).transpose(1, 2)
@@ -344,19 +357,19 @@ def llama_forward(x, T, n_heads, cos, sin, mask, cfg: QCfg, act_quant=True, eps=
         rep = n_heads // n_kv
         k = k[:, :, None].expand(b, n_kv, rep, L, d).reshape(b, n_heads, L, d)
         v = v[:, :, None].expand(b, n_kv, rep, L, d).reshape(b, n_heads, L, d)
-    q = aq(q, cfg, act_quant)
-    k = aq(k, cfg, act_quant)
+    q = S(aq(q, cfg, act_quant))
+    k = S(aq(k, cfg, act_quant))
     s = torch.matmul(q, k.transpose(2, 3)) / math.sqrt(d)
     if mask is not None:
         s = s + mask
         s = torch.max(s, torch.tensor(torch.finfo(s.dtype).min, device=s.device))
-    p = F.softmax(s, dim=-1, dtype=torch.float32).to(q.dtype)
-    v = aq(v, cfg, act_quant)
-    o = torch.matmul(p, v).transpose(1, 2).reshape(b, L, H)
-    h1 = x + lin(o, "o")
-    a2 = rms_norm(h1, T["ln2w"], T["ln2b"], eps)
-    m = F.silu(lin(a2, "gate")) * lin(a2, "up")
-    return h1 + lin(m, "down")
+    p = S(F.softmax(s, dim=-1, dtype=torch.float32).to(q.dtype))
+    v = S(aq(v, cfg, act_quant))
+    o = S(torch.matmul(p, v).transpose(1, 2).reshape(b, L, H))
+    h1 = lin(o, "o", x)
+    a2 = S(rms_norm(h1, T["ln2w"], T["ln2b"], eps))
+    m = S(F.silu(lin(a2, "gate")) * lin(a2, "up"))
+    return lin(m, "down", h1)
 
 
 def llama_inplace(Wt, P, cfg: QCfg):
@@ -400,23 +413,25 @@ def opt_forward(x, T, n_heads, mask, cfg: QCfg, act_quant=True, eps=1e-5):
     split (:124-130)."""
     b, L, H = x.shape
     d = H // n_heads
-    lin = lambda t, n: F.linear(aq(t, cfg, act_quant), T[f"{n}.w"], T[f"{n}.b"])
+    S = lambda t: st(t, cfg)
+    lin = lambda t, n, res=None, sc=1.0: S((F.linear(S(aq(t, cfg, act_quant)), S(T[f"{n}.w"]), T[f"{n}.b"]) * sc) if res is None
+                                           else (res + F.linear(S(aq(t, cfg, act_quant)), S(T[f"{n}.w"]), T[f"{n}.b"])))
     sh = lambda t: t.view(b, L, n_heads, d).transpose(1, 2).contiguous().view(b * n_heads, L, d)
-    a1 = layer_norm(x, T["ln1w"], T["ln1b"], eps)
-    q = aq(lin(a1, "q") * d ** -0.5, cfg, act_quant)
-    k = aq(lin(a1, "k"), cfg, act_quant)
-    v = aq(lin(a1, "v"), cfg, act_quant)
+    a1 = S(layer_norm(x, T["ln1w"], T["ln1b"], eps))
+    q = S(aq(lin(a1, "q", sc=d ** -0.5), cfg, act_quant))
+    k = S(aq(lin(a1, "k"), cfg, act_quant))
+    v = S(aq(lin(a1, "v"), cfg, act_quant))
     s = torch.bmm(sh(q), sh(k).transpose(1, 2))
     if mask is not None:
         s = s.view(b, n_heads, L, L) + mask
         s = torch.max(s, torch.tensor(torch.finfo(s.dtype).min, device=s.device)).view(b * n_heads, L, L)
-    p = F.softmax(s, dim=-1)
-    o = torch.bmm(p, sh(v)).view(b, n_heads, L, d).transpose(1, 2).reshape(b, L, H)
-    h1 = x + lin(o, "o")
+    p = S(F.softmax(s, dim=-1))
+    o = S(torch.bmm(p, sh(v)).view(b, n_heads, L, d).transpose(1, 2).reshape(b, L, H))
+    h1 = lin(o, "o", x)
     r = h1.reshape(-1, H)
-    a2 = layer_norm(r, T["ln2w"], T["ln2b"], eps)
-    f = lin(F.relu(lin(a2, "fc1")), "fc2")
-    return (r + f).view(b, L, H)
+    a2 = S(layer_norm(r, T["ln2w"], T["ln2b"], eps))
+    f = lin(S(F.relu(lin(a2, "fc1"))), "fc2", r)
+    return f.view(b, L, H)
 
 
 # --------------------------------------------------------------------------
@@ -431,9 +446,11 @@ def calibrate_block(family: str, Wt, P, cfg: QCfg, inps, n_heads, *, epochs, bat
     dict(losses, P (trained), T_final, quant_out, fp_out, grads)."""
     nsamples, L, H = inps.shape
     d = H // n_heads
-    mask = causal_mask(L)
+    dev = inps.device
+    mask = causal_mask(L).to(dev)
     if family == "llama":
         cos, sin = rope_tables(d, L)
+        cos, sin = cos.to(dev), sin.to(dev)
         eps = 1e-6 if eps is None else eps
         prep = llama_prepare
         fwd = lambda x, T, aqf: llama_forward(x, T, n_heads, cos, sin, mask, cfg, aqf, eps, n_kv_heads)
@@ -441,7 +458,7 @@ def calibrate_block(family: str, Wt, P, cfg: QCfg, inps, n_heads, *, epochs, bat
         eps = 1e-5 if eps is None else eps
         prep = opt_prepare
         fwd = lambda x, T, aqf: opt_forward(x, T, n_heads, mask, cfg, aqf, eps)
-    no_let = QCfg(cfg.wbits, cfg.abits, cfg.group_size, cfg.symmetric, cfg.lwc, False, cfg.recip_div)
+    no_let = QCfg(cfg.wbits, cfg.abits, cfg.group_size, cfg.symmetric, cfg.lwc, False, cfg.recip_div, cfg.emu16)
     with torch.no_grad():
         T_fp = prep(Wt, P, no_let, quant=False)
         fp_out = torch.stack([fwd(inps[j:j + 1], T_fp, False)[0] for j in range(nsamples)])

@@ -357,5 +357,7 @@ if __name__ == "__main__":
     llama_block("w4a4_lwc_let_bs2", 256, 384, 2, 32, 4, make_args(4, 4, None, True, True), epochs=2, batch_size=2)
     llama_block("w3a16g64_lwc", 256, 384, 2, 32, 4, make_args(3, 16, 64, True, False), epochs=2)
     llama_block("w6a6_lwc_let_aug", 256, 384, 2, 32, 4, make_args(6, 6, None, True, True), epochs=1, aug_loss=True)
+    llama_block("w4a16g64_lwc_let", 256, 384, 2, 32, 4, make_args(4, 16, 64, True, True), epochs=2)
     opt_block("w4a16g64_lwc", 128, 256, 2, 32, 4, make_args(4, 16, 64, True, False), epochs=2)
+    opt_block("w4a16_lwc_let", 128, 256, 2, 32, 4, make_args(4, 16, None, True, True), epochs=2)
     opt_block("w4a4_lwc_let", 128, 256, 2, 32, 4, make_args(4, 4, None, True, True), epochs=2)

@@ -1,0 +1,147 @@
+"""The reference's module API as a drop-in: the training loop of quantize/omniquant.py:203-250 written
+against the block wrapper (smooth_and_quant_temporary -> forward -> MSELoss -> backward -> AdamW.step ->
+smooth_and_quant_inplace), plus the stand-alone operators, all on the CUDA kernels."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import BlockFixture, LLAMA_MAP
+
+pytestmark = pytest.mark.gpu
+
+
+def make_args(fx):
+    a = SimpleNamespace(wbits=fx.wbits, abits=fx.abits, group_size=fx.group_size, lwc=fx.lwc, let=fx.let, symmetric=False,
+                        let_lr=5e-3, lwc_lr=1e-2, wd=0.0, alpha=0.5, recip_div=False)
+    a.weight_quant_params = dict(n_bits=fx.wbits, per_channel_axes=[0], symmetric=False, dynamic_method="per_channel",
+                                 group_size=fx.group_size, lwc=fx.lwc)
+    tok = dict(n_bits=fx.abits, per_channel_axes=[], symmetric=False, dynamic_method="per_token")
+    a.act_quant_params, a.q_quant_params, a.k_quant_params, a.v_quant_params = dict(tok), dict(tok), dict(tok), dict(tok)
+    a.p_quant_params = dict(n_bits=16, metric="fix0to1")
+    return a
+
+
+def hf_llama_layer(fx):
+    from transformers import LlamaConfig
+    from transformers.models.llama.modeling_llama import LlamaDecoderLayer
+    cfg = LlamaConfig(hidden_size=fx.H, intermediate_size=fx.F, num_attention_heads=fx.heads, num_key_value_heads=fx.heads,
+                      num_hidden_layers=1, vocab_size=64, max_position_embeddings=2048, rms_norm_eps=1e-6)
+    layer = LlamaDecoderLayer(cfg, 0)
+    W = fx.weights()
+    with torch.no_grad():
+        for s, long in LLAMA_MAP.items():
+            m = layer
+            for p in long.split("."):
+                m = getattr(m, p)
+            m.weight.copy_(W[s])
+        layer.input_layernorm.weight.copy_(W["ln1"])
+        layer.post_attention_layernorm.weight.copy_(W["ln2"])
+    return cfg, layer.half().cuda()
+
+
+@pytest.mark.parametrize("fname", ["llama_w4a16g64_lwc_let.npz", "llama_w4a4_lwc_let.npz"])
+def test_reference_style_loop_on_block_wrapper(fname):
+    from omniquant_b200.models.int_llama_layer import QuantLlamaDecoderLayer
+    from omniquant_b200.quantize.int_linear import QuantLinear
+    fx = BlockFixture(fname)
+    args = make_args(fx)
+    cfg, layer = hf_llama_layer(fx)
+    qlayer = QuantLlamaDecoderLayer(cfg, layer, args).cuda()
+    x = fx.inps.cuda().to(torch.bfloat16)
+    T = fx.T
+    mask = torch.triu(torch.full((T, T), torch.finfo(torch.float32).min, device="cuda"), diagonal=1)[None, None]
+    pos = torch.arange(T, device="cuda")[None]
+    # FP targets
+    qlayer.set_quant_state(weight_quant=False, act_quant=False)
+    with torch.no_grad():
+        fp = torch.stack([qlayer(x[j:j + 1], attention_mask=mask, position_ids=pos)[0][0] for j in range(fx.nsamples)])
+    assert float((fp.float().cpu() - fx.fp_out).norm() / fx.fp_out.norm()) < 1e-2
+    qlayer.set_quant_state(weight_quant=False, act_quant=True)
+    qlayer.let = True
+    init = fx.init_params()
+    for short, long in (("qkv_s", "qkv_smooth_scale"), ("qkv_d", "qkv_smooth_shift"), ("out_s", "out_smooth_scale"),
+                        ("out_d", "out_smooth_shift"), ("fc1_s", "fc1_smooth_scale"), ("fc1_d", "fc1_smooth_shift"),
+                        ("qkt_s", "qkt_smooth_scale")):
+        qlayer.register_parameter(long, torch.nn.Parameter(init[short].cuda()))
+    qlayer.float()
+    opt = torch.optim.AdamW([{"params": qlayer.let_parameters(True), "lr": 5e-3},
+                             {"params": qlayer.lwc_parameters(), "lr": 1e-2}], weight_decay=0)
+    assert len(list(qlayer.omni_parameters())) == 7 + 14
+    keys = list(qlayer.omni_state_dict().keys())
+    assert "qkv_smooth_scale" in keys and "self_attn.q_proj.weight_quantizer.upbound_factor" in keys
+    loss_fn = torch.nn.MSELoss()
+    losses = []
+    for _ in range(fx.epochs):
+        for j in range(fx.nsamples):
+            qlayer.smooth_and_quant_temporary(seq_len=T, batch=1)
+            out = qlayer(x[j:j + 1], attention_mask=mask, position_ids=pos)[0]
+            loss = loss_fn(fp[j:j + 1].float(), out.float())
+            losses.append(float(loss))
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+    ref = fx.losses
+    rel = np.abs(np.array(losses) - ref) / ref
+    print(fname, "module-loop losses", losses[:4], "ref", ref[:4], "max rel", rel.max())
+    assert rel.max() < 8e-2 and abs(np.mean(losses) - ref.mean()) / ref.mean() < 3e-2
+    qlayer.clear_temp_variable()
+    qlayer.smooth_and_quant_inplace()
+    with torch.no_grad():
+        qo = torch.stack([qlayer(x[j:j + 1], attention_mask=mask, position_ids=pos)[0][0] for j in range(fx.nsamples)])
+    assert float((qo.float().cpu() - fx.quant_out).norm() / fx.quant_out.norm()) < 8e-2
+    qlayer.register_scales_and_zeros()
+    lin = {n: m for n, m in qlayer.named_modules() if isinstance(m, QuantLinear)}
+    assert len(lin) == 7
+    Q = fx.quantized()
+    w = lin["self_attn.q_proj"].weight.float().cpu()
+    assert float((w - Q["q.w"]).abs().mean() / Q["q.w"].abs().mean()) < 5e-2
+    assert lin["self_attn.q_proj"].weight_quantizer.scales.shape == Q["q.scales"].shape
+    assert qlayer.input_layernorm.bias is not None and lin["self_attn.q_proj"].bias is not None   # folded LET buffers
+    # few levels per row/group after fake-quant
+    g = fx.group_size or w.shape[1]
+    assert all(len(torch.unique(row)) <= 2 ** fx.wbits for row in w.reshape(-1, g)[:16])
+
+
+def test_standalone_operators():
+    from omniquant_b200.quantize.int_linear import QuantLinear
+    from omniquant_b200.quantize.int_matmul import QuantMatMul
+    from omniquant_b200.quantize.omni_norm import OmniLayerNorm, OmniLlamaRMSNorm
+    from omniquant_b200.quantize.quantizer import UniformAffineQuantizer
+    from oracle import oq_oracle as orc
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(256, 384).cuda()
+    wq = dict(n_bits=4, per_channel_axes=[0], symmetric=False, dynamic_method="per_channel", group_size=64, lwc=True)
+    aq = dict(n_bits=4, per_channel_axes=[], symmetric=False, dynamic_method="per_token")
+    ql = QuantLinear(lin, wq, aq).cuda()
+    ql.set_quant_state(weight_quant=True, act_quant=True)
+    x = torch.randn(2, 40, 256, device="cuda").to(torch.bfloat16)
+    y = ql(x)
+    with torch.no_grad():
+        w_ref = orc.fake_quant(lin.weight.detach().float(), 4, False, 64, ql.weight_quantizer.upbound_factor.detach(),
+                               ql.weight_quantizer.lowbound_factor.detach())
+        x_ref = orc.fake_quant(x.float(), 4)
+        y_ref = torch.nn.functional.linear(x_ref, w_ref, lin.bias.float())
+    torch.testing.assert_close(y.float(), y_ref, rtol=3e-2, atol=3e-2)
+    y.float().square().mean().backward()
+    assert ql.weight_quantizer.upbound_factor.grad is not None and torch.isfinite(ql.weight_quantizer.upbound_factor.grad).all()
+    # quantiser: identity cases
+    p = UniformAffineQuantizer(n_bits=16, metric="fix0to1")
+    t = torch.rand(4, 4, device="cuda")
+    assert p(t) is t
+    with pytest.raises(Exception):
+        UniformAffineQuantizer(**aq)(torch.randn(4, 8))          # CPU tensor: no fallback
+    # matmul + norms
+    mm = QuantMatMul(aq, aq, matmul_func=torch.bmm).cuda()
+    mm.set_quant_state(False, True)
+    a, b = torch.randn(3, 64, 128, device="cuda").to(torch.bfloat16), torch.randn(3, 128, 72, device="cuda").to(torch.bfloat16)
+    out = mm(mm.quant_x1(a), b)
+    ref = torch.bmm(orc.fake_quant(a.float(), 4), b.float())
+    torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=1e-1)
+    ln = torch.nn.LayerNorm(256).cuda()
+    xs = torch.randn(8, 256, device="cuda")
+    torch.testing.assert_close(OmniLayerNorm(ln).cuda()(xs), ln(xs), rtol=2e-2, atol=2e-2)
+    rn = SimpleNamespace(weight=torch.nn.Parameter(torch.rand(256, device="cuda") + 0.5))
+    torch.testing.assert_close(OmniLlamaRMSNorm(rn, eps=1e-6).cuda()(xs), orc.rms_norm(xs, rn.weight.detach(), None, 1e-6),
+                               rtol=2e-2, atol=2e-2)
