@@ -54,12 +54,14 @@ int oq_weight_quant_fwd(const float* W, int N, int K, const float* col_scale, co
 
 /* Backward of the above (autograd of quantizer.py:84-147 + transformation.py folds).
  * grad_wq: dL/dW_q [N,K] (bf16, or fp32 when grad_is_f32).  xmin/xmax: raw group extrema saved by the
- * forward.  Writes d_up/d_low [N*G]; writes drow[n] = sum_k dW'[n,k]*(W*col)[n,k]; atomically ADDS
+ * forward; scale_saved/zp_saved (optional, both or neither): its scale_out/zp_out, which spares the backward
+ * the per-row sigmoid + division chain.  Writes d_up/d_low [N*G]; writes drow[n] = sum_k dW'[n,k]*(W*col)[n,k]; atomically ADDS
  * dcol_acc[k] += sum_n dW'[n,k]*rowfac[n]*W[n,k] and dshift_acc[k] += sum_n W[n,k]*e_row[n]
  * (caller zeroes them once per step); optionally writes the full dL/dW' (fp32 [N,K]). */
 int oq_weight_quant_bwd(const float* W, int N, int K, const float* col_scale, const float* row_scale, int row_op,
                         int n_bits, int symmetric, int group_size, const float* up, const float* low, int recip_div,
-                        const float* xmin, const float* xmax, const void* grad_wq, int grad_is_f32, long ld_grad,
+                        const float* xmin, const float* xmax, const float* scale_saved, const float* zp_saved,
+                        const void* grad_wq, int grad_is_f32, long ld_grad,
                         const float* e_row, float* d_up, float* d_low, float* dcol_acc, float* drow, float* dshift_acc,
                         float* dW_full, oq_stream_t stream);
 

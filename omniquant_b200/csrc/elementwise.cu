@@ -130,6 +130,115 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const bf16* P, const f
   }
 }
 
+// ---- register-resident softmax rows (Tk <= 1024*NV, Tk % 4 == 0): one read of S / dP, one write of P / dS.
+// Causal rows read j <= i only and write zeros only up to the end of the 128-wide diagonal tile: the k-limited
+// P.V / dS.K / P^T.dO / dS^T.Q GEMMs (causal modes 2 and 3) never read beyond it.
+template <int NV>
+__global__ void __launch_bounds__(256) softmax_fwd_reg(const float* S, bf16* P, const float* mask, long mask_bstride, int Tq,
+                                                       int Tk, int causal) {
+  __shared__ float scratch[2 * 8];
+  const long row = blockIdx.x;
+  const int i = (int)(row % Tq);
+  const long b = row / Tq;
+  const float* s = S + row * (long)Tk;
+  bf16* p = P + row * (long)Tk;
+  const float* mk = mask ? mask + b * mask_bstride + (long)i * Tk : nullptr;
+  const int lim = causal ? min(Tk, i + (Tk - Tq) + 1) : Tk;
+  const int wlim = causal ? min(Tk, (lim + 127) & ~127) : Tk;
+  float4 v[NV];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int j = 4 * (threadIdx.x + c * 256);
+    v[c] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (j < lim) {
+      float4 t = *reinterpret_cast<const float4*>(s + j);
+      if (mk) {
+        const float4 m4 = *reinterpret_cast<const float4*>(mk + j);
+        t.x = fmaxf(t.x + m4.x, -3.4028234663852886e38f); t.y = fmaxf(t.y + m4.y, -3.4028234663852886e38f);
+        t.z = fmaxf(t.z + m4.z, -3.4028234663852886e38f); t.w = fmaxf(t.w + m4.w, -3.4028234663852886e38f);
+      }
+      if (j + 1 >= lim) t.y = -INFINITY;
+      if (j + 2 >= lim) t.z = -INFINITY;
+      if (j + 3 >= lim) t.w = -INFINITY;
+      v[c] = t;
+      mx = fmaxf(fmaxf(mx, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  mx = warp_reduce(mx, OpMax());
+  if (lane == 0) scratch[warp] = mx;
+  __syncthreads();
+  mx = scratch[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, scratch[w]);
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    v[c].x = __expf(v[c].x - mx); v[c].y = __expf(v[c].y - mx); v[c].z = __expf(v[c].z - mx); v[c].w = __expf(v[c].w - mx);
+    sum += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+  }
+  sum = warp_reduce(sum, OpSum());
+  if (lane == 0) scratch[8 + warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += scratch[8 + w];
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int j = 4 * (threadIdx.x + c * 256);
+    if (j < wlim) {
+      const float o[4] = {v[c].x * inv, v[c].y * inv, v[c].z * inv, v[c].w * inv};
+      store_bf4(p + j, o);
+    }
+  }
+}
+template <int NV>
+__global__ void __launch_bounds__(256) softmax_bwd_reg(const bf16* P, const float* dP, bf16* dS, int Tq, int Tk, int causal) {
+  __shared__ float scratch[8];
+  const long row = blockIdx.x;
+  const int i = (int)(row % Tq);
+  const int lim = causal ? min(Tk, i + (Tk - Tq) + 1) : Tk;
+  const int wlim = causal ? min(Tk, (lim + 127) & ~127) : Tk;
+  const bf16* p = P + row * (long)Tk;
+  const float* dp = dP + row * (long)Tk;
+  bf16* ds = dS + row * (long)Tk;
+  float pv[NV][4];
+  float4 g[NV];
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int j = 4 * (threadIdx.x + c * 256);
+    pv[c][0] = pv[c][1] = pv[c][2] = pv[c][3] = 0.f;
+    g[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < lim) {
+      load_bf4(p + j, pv[c]);
+      g[c] = *reinterpret_cast<const float4*>(dp + j);
+      if (j + 1 >= lim) { pv[c][1] = 0.f; g[c].y = 0.f; }
+      if (j + 2 >= lim) { pv[c][2] = 0.f; g[c].z = 0.f; }
+      if (j + 3 >= lim) { pv[c][3] = 0.f; g[c].w = 0.f; }
+      acc += pv[c][0] * g[c].x + pv[c][1] * g[c].y + pv[c][2] * g[c].z + pv[c][3] * g[c].w;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  acc = warp_reduce(acc, OpSum());
+  if (lane == 0) scratch[warp] = acc;
+  __syncthreads();
+  acc = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) acc += scratch[w];
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int j = 4 * (threadIdx.x + c * 256);
+    if (j < wlim) {
+      const float o[4] = {pv[c][0] * (g[c].x - acc), pv[c][1] * (g[c].y - acc), pv[c][2] * (g[c].z - acc),
+                          pv[c][3] * (g[c].w - acc)};
+      store_bf4(ds + j, o);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- MSE
 // loss += inv_numel * sum((out-target)^2 [+ (out-target2)^2]);  dout = 2*inv_numel*((out-target) [+ (out-target2)])
 __global__ void __launch_bounds__(256) mse_kernel(const bf16* out, const bf16* tgt, const bf16* tgt2, long n8,
@@ -251,13 +360,25 @@ extern "C" int oq_relu_bwd(const void* x, const void* dy, void* dx, long n, cuda
 extern "C" int oq_softmax_fwd(const float* S, void* P, const float* mask, long mask_bstride, long batch, int Tq, int Tk,
                               int causal, cudaStream_t stream) {
   OQ_REQUIRE(S && P && batch > 0 && Tq > 0 && Tk > 0 && batch * Tq < (1L << 31), "oq_softmax_fwd: bad arguments");
-  softmax_fwd_kernel<<<(unsigned)(batch * Tq), 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);
+  const unsigned grid = (unsigned)(batch * Tq);
+  const bool fast = Tk % 4 == 0 && al16(S) && ((uintptr_t)P % 8 == 0) && al16(mask);
+  if (fast && Tk <= 1024) softmax_fwd_reg<1><<<grid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);
+  else if (fast && Tk <= 2048) softmax_fwd_reg<2><<<grid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);
+  else if (fast && Tk <= 4096) softmax_fwd_reg<4><<<grid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);
+  else if (fast && Tk <= 8192) softmax_fwd_reg<8><<<grid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);
+  else softmax_fwd_kernel<<<grid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);
   return oq_check_launch("oq_softmax_fwd");
 }
 extern "C" int oq_softmax_bwd(const void* P, const float* dP, void* dS, long batch, int Tq, int Tk, int causal,
                               cudaStream_t stream) {
   OQ_REQUIRE(P && dP && dS && batch > 0 && Tq > 0 && Tk > 0 && batch * Tq < (1L << 31), "oq_softmax_bwd: bad arguments");
-  softmax_bwd_kernel<<<(unsigned)(batch * Tq), 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal);
+  const unsigned grid = (unsigned)(batch * Tq);
+  const bool fast = Tk % 4 == 0 && al16(dP) && ((uintptr_t)P % 8 == 0) && ((uintptr_t)dS % 8 == 0);
+  if (fast && Tk <= 1024) softmax_bwd_reg<1><<<grid, 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal);
+  else if (fast && Tk <= 2048) softmax_bwd_reg<2><<<grid, 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal);
+  else if (fast && Tk <= 4096) softmax_bwd_reg<4><<<grid, 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal);
+  else if (fast && Tk <= 8192) softmax_bwd_reg<8><<<grid, 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal);
+  else softmax_bwd_kernel<<<grid, 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal);
   return oq_check_launch("oq_softmax_bwd");
 }
 extern "C" int oq_mse_fwd_bwd(const void* out, const void* target, const void* target2, long n, float inv_numel,

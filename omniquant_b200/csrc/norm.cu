@@ -175,10 +175,10 @@ extern "C" int oq_norm_bwd(const void* x, long rows, int C, long ldx, const floa
                    (uintptr_t)dx_add % 16 == 0;
   const int grid = (int)std::min<long>(rows, smem ? (long)oq_num_sms() * 2 : rows);
   if (vec) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(norm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 40 * 1024) cudaFuncSetAttribute(norm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     norm_bwd_kernel<true><<<grid, 256, smem, stream>>>(a);
   } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(norm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 40 * 1024) cudaFuncSetAttribute(norm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     norm_bwd_kernel<false><<<grid, 256, smem, stream>>>(a);
   }
   return oq_check_launch("oq_norm_bwd");

@@ -126,3 +126,20 @@ OQ_HD void oq_scale_grad(float R, float xmin, float xmax, float su, float sl, in
     *gminp = -R / Q;
   }
 }
+
+// rint(x / scale) with the division replaced by a multiply in the common case, bit-identical to
+// rintf(x / scale): the product x*inv_scale is within 1.8e-7*|q| of the correctly rounded quotient, so the
+// two can only round to different integers when the product sits that close to a half-integer -- then (and
+// for NaN/Inf) the exact IEEE division decides.  `inv_ok` = isnormal(inv_scale), evaluated once per group.
+OQ_HD float oq_rint_div(float x, float scale, float inv_scale, int inv_ok) {
+  if (!inv_ok) return rintf(OQ_DIV(x, scale));
+  const float qa = OQ_MUL(x, inv_scale);
+  float r = rintf(qa);
+  const float d = fabsf(qa - r);
+  if (!(fabsf(d - 0.5f) > fabsf(qa) * 2.4e-7f + 1e-30f)) r = rintf(OQ_DIV(x, scale));
+  return r;
+}
+OQ_HD int oq_inv_ok(float inv_scale) {
+  const float a = fabsf(inv_scale);
+  return (a >= 1.1754944e-38f) && (a <= 3.4028235e38f);
+}

@@ -14,6 +14,8 @@
 // Team = one warp per quantisation group (group_size > 0) or one 256-thread
 // block per output channel (per-channel).  Grid = a multiple of the SM count,
 // teams stride over groups/rows.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -37,6 +39,7 @@ struct WqArgs {
   // backward inputs
   const void* g; int g_is_f32; long ld_g;
   const float* xmin_in; const float* xmax_in;
+  const float* scale_in; const float* zp_in;  // optional: scale / zero point saved by the forward
   const float* e_row;  // [N] or null
   // backward outputs
   float* d_up; float* d_low;   // [N*G] written
@@ -278,6 +281,10 @@ int pick_grid(long n_items, bool team_warp, int per_sm) {
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+#include "weight_quant_fast.cuh"
+
+bool al(const void* p, int b) { return ((uintptr_t)p % b) == 0; }
+
 }  // namespace
 
 extern "C" int oq_weight_quant_fwd(const float* W, int N, int K, const float* col_scale, const float* row_scale,
@@ -305,6 +312,21 @@ extern "C" int oq_weight_quant_fwd(const float* W, int N, int K, const float* co
     cudaError_t e = cudaMemsetAsync(matvec_out, 0, sizeof(float) * N, stream);
     if (e != cudaSuccess) return (int)e;
   }
+  // fast register-resident paths (weight_quant_fast.cuh); the generic kernels below cover everything else
+  const bool let = col_scale || row_scale || shift;
+  const bool fast_al = vec && al(col_scale, 16) && al(shift, 16);
+  if (fast_al && !team_warp && K <= 16384) {
+    const size_t smem = let ? sizeof(float) * 2 * K : 0;
+    const int g = (int)std::min<long>(N, (long)oq_num_sms() * (K > 8192 ? 2 : 4));
+    if (let ? launch_pc_fwd<true>(a, g, smem, stream) : launch_pc_fwd<false>(a, g, 0, stream))
+      return oq_check_launch("oq_weight_quant_fwd");
+  }
+  if (fast_al && team_warp && K % group_size == 0) {
+    const long slots = ((long)N * G * (group_size >= 128 ? 32 : group_size / 4) + 31) / 32;
+    const int g = (int)std::max<long>(1, std::min<long>((slots + 7) / 8, (long)oq_num_sms() * 8));
+    if (let ? launch_grp<true, false>(a, g, 0, stream) : launch_grp<false, false>(a, g, 0, stream))
+      return oq_check_launch("oq_weight_quant_fwd");
+  }
   const int grid = pick_grid((long)N * G, team_warp, 8);
   if (team_warp) {
     if (vec) wq_fwd_kernel<true, true><<<grid, 256, 0, stream>>>(a);
@@ -319,16 +341,18 @@ extern "C" int oq_weight_quant_fwd(const float* W, int N, int K, const float* co
 extern "C" int oq_weight_quant_bwd(const float* W, int N, int K, const float* col_scale, const float* row_scale,
                                    int row_op, int n_bits, int symmetric, int group_size, const float* up,
                                    const float* low, int recip_div, const float* xmin, const float* xmax,
-                                   const void* grad_wq, int grad_is_f32, long ld_grad, const float* e_row,
+                                   const float* scale_saved, const float* zp_saved, const void* grad_wq, int grad_is_f32, long ld_grad, const float* e_row,
                                    float* d_up, float* d_low, float* dcol_acc, float* drow, float* dshift_acc,
                                    float* dW_full, cudaStream_t stream) {
   OQ_REQUIRE(W && grad_wq && xmin && xmax && N > 0 && K > 0, "oq_weight_quant_bwd: null input or bad shape");
   OQ_REQUIRE(n_bits >= 2 && n_bits <= 8, "oq_weight_quant_bwd: n_bits %d not in [2,8]", n_bits);
   OQ_REQUIRE((up == nullptr) == (low == nullptr), "oq_weight_quant_bwd: up/low must both be set or both null");
   OQ_REQUIRE(!dshift_acc || e_row, "oq_weight_quant_bwd: dshift needs e_row");
+  OQ_REQUIRE((scale_saved == nullptr) == (zp_saved == nullptr), "oq_weight_quant_bwd: scale/zp must both be given or both null");
   WqArgs a = {};
   a.W = W; a.N = N; a.K = K; a.col = col_scale; a.row = row_scale; a.row_op = row_op;
   a.n_bits = n_bits; a.symmetric = symmetric; a.group = group_size; a.recip_div = recip_div; a.up = up; a.low = low;
+  a.scale_in = scale_saved; a.zp_in = zp_saved;
   a.g = grad_wq; a.g_is_f32 = grad_is_f32; a.ld_g = ld_grad ? ld_grad : K; a.xmin_in = xmin; a.xmax_in = xmax;
   a.e_row = e_row; a.d_up = d_up; a.d_low = d_low; a.dcol = dcol_acc; a.drow = drow; a.dshift = dshift_acc; a.dW = dW_full;
   const bool team_warp = group_size > 0;
@@ -339,13 +363,31 @@ extern "C" int oq_weight_quant_bwd(const float* W, int N, int K, const float* co
     cudaError_t e = cudaMemsetAsync(drow, 0, sizeof(float) * N, stream);
     if (e != cudaSuccess) return (int)e;
   }
+  const bool let = col_scale || row_scale || e_row || dcol_acc || dshift_acc;
+  const bool fast_al = (K % 4 == 0) && (group_size % 4 == 0) && (a.ld_g % 4 == 0) && al(W, 16) && al(grad_wq, 16) &&
+                       al(col_scale, 16) && al(dW_full, 16);
+  if (fast_al && !team_warp && K <= 16384) {
+    const size_t sm2 = let ? sizeof(float) * 3 * K : 0;
+    if (sm2 <= 200 * 1024) {
+      const int g = (int)std::min<long>(N, (long)oq_num_sms() * (K > 4096 ? 2 : 3));
+      if (let ? launch_pc_bwd<true>(a, g, sm2, stream) : launch_pc_bwd<false>(a, g, 0, stream))
+        return oq_check_launch("oq_weight_quant_bwd");
+    }
+  }
+  if (fast_al && team_warp && K % group_size == 0) {
+    const size_t sm2 = let ? sizeof(float) * 2 * K : 0;
+    const long slots = ((long)N * G * (group_size >= 128 ? 32 : group_size / 4) + 31) / 32;
+    const int g = (int)std::max<long>(1, std::min<long>((slots + 7) / 8, (long)oq_num_sms() * (let ? 3 : 8)));
+    if (sm2 <= 200 * 1024 && (let ? launch_grp<true, true>(a, g, sm2, stream) : launch_grp<false, true>(a, g, 0, stream)))
+      return oq_check_launch("oq_weight_quant_bwd");
+  }
   // column accumulators are flushed once per block: fewer, longer-lived blocks when they are in use
   const int grid = pick_grid((long)N * G, team_warp, smem ? 2 : 8);
   if (team_warp) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(wq_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 40 * 1024) cudaFuncSetAttribute(wq_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     wq_bwd_kernel<true><<<grid, 256, smem, stream>>>(a);
   } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(wq_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 40 * 1024) cudaFuncSetAttribute(wq_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     wq_bwd_kernel<false><<<grid, 256, smem, stream>>>(a);
   }
   return oq_check_launch("oq_weight_quant_bwd");

@@ -1,0 +1,599 @@
+// Register-resident fast paths of the weight fake-quant forward / backward (included by weight_quant.cu).
+//
+// Per-channel (group_size 0): one 256-thread block per output row, the whole row held in registers as NV
+// float4 per thread (K <= 1024*NV), all loads of a row issued back to back and the next row prefetched, one
+// block barrier per row.  Grouped: LPG lanes x VPL float4 per lane hold one group (group = 4*LPG*VPL), a warp
+// holds 32/LPG groups at once.  Same arithmetic (oq_math.h) as the generic kernels; the division inside
+// round(x/scale) goes through oq_rint_div (bit-identical, divides only near rounding boundaries).
+#pragma once
+
+// ------------------------------------------------------------------ block reduction with one barrier
+// Each thread contributes NS sums and NM maxima; results broadcast.  `scratch` holds 2*(NS+NM)*8 floats and
+// is double-buffered on `par` so that no trailing barrier is needed between consecutive rows.
+template <int NS, int NM>
+__device__ __forceinline__ void block_reduce_1sync(float (&s)[NS > 0 ? NS : 1], float (&m)[NM > 0 ? NM : 1], float* scratch,
+                                                   int par) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) s[i] = warp_reduce(s[i], OpSum());
+#pragma unroll
+  for (int i = 0; i < NM; ++i) m[i] = warp_reduce(m[i], OpMax());
+  float* buf = scratch + par * (NS + NM) * 8;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) buf[i * 8 + warp] = s[i];
+#pragma unroll
+    for (int i = 0; i < NM; ++i) buf[(NS + i) * 8 + warp] = m[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += buf[i * 8 + w];
+    s[i] = t;
+  }
+#pragma unroll
+  for (int i = 0; i < NM; ++i) {
+    float t = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t = fmaxf(t, buf[(NS + i) * 8 + w]);
+    m[i] = t;
+  }
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float& f4(float4& v, int j) { return reinterpret_cast<float*>(&v)[j]; }
+
+// ================================================================== per-channel forward
+template <int NV, bool LET>
+__global__ void __launch_bounds__(256) wq_pc_fwd(WqArgs a) {
+  extern __shared__ float4 dsm4[];
+  __shared__ float scratch[2 * 3 * 8];
+  const int tid = threadIdx.x, K4 = a.K >> 2;
+  float4* colv = dsm4;            // [K4] when LET && a.col
+  float4* shv = dsm4 + K4;        // [K4] when LET && a.shift
+  if (LET) {
+    for (int i = tid; i < K4; i += 256) {
+      if (a.col) colv[i] = ld4(a.col + 4 * i);
+      if (a.shift) shv[i] = ld4(a.shift + 4 * i);
+    }
+    __syncthreads();
+  }
+  const int lwc = a.up != nullptr;
+  const bool has_col = LET && a.col != nullptr;
+  const bool has_shift = LET && a.shift != nullptr;
+  float4 wn[NV];
+  int n = blockIdx.x;
+  if (n < a.N) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = tid + i * 256;
+      wn[i] = idx < K4 ? ld4(a.W + (long)n * a.K + 4 * idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  int par = 0;
+  for (; n < a.N; n += gridDim.x, par ^= 1) {
+    float4 w[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) w[i] = wn[i];
+    const int nn = n + gridDim.x;
+    if (nn < a.N) {  // prefetch the next row while this one is processed
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int idx = tid + i * 256;
+        if (idx < K4) wn[i] = ld4(a.W + (long)nn * a.K + 4 * idx);
+      }
+    }
+    const float rs = (LET && a.row) ? a.row[n] : 1.0f;
+    const int rop = (LET && a.row) ? a.row_op : 0;
+    float sm[1] = {0.f}, mm[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = tid + i * 256;
+      if (idx < K4) {
+        float4 c4 = has_col ? colv[idx] : make_float4(1.f, 1.f, 1.f, 1.f);
+        if (has_shift) {
+          const float4 s4 = shv[idx];
+          sm[0] += w[i].x * s4.x + w[i].y * s4.y + w[i].z * s4.z + w[i].w * s4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float f = oq_fold(f4(w[i], j), f4(c4, j), has_col, rs, rop);
+          f4(w[i], j) = f;  // keep the folded value
+          mm[0] = fmaxf(mm[0], -f);
+          mm[1] = fmaxf(mm[1], f);
+        }
+      }
+    }
+    block_reduce_1sync<1, 2>(sm, mm, scratch, par);
+    const float xmin = -mm[0], xmax = mm[1];
+    const float su = lwc ? oq_sigmoidf(a.up[n]) : 1.0f;
+    const float sl = lwc ? oq_sigmoidf(a.low[n]) : 1.0f;
+    const OqQParams q = oq_qparams(xmin, xmax, su, sl, lwc, a.n_bits, a.symmetric, a.recip_div);
+    if (tid == 0) {
+      if (a.scale_out) a.scale_out[n] = q.scale;
+      if (a.zp_out) a.zp_out[n] = q.zp;
+      if (a.xmin_out) a.xmin_out[n] = xmin;
+      if (a.xmax_out) a.xmax_out[n] = xmax;
+      if (has_shift && a.mv) a.mv[n] = sm[0];
+    }
+    const float inv = OQ_DIV(1.0f, q.scale);
+    const int inv_ok = oq_inv_ok(inv);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = tid + i * 256;
+      if (idx < K4) {
+        float y[4], c[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float t = OQ_ADD(oq_rint_div(f4(w[i], j), q.scale, inv, inv_ok), q.zp);
+          c[j] = oq_clampf(t, 0.0f, q.qmax);
+          y[j] = oq_dequant(c[j], q);
+        }
+        const long o = (long)n * a.K + 4 * idx;
+        if (a.q_bf) store_bf4(a.q_bf + (long)n * a.ld_bf + 4 * idx, y);
+        if (a.q_f32) *reinterpret_cast<float4*>(a.q_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
+        if (a.codes)
+          *reinterpret_cast<uchar4*>(a.codes + o) =
+              make_uchar4((unsigned char)c[0], (unsigned char)c[1], (unsigned char)c[2], (unsigned char)c[3]);
+      }
+    }
+  }
+}
+
+// ================================================================== per-channel backward
+// dynamic smem (LET): col[K] | colacc[K] | shacc[K]
+template <int NV, bool LET>
+__global__ void __launch_bounds__(256) wq_pc_bwd(WqArgs a) {
+  extern __shared__ float4 dsm4[];
+  __shared__ float scratch[2 * 6 * 8];
+  const int tid = threadIdx.x, K4 = a.K >> 2;
+  float4* colv = dsm4;
+  float4* colacc = dsm4 + K4;
+  float4* shacc = dsm4 + 2 * K4;
+  const bool has_col = LET && a.col != nullptr;
+  const bool want_col = LET && a.dcol != nullptr;
+  const bool want_sh = LET && a.dshift != nullptr;
+  if (LET) {
+    for (int i = tid; i < K4; i += 256) {
+      if (has_col) colv[i] = ld4(a.col + 4 * i);
+      colacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      shacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+  }
+  const int lwc = a.up != nullptr;
+  int par = 0;
+  auto load_row = [&](int row, float4 (&ww)[NV], float4 (&gg)[NV]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = tid + i * 256;
+      if (idx < K4) {
+        ww[i] = ld4(a.W + (long)row * a.K + 4 * idx);
+        if (a.g_is_f32) {
+          gg[i] = ld4(reinterpret_cast<const float*>(a.g) + (long)row * a.ld_g + 4 * idx);
+        } else {
+          float t[4];
+          load_bf4(reinterpret_cast<const bf16*>(a.g) + (long)row * a.ld_g + 4 * idx, t);
+          gg[i] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+    }
+  };
+  constexpr bool PREFETCH = false;   // measured: the extra registers (3 -> 2 blocks/SM) cost more than the overlap wins
+  float4 wn[PREFETCH ? NV : 1], gn[PREFETCH ? NV : 1];
+  if constexpr (PREFETCH) {
+    if ((int)blockIdx.x < a.N) load_row(blockIdx.x, wn, gn);
+  }
+  for (int n = blockIdx.x; n < a.N; n += gridDim.x, par ^= 1) {
+    float4 w[NV], g[NV];
+    if constexpr (PREFETCH) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) { w[i] = wn[i]; g[i] = gn[i]; }
+      if (n + (int)gridDim.x < a.N) load_row(n + gridDim.x, wn, gn);
+    } else {
+      load_row(n, w, g);
+    }
+    const float rs = (LET && a.row) ? a.row[n] : 1.0f;
+    const int rop = (LET && a.row) ? a.row_op : 0;
+    const float rfac = rop == 1 ? rs : (rop == 2 ? 1.0f / rs : 1.0f);
+    const float en = (LET && a.e_row) ? a.e_row[n] : 0.0f;
+    const float xmin = a.xmin_in[n], xmax = a.xmax_in[n];
+    OqQParams q;
+    if (a.scale_in) {  // saved by the forward: skips two sigmoids and the scale / zero-point divisions per row
+      q.scale = a.scale_in[n];
+      q.zp = a.zp_in[n];
+      q.qmax = (float)((1 << a.n_bits) - 1);
+    } else {
+      q = oq_qparams(xmin, xmax, lwc ? oq_sigmoidf(a.up[n]) : 1.0f, lwc ? oq_sigmoidf(a.low[n]) : 1.0f, lwc, a.n_bits,
+                     a.symmetric, a.recip_div);
+    }
+    const float inv = OQ_DIV(1.0f, q.scale);
+    const int inv_ok = oq_inv_ok(inv);
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // R, #max, #min, rowdot, sum w1@max, sum w1@min
+    float dummy[1] = {-INFINITY};
+    bool tie = false;
+    // The backward is tolerance-checked (not bit-exact), so the fold uses a reciprocal multiply and the arg-max /
+    // arg-min elements are recognised within 2 ulp of the saved extrema (which the forward computed exactly).
+    const float rmul = rop == 1 ? rs : (rop == 2 ? 1.0f / rs : 1.0f);
+    const float tie_tol_max = 2.4e-7f * fabsf(xmax), tie_tol_min = 2.4e-7f * fabsf(xmin);
+    const bool tie_all = !(lwc && xmax > 0.0f && xmin < 0.0f) || a.symmetric;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = tid + i * 256;
+      if (idx < K4) {
+        const float4 c4 = has_col ? colv[idx] : make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 ca = make_float4(0.f, 0.f, 0.f, 0.f), sa = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float wv = f4(w[i], j);
+          const float w1 = has_col ? wv * f4(const_cast<float4&>(c4), j) : wv;
+          const float f = w1 * rmul;          // (W*col) {*,/} row with the division as a reciprocal multiply
+          const float qa = f * inv;
+          const float t = rintf(qa) + q.zp;
+          const bool inr = (t >= 0.0f) && (t <= q.qmax);
+          const float c = oq_clampf(t, 0.0f, q.qmax);
+          const float gk = f4(g[i], j);
+          acc[0] += gk * ((c - q.zp) - (inr ? qa : 0.0f));
+          if (tie_all || t >= q.qmax - 1.0f || t <= 1.0f) {   // with an LWC clip (sigmoid < 1) the extrema land on the outermost codes (+-1 from the double rounding of scale and zero point)
+            const bool ismax = fabsf(f - xmax) <= tie_tol_max, ismin = fabsf(f - xmin) <= tie_tol_min;
+            if (ismax) { acc[1] += 1.0f; acc[4] += w1; }
+            if (ismin) { acc[2] += 1.0f; acc[5] += w1; }
+            tie |= ismax | ismin;
+          }
+          const float d2 = inr ? gk : 0.0f;
+          acc[3] += d2 * w1;
+          f4(ca, j) = d2 * rfac * wv;
+          f4(sa, j) = wv * en;
+          f4(g[i], j) = d2;  // keep the straight-through part for the optional full-gradient output
+        }
+        if (want_col) {
+          float4 t = colacc[idx];
+          t.x += ca.x; t.y += ca.y; t.z += ca.z; t.w += ca.w;
+          colacc[idx] = t;
+        }
+        if (want_sh) {
+          float4 t = shacc[idx];
+          t.x += sa.x; t.y += sa.y; t.z += sa.z; t.w += sa.w;
+          shacc[idx] = t;
+        }
+      }
+    }
+    block_reduce_1sync<6, 0>(acc, dummy, scratch, par);
+    float cmax = 0.f, cmin = 0.f;
+    if (tid == 0 || tie || a.dW) {   // only the threads that need the clip-path constants evaluate the sigmoids
+      const float su = lwc ? oq_sigmoidf(a.up[n]) : 1.0f;
+      const float sl = lwc ? oq_sigmoidf(a.low[n]) : 1.0f;
+      float gmaxp, gminp;
+      oq_scale_grad(acc[0], xmin, xmax, su, sl, lwc, a.n_bits, a.symmetric, a.recip_div, &gmaxp, &gminp);
+      cmax = acc[1] > 0.f ? gmaxp * su / acc[1] : 0.0f;
+      cmin = acc[2] > 0.f ? gminp * sl / acc[2] : 0.0f;
+      if (tid == 0) {
+        if (lwc && a.d_up) a.d_up[n] = gmaxp * xmax * su * (1.0f - su);
+        if (lwc && a.d_low) a.d_low[n] = gminp * xmin * sl * (1.0f - sl);
+        if (a.drow) a.drow[n] = acc[3] + cmax * acc[4] + cmin * acc[5];
+      }
+    }
+    if (tie || a.dW) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int idx = tid + i * 256;
+        if (idx < K4) {
+          const float4 c4 = has_col ? colv[idx] : make_float4(1.f, 1.f, 1.f, 1.f);
+          float4 corr4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          bool any = false;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float wv = f4(w[i], j);
+            const float w1 = has_col ? wv * f4(const_cast<float4&>(c4), j) : wv;
+            const float f = w1 * rmul;
+            float corr = 0.0f;
+            if (fabsf(f - xmax) <= tie_tol_max) corr += cmax;
+            if (fabsf(f - xmin) <= tie_tol_min) corr += cmin;
+            f4(corr4, j) = corr;
+            any |= corr != 0.0f;
+          }
+          if (any && want_col) {
+            float4 t = colacc[idx];
+            t.x += corr4.x * rfac * w[i].x; t.y += corr4.y * rfac * w[i].y;
+            t.z += corr4.z * rfac * w[i].z; t.w += corr4.w * rfac * w[i].w;
+            colacc[idx] = t;
+          }
+          if (a.dW)
+            *reinterpret_cast<float4*>(a.dW + (long)n * a.K + 4 * idx) =
+                make_float4(g[i].x + corr4.x, g[i].y + corr4.y, g[i].z + corr4.z, g[i].w + corr4.w);
+        }
+      }
+    }
+  }
+  if (LET) {
+    __syncthreads();
+    for (int i = tid; i < a.K; i += 256) {
+      if (want_col) atomicAdd(a.dcol + i, reinterpret_cast<float*>(colacc)[i]);
+      if (want_sh) atomicAdd(a.dshift + i, reinterpret_cast<float*>(shacc)[i]);
+    }
+  }
+}
+
+// ================================================================== grouped kernels
+template <int LPG>
+__device__ __forceinline__ float grp_sum(float v) {
+#pragma unroll
+  for (int o = LPG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int LPG>
+__device__ __forceinline__ float grp_max(float v) {
+#pragma unroll
+  for (int o = LPG / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// group = 4*LPG*VPL contiguous weights; requires K % group == 0.  LET: col/shift read through L1.
+template <int LPG, int VPL, bool LET>
+__global__ void __launch_bounds__(256) wq_grp_fwd(WqArgs a) {
+  constexpr int GPS = 32 / LPG;        // groups per warp slot
+  constexpr int GSZ = 4 * LPG * VPL;
+  const int lane = threadIdx.x & 31, sub = lane / LPG, sl_ = lane % LPG;
+  const int G = a.K / GSZ;
+  const long n_groups = (long)a.N * G;
+  const long n_slots = (n_groups + GPS - 1) / GPS;
+  const long wid = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long nw = (long)gridDim.x * (blockDim.x >> 5);
+  const int lwc = a.up != nullptr;
+  const bool has_col = LET && a.col != nullptr, has_shift = LET && a.shift != nullptr;
+  for (long slot = wid; slot < n_slots; slot += nw) {
+    const long item = slot * GPS + sub;
+    const bool valid = item < n_groups;
+    const long it = valid ? item : n_groups - 1;
+    const int n = (int)(it / G), gi = (int)(it % G);
+    const long base = (long)n * a.K + (long)gi * GSZ;
+    const int kb = gi * GSZ;
+    float4 w[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) w[v] = ld4(a.W + base + 4 * (sl_ + v * LPG));
+    const float rs = (LET && a.row) ? a.row[n] : 1.0f;
+    const int rop = (LET && a.row) ? a.row_op : 0;
+    float mn = INFINITY, mx = -INFINITY, mv = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int k = kb + 4 * (sl_ + v * LPG);
+      float4 c4 = has_col ? ld4(a.col + k) : make_float4(1.f, 1.f, 1.f, 1.f);
+      if (has_shift) {
+        const float4 s4 = ld4(a.shift + k);
+        mv += w[v].x * s4.x + w[v].y * s4.y + w[v].z * s4.z + w[v].w * s4.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float f = oq_fold(f4(w[v], j), f4(c4, j), has_col, rs, rop);
+        f4(w[v], j) = f;
+        mn = fminf(mn, f);
+        mx = fmaxf(mx, f);
+      }
+    }
+    mn = -grp_max<LPG>(-mn);
+    mx = grp_max<LPG>(mx);
+    if (has_shift) mv = grp_sum<LPG>(mv);
+    const float su = lwc ? oq_sigmoidf(a.up[it]) : 1.0f;
+    const float sl = lwc ? oq_sigmoidf(a.low[it]) : 1.0f;
+    const OqQParams q = oq_qparams(mn, mx, su, sl, lwc, a.n_bits, a.symmetric, a.recip_div);
+    if (sl_ == 0 && valid) {
+      if (a.scale_out) a.scale_out[item] = q.scale;
+      if (a.zp_out) a.zp_out[item] = q.zp;
+      if (a.xmin_out) a.xmin_out[item] = mn;
+      if (a.xmax_out) a.xmax_out[item] = mx;
+      if (has_shift && a.mv) atomicAdd(a.mv + n, mv);
+    }
+    const float inv = OQ_DIV(1.0f, q.scale);
+    const int inv_ok = oq_inv_ok(inv);
+    if (valid) {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int ko = 4 * (sl_ + v * LPG);
+        float y[4], c[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float t = OQ_ADD(oq_rint_div(f4(w[v], j), q.scale, inv, inv_ok), q.zp);
+          c[j] = oq_clampf(t, 0.0f, q.qmax);
+          y[j] = oq_dequant(c[j], q);
+        }
+        if (a.q_bf) store_bf4(a.q_bf + (long)n * a.ld_bf + kb + ko, y);
+        if (a.q_f32) *reinterpret_cast<float4*>(a.q_f32 + base + ko) = make_float4(y[0], y[1], y[2], y[3]);
+        if (a.codes)
+          *reinterpret_cast<uchar4*>(a.codes + base + ko) =
+              make_uchar4((unsigned char)c[0], (unsigned char)c[1], (unsigned char)c[2], (unsigned char)c[3]);
+      }
+    }
+  }
+}
+
+// dynamic smem (LET): colacc[K] | shacc[K] (shared-memory atomics: several warps hit the same columns)
+template <int LPG, int VPL, bool LET>
+__global__ void __launch_bounds__(256) wq_grp_bwd(WqArgs a) {
+  extern __shared__ float4 dsm4[];
+  constexpr int GPS = 32 / LPG;
+  constexpr int GSZ = 4 * LPG * VPL;
+  float* colacc = reinterpret_cast<float*>(dsm4);
+  float* shacc = colacc + a.K;
+  const bool has_col = LET && a.col != nullptr;
+  const bool want_col = LET && a.dcol != nullptr, want_sh = LET && a.dshift != nullptr;
+  if (LET) {
+    for (int i = threadIdx.x; i < a.K; i += blockDim.x) { colacc[i] = 0.f; shacc[i] = 0.f; }
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, sub = lane / LPG, sl_ = lane % LPG;
+  const int G = a.K / GSZ;
+  const long n_groups = (long)a.N * G;
+  const long n_slots = (n_groups + GPS - 1) / GPS;
+  const long wid = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long nw = (long)gridDim.x * (blockDim.x >> 5);
+  const int lwc = a.up != nullptr;
+  for (long slot = wid; slot < n_slots; slot += nw) {
+    const long item = slot * GPS + sub;
+    const bool valid = item < n_groups;
+    const long it = valid ? item : n_groups - 1;
+    const int n = (int)(it / G), gi = (int)(it % G);
+    const long base = (long)n * a.K + (long)gi * GSZ;
+    const int kb = gi * GSZ;
+    float4 w[VPL], g[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int ko = 4 * (sl_ + v * LPG);
+      w[v] = ld4(a.W + base + ko);
+      if (a.g_is_f32) {
+        g[v] = ld4(reinterpret_cast<const float*>(a.g) + (long)n * a.ld_g + kb + ko);
+      } else {
+        float t[4];
+        load_bf4(reinterpret_cast<const bf16*>(a.g) + (long)n * a.ld_g + kb + ko, t);
+        g[v] = make_float4(t[0], t[1], t[2], t[3]);
+      }
+    }
+    const float rs = (LET && a.row) ? a.row[n] : 1.0f;
+    const int rop = (LET && a.row) ? a.row_op : 0;
+    const float rfac = rop == 1 ? rs : (rop == 2 ? 1.0f / rs : 1.0f);
+    const float en = (LET && a.e_row) ? a.e_row[n] : 0.0f;
+    const float xmin = a.xmin_in[it], xmax = a.xmax_in[it];
+    const float su = lwc ? oq_sigmoidf(a.up[it]) : 1.0f;
+    const float sl = lwc ? oq_sigmoidf(a.low[it]) : 1.0f;
+    OqQParams q;
+    if (a.scale_in) {
+      q.scale = a.scale_in[it];
+      q.zp = a.zp_in[it];
+      q.qmax = (float)((1 << a.n_bits) - 1);
+    } else {
+      q = oq_qparams(xmin, xmax, su, sl, lwc, a.n_bits, a.symmetric, a.recip_div);
+    }
+    const float inv = OQ_DIV(1.0f, q.scale);
+    const int inv_ok = oq_inv_ok(inv);
+    float R = 0.f, nmax = 0.f, nmin = 0.f, rowdot = 0.f, smax = 0.f, smin = 0.f;
+    float4 fv[VPL];
+    const float rmul = rop == 1 ? rs : (rop == 2 ? 1.0f / rs : 1.0f);
+    const float tie_tol_max = 2.4e-7f * fabsf(xmax), tie_tol_min = 2.4e-7f * fabsf(xmin);
+    const bool tie_all = !(lwc && xmax > 0.0f && xmin < 0.0f) || a.symmetric;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int k = kb + 4 * (sl_ + v * LPG);
+      float4 c4 = has_col ? ld4(a.col + k) : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float wv = f4(w[v], j);
+        const float w1 = has_col ? wv * f4(c4, j) : wv;
+        const float f = w1 * rmul;
+        f4(fv[v], j) = f;
+        const float qa = f * inv;
+        const float t = rintf(qa) + q.zp;
+        const bool inr = (t >= 0.0f) && (t <= q.qmax);
+        const float c = oq_clampf(t, 0.0f, q.qmax);
+        const float gk = valid ? f4(g[v], j) : 0.0f;
+        R += gk * ((c - q.zp) - (inr ? qa : 0.0f));
+        if (tie_all || t >= q.qmax - 1.0f || t <= 1.0f) {
+          if (fabsf(f - xmax) <= tie_tol_max) { nmax += 1.0f; smax += w1; }
+          if (fabsf(f - xmin) <= tie_tol_min) { nmin += 1.0f; smin += w1; }
+        }
+        const float d2 = inr ? gk : 0.0f;
+        rowdot += d2 * w1;
+        f4(g[v], j) = d2;
+        if (valid && want_col) atomicAdd(colacc + k + j, d2 * rfac * wv);
+        if (valid && want_sh) atomicAdd(shacc + k + j, wv * en);
+      }
+    }
+    R = grp_sum<LPG>(R); nmax = grp_sum<LPG>(nmax); nmin = grp_sum<LPG>(nmin);
+    float gmaxp, gminp;
+    oq_scale_grad(R, xmin, xmax, su, sl, lwc, a.n_bits, a.symmetric, a.recip_div, &gmaxp, &gminp);
+    const float cmax = nmax > 0.f ? gmaxp * su / nmax : 0.0f;
+    const float cmin = nmin > 0.f ? gminp * sl / nmin : 0.0f;
+    if (a.drow) {
+      rowdot = grp_sum<LPG>(rowdot); smax = grp_sum<LPG>(smax); smin = grp_sum<LPG>(smin);
+      if (sl_ == 0 && valid) atomicAdd(a.drow + n, rowdot + cmax * smax + cmin * smin);
+    }
+    if (sl_ == 0 && valid && lwc) {
+      if (a.d_up) a.d_up[item] = gmaxp * xmax * su * (1.0f - su);
+      if (a.d_low) a.d_low[item] = gminp * xmin * sl * (1.0f - sl);
+    }
+    if (valid && (want_col || a.dW)) {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int ko = 4 * (sl_ + v * LPG);
+        float4 o4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float f = f4(fv[v], j);
+          float corr = 0.0f;
+          if (fabsf(f - xmax) <= tie_tol_max) corr += cmax;
+          if (fabsf(f - xmin) <= tie_tol_min) corr += cmin;
+          if (corr != 0.0f && want_col) atomicAdd(colacc + kb + ko + j, corr * rfac * f4(w[v], j));
+          f4(o4, j) = f4(g[v], j) + corr;
+        }
+        if (a.dW) *reinterpret_cast<float4*>(a.dW + base + ko) = o4;
+      }
+    }
+  }
+  if (LET) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.K; i += blockDim.x) {
+      if (want_col && colacc[i] != 0.f) atomicAdd(a.dcol + i, colacc[i]);
+      if (want_sh && shacc[i] != 0.f) atomicAdd(a.dshift + i, shacc[i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ dispatch helpers
+template <bool LET>
+static bool launch_pc_fwd(const WqArgs& a, int grid, size_t smem, cudaStream_t s) {
+  const int nv = (a.K / 4 + 255) / 256;
+#define OQ_PC_FWD(NVV)                                                                                          \
+  {                                                                                                             \
+    if (smem > 40 * 1024) cudaFuncSetAttribute(wq_pc_fwd<NVV, LET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    wq_pc_fwd<NVV, LET><<<grid, 256, smem, s>>>(a);                                                             \
+    return true;                                                                                                \
+  }
+  if (nv <= 1) OQ_PC_FWD(1)
+  if (nv <= 2) OQ_PC_FWD(2)
+  if (nv <= 4) OQ_PC_FWD(4)
+  if (nv <= 8) OQ_PC_FWD(8)
+  if (nv <= 11) OQ_PC_FWD(11)
+  if (nv <= 16) OQ_PC_FWD(16)
+#undef OQ_PC_FWD
+  return false;
+}
+template <bool LET>
+static bool launch_pc_bwd(const WqArgs& a, int grid, size_t smem, cudaStream_t s) {
+  const int nv = (a.K / 4 + 255) / 256;
+#define OQ_PC_BWD(NVV)                                                                                          \
+  {                                                                                                             \
+    if (smem > 40 * 1024) cudaFuncSetAttribute(wq_pc_bwd<NVV, LET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    wq_pc_bwd<NVV, LET><<<grid, 256, smem, s>>>(a);                                                             \
+    return true;                                                                                                \
+  }
+  if (nv <= 1) OQ_PC_BWD(1)
+  if (nv <= 2) OQ_PC_BWD(2)
+  if (nv <= 4) OQ_PC_BWD(4)
+  if (nv <= 8) OQ_PC_BWD(8)
+  if (nv <= 11) OQ_PC_BWD(11)
+  if (nv <= 16) OQ_PC_BWD(16)
+#undef OQ_PC_BWD
+  return false;
+}
+template <bool LET, bool BWD>
+static bool launch_grp(const WqArgs& a, int grid, size_t smem, cudaStream_t s) {
+#define OQ_GRP(L, V)                                                                                             \
+  {                                                                                                              \
+    if (BWD) {                                                                                                   \
+      if (smem > 40 * 1024) cudaFuncSetAttribute(wq_grp_bwd<L, V, LET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      wq_grp_bwd<L, V, LET><<<grid, 256, smem, s>>>(a);                                                          \
+    } else {                                                                                                     \
+      wq_grp_fwd<L, V, LET><<<grid, 256, 0, s>>>(a);                                                             \
+    }                                                                                                            \
+    return true;                                                                                                 \
+  }
+  switch (a.group) {
+    case 32: OQ_GRP(8, 1)
+    case 64: OQ_GRP(16, 1)
+    case 128: OQ_GRP(32, 1)
+    case 256: OQ_GRP(32, 2)
+    case 512: OQ_GRP(32, 4)
+    default: return false;
+  }
+#undef OQ_GRP
+}

@@ -143,7 +143,8 @@ class BlockEngine:
         # ---- per-unit quantiser state + bf16 operands
         self.Wq = {g: torch.empty_like(w, dtype=BF16) for g, w in self.W.items()}
         self.Wfp = None
-        self.qstat = {u.name: dict(xmin=z(u.N * G(u.K)), xmax=z(u.N * G(u.K)), mv=z(u.N)) for u in U}
+        self.qstat = {u.name: dict(xmin=z(u.N * G(u.K)), xmax=z(u.N * G(u.K)), scale=z(u.N * G(u.K)), zp=z(u.N * G(u.K)),
+                                    mv=z(u.N)) for u in U}
         self.tmp = {}     # folded vectors of the current step
         self.bufs = {}
         self.loss_slot = z(1)
@@ -179,12 +180,13 @@ class BlockEngine:
         for u in self.units:
             up, low = self.lwc(u)
             st = self.qstat[u.name]
-            kw = {}
+            kw = dict(scale_out=st["scale"], zp_out=st["zp"])
             if final:
                 G = st["xmin"].numel()
                 extra[u.name] = dict(weight=torch.empty(u.N, u.K, device=self.dev), scales=torch.empty(G, device=self.dev),
                                      zeros=torch.empty(G, device=self.dev))
                 kw = dict(wq_f32=extra[u.name]["weight"], scale_out=extra[u.name]["scales"], zp_out=extra[u.name]["zeros"])
+                st["scale"], st["zp"] = extra[u.name]["scales"], extra[u.name]["zeros"]
             if q.wbits >= 16:
                 self.wview(u, self.Wq).copy_(self.wview(u, self.W))     # weights left un-quantised
                 continue
@@ -460,7 +462,7 @@ class BlockEngine:
                                  e_row=er.contiguous() if (er is not None and u.shift) else None,
                                  d_up=g.get(f"{u.name}.up"), d_low=g.get(f"{u.name}.low"),
                                  dcol_acc=colacc[u.col] if u.col else None, drow=self._drow[u.name] if u.row else None,
-                                 dshift_acc=shacc[u.shift] if u.shift else None)
+                                 dshift_acc=shacc[u.shift] if u.shift else None, scale=st["scale"], zp=st["zp"])
         if not let:
             return
         t = self.tmp

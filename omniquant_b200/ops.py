@@ -61,14 +61,14 @@ def weight_quant_fwd(W, *, n_bits, symmetric=False, group_size=0, up=None, low=N
 
 def weight_quant_bwd(W, grad_wq, xmin, xmax, *, n_bits, symmetric=False, group_size=0, up=None, low=None,
                      col_scale=None, row_scale=None, row_op=0, recip_div=True, e_row=None, d_up=None, d_low=None,
-                     dcol_acc=None, drow=None, dshift_acc=None, dW_full=None):
+                     dcol_acc=None, drow=None, dshift_acc=None, dW_full=None, scale=None, zp=None):
     _chk(W, F32, "W")
     if grad_wq.dtype not in (BF16, F32):
         raise OqError("grad_wq must be bf16 or fp32")
     N, K = W.shape
     ldg = _rowmajor(grad_wq, "grad_wq")
     lib().call("oq_weight_quant_bwd", _p(W), N, K, _p(col_scale), _p(row_scale), row_op, n_bits, int(symmetric),
-               int(group_size or 0), _p(up), _p(low), int(recip_div), _p(xmin), _p(xmax), _p(grad_wq),
+               int(group_size or 0), _p(up), _p(low), int(recip_div), _p(xmin), _p(xmax), _p(scale), _p(zp), _p(grad_wq),
                int(grad_wq.dtype == F32), ldg, _p(e_row), _p(d_up), _p(d_low), _p(dcol_acc), _p(drow), _p(dshift_acc),
                _p(dW_full), _stream())
 

@@ -426,19 +426,39 @@ def test_swiglu_relu(ops):
 def test_softmax_fwd_bwd(ops):
     gen = torch.Generator().manual_seed(8)
     B, T = 3, 200
+    _softmax_case(ops, 2, 2048)
     S = (torch.randn(B, T, T, generator=gen) * 3).requires_grad_(True)
     mask = orc.causal_mask(T)[0]
     ref = torch.softmax(torch.max(S + mask, torch.tensor(torch.finfo(torch.float32).min)), -1)
     dP = torch.randn(B, T, T, generator=gen)
     ref.backward(dP)
     for kw in (dict(causal=True), dict(mask=mask.cuda())):
-        P = torch.empty(B, T, T, device="cuda", dtype=torch.bfloat16)
+        # causal rows are only written up to the end of their 128-wide diagonal tile (the k-limited GEMMs read no
+        # further): start from zeros so the untouched tail compares equal to the reference's exact zeros
+        P = torch.zeros(B, T, T, device="cuda", dtype=torch.bfloat16)
         ops.softmax_fwd(S.detach().cuda(), P, **kw)
-        dS = torch.empty_like(P)
+        dS = torch.zeros_like(P)
         ops.softmax_bwd(P, dP.cuda(), dS, causal=kw.get("causal", False))
         torch.cuda.synchronize()
         torch.testing.assert_close(P.cpu().float(), ref.detach(), rtol=1e-2, atol=4e-3)
         torch.testing.assert_close(dS.cpu().float(), S.grad, rtol=5e-2, atol=1e-2)
+
+
+def _softmax_case(ops, B, T):
+    gen = torch.Generator(device="cuda").manual_seed(T)
+    S = torch.randn(B, T, T, device="cuda", generator=gen) * 3
+    dP = torch.randn(B, T, T, device="cuda", generator=gen)
+    tri = torch.tril(torch.ones(T, T, device="cuda", dtype=torch.bool))
+    Sr = S.clone().requires_grad_(True)
+    ref = torch.softmax(Sr.masked_fill(~tri, float("-inf")), -1)
+    ref.backward(dP)
+    P = torch.zeros(B, T, T, device="cuda", dtype=torch.bfloat16)
+    ops.softmax_fwd(S, P, causal=True)
+    dS = torch.zeros_like(P)
+    ops.softmax_bwd(P, dP, dS, causal=True)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(P.float(), ref.detach(), rtol=1e-2, atol=4e-3)
+    torch.testing.assert_close(dS.float(), Sr.grad, rtol=5e-2, atol=1e-2)
 
 
 def test_mse_adamw_colsum_truncate_transpose(ops):
