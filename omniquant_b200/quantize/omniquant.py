@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from .. import engine as E
+from ..parallel import make_allreduce, shard_indices, world_info
 from ..models.int_llama_layer import QuantLlamaDecoderLayer
 from ..models.int_opt_layer import QuantOPTDecoderLayer
 from .int_linear import QuantLinear
@@ -103,13 +104,6 @@ def init_let_parameters(qlayer, layer_idx, fam, args, act_scales, act_shifts, de
                 qlayer.register_parameter(f"{tag}_smooth_scale", nn.Parameter(scale))
 
 
-def _dist():
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        return dist, dist.get_rank(), dist.get_world_size()
-    return None, 0, 1
-
-
 def omniquant(lm, args, dataloader, act_scales, act_shifts, logger=None, inps=None):
     """Calibrate every decoder block of ``lm.model``.  ``inps`` (optional, [nsamples, seqlen, H]) bypasses the
     embedding capture for synthetic runs."""
@@ -120,7 +114,7 @@ def omniquant(lm, args, dataloader, act_scales, act_shifts, logger=None, inps=No
     model.config.use_cache = False
     fam = _family(model, args.net)
     layers = fam["layers"]
-    dist, rank, world = _dist()
+    rank, world = world_info()
     if args.batch_size % world != 0:
         raise ValueError(f"--batch_size {args.batch_size} must be a multiple of the world size {world}")
     b_local = args.batch_size // world
@@ -135,13 +129,11 @@ def omniquant(lm, args, dataloader, act_scales, act_shifts, logger=None, inps=No
         torch.cuda.empty_cache()
     inps = inps.to(dev, torch.bfloat16)
     # sample sharding: global step j consumes samples [j*B, (j+1)*B); rank r owns b_local of them
-    idx = [j * args.batch_size + rank * b_local + i for j in range(args.nsamples // args.batch_size) for i in range(b_local)]
+    idx = shard_indices(args.nsamples, args.batch_size, rank, world)
     quant_inps = inps[idx].contiguous()
     fp_inps = quant_inps.clone()
     del inps
-    allreduce = None
-    if dist is not None:
-        allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    allreduce = make_allreduce()
     omni_parameters = torch.load(args.resume) if getattr(args, "resume", None) else {}
     T = lm.seqlen
     use_graph = getattr(args, "cuda_graph", True)
