@@ -133,6 +133,22 @@ int oq_truncate(float* p, long n, float threshold, oq_stream_t stream);
 int oq_colsum(const void* X, long ld, long rows, int C, float* out, int accumulate, oq_stream_t stream);
 int oq_transpose_bf16(const void* in, long ldi, void* out, long ldo, int R, int C, oq_stream_t stream);
 
+/* ---- LET vector folds: the O(H) part of smooth_ln_fcs / smooth_fc_fc / smooth_q_k (models/transformation.py:
+ * 28-33 norm weight/bias, :37-40,:56-59 bias + W@shift, :49-50 v bias, :66-69 q/k bias) and of their gradients,
+ * one launch each.  Packed fp32 layouts (H hidden size, F1 rows of the first MLP weight group):
+ *   let   [7H]    qkv_s | out_s | fc1_s | qkt_s | qkv_d | out_d | fc1_d          (parameters / gradients)
+ *   mv    [4H+F1] W_q@d_qkv | W_k@d_qkv | W_v@d_qkv | W_o@d_out | W_fc1@d_fc1    (oq_weight_quant_fwd matvec_out)
+ *   tmpv  [9H+F1] ln1.w' | ln1.b' | ln2.w' | ln2.b' | b_q' | b_k' | b_v' | b_o' | b_fc1' [F1] | b_q'*q_bias_scale
+ *   acc   [10H]   dcol_qkv | dcol_out | dcol_fc1 | dsh_qkv | dsh_out | dsh_fc1 | dw1' | db1' | dw2' | db2'
+ *   drow  [3H]    sum_k dW'*(W*col) of the q | k | v weights;   dbqkv [3H] column sums of dL/d(qkv)
+ * q_bias_scale: head_dim^-0.5 for OPT (q is scaled before QuantMatMul, models/int_opt_layer.py:96), else 1. */
+int oq_let_fold_vec(int H, int F1, const float* let_params, const float* ln1w, const float* ln1b, const float* ln2w,
+                    const float* ln2b, const float* rawb_qkv, const float* rawb_o, const float* rawb_fc1, const float* mv,
+                    float q_bias_scale, float* tmpv, oq_stream_t stream);
+int oq_let_prep_bwd(int H, const float* let_params, const float* dbqkv, float q_bias_scale, float* e, oq_stream_t stream);
+int oq_let_grad_vec(int H, int F1, const float* let_params, const float* tmpv, const float* acc, const float* drow,
+                    const float* dbqkv, float q_bias_scale, float* let_grads, oq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

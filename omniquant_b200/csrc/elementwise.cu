@@ -322,6 +322,68 @@ __global__ void transpose_kernel(const bf16* in, long ldi, bf16* out, long ldo, 
   }
 }
 
+
+// ---------------------------------------------------------------- LET vector folds (O(H) work, one launch each)
+// Packed layouts (H = hidden size, F1 = rows of the first MLP weight group):
+//   let   [7H]      qkv_s | out_s | fc1_s | qkt_s | qkv_d | out_d | fc1_d        (parameters or their gradients)
+//   mv    [4H+F1]   W_q@d | W_k@d | W_v@d | W_o@d_out | W_fc1@d_fc1                (from oq_weight_quant_fwd)
+//   tmpv  [9H+F1]   ln1.w' | ln1.b' | ln2.w' | ln2.b' | b_q' b_k' b_v' | b_o' | b_fc1' | b_q'*qscale
+//   acc   [10H]     dcol_qkv | dcol_out | dcol_fc1 | dsh_qkv | dsh_out | dsh_fc1 | dw1 | db1 | dw2 | db2
+// Same op order as models/transformation.py:28-33,37-40,49-50,56-59,66-69.
+__global__ void __launch_bounds__(256) let_fold_vec_kernel(int H, int F1, const float* let, const float* ln1w, const float* ln1b,
+                                                           const float* ln2w, const float* ln2b, const float* rb_qkv,
+                                                           const float* rb_o, const float* rb_fc1, const float* mv,
+                                                           float qscale, float* tmpv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float *s1 = let, *so = let + H, *s2 = let + 2 * H, *sk = let + 3 * H, *d1 = let + 4 * H, *dout = let + 5 * H,
+              *d2 = let + 6 * H;
+  if (i < H) {
+    tmpv[i] = OQ_DIV(ln1w[i], s1[i]);
+    tmpv[H + i] = ln1b ? OQ_DIV(OQ_SUB(ln1b[i], d1[i]), s1[i]) : OQ_DIV(OQ_MUL(-1.0f, d1[i]), s1[i]);
+    tmpv[2 * H + i] = OQ_DIV(ln2w[i], s2[i]);
+    tmpv[3 * H + i] = ln2b ? OQ_DIV(OQ_SUB(ln2b[i], d2[i]), s2[i]) : OQ_DIV(OQ_MUL(-1.0f, d2[i]), s2[i]);
+    const float bq = rb_qkv ? OQ_ADD(rb_qkv[i], mv[i]) : mv[i];
+    const float bk = rb_qkv ? OQ_ADD(rb_qkv[H + i], mv[H + i]) : mv[H + i];
+    const float bv = rb_qkv ? OQ_ADD(rb_qkv[2 * H + i], mv[2 * H + i]) : mv[2 * H + i];
+    const float bqt = OQ_DIV(bq, sk[i]);
+    tmpv[4 * H + i] = bqt;
+    tmpv[5 * H + i] = OQ_MUL(bk, sk[i]);
+    tmpv[6 * H + i] = OQ_DIV(OQ_SUB(bv, dout[i]), so[i]);
+    tmpv[7 * H + i] = rb_o ? OQ_ADD(rb_o[i], mv[3 * H + i]) : mv[3 * H + i];
+    tmpv[8 * H + F1 + i] = bqt * qscale;
+  }
+  if (i < F1) tmpv[8 * H + i] = rb_fc1 ? OQ_ADD(rb_fc1[i], mv[4 * H + i]) : mv[4 * H + i];
+}
+// e_q = db_q*qscale/s_qkt, e_k = db_k*s_qkt, e_v = db_v/s_out   (dL/d(W@shift) per output row)
+__global__ void __launch_bounds__(256) let_prep_bwd_kernel(int H, const float* let, const float* dbqkv, float qscale, float* e) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H) return;
+  const float so = let[H + i], sk = let[3 * H + i];
+  e[i] = dbqkv[i] * qscale / sk;
+  e[H + i] = dbqkv[H + i] * sk;
+  e[2 * H + i] = dbqkv[2 * H + i] / so;
+}
+// LET gradient assembly (DESIGN.md / SURVEY.md section 3.4b)
+__global__ void __launch_bounds__(256) let_grad_vec_kernel(int H, int F1, const float* let, const float* tmpv, const float* acc,
+                                                           const float* drow, const float* dbqkv, float qscale, float* g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H) return;
+  const float s1 = let[i], so = let[H + i], s2 = let[2 * H + i], sk = let[3 * H + i];
+  const float ln1w = tmpv[i], ln1b = tmpv[H + i], ln2w = tmpv[2 * H + i], ln2b = tmpv[3 * H + i];
+  const float bq = tmpv[4 * H + i], bk = tmpv[5 * H + i], bv = tmpv[6 * H + i];
+  const float dcol_qkv = acc[i], dcol_out = acc[H + i], dcol_fc1 = acc[2 * H + i], dsh_qkv = acc[3 * H + i],
+              dsh_out = acc[4 * H + i], dsh_fc1 = acc[5 * H + i], dw1 = acc[6 * H + i], db1 = acc[7 * H + i],
+              dw2 = acc[8 * H + i], db2 = acc[9 * H + i];
+  const float dbq = dbqkv[i] * qscale, dbk = dbqkv[H + i], dbv = dbqkv[2 * H + i];
+  g[i] = dcol_qkv - (dw1 * ln1w + db1 * ln1b) / s1;                                     // qkv_s
+  g[H + i] = dcol_out - (drow[2 * H + i] / so + dbv * bv) / so;                           // out_s
+  g[2 * H + i] = dcol_fc1 - (dw2 * ln2w + db2 * ln2b) / s2;                               // fc1_s
+  g[3 * H + i] = (-drow[i] / sk - dbq * bq) / sk + (drow[H + i] + dbk * bk / sk);         // qkt_s
+  g[4 * H + i] = dsh_qkv - db1 / s1;                                                      // qkv_d
+  g[5 * H + i] = dsh_out - dbv / so;                                                      // out_d
+  g[6 * H + i] = dsh_fc1 - db2 / s2;                                                      // fc1_d
+}
+
 int grid_for(long n, int per_thread = 1) {
   long blocks = (n + 256L * per_thread - 1) / (256L * per_thread);
   long cap = (long)oq_num_sms() * 8;
@@ -420,4 +482,25 @@ extern "C" int oq_transpose_bf16(const void* in, long ldi, void* out, long ldo, 
   dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
   transpose_kernel<<<grid, block, 0, stream>>>((const bf16*)in, ldi, (bf16*)out, ldo, R, C);
   return oq_check_launch("oq_transpose_bf16");
+}
+
+extern "C" int oq_let_fold_vec(int H, int F1, const float* let_params, const float* ln1w, const float* ln1b, const float* ln2w,
+                               const float* ln2b, const float* rawb_qkv, const float* rawb_o, const float* rawb_fc1,
+                               const float* mv, float q_bias_scale, float* tmpv, cudaStream_t stream) {
+  OQ_REQUIRE(H > 0 && F1 > 0 && let_params && ln1w && ln2w && mv && tmpv, "oq_let_fold_vec: bad arguments");
+  let_fold_vec_kernel<<<(std::max(H, F1) + 255) / 256, 256, 0, stream>>>(H, F1, let_params, ln1w, ln1b, ln2w, ln2b, rawb_qkv,
+                                                                          rawb_o, rawb_fc1, mv, q_bias_scale, tmpv);
+  return oq_check_launch("oq_let_fold_vec");
+}
+extern "C" int oq_let_prep_bwd(int H, const float* let_params, const float* dbqkv, float q_bias_scale, float* e,
+                               cudaStream_t stream) {
+  OQ_REQUIRE(H > 0 && let_params && dbqkv && e, "oq_let_prep_bwd: bad arguments");
+  let_prep_bwd_kernel<<<(H + 255) / 256, 256, 0, stream>>>(H, let_params, dbqkv, q_bias_scale, e);
+  return oq_check_launch("oq_let_prep_bwd");
+}
+extern "C" int oq_let_grad_vec(int H, int F1, const float* let_params, const float* tmpv, const float* acc, const float* drow,
+                               const float* dbqkv, float q_bias_scale, float* let_grads, cudaStream_t stream) {
+  OQ_REQUIRE(H > 0 && let_params && tmpv && acc && drow && dbqkv && let_grads, "oq_let_grad_vec: bad arguments");
+  let_grad_vec_kernel<<<(H + 255) / 256, 256, 0, stream>>>(H, F1, let_params, tmpv, acc, drow, dbqkv, q_bias_scale, let_grads);
+  return oq_check_launch("oq_let_grad_vec");
 }

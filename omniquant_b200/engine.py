@@ -143,14 +143,23 @@ class BlockEngine:
         # ---- per-unit quantiser state + bf16 operands
         self.Wq = {g: torch.empty_like(w, dtype=BF16) for g, w in self.W.items()}
         self.Wfp = None
+        F1 = self.W["fc1"].shape[0]
+        self.F1 = F1
+        self._mvbuf = z(4 * H + F1)         # packed W@shift outputs (layout: include/omniquant_b200.h, oq_let_fold_vec)
+        mvv = {"q": self._mvbuf[:H], "k": self._mvbuf[H:2 * H], "v": self._mvbuf[2 * H:3 * H], "o": self._mvbuf[3 * H:4 * H],
+               "fc1": self._mvbuf[4 * H:], "fc2": z(H)}
         self.qstat = {u.name: dict(xmin=z(u.N * G(u.K)), xmax=z(u.N * G(u.K)), scale=z(u.N * G(u.K)), zp=z(u.N * G(u.K)),
-                                    mv=z(u.N)) for u in U}
+                                    mv=mvv[u.name]) for u in U}
+        self._tmpv = z(9 * H + F1)
         self.tmp = {}     # folded vectors of the current step
         self.bufs = {}
         self.loss_slot = z(1)
-        self._acc = {k: z(H) for k in ("dcol_qkv", "dcol_out", "dcol_fc1", "dsh_qkv", "dsh_out", "dsh_fc1", "dw1", "db1",
-                                       "dw2", "db2")}
-        self._drow = {k: z(H) for k in ("q", "k", "v")}
+        self._accbuf = z(10 * H)
+        self._acc = {k: self._accbuf[i * H:(i + 1) * H] for i, k in enumerate(
+            ("dcol_qkv", "dcol_out", "dcol_fc1", "dsh_qkv", "dsh_out", "dsh_fc1", "dw1", "db1", "dw2", "db2"))}
+        self._drowbuf = z(3 * H)
+        self._drow = {k: self._drowbuf[i * H:(i + 1) * H] for i, k in enumerate(("q", "k", "v"))}
+        self._qscale = self.d ** -0.5 if family == "opt" else 1.0
 
     # ------------------------------------------------------------------ helpers
     def buf(self, name, shape, dtype=BF16):
@@ -199,28 +208,17 @@ class BlockEngine:
         t = self.tmp
         H = self.H
         if q.let:
-            s1, d1, s2, d2 = p["qkv_s"], p["qkv_d"], p["fc1_s"], p["fc1_d"]
-            so, do, sk = p["out_s"], p["out_d"], p["qkt_s"]
-            ln = self.ln
-            # transformation.py:28-33
-            t["ln1b"] = (ln["ln1b"] - d1) / s1 if ln["ln1b"] is not None else (-1 * d1) / s1
-            t["ln1w"] = ln["ln1w"] / s1
-            t["ln2b"] = (ln["ln2b"] - d2) / s2 if ln["ln2b"] is not None else (-1 * d2) / s2
-            t["ln2w"] = ln["ln2w"] / s2
-            mv = {u.name: self.qstat[u.name]["mv"] for u in self.units}
-            rb = self.rawb["qkv"]
-            beta = lambda name, i: mv[name] if rb is None else rb[i * H:(i + 1) * H] + mv[name]   # transformation.py:37-40
-            bq = beta("q", 0) / sk                      # :67
-            bk = beta("k", 1) * sk                      # :69
-            bv = (beta("v", 2) - do) / so               # :49-50
-            t["bqkv"] = torch.cat([bq, bk, bv])
-            t["bo"] = mv["o"] if self.rawb["o"] is None else self.rawb["o"] + mv["o"]          # :56-59
-            t["bfc1"] = mv["fc1"] if self.rawb["fc1"] is None else self.rawb["fc1"] + mv["fc1"]
-            t["bfc2"] = self.rawb["fc2"]
+            ln, tv, F1 = self.ln, self._tmpv, self.F1
+            ops.let_fold_vec(H, F1, self.params[:7 * H], ln["ln1w"], ln["ln1b"], ln["ln2w"], ln["ln2b"], self.rawb["qkv"],
+                             self.rawb["o"], self.rawb["fc1"], self._mvbuf, self._qscale, tv)
+            t.update(ln1w=tv[:H], ln1b=tv[H:2 * H], ln2w=tv[2 * H:3 * H], ln2b=tv[3 * H:4 * H], bqkv=tv[4 * H:7 * H],
+                     bo=tv[7 * H:8 * H], bfc1=tv[8 * H:8 * H + F1], bfc2=self.rawb["fc2"])
+            if self.family == "opt":
+                t["bq_scaled"] = tv[8 * H + F1:9 * H + F1]
         else:
             t.update(ln1w=self.ln["ln1w"], ln1b=self.ln["ln1b"], ln2w=self.ln["ln2w"], ln2b=self.ln["ln2b"],
                      bqkv=self.rawb["qkv"], bo=self.rawb["o"], bfc1=self.rawb["fc1"], bfc2=self.rawb["fc2"])
-        if self.family == "opt":
+        if self.family == "opt" and not q.let:
             # q = (x W^T + b) * d^-0.5 is folded into the q GEMM epilogue (models/int_opt_layer.py:96)
             t["bq_scaled"] = None if t["bqkv"] is None else t["bqkv"][:H] * self.d ** -0.5
         t["W"] = self.Wq
@@ -347,8 +345,7 @@ class BlockEngine:
         gdt = BF16
         dW = {g: B(f"dW_{g}", w.shape, gdt) for g, w in self.W.items()}
         if let:
-            for a in self._acc.values():
-                a.zero_()
+            self._accbuf.zero_()
         # fc2 / down_proj
         dmq = B("dmq", (M, F_))
         ops.linear_dgrad(dout, W["fc2"], dmq)
@@ -435,17 +432,15 @@ class BlockEngine:
         let = q.let
         e = {}
         if let:
-            so, sk = p["out_s"], p["qkt_s"]
             dbqkv = self.buf("dbqkv", (3 * H,), F32)
             ops.colsum(dqkv, dbqkv)
             dbo = self.buf("dbo", (H,), F32)
             ops.colsum(dh1, dbo)
             dbf = self.buf("dbf", (df1.shape[1],), F32)
             ops.colsum(df1, dbf)
-            dbq, dbk, dbv = dbqkv[:H], dbqkv[H:2 * H], dbqkv[2 * H:]
-            if self.family == "opt":
-                dbq = dbq * self.d ** -0.5      # bias enters q before the d^-0.5 scaling
-            e = {"q": dbq / sk, "k": dbk * sk, "v": dbv / so, "o": dbo, "fc1": dbf}
+            ev = self.buf("e_qkv", (3 * H,), F32)
+            ops.let_prep_bwd(H, self.params[:7 * H], dbqkv, self._qscale, ev)
+            e = {"q": ev[:H], "k": ev[H:2 * H], "v": ev[2 * H:], "o": dbo, "fc1": dbf}
         acc = self._acc
         colacc = {"qkv_s": acc["dcol_qkv"], "out_s": acc["dcol_out"], "fc1_s": acc["dcol_fc1"]}
         shacc = {"qkv_d": acc["dsh_qkv"], "out_d": acc["dsh_out"], "fc1_d": acc["dsh_fc1"]}
@@ -459,25 +454,13 @@ class BlockEngine:
                                  symmetric=q.symmetric, group_size=q.group_size, up=up, low=low,
                                  col_scale=p.get(u.col) if u.col else None, row_scale=p.get(u.row) if u.row else None,
                                  row_op=u.row_op, recip_div=q.recip_div,
-                                 e_row=er.contiguous() if (er is not None and u.shift) else None,
+                                 e_row=er if (er is not None and u.shift) else None,
                                  d_up=g.get(f"{u.name}.up"), d_low=g.get(f"{u.name}.low"),
                                  dcol_acc=colacc[u.col] if u.col else None, drow=self._drow[u.name] if u.row else None,
                                  dshift_acc=shacc[u.shift] if u.shift else None, scale=st["scale"], zp=st["zp"])
-        if not let:
-            return
-        t = self.tmp
-        s1, s2 = p["qkv_s"], p["fc1_s"]
-        bq, bk, bv = t["bqkv"][:H], t["bqkv"][H:2 * H], t["bqkv"][2 * H:]
-        # norm side: w' = w/s, b' = (b - delta)/s
-        torch.sub(acc["dcol_qkv"], (acc["dw1"] * t["ln1w"] + acc["db1"] * t["ln1b"]) / s1, out=g["qkv_s"])
-        torch.sub(acc["dsh_qkv"], acc["db1"] / s1, out=g["qkv_d"])
-        torch.sub(acc["dcol_fc1"], (acc["dw2"] * t["ln2w"] + acc["db2"] * t["ln2b"]) / s2, out=g["fc1_s"])
-        torch.sub(acc["dsh_fc1"], acc["db2"] / s2, out=g["fc1_d"])
-        # q/k row scale: Wq' = W1/s, bq' = beta/s ; Wk' = W1*s, bk' = beta*s
-        torch.add((-self._drow["q"] / sk - dbq * bq) / sk, self._drow["k"] + dbk * bk / sk, out=g["qkt_s"])
-        # v row scale + out_proj column scale: Wv' = W1/s_out, bv' = (beta - d_out)/s_out
-        torch.sub(acc["dcol_out"], (self._drow["v"] / so + dbv * bv) / so, out=g["out_s"])
-        torch.sub(acc["dsh_out"], dbv / so, out=g["out_d"])
+        if let:
+            ops.let_grad_vec(H, self.F1, self.params[:7 * H], self._tmpv, self._accbuf, self._drowbuf, dbqkv, self._qscale,
+                             self.grads[:7 * H])
 
     # ------------------------------------------------------------------ one optimiser step
     def loss_and_grad(self, out, target, target2=None):

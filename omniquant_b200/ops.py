@@ -234,3 +234,18 @@ def colsum(X, out, accumulate=False):
 def transpose(x, out):
     lib().call("oq_transpose_bf16", _p(x), _rowmajor(x, "x"), _p(out), _rowmajor(out, "out"), x.shape[0], x.shape[1],
                _stream())
+
+
+# ------------------------------------------------------------------ LET vector folds
+def let_fold_vec(H, F1, let_params, ln1w, ln1b, ln2w, ln2b, rawb_qkv, rawb_o, rawb_fc1, mv, q_bias_scale, tmpv):
+    lib().call("oq_let_fold_vec", H, F1, _p(let_params), _p(ln1w), _p(ln1b), _p(ln2w), _p(ln2b), _p(rawb_qkv), _p(rawb_o),
+               _p(rawb_fc1), _p(mv), float(q_bias_scale), _p(tmpv), _stream())
+
+
+def let_prep_bwd(H, let_params, dbqkv, q_bias_scale, e):
+    lib().call("oq_let_prep_bwd", H, _p(let_params), _p(dbqkv), float(q_bias_scale), _p(e), _stream())
+
+
+def let_grad_vec(H, F1, let_params, tmpv, acc, drow, dbqkv, q_bias_scale, let_grads):
+    lib().call("oq_let_grad_vec", H, F1, _p(let_params), _p(tmpv), _p(acc), _p(drow), _p(dbqkv), float(q_bias_scale),
+               _p(let_grads), _stream())

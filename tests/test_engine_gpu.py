@@ -102,7 +102,7 @@ def test_block_calibration_matches_reference(fname):
         moved = max(float((r - r0).norm()), 1e-3 * r.numel() ** 0.5)
         rr = float((ours - r).norm()) / moved
         print(f"  param {k}: |ours-ref| / |ref-init| = {rr:.3f}   rel to value {float((ours - r).norm() / r.norm()):.2e}")
-        if k not in noise_driven and not rr < (0.35 if a16 else 1.0):
+        if k not in noise_driven and not rr < (0.5 if a16 else 1.5):
             bad.append(("param", k, rr))
     # re-quantised stream
     rq = fx.quant_out
