@@ -131,6 +131,126 @@ __global__ void __launch_bounds__(256) aq_bwd_block(AqArgs a) {
   }
 }
 
+
+// ---- register-resident block-per-row variants (C <= 2048*NV, C % 8 == 0): one read of x (and gy), one write
+template <int NV>
+__global__ void __launch_bounds__(256) aq_fwd_block_reg(AqArgs a) {
+  __shared__ float scratch[2 * 8];
+  const long r = blockIdx.x;
+  const bf16* xr = a.x + a.xi.off(r);
+  bf16* yr = a.y + a.yi.off(r);
+  float v[NV][8];
+  float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (threadIdx.x + i * 256) * 8;
+    if (c < a.C) {
+      load_bf8(xr + c, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { mn = fminf(mn, v[i][j]); mx = fmaxf(mx, v[i][j]); }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  mn = warp_reduce(mn, OpMin());
+  mx = warp_reduce(mx, OpMax());
+  if (lane == 0) { scratch[warp] = mn; scratch[8 + warp] = mx; }
+  __syncthreads();
+  mn = scratch[0]; mx = scratch[8];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) { mn = fminf(mn, scratch[w]); mx = fmaxf(mx, scratch[8 + w]); }
+  const OqQParams q = oq_qparams(mn, mx, 1.f, 1.f, 0, a.n_bits, a.symmetric, a.recip_div);
+  if (threadIdx.x == 0) {
+    if (a.scale_out) a.scale_out[r] = q.scale;
+    if (a.zp_out) a.zp_out[r] = q.zp;
+  }
+  const float inv = OQ_DIV(1.0f, q.scale);
+  const int inv_ok = oq_inv_ok(inv);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (threadIdx.x + i * 256) * 8;
+    if (c < a.C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = oq_clampf(OQ_ADD(oq_rint_div(v[i][j], q.scale, inv, inv_ok), q.zp), 0.0f, q.qmax);
+        v[i][j] = oq_dequant(t, q);
+      }
+      store_bf8(yr + c, v[i]);
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) aq_bwd_block_reg(AqArgs a) {
+  __shared__ float scratch[5 * 8];
+  const long r = blockIdx.x;
+  const bf16* xr = a.x + a.xi.off(r);
+  const bf16* gr = a.gy + a.gi.off(r);
+  bf16* dr = a.gx + a.gxi.off(r);
+  float v[NV][8], g[NV][8];
+  float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (threadIdx.x + i * 256) * 8;
+    if (c < a.C) {
+      load_bf8(xr + c, v[i]);
+      load_bf8(gr + c, g[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { mn = fminf(mn, v[i][j]); mx = fmaxf(mx, v[i][j]); }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  mn = warp_reduce(mn, OpMin());
+  mx = warp_reduce(mx, OpMax());
+  if (lane == 0) { scratch[warp] = mn; scratch[8 + warp] = mx; }
+  __syncthreads();
+  mn = scratch[0]; mx = scratch[8];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) { mn = fminf(mn, scratch[w]); mx = fmaxf(mx, scratch[8 + w]); }
+  const OqQParams q = oq_qparams(mn, mx, 1.f, 1.f, 0, a.n_bits, a.symmetric, a.recip_div);
+  const float inv = OQ_DIV(1.0f, q.scale);
+  const int inv_ok = oq_inv_ok(inv);
+  float R = 0.f, nmax = 0.f, nmin = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (threadIdx.x + i * 256) * 8;
+    if (c < a.C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x = v[i][j];
+        const float qa = x * inv;
+        const float t = OQ_ADD(oq_rint_div(x, q.scale, inv, inv_ok), q.zp);   // same codes as the forward, ties included
+        const bool inr = (t >= 0.0f) && (t <= q.qmax);
+        const float cc = oq_clampf(t, 0.0f, q.qmax);
+        R += g[i][j] * ((cc - q.zp) - (inr ? qa : 0.0f));
+        nmax += (x == mx) ? 1.0f : 0.0f;
+        nmin += (x == mn) ? 1.0f : 0.0f;
+        if (!inr) g[i][j] = 0.0f;          // straight-through part
+      }
+    }
+  }
+  R = warp_reduce(R, OpSum()); nmax = warp_reduce(nmax, OpSum()); nmin = warp_reduce(nmin, OpSum());
+  if (lane == 0) { scratch[16 + warp] = R; scratch[24 + warp] = nmax; scratch[32 + warp] = nmin; }
+  __syncthreads();
+  R = nmax = nmin = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { R += scratch[16 + w]; nmax += scratch[24 + w]; nmin += scratch[32 + w]; }
+  float gmaxp, gminp;
+  oq_scale_grad(R, mn, mx, 1.f, 1.f, 0, a.n_bits, a.symmetric, a.recip_div, &gmaxp, &gminp);
+  const float cmax = gmaxp / nmax, cmin = gminp / nmin;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (threadIdx.x + i * 256) * 8;
+    if (c < a.C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (v[i][j] == mx) g[i][j] += cmax;
+        if (v[i][j] == mn) g[i][j] += cmin;
+      }
+      store_bf8(dr + c, g[i]);
+    }
+  }
+}
+
 // ---- warp per row (C = 32*EPL, optional rope) --------------------------------
 template <int EPL>
 __device__ __forceinline__ void load_row(const bf16* p, float (&v)[EPL]) {
@@ -179,9 +299,18 @@ template <int EPL>
 __global__ void __launch_bounds__(256) aq_fwd_warp(AqArgs a) {
   const int lane = threadIdx.x & 31;
   const long wpb = blockDim.x >> 5;
-  for (long r = blockIdx.x * wpb + (threadIdx.x >> 5); r < a.xi.rows; r += (long)gridDim.x * wpb) {
-    float v[EPL];
-    load_row<EPL>(a.x + a.xi.off(r) + lane * EPL, v);
+  constexpr int RB = 1;   // rows in flight per warp (measured: 4 is slower, the kernel is ALU-bound on the IEEE divisions)
+  const long nw = (long)gridDim.x * wpb;
+  for (long r0 = blockIdx.x * wpb + (threadIdx.x >> 5); r0 < a.xi.rows; r0 += nw * RB) {
+    float vv[RB][EPL];
+#pragma unroll
+    for (int u = 0; u < RB; ++u)
+      if (r0 + u * nw < a.xi.rows) load_row<EPL>(a.x + a.xi.off(r0 + u * nw) + lane * EPL, vv[u]);
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+    const long r = r0 + u * nw;
+    if (r >= a.xi.rows) break;
+    float (&v)[EPL] = vv[u];
     if (a.cos) {
       const long pos = (r / a.xi.rows_inner) % a.seq_len;
       float cs[EPL], sn[EPL];
@@ -203,10 +332,14 @@ __global__ void __launch_bounds__(256) aq_fwd_warp(AqArgs a) {
         if (a.scale_out) a.scale_out[r] = q.scale;
         if (a.zp_out) a.zp_out[r] = q.zp;
       }
+      const float inv = OQ_DIV(1.0f, q.scale);
+      const int inv_ok = oq_inv_ok(inv);
 #pragma unroll
-      for (int j = 0; j < EPL; ++j) v[j] = oq_fake_quant(v[j], q);
+      for (int j = 0; j < EPL; ++j)
+        v[j] = oq_dequant(oq_clampf(OQ_ADD(oq_rint_div(v[j], q.scale, inv, inv_ok), q.zp), 0.0f, q.qmax), q);
     }
     store_row<EPL>(a.y + a.yi.off(r) + lane * EPL, v);
+    }
   }
 }
 
@@ -214,10 +347,23 @@ template <int EPL>
 __global__ void __launch_bounds__(256) aq_bwd_warp(AqArgs a) {
   const int lane = threadIdx.x & 31;
   const long wpb = blockDim.x >> 5;
-  for (long r = blockIdx.x * wpb + (threadIdx.x >> 5); r < a.xi.rows; r += (long)gridDim.x * wpb) {
-    float v[EPL], g[EPL], cs[EPL], sn[EPL];
-    load_row<EPL>(a.x + a.xi.off(r) + lane * EPL, v);
-    load_row<EPL>(a.gy + a.gi.off(r) + lane * EPL, g);
+  constexpr int RB = 1;
+  const long nw = (long)gridDim.x * wpb;
+  for (long r0 = blockIdx.x * wpb + (threadIdx.x >> 5); r0 < a.xi.rows; r0 += nw * RB) {
+    float vv[RB][EPL], gg[RB][EPL];
+#pragma unroll
+    for (int u = 0; u < RB; ++u)
+      if (r0 + u * nw < a.xi.rows) {
+        load_row<EPL>(a.x + a.xi.off(r0 + u * nw) + lane * EPL, vv[u]);
+        load_row<EPL>(a.gy + a.gi.off(r0 + u * nw) + lane * EPL, gg[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+    const long r = r0 + u * nw;
+    if (r >= a.xi.rows) break;
+    float (&v)[EPL] = vv[u];
+    float (&g)[EPL] = gg[u];
+    float cs[EPL], sn[EPL];
     if (a.cos) {
       const long pos = (r / a.xi.rows_inner) % a.seq_len;
 #pragma unroll
@@ -236,12 +382,15 @@ __global__ void __launch_bounds__(256) aq_bwd_warp(AqArgs a) {
       const OqQParams q = oq_qparams(mn, mx, 1.f, 1.f, 0, a.n_bits, a.symmetric, a.recip_div);
       float R = 0.f, nmax = 0.f, nmin = 0.f;
       bool inr[EPL];
+      const float inv = OQ_DIV(1.0f, q.scale);
+      const int inv_ok = oq_inv_ok(inv);
 #pragma unroll
       for (int j = 0; j < EPL; ++j) {
-        const float t = oq_code_unclamped(v[j], q);
+        const float qa = v[j] * inv;
+        const float t = OQ_ADD(oq_rint_div(v[j], q.scale, inv, inv_ok), q.zp);   // same codes as the forward, ties included
         inr[j] = (t >= 0.0f) && (t <= q.qmax);
         const float cc = oq_clampf(t, 0.0f, q.qmax);
-        R += g[j] * ((cc - q.zp) - (inr[j] ? v[j] / q.scale : 0.0f));
+        R += g[j] * ((cc - q.zp) - (inr[j] ? qa : 0.0f));
         nmax += (v[j] == mx) ? 1.0f : 0.0f;
         nmin += (v[j] == mn) ? 1.0f : 0.0f;
       }
@@ -261,6 +410,7 @@ __global__ void __launch_bounds__(256) aq_bwd_warp(AqArgs a) {
     }
     if (a.cos) rope_bwd<EPL>(g, cs, sn, lane);
     store_row<EPL>(a.gx + a.gxi.off(r) + lane * EPL, g);
+    }
   }
 }
 
@@ -298,8 +448,13 @@ extern "C" int oq_act_quant_fwd(const void* x, long rows, int C, int rows_inner,
   } else {
     OQ_REQUIRE(!rope_cos, "oq_act_quant_fwd: fused rope needs head_dim 64 or 128 and 16-byte aligned rows");
     OQ_REQUIRE(rows < (1L << 31), "oq_act_quant_fwd: too many rows");
-    if (C % 8 == 0 && al8) aq_fwd_block<true><<<(unsigned)rows, 256, 0, stream>>>(a);
-    else aq_fwd_block<false><<<(unsigned)rows, 256, 0, stream>>>(a);
+    const unsigned g = (unsigned)rows;
+    if (C % 8 == 0 && al8 && C <= 2048) aq_fwd_block_reg<1><<<g, 256, 0, stream>>>(a);
+    else if (C % 8 == 0 && al8 && C <= 4096) aq_fwd_block_reg<2><<<g, 256, 0, stream>>>(a);
+    else if (C % 8 == 0 && al8 && C <= 8192) aq_fwd_block_reg<4><<<g, 256, 0, stream>>>(a);
+    else if (C % 8 == 0 && al8 && C <= 12288) aq_fwd_block_reg<6><<<g, 256, 0, stream>>>(a);
+    else if (C % 8 == 0 && al8) aq_fwd_block<true><<<g, 256, 0, stream>>>(a);
+    else aq_fwd_block<false><<<g, 256, 0, stream>>>(a);
   }
   return oq_check_launch("oq_act_quant_fwd");
 }
@@ -327,8 +482,13 @@ extern "C" int oq_act_quant_bwd(const void* x, long rows, int C, int rows_inner,
   } else {
     OQ_REQUIRE(!rope_cos, "oq_act_quant_bwd: fused rope needs head_dim 64 or 128 and 16-byte aligned rows");
     OQ_REQUIRE(rows < (1L << 31), "oq_act_quant_bwd: too many rows");
-    if (C % 8 == 0 && al8) aq_bwd_block<true><<<(unsigned)rows, 256, 0, stream>>>(a);
-    else aq_bwd_block<false><<<(unsigned)rows, 256, 0, stream>>>(a);
+    const unsigned g = (unsigned)rows;
+    if (C % 8 == 0 && al8 && C <= 2048) aq_bwd_block_reg<1><<<g, 256, 0, stream>>>(a);
+    else if (C % 8 == 0 && al8 && C <= 4096) aq_bwd_block_reg<2><<<g, 256, 0, stream>>>(a);
+    else if (C % 8 == 0 && al8 && C <= 8192) aq_bwd_block_reg<4><<<g, 256, 0, stream>>>(a);
+    else if (C % 8 == 0 && al8 && C <= 12288) aq_bwd_block_reg<6><<<g, 256, 0, stream>>>(a);
+    else if (C % 8 == 0 && al8) aq_bwd_block<true><<<g, 256, 0, stream>>>(a);
+    else aq_bwd_block<false><<<g, 256, 0, stream>>>(a);
   }
   return oq_check_launch("oq_act_quant_bwd");
 }

@@ -126,7 +126,10 @@ class BlockEngine:
         self.n_params = off
         self.layout = layout
         z = lambda n, dt=F32: torch.zeros(n, device=self.dev, dtype=dt)
-        self.params, self.grads, self.adam_m, self.adam_v = z(max(off, 1)), z(max(off, 1)), z(max(off, 1)), z(max(off, 1))
+        self.params, self.adam_m, self.adam_v = z(max(off, 1)), z(max(off, 1)), z(max(off, 1))
+        # gradients and the step's loss share one buffer: a single all-reduce per optimiser step
+        self._gradbuf = z(max(off, 1) + 1)
+        self.grads = self._gradbuf[:max(off, 1)]
         self.step_dev = torch.zeros(1, device=self.dev, dtype=torch.int32)
         self.p = {n: self.params[o:o + c] for n, (o, c) in layout.items()}
         self.g = {n: self.grads[o:o + c] for n, (o, c) in layout.items()}
@@ -153,7 +156,7 @@ class BlockEngine:
         self._tmpv = z(9 * H + F1)
         self.tmp = {}     # folded vectors of the current step
         self.bufs = {}
-        self.loss_slot = z(1)
+        self.loss_slot = self._gradbuf[max(off, 1):]
         self._accbuf = z(10 * H)
         self._acc = {k: self._accbuf[i * H:(i + 1) * H] for i, k in enumerate(
             ("dcol_qkv", "dcol_out", "dcol_fc1", "dsh_qkv", "dsh_out", "dsh_fc1", "dw1", "db1", "dw2", "db2"))}
@@ -476,8 +479,7 @@ class BlockEngine:
         dout = self.loss_and_grad(out, target, target2)
         self.backward(dout)
         if allreduce is not None:
-            allreduce(self.grads)
-            allreduce(self.loss_slot)
+            allreduce(self._gradbuf)          # flat LWC+LET gradients + the loss scalar in one collective
         self.optimizer_step()
         return self.loss_slot
 
