@@ -54,11 +54,16 @@ def block_weights(seed=0):
     return W
 
 
-def calib_inputs(n, seed=1234):
-    g = torch.Generator().manual_seed(seed)
-    x = torch.randn(n, T, H, generator=g, dtype=torch.float32)
-    x[:, :, ::512] *= 8.0          # a few outlier channels, what LET exists for
-    return x.to(torch.bfloat16)
+def calib_inputs(indices, seed=1234):
+    """Synthetic block inputs for the given global sample indices (one generator per sample, so every rank
+    builds only its own shard and the data does not depend on the world size)."""
+    out = torch.empty(len(indices), T, H, dtype=torch.bfloat16)
+    for i, j in enumerate(indices):
+        g = torch.Generator().manual_seed(seed + int(j))
+        x = torch.randn(T, H, generator=g, dtype=torch.float32)
+        x[:, ::512] *= 8.0          # a few outlier channels, what LET exists for
+        out[i] = x.to(torch.bfloat16)
+    return out
 
 
 def let_init(W, seed=1234):
@@ -123,9 +128,7 @@ def run_ours(a):
     W = {k: v.to(dev) for k, v in W_host.items()}       # resident in HBM before the timed region
     n_local = NSAMPLES // world
     # rank r owns samples r, r+world, ... (global step j = samples [j*world, (j+1)*world), reference --batch_size world)
-    x_all = calib_inputs(NSAMPLES)
-    x_host = x_all[rank::world].contiguous().pin_memory()
-    del x_all
+    x_host = calib_inputs(range(rank, NSAMPLES, world)).pin_memory()
     x_dev = x_host.to(dev)
     q = QuantConfig(wbits=WBITS, abits=ABITS, group_size=0, lwc=True, let=True, recip_div=True)
     init = let_init(W_host)
@@ -229,6 +232,27 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+class _StridedHostInputs:
+    """Duck-typed stand-in for the global calibration tensor on a rank that only holds its own shard in pinned
+    host memory: omniquant() calls .to(device, dtype) and then indexes the rank's rows."""
+
+    def __init__(self, shard, rank, world):
+        self.shard, self.rank, self.world = shard, rank, world
+
+    def to(self, dev, dtype):
+        return _StridedDeviceInputs(self.shard.to(dev, dtype, non_blocking=True), self.rank, self.world)
+
+
+class _StridedDeviceInputs:
+    def __init__(self, shard, rank, world):
+        self.shard, self.rank, self.world = shard, rank, world
+
+    def __getitem__(self, idx):
+        local = [(i - self.rank) // self.world for i in idx]
+        assert all(i % self.world == self.rank for i in idx)
+        return self.shard[local]
+
+
 def run_e2e(a, W, x_host, dev, world, rank):
     """One block through omniquant() (the call a user makes): weights from pinned host memory, calibration
     activations from pinned host memory, quantised block + learned parameters back on the host."""
@@ -274,6 +298,13 @@ def run_e2e(a, W, x_host, dev, world, rank):
                            resume=None, real_quant=False, output_dir=None, cuda_graph=(world == 1))
     quant_param_dicts(args)
 
+    # omniquant() shards `inps` by rank itself and only touches this rank's rows: hand it a pinned host view of the
+    # global [nsamples, T, H] tensor in which the rank's own samples sit at stride `world` (other rows unused)
+    if world == 1:
+        inps_view = x_host
+    else:
+        inps_view = _StridedHostInputs(x_host, rank, world)
+
     def one():
         model = torch.nn.Module()
         model.config = cfg
@@ -284,14 +315,7 @@ def run_e2e(a, W, x_host, dev, world, rank):
         lm = SimpleNamespace(model=model, device=dev, _device=dev, seqlen=T)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        # omniquant() shards `inps` by rank itself: hand it the global view this rank can index (its own samples
-        # interleaved at stride world); with world == 1 that is simply the pinned host tensor
-        if world == 1:
-            inps = x_host
-        else:
-            inps = torch.empty(x_host.shape[0] * world, T, H, dtype=torch.bfloat16).pin_memory()
-            inps[rank::world] = x_host
-        omniquant(lm, args, None, act, None, None, inps=inps)
+        omniquant(lm, args, None, act, None, None, inps=inps_view)
         w0 = model.model.layers[0].self_attn.q_proj.weight
         assert w0.device.type == "cpu"
         torch.cuda.synchronize()
@@ -329,7 +353,7 @@ def cpu_baseline(steps=1):
     for k in ("qkv_d", "out_d", "fc1_d"):
         P[k] = torch.zeros(H)
     P["qkt_s"] = torch.ones(H)
-    x = calib_inputs(2).float()
+    x = calib_inputs(range(2)).float()
     cos, sin = orc.rope_tables(H // HEADS, T)
     mask = orc.causal_mask(T)
     with torch.no_grad():

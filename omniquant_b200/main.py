@@ -28,6 +28,7 @@ ARCH = {  # hidden, ffn, heads, layers
     "opt-125m": (768, 3072, 12, 12), "opt-1.3b": (2048, 8192, 32, 24), "opt-6.7b": (4096, 16384, 32, 32),
     "llama-7b": (4096, 11008, 32, 32), "Llama-2-7b": (4096, 11008, 32, 32), "llama-13b": (5120, 13824, 40, 40),
     "Llama-2-13b": (5120, 13824, 40, 40),
+    "llama-tiny": (256, 512, 2, 2), "opt-tiny": (256, 1024, 4, 2),       # smoke-test sizes
 }
 
 
@@ -93,12 +94,12 @@ def synthetic_model(net, num_layers=None, seed=0):
     L = num_layers or L
     torch.manual_seed(seed)
     if "opt" in net.lower():
-        cfg = OPTConfig(hidden_size=H, ffn_dim=F_, num_attention_heads=heads, num_hidden_layers=L, vocab_size=50272,
-                        max_position_embeddings=2048, word_embed_proj_dim=H)
+        cfg = OPTConfig(hidden_size=H, ffn_dim=F_, num_attention_heads=heads, num_hidden_layers=L,
+                        vocab_size=50272 if H >= 768 else 512, max_position_embeddings=2048, word_embed_proj_dim=H)
         model = OPTForCausalLM(cfg)
     else:
         cfg = LlamaConfig(hidden_size=H, intermediate_size=F_, num_attention_heads=heads, num_key_value_heads=heads,
-                          num_hidden_layers=L, vocab_size=32000, max_position_embeddings=2048)
+                          num_hidden_layers=L, vocab_size=32000 if H >= 768 else 512, max_position_embeddings=2048)
         model = LlamaForCausalLM(cfg)
     return model.half().eval()
 

@@ -11,7 +11,6 @@ device (no per-step ``.item()``), the step can be replayed as a CUDA graph, and 
 all-reduce of the flat LWC/LET gradient buffer per step (== the reference with
 ``--batch_size world_size``).  AutoGPTQ real-quant packing (:255-278) is out of scope.
 """
-import gc
 import os
 
 import torch
@@ -181,10 +180,7 @@ def omniquant(lm, args, dataloader, act_scales, act_shifts, logger=None, inps=No
         if getattr(args, "real_quant", False):
             raise NotImplementedError("--real_quant (AutoGPTQ packing) is out of scope of the calibration hot path")
         del layer, eng
-        torch.cuda.empty_cache()
 
     del quant_inps, fp_inps
-    torch.cuda.empty_cache()
-    gc.collect()
     model.config.use_cache = use_cache
     return model

@@ -1,0 +1,41 @@
+"""omniquant() / main.py end to end on the GPU: the reference's command line on a random-init model of a tiny
+architecture (embedding capture through the HF model, per-block calibration, omni_parameters.pth with the
+reference's key names, quantised blocks back on the CPU in fp16)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("net,flags", [
+    ("llama-tiny", ["--wbits", "4", "--abits", "4", "--lwc", "--let"]),
+    ("opt-tiny", ["--wbits", "4", "--abits", "16", "--group_size", "128", "--lwc"]),
+    ("opt-tiny", ["--wbits", "4", "--abits", "4", "--lwc", "--let", "--aug_loss", "--batch_size", "2"]),
+])
+def test_main_synthetic(tmp_path, net, flags):
+    from omniquant_b200.main import main
+    from omniquant_b200.quantize.int_linear import QuantLinear
+    out = str(tmp_path / "log")
+    model = main(["--model", net, "--synthetic", "--nsamples", "4", "--seqlen", "128", "--epochs", "2", "--output_dir", out,
+                  "--cache_dir", str(tmp_path / "cache")] + flags)
+    ck = torch.load(os.path.join(out, "omni_parameters.pth"))
+    assert sorted(ck.keys()) == [0, 1]
+    keys = set(ck[0].keys())
+    if "--let" in flags:
+        assert {"qkv_smooth_scale", "qkv_smooth_shift", "out_smooth_scale", "fc1_smooth_shift", "qkt_smooth_scale"} <= keys
+    assert any(k.endswith("q_proj.weight_quantizer.upbound_factor") for k in keys)
+    layers = model.model.layers if "llama" in net else model.model.decoder.layers
+    for layer in layers:
+        lin = [m for m in layer.modules() if isinstance(m, QuantLinear)]
+        assert len(lin) == (7 if "llama" in net else 6)
+        for m in lin:
+            assert m.weight.device.type == "cpu" and m.weight.dtype == torch.float16
+            assert torch.isfinite(m.weight.float()).all()
+            assert hasattr(m.weight_quantizer, "scales") and hasattr(m.weight_quantizer, "zeros")
+            w = m.weight.float()
+            g = 128 if "--group_size" in flags else w.shape[1]
+            assert all(len(torch.unique(r)) <= 16 for r in w.reshape(-1, g)[:8])      # 4-bit levels per row / group
+    for v in ck[1].values():
+        assert torch.isfinite(v.float()).all()
