@@ -95,12 +95,12 @@ int oq_norm_bwd(const void* x, long rows, int C, long ldx, const float* w, int k
  * C[b] = alpha * A[b] * B[b]^T (+ bias[n]) (+ residual[b]),  fp32 accumulation in TMEM.
  *   a_mn=0: A[m,k] at A + b*strideA + m*lda + k     a_mn=1: A[m,k] at A + b*strideA + k*lda + m
  *   b_mn=0: B[n,k] at B + b*strideB + n*ldb + k     b_mn=1: B[n,k] at B + b*strideB + k*ldb + n
- * C bf16 or fp32 (c_is_f32).  causal: 0 none; 1 skip output tiles strictly above the diagonal (QK^T, dP);
+ * c_dtype: 0 bf16, 1 fp32, 2 fp16 (the attention scores, as the reference's fp16 autocast stores them).  causal: 0 none; 1 skip output tiles strictly above the diagonal (QK^T, dP);
  * 2 reduce only k < m0+128 (P.V, dS.K); 3 reduce only k >= m0 (P^T.dO, dS^T.Q).  tile_n 0 = auto.
  * Replaces F.linear in QuantLinear.forward (quantize/int_linear.py:62) + its autograd dgrad/wgrad, and
  * torch.matmul/bmm in QuantMatMul.forward (quantize/int_matmul.py:41-43). */
 int oq_gemm_bf16(const void* A, int a_mn, long lda, long strideA, const void* B, int b_mn, long ldb, long strideB,
-                 void* C, int c_is_f32, long ldc, long strideC, int M, int N, int K, int batch, const float* bias,
+                 void* C, int c_dtype, long ldc, long strideC, int M, int N, int K, int batch, const float* bias,
                  const void* residual, long ldr, long strideR, float alpha, int causal, int tile_n, int max_ctas,
                  oq_stream_t stream);
 
@@ -112,11 +112,13 @@ int oq_swiglu_bwd(const void* gu, long ldgu, const void* dm, long lddm, void* dg
 /* ReLU of QuantOPTDecoderLayer.forward (models/int_opt_layer.py:318). */
 int oq_relu_fwd(const void* x, void* y, long n, oq_stream_t stream);
 int oq_relu_bwd(const void* x, const void* dy, void* dx, long n, oq_stream_t stream);
-/* P = softmax_fp32(max(S + mask, finfo.min)) -> bf16 (models/int_llama_layer.py:156-160). S fp32 [batch,Tq,Tk]. */
-int oq_softmax_fwd(const float* S, void* P, const float* mask, long mask_bstride, long batch, int Tq, int Tk,
+/* P = softmax_fp32(max(S + mask, finfo.min)) -> bf16 (models/int_llama_layer.py:156-160).  S [batch,Tq,Tk] in
+ * fp32 (s_dtype 1) or fp16 (s_dtype 2). */
+int oq_softmax_fwd(const void* S, int s_dtype, void* P, const float* mask, long mask_bstride, long batch, int Tq, int Tk,
                    int causal, oq_stream_t stream);
-/* dS = P * (dP - rowsum(P*dP)) -> bf16 (dS may alias P); causal rows only read/write j <= i. */
-int oq_softmax_bwd(const void* P, const float* dP, void* dS, long batch, int Tq, int Tk, int causal,
+/* dS = P * (dP - rowsum(P*dP)) -> bf16 (dS may alias P); causal rows only read/write j <= i.  dP in bf16
+ * (dp_dtype 0) or fp32 (1). */
+int oq_softmax_bwd(const void* P, const void* dP, int dp_dtype, void* dS, long batch, int Tq, int Tk, int causal,
                    oq_stream_t stream);
 /* loss_acc += mean((out-target)^2) [+ mean((out-target2)^2)]; dout = d loss / d out
  * (torch.nn.MSELoss at quantize/omniquant.py:142,220-222 and its backward). */

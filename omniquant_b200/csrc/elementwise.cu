@@ -5,6 +5,8 @@
 // AdamW on the flat LWC/LET parameter buffer (quantize/omniquant.py:207-208 +
 // utils.py:32-46), bias-gradient column sums, truncate_number
 // (models/transformation.py:5-20) and a bf16 transpose.  All HBM-bound.
+#include <cuda_fp16.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -130,17 +132,37 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const bf16* P, const f
   }
 }
 
+
+// 4 scores / gradients from fp32, fp16 or bf16 storage
+__device__ __forceinline__ float4 ld4_f32(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4_f16(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float4 ld4_bf16(const bf16* p) {
+  float t[4];
+  load_bf4(p, t);
+  return make_float4(t[0], t[1], t[2], t[3]);
+}
+template <int DT>   // 1 fp32, 2 fp16, 0 bf16
+__device__ __forceinline__ float4 ld4_any(const void* base, long idx) {
+  if constexpr (DT == 1) return ld4_f32(reinterpret_cast<const float*>(base) + idx);
+  else if constexpr (DT == 2) return ld4_f16(reinterpret_cast<const __half*>(base) + idx);
+  else return ld4_bf16(reinterpret_cast<const bf16*>(base) + idx);
+}
+
 // ---- register-resident softmax rows (Tk <= 1024*NV, Tk % 4 == 0): one read of S / dP, one write of P / dS.
 // Causal rows read j <= i only and write zeros only up to the end of the 128-wide diagonal tile: the k-limited
 // P.V / dS.K / P^T.dO / dS^T.Q GEMMs (causal modes 2 and 3) never read beyond it.
-template <int NV>
-__global__ void __launch_bounds__(256) softmax_fwd_reg(const float* S, bf16* P, const float* mask, long mask_bstride, int Tq,
+template <int NV, int DT>
+__global__ void __launch_bounds__(256) softmax_fwd_reg(const void* S, bf16* P, const float* mask, long mask_bstride, int Tq,
                                                        int Tk, int causal) {
   __shared__ float scratch[2 * 8];
   const long row = blockIdx.x;
   const int i = (int)(row % Tq);
   const long b = row / Tq;
-  const float* s = S + row * (long)Tk;
+  const long sbase = row * (long)Tk;
   bf16* p = P + row * (long)Tk;
   const float* mk = mask ? mask + b * mask_bstride + (long)i * Tk : nullptr;
   const int lim = causal ? min(Tk, i + (Tk - Tq) + 1) : Tk;
@@ -152,7 +174,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_reg(const float* S, bf16* P, 
     const int j = 4 * (threadIdx.x + c * 256);
     v[c] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     if (j < lim) {
-      float4 t = *reinterpret_cast<const float4*>(s + j);
+      float4 t = ld4_any<DT>(S, sbase + j);
       if (mk) {
         const float4 m4 = *reinterpret_cast<const float4*>(mk + j);
         t.x = fmaxf(t.x + m4.x, -3.4028234663852886e38f); t.y = fmaxf(t.y + m4.y, -3.4028234663852886e38f);
@@ -194,15 +216,15 @@ __global__ void __launch_bounds__(256) softmax_fwd_reg(const float* S, bf16* P, 
     }
   }
 }
-template <int NV>
-__global__ void __launch_bounds__(256) softmax_bwd_reg(const bf16* P, const float* dP, bf16* dS, int Tq, int Tk, int causal) {
+template <int NV, int DT>
+__global__ void __launch_bounds__(256) softmax_bwd_reg(const bf16* P, const void* dP, bf16* dS, int Tq, int Tk, int causal) {
   __shared__ float scratch[8];
   const long row = blockIdx.x;
   const int i = (int)(row % Tq);
   const int lim = causal ? min(Tk, i + (Tk - Tq) + 1) : Tk;
   const int wlim = causal ? min(Tk, (lim + 127) & ~127) : Tk;
   const bf16* p = P + row * (long)Tk;
-  const float* dp = dP + row * (long)Tk;
+  const long dbase = row * (long)Tk;
   bf16* ds = dS + row * (long)Tk;
   float pv[NV][4];
   float4 g[NV];
@@ -214,7 +236,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_reg(const bf16* P, const floa
     g[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (j < lim) {
       load_bf4(p + j, pv[c]);
-      g[c] = *reinterpret_cast<const float4*>(dp + j);
+      g[c] = ld4_any<DT>(dP, dbase + j);
       if (j + 1 >= lim) { pv[c][1] = 0.f; g[c].y = 0.f; }
       if (j + 2 >= lim) { pv[c][2] = 0.f; g[c].z = 0.f; }
       if (j + 3 >= lim) { pv[c][3] = 0.f; g[c].w = 0.f; }
@@ -419,28 +441,44 @@ extern "C" int oq_relu_bwd(const void* x, const void* dy, void* dx, long n, cuda
   relu_bwd_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, n / 8);
   return oq_check_launch("oq_relu_bwd");
 }
-extern "C" int oq_softmax_fwd(const float* S, void* P, const float* mask, long mask_bstride, long batch, int Tq, int Tk,
-                              int causal, cudaStream_t stream) {
+extern "C" int oq_softmax_fwd(const void* S, int s_dtype, void* P, const float* mask, long mask_bstride, long batch, int Tq,
+                              int Tk, int causal, cudaStream_t stream) {
   OQ_REQUIRE(S && P && batch > 0 && Tq > 0 && Tk > 0 && batch * Tq < (1L << 31), "oq_softmax_fwd: bad arguments");
+  OQ_REQUIRE(s_dtype == 1 || s_dtype == 2, "oq_softmax_fwd: scores must be fp32 (1) or fp16 (2)");
   const unsigned grid = (unsigned)(batch * Tq);
-  const bool fast = Tk % 4 == 0 && al16(S) && ((uintptr_t)P % 8 == 0) && al16(mask);
-  if (fast && Tk <= 1024) softmax_fwd_reg<1><<<grid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);
-  else if (fast && Tk <= 2048) softmax_fwd_reg<2><<<grid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);
-  else if (fast && Tk <= 4096) softmax_fwd_reg<4><<<grid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);
-  else if (fast && Tk <= 8192) softmax_fwd_reg<8><<<grid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);
-  else softmax_fwd_kernel<<<grid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);
+  const bool fast = Tk % 4 == 0 && al16(S) && ((uintptr_t)P % 8 == 0) && al16(mask) && Tk <= 8192;
+  OQ_REQUIRE(fast || s_dtype == 1, "oq_softmax_fwd: fp16 scores need Tk %% 4 == 0, Tk <= 8192 and aligned pointers");
+#define OQ_SMF(NV)                                                                                                   \
+  {                                                                                                                  \
+    if (s_dtype == 1) softmax_fwd_reg<NV, 1><<<grid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal); \
+    else softmax_fwd_reg<NV, 2><<<grid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);          \
+  }
+  if (fast && Tk <= 1024) OQ_SMF(1)
+  else if (fast && Tk <= 2048) OQ_SMF(2)
+  else if (fast && Tk <= 4096) OQ_SMF(4)
+  else if (fast) OQ_SMF(8)
+  else softmax_fwd_kernel<<<grid, 256, 0, stream>>>((const float*)S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);
+#undef OQ_SMF
   return oq_check_launch("oq_softmax_fwd");
 }
-extern "C" int oq_softmax_bwd(const void* P, const float* dP, void* dS, long batch, int Tq, int Tk, int causal,
+extern "C" int oq_softmax_bwd(const void* P, const void* dP, int dp_dtype, void* dS, long batch, int Tq, int Tk, int causal,
                               cudaStream_t stream) {
   OQ_REQUIRE(P && dP && dS && batch > 0 && Tq > 0 && Tk > 0 && batch * Tq < (1L << 31), "oq_softmax_bwd: bad arguments");
+  OQ_REQUIRE(dp_dtype == 0 || dp_dtype == 1, "oq_softmax_bwd: dP must be bf16 (0) or fp32 (1)");
   const unsigned grid = (unsigned)(batch * Tq);
-  const bool fast = Tk % 4 == 0 && al16(dP) && ((uintptr_t)P % 8 == 0) && ((uintptr_t)dS % 8 == 0);
-  if (fast && Tk <= 1024) softmax_bwd_reg<1><<<grid, 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal);
-  else if (fast && Tk <= 2048) softmax_bwd_reg<2><<<grid, 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal);
-  else if (fast && Tk <= 4096) softmax_bwd_reg<4><<<grid, 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal);
-  else if (fast && Tk <= 8192) softmax_bwd_reg<8><<<grid, 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal);
-  else softmax_bwd_kernel<<<grid, 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal);
+  const bool fast = Tk % 4 == 0 && al16(dP) && ((uintptr_t)P % 8 == 0) && ((uintptr_t)dS % 8 == 0) && Tk <= 8192;
+  OQ_REQUIRE(fast || dp_dtype == 1, "oq_softmax_bwd: bf16 dP needs Tk %% 4 == 0, Tk <= 8192 and aligned pointers");
+#define OQ_SMB(NV)                                                                                                  \
+  {                                                                                                                 \
+    if (dp_dtype == 1) softmax_bwd_reg<NV, 1><<<grid, 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal); \
+    else softmax_bwd_reg<NV, 0><<<grid, 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal);           \
+  }
+  if (fast && Tk <= 1024) OQ_SMB(1)
+  else if (fast && Tk <= 2048) OQ_SMB(2)
+  else if (fast && Tk <= 4096) OQ_SMB(4)
+  else if (fast) OQ_SMB(8)
+  else softmax_bwd_kernel<<<grid, 256, 0, stream>>>((const bf16*)P, (const float*)dP, (bf16*)dS, Tq, Tk, causal);
+#undef OQ_SMB
   return oq_check_launch("oq_softmax_bwd");
 }
 extern "C" int oq_mse_fwd_bwd(const void* out, const void* target, const void* target2, long n, float inv_numel,

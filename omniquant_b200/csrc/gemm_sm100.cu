@@ -18,6 +18,7 @@
 // warps 4-7 = epilogue (TMEM -> registers -> global), two TMEM accumulator
 // stages so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 
@@ -34,7 +35,7 @@ struct GemmParams {
   int M, N, K, batch;
   int a_mn, b_mn;
   void* C;
-  int c_f32;
+  int c_dtype;  // 0 bf16, 1 fp32, 2 fp16
   long ldc, strideC;
   const float* bias;
   const bf16* res;
@@ -269,7 +270,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool vec_ok = p.c_f32 ? (p.ldc % 4 == 0 && p.strideC % 4 == 0) : (p.ldc % 8 == 0 && p.strideC % 8 == 0);
+    const bool vec_ok = p.c_dtype == 1 ? (p.ldc % 4 == 0 && p.strideC % 4 == 0) : (p.ldc % 8 == 0 && p.strideC % 8 == 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int m0, nb, b;
       tile_coords(p, tile, m0, nb, b);
@@ -312,7 +313,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (j < valid) v[j] += bf2f(resr[nc + j]);
             }
           }
-          if (p.c_f32) {
+          if (p.c_dtype == 1) {
             float* cr = reinterpret_cast<float*>(p.C) + (long)b * p.strideC + (long)row * p.ldc + nc;
             if (valid == 32 && vec_ok) {
 #pragma unroll
@@ -321,6 +322,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (j < valid) cr[j] = v[j];
+            }
+          } else if (p.c_dtype == 2) {
+            __half* cr = reinterpret_cast<__half*>(p.C) + (long)b * p.strideC + (long)row * p.ldc + nc;
+            if (valid == 32 && vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 u;
+                __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+                __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(cr + j) = u;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < valid) cr[j] = __float2half_rn(v[j]);
             }
           } else {
             bf16* cr = reinterpret_cast<bf16*>(p.C) + (long)b * p.strideC + (long)row * p.ldc + nc;
@@ -413,7 +431,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int max_c
 }  // namespace
 
 extern "C" int oq_gemm_bf16(const void* A, int a_mn, long lda, long strideA, const void* B, int b_mn, long ldb,
-                            long strideB, void* C, int c_is_f32, long ldc, long strideC, int M, int N, int K, int batch,
+                            long strideB, void* C, int c_dtype, long ldc, long strideC, int M, int N, int K, int batch,
                             const float* bias, const void* residual, long ldr, long strideR, float alpha, int causal,
                             int tile_n, int max_ctas, cudaStream_t stream) {
   OQ_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "oq_gemm_bf16: null pointer or bad shape M=%d N=%d K=%d batch=%d",
@@ -423,6 +441,7 @@ extern "C" int oq_gemm_bf16(const void* A, int a_mn, long lda, long strideA, con
              lda, ldb, strideA, strideB);
   OQ_REQUIRE((uintptr_t)A % 16 == 0 && (uintptr_t)B % 16 == 0, "oq_gemm_bf16: operand base pointers must be 16-byte aligned");
   OQ_REQUIRE(causal >= 0 && causal <= 3, "oq_gemm_bf16: bad causal mode %d", causal);
+  OQ_REQUIRE(c_dtype >= 0 && c_dtype <= 2, "oq_gemm_bf16: c_dtype must be 0 (bf16), 1 (fp32) or 2 (fp16)");
   OQ_REQUIRE(tile_n == 0 || tile_n == 128 || tile_n == 256, "oq_gemm_bf16: tile_n must be 0, 128 or 256");
   if (tile_n == 0) {
     // BN=256 halves the A re-reads; use BN=128 when N is small or the wider tile leaves SMs idle
@@ -431,7 +450,7 @@ extern "C" int oq_gemm_bf16(const void* A, int a_mn, long lda, long strideA, con
   }
   GemmParams p = {};
   p.M = M; p.N = N; p.K = K; p.batch = batch; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
-  p.C = C; p.c_f32 = c_is_f32; p.ldc = ldc; p.strideC = strideC; p.bias = bias; p.res = (const bf16*)residual;
+  p.C = C; p.c_dtype = c_dtype; p.ldc = ldc; p.strideC = strideC; p.bias = bias; p.res = (const bf16*)residual;
   p.ldr = ldr; p.strideR = strideR; p.alpha = alpha; p.causal = causal;
   CUtensorMap ta, tb;
   // K-major: inner = K, rows = M|N, box rows = BM|BN.   MN-major: inner = M|N, rows = K, box = 64 x 64.

@@ -291,7 +291,7 @@ class BlockEngine:
             alpha = 1.0
         self.qkv, self.qkvq, self.att_alpha = qkv, qkvq, alpha
         P = B("P", (nb, h, T, T))
-        S = B("S", (h, T, T), F32)
+        S = B("S", (h, T, T), torch.float16)     # scores in fp16 like the reference's autocast (int_llama_layer.py:143)
         O = B("O", (M, H))
         cz = 1 if self.causal else 0
         for s in range(nb):
@@ -374,7 +374,7 @@ class BlockEngine:
         # attention
         qkv, qkvq, alpha = self.qkv, self.qkvq, self.att_alpha
         dqkvq = B("dqkvq", (M, 3 * H))
-        dP = B("S", (h, T, T), F32)
+        dP = B("S", (h, T, T), torch.float16).view(BF16)   # same scratch storage as the scores
         cz = 1 if self.causal else 0
         for s in range(nb):
             r = slice(s * T, (s + 1) * T)

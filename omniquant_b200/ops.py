@@ -121,6 +121,7 @@ def norm_bwd(x, w, kind, mean, rstd, dy, dx=None, dx_add=None, dw_acc=None, db_a
 
 
 # ------------------------------------------------------------------ GEMM
+_CDT = {BF16: 0, F32: 1, torch.float16: 2}
 GEMM_TIMER = None   # bench.py sets this to a list to collect (event0, event1, flops, tile) per GEMM launch
 
 
@@ -132,13 +133,13 @@ def gemm(A, B, C, *, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=No
          strideC=0, bias=None, residual=None, ldr=0, strideR=0, alpha=1.0, causal=0, tile_n=0, max_ctas=0):
     """C[b] = alpha * A[b] @ B[b]^T (+bias) (+residual); raw strided form (see the header)."""
     _chk(A, BF16, "A"); _chk(B, BF16, "B"); _chk(bias, F32, "bias"); _chk(residual, BF16, "residual")
-    if C.dtype not in (BF16, F32):
-        raise OqError("C must be bf16 or fp32")
+    if C.dtype not in _CDT:
+        raise OqError("C must be bf16, fp32 or fp16")
     if GEMM_TIMER is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     lib().call("oq_gemm_bf16", _p(A), int(a_mn), lda, strideA, _p(B), int(b_mn), ldb, strideB, _p(C),
-               int(C.dtype == F32), ldc, strideC, M, N, K, batch, _p(bias), _p(residual), ldr, strideR, float(alpha),
+               _CDT[C.dtype], ldc, strideC, M, N, K, batch, _p(bias), _p(residual), ldr, strideR, float(alpha),
                causal, tile_n, max_ctas, _stream())
     if GEMM_TIMER is not None:
         e1.record()
@@ -188,20 +189,24 @@ def relu_bwd(x, dy, dx):
 
 
 def softmax_fwd(S, P, mask=None, causal=False):
-    """S fp32 [B,Tq,Tk] contiguous -> P bf16."""
-    _chk(S, F32, "S"); _chk(P, BF16, "P"); _chk(mask, F32, "mask")
+    """S fp32 or fp16 [B,Tq,Tk] contiguous -> P bf16."""
+    _chk(P, BF16, "P"); _chk(mask, F32, "mask")
+    if S.dtype not in (F32, torch.float16):
+        raise OqError("S must be fp32 or fp16")
     B, Tq, Tk = S.shape
     mbs = 0
     if mask is not None:
         mask = mask.reshape(-1, Tq, Tk)
         mbs = 0 if mask.shape[0] == 1 else Tq * Tk
-    lib().call("oq_softmax_fwd", _p(S), _p(P), _p(mask), mbs, B, Tq, Tk, int(causal), _stream())
+    lib().call("oq_softmax_fwd", _p(S), 1 if S.dtype == F32 else 2, _p(P), _p(mask), mbs, B, Tq, Tk, int(causal), _stream())
 
 
 def softmax_bwd(P, dP, dS, causal=False):
-    _chk(P, BF16, "P"); _chk(dP, F32, "dP"); _chk(dS, BF16, "dS")
+    _chk(P, BF16, "P"); _chk(dS, BF16, "dS")
+    if dP.dtype not in (F32, BF16):
+        raise OqError("dP must be fp32 or bf16")
     B, Tq, Tk = P.shape
-    lib().call("oq_softmax_bwd", _p(P), _p(dP), _p(dS), B, Tq, Tk, int(causal), _stream())
+    lib().call("oq_softmax_bwd", _p(P), _p(dP), int(dP.dtype == F32), _p(dS), B, Tq, Tk, int(causal), _stream())
 
 
 def mse_fwd_bwd(out, target, loss_acc, dout=None, target2=None):

@@ -264,6 +264,13 @@ def st(t, cfg):
     return t + (t.to(cfg.emu16).to(t.dtype) - t).detach()
 
 
+def st_scores(t, cfg):
+    """the engine keeps attention scores in fp16 (like the reference's fp16 autocast), everything else in emu16."""
+    if cfg.emu16 is None:
+        return t
+    return t + (t.to(torch.float16).to(t.dtype) - t).detach()
+
+
 LLAMA_LINEARS = ("q", "k", "v", "o", "gate", "up", "down")
 OPT_LINEARS = ("q", "k", "v", "o", "fc1", "fc2")
 
@@ -359,7 +366,7 @@ def llama_forward(x, T, n_heads, cos, sin, mask, cfg: QCfg, act_quant=True, eps=
         v = v[:, :, None].expand(b, n_kv, rep, L, d).reshape(b, n_heads, L, d)
     q = S(aq(q, cfg, act_quant))
     k = S(aq(k, cfg, act_quant))
-    s = torch.matmul(q, k.transpose(2, 3)) / math.sqrt(d)
+    s = st_scores(torch.matmul(q, k.transpose(2, 3)) / math.sqrt(d), cfg)
     if mask is not None:
         s = s + mask
         s = torch.max(s, torch.tensor(torch.finfo(s.dtype).min, device=s.device))
@@ -421,7 +428,7 @@ def opt_forward(x, T, n_heads, mask, cfg: QCfg, act_quant=True, eps=1e-5):
     q = S(aq(lin(a1, "q", sc=d ** -0.5), cfg, act_quant))
     k = S(aq(lin(a1, "k"), cfg, act_quant))
     v = S(aq(lin(a1, "v"), cfg, act_quant))
-    s = torch.bmm(sh(q), sh(k).transpose(1, 2))
+    s = st_scores(torch.bmm(sh(q), sh(k).transpose(1, 2)), cfg)
     if mask is not None:
         s = s.view(b, n_heads, L, L) + mask
         s = torch.max(s, torch.tensor(torch.finfo(s.dtype).min, device=s.device)).view(b * n_heads, L, L)
