@@ -46,6 +46,22 @@ def peaks():
     return 1400.0, 6650.0, "fallback"
 
 
+def gemm_traffic_from_ncu():
+    """Per-launch DRAM bytes (read + write) of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r1_gemm_ncu_full_summary.csv, QuantLinear launches of gemm_kernel<256>), or None."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1_gemm_ncu_full_summary.csv")
+    if not os.path.exists(path):
+        return None
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]
+    name = [i for i, h in enumerate(hdr) if h.startswith("Kernel Name")][0]
+    rd = [i for i, h in enumerate(hdr) if h.startswith("dram__bytes_read.sum")][0]
+    wr = [i for i, h in enumerate(hdr) if h.startswith("dram__bytes_write.sum")][0]
+    vals = [(float(r[rd]) + float(r[wr])) * 1e6 for r in rows[1:] if "gemm_kernel<256>" in r[name] and float(r[wr]) < 200]
+    return round(sum(vals) / len(vals)) if vals else None
+
+
 def block_weights(seed=0):
     g = torch.Generator().manual_seed(seed)
     r = lambda *s: (torch.randn(*s, generator=g) * 0.02).half()
@@ -119,6 +135,7 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
     assert NSAMPLES % world == 0
@@ -195,7 +212,9 @@ def run_ours(a):
     lin_ms, lin_fl = sum(t for t, _ in lin), sum(f for _, f in lin)
     achieved = lin_fl / (lin_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "gemm_kernel<256> (QuantLinear fwd/dgrad/wgrad)", "achieved": round(achieved, 1),
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": None,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": gemm_traffic_from_ncu(),
+                "traffic_note": "mean DRAM read+write bytes per QuantLinear launch, ncu --set full (profiles/r1_gemm_ncu_full_summary.csv); "
+                                "algorithmic operand+result bytes per launch average 1.7e8",
                 "peak_source": f"bf16_tflops_sustained, {which}", "launches_timed": len(lin),
                 "avg_launch_ms": round(lin_ms / max(len(lin), 1), 4),
                 "attention_gemm_tflops": round(sum(f for _, f in att) / (sum(t for t, _ in att) * 1e-3) / 1e12, 1) if att else None}
