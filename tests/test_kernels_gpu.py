@@ -121,6 +121,28 @@ def test_weight_quant_large_bit_exact(ops):
         assert torch.equal(out["wq_f32"], deq)
 
 
+def test_weight_quant_full_size_properties(ops):
+    """Size-independent properties at LLaMA-7B weight sizes (no oracle needed): power-of-two scaling leaves codes
+    and zero points untouched and scales `scale` / dequant exactly; codes in range; dequant == (code - zp) * scale."""
+    gen = torch.Generator(device="cuda").manual_seed(21)
+    for (N, K, grp, nb) in [(4096, 11008, 0, 4), (11008, 4096, 128, 3), (4096, 4096, 64, 2)]:
+        W = (torch.randn(N, K, device="cuda", generator=gen) * 0.02).half().float()
+        G = K // grp if grp else 1
+        up = torch.randn(N * G, device="cuda", generator=gen) + 3
+        low = torch.randn(N * G, device="cuda", generator=gen) + 3
+        a = run_wq(ops, W, nb, False, grp, up, low, True)
+        b = run_wq(ops, W * 4.0, nb, False, grp, up, low, True)
+        assert torch.equal(a["codes"], b["codes"])
+        assert torch.equal(a["zp_out"], b["zp_out"])
+        assert torch.equal(a["scale_out"] * 4.0, b["scale_out"])
+        assert torch.equal(a["wq_f32"] * 4.0, b["wq_f32"])
+        assert int(a["codes"].max()) <= 2 ** nb - 1
+        rep = lambda v: v.view(N, G, 1).expand(N, G, K // G).reshape(N, K)
+        assert torch.equal((a["codes"].float() - rep(a["zp_out"])) * rep(a["scale_out"]), a["wq_f32"])
+        # every level of the 2^n grid is used somewhere
+        assert len(torch.unique(a["codes"])) == 2 ** nb
+
+
 def test_weight_quant_let_fold_and_matvec(ops):
     """fold (W*col)/row and (W*col)*row in the reference's op order + W@shift."""
     gen = torch.Generator(device="cuda").manual_seed(3)
