@@ -143,10 +143,11 @@ int oq_transpose_bf16(const void* in, long ldi, void* out, long ldo, int R, int 
  *   tmpv  [9H+F1] ln1.w' | ln1.b' | ln2.w' | ln2.b' | b_q' | b_k' | b_v' | b_o' | b_fc1' [F1] | b_q'*q_bias_scale
  *   acc   [10H]   dcol_qkv | dcol_out | dcol_fc1 | dsh_qkv | dsh_out | dsh_fc1 | dw1' | db1' | dw2' | db2'
  *   drow  [3H]    sum_k dW'*(W*col) of the q | k | v weights;   dbqkv [3H] column sums of dL/d(qkv)
+ * part: 0 everything, 1 norm vectors + q/k/v biases, 2 o / fc1 biases (lets the two halves run on different streams).
  * q_bias_scale: head_dim^-0.5 for OPT (q is scaled before QuantMatMul, models/int_opt_layer.py:96), else 1. */
 int oq_let_fold_vec(int H, int F1, const float* let_params, const float* ln1w, const float* ln1b, const float* ln2w,
                     const float* ln2b, const float* rawb_qkv, const float* rawb_o, const float* rawb_fc1, const float* mv,
-                    float q_bias_scale, float* tmpv, oq_stream_t stream);
+                    float q_bias_scale, float* tmpv, int part, oq_stream_t stream);
 int oq_let_prep_bwd(int H, const float* let_params, const float* dbqkv, float q_bias_scale, float* e, oq_stream_t stream);
 int oq_let_grad_vec(int H, int F1, const float* let_params, const float* tmpv, const float* acc, const float* drow,
                     const float* dbqkv, float q_bias_scale, float* let_grads, oq_stream_t stream);

@@ -355,11 +355,11 @@ __global__ void transpose_kernel(const bf16* in, long ldi, bf16* out, long ldo, 
 __global__ void __launch_bounds__(256) let_fold_vec_kernel(int H, int F1, const float* let, const float* ln1w, const float* ln1b,
                                                            const float* ln2w, const float* ln2b, const float* rb_qkv,
                                                            const float* rb_o, const float* rb_fc1, const float* mv,
-                                                           float qscale, float* tmpv) {
+                                                           float qscale, float* tmpv, int part) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const float *s1 = let, *so = let + H, *s2 = let + 2 * H, *sk = let + 3 * H, *d1 = let + 4 * H, *dout = let + 5 * H,
               *d2 = let + 6 * H;
-  if (i < H) {
+  if (i < H && part != 2) {
     tmpv[i] = OQ_DIV(ln1w[i], s1[i]);
     tmpv[H + i] = ln1b ? OQ_DIV(OQ_SUB(ln1b[i], d1[i]), s1[i]) : OQ_DIV(OQ_MUL(-1.0f, d1[i]), s1[i]);
     tmpv[2 * H + i] = OQ_DIV(ln2w[i], s2[i]);
@@ -371,10 +371,10 @@ __global__ void __launch_bounds__(256) let_fold_vec_kernel(int H, int F1, const 
     tmpv[4 * H + i] = bqt;
     tmpv[5 * H + i] = OQ_MUL(bk, sk[i]);
     tmpv[6 * H + i] = OQ_DIV(OQ_SUB(bv, dout[i]), so[i]);
-    tmpv[7 * H + i] = rb_o ? OQ_ADD(rb_o[i], mv[3 * H + i]) : mv[3 * H + i];
     tmpv[8 * H + F1 + i] = bqt * qscale;
   }
-  if (i < F1) tmpv[8 * H + i] = rb_fc1 ? OQ_ADD(rb_fc1[i], mv[4 * H + i]) : mv[4 * H + i];
+  if (i < H && part != 1) tmpv[7 * H + i] = rb_o ? OQ_ADD(rb_o[i], mv[3 * H + i]) : mv[3 * H + i];
+  if (i < F1 && part != 1) tmpv[8 * H + i] = rb_fc1 ? OQ_ADD(rb_fc1[i], mv[4 * H + i]) : mv[4 * H + i];
 }
 // e_q = db_q*qscale/s_qkt, e_k = db_k*s_qkt, e_v = db_v/s_out   (dL/d(W@shift) per output row)
 __global__ void __launch_bounds__(256) let_prep_bwd_kernel(int H, const float* let, const float* dbqkv, float qscale, float* e) {
@@ -524,10 +524,11 @@ extern "C" int oq_transpose_bf16(const void* in, long ldi, void* out, long ldo, 
 
 extern "C" int oq_let_fold_vec(int H, int F1, const float* let_params, const float* ln1w, const float* ln1b, const float* ln2w,
                                const float* ln2b, const float* rawb_qkv, const float* rawb_o, const float* rawb_fc1,
-                               const float* mv, float q_bias_scale, float* tmpv, cudaStream_t stream) {
+                               const float* mv, float q_bias_scale, float* tmpv, int part, cudaStream_t stream) {
   OQ_REQUIRE(H > 0 && F1 > 0 && let_params && ln1w && ln2w && mv && tmpv, "oq_let_fold_vec: bad arguments");
+  OQ_REQUIRE(part >= 0 && part <= 2, "oq_let_fold_vec: part must be 0 (all), 1 (norms + q/k/v biases) or 2 (o / fc1 biases)");
   let_fold_vec_kernel<<<(std::max(H, F1) + 255) / 256, 256, 0, stream>>>(H, F1, let_params, ln1w, ln1b, ln2w, ln2b, rawb_qkv,
-                                                                          rawb_o, rawb_fc1, mv, q_bias_scale, tmpv);
+                                                                          rawb_o, rawb_fc1, mv, q_bias_scale, tmpv, part);
   return oq_check_launch("oq_let_fold_vec");
 }
 extern "C" int oq_let_prep_bwd(int H, const float* let_params, const float* dbqkv, float q_bias_scale, float* e,

@@ -58,7 +58,8 @@ class BlockEngine:
 
     def __init__(self, family: str, weights: Dict[str, torch.Tensor], *, n_heads: int, seq_len: int, qcfg: QuantConfig,
                  eps: float, device="cuda", batch: int = 1, let_init: Optional[Dict[str, torch.Tensor]] = None,
-                 let_lr=5e-3, lwc_lr=1e-2, wd=0.0, world_size=1, causal=True, mask: Optional[torch.Tensor] = None):
+                 let_lr=5e-3, lwc_lr=1e-2, wd=0.0, world_size=1, causal=True, mask: Optional[torch.Tensor] = None,
+                 overlap: bool = True):
         assert family in ("llama", "opt")
         self.family, self.q, self.eps, self.dev = family, qcfg, float(eps), torch.device(device)
         self.h, self.T, self.b = n_heads, seq_len, batch
@@ -163,6 +164,27 @@ class BlockEngine:
         self._drowbuf = z(3 * H)
         self._drow = {k: self._drowbuf[i * H:(i + 1) * H] for i, k in enumerate(("q", "k", "v"))}
         self._qscale = self.d ** -0.5 if family == "opt" else 1.0
+        self.overlap = overlap and self.dev.type == "cuda"
+        self.side = torch.cuda.Stream(device=self.dev) if self.overlap else None
+        self._pending = False
+
+    # ------------------------------------------------------------------ side stream
+    # The quantiser kernels are instruction-bound and the persistent GEMM leaves SMs idle in its last wave, so
+    # the weight fake-quant of the later weights (forward) and the per-weight quantiser backward run on a second
+    # stream beside the GEMMs of the main stream.  fork = side waits for main; join = main waits for side.
+    def _fork(self):
+        if self.overlap:
+            self.side.wait_stream(torch.cuda.current_stream())
+            self._pending = True
+
+    def _join(self):
+        if self._pending:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._pending = False
+
+    def _on_side(self):
+        import contextlib
+        return torch.cuda.stream(self.side) if self.overlap else contextlib.nullcontext()
 
     # ------------------------------------------------------------------ helpers
     def buf(self, name, shape, dtype=BF16):
@@ -189,7 +211,8 @@ class BlockEngine:
         if q.let:
             ops.truncate_(self.params[:4 * self.H], 1e-2)   # the four *_smooth_scale vectors are contiguous
         extra = {}
-        for u in self.units:
+
+        def quant_unit(u):
             up, low = self.lwc(u)
             st = self.qstat[u.name]
             kw = dict(scale_out=st["scale"], zp_out=st["zp"])
@@ -201,19 +224,35 @@ class BlockEngine:
                 st["scale"], st["zp"] = extra[u.name]["scales"], extra[u.name]["zeros"]
             if q.wbits >= 16:
                 self.wview(u, self.Wq).copy_(self.wview(u, self.W))     # weights left un-quantised
-                continue
+                return
             ops.weight_quant_fwd(self.wview(u, self.W), n_bits=q.wbits, symmetric=q.symmetric, group_size=q.group_size,
                                  up=up, low=low, col_scale=p.get(u.col) if u.col else None,
                                  row_scale=p.get(u.row) if u.row else None, row_op=u.row_op,
                                  shift=p.get(u.shift) if u.shift else None, matvec_out=st["mv"] if u.shift else None,
                                  recip_div=q.recip_div, wq_bf16=self.wview(u, self.Wq), xmin_out=st["xmin"],
                                  xmax_out=st["xmax"], **kw)
+
         t = self.tmp
         H = self.H
+        ln, tv, F1 = self.ln, self._tmpv, self.F1
+        fold = lambda part: ops.let_fold_vec(H, F1, self.params[:7 * H], ln["ln1w"], ln["ln1b"], ln["ln2w"], ln["ln2b"],
+                                             self.rawb["qkv"], self.rawb["o"], self.rawb["fc1"], self._mvbuf, self._qscale,
+                                             tv, part)
+        first = [u for u in self.units if u.group == "qkv"]
+        later = [u for u in self.units if u.group != "qkv"]
+        for u in first:                 # what the first GEMM of the forward needs, on the main stream
+            quant_unit(u)
         if q.let:
-            ln, tv, F1 = self.ln, self._tmpv, self.F1
-            ops.let_fold_vec(H, F1, self.params[:7 * H], ln["ln1w"], ln["ln1b"], ln["ln2w"], ln["ln2b"], self.rawb["qkv"],
-                             self.rawb["o"], self.rawb["fc1"], self._mvbuf, self._qscale, tv)
+            fold(1)
+        self._fork()
+        with self._on_side():           # o / fc1 / fc2 beside the qkv GEMM and the attention of the main stream
+            for u in later:
+                quant_unit(u)
+            if q.let:
+                fold(2)
+        if final:
+            self._join()
+        if q.let:
             t.update(ln1w=tv[:H], ln1b=tv[H:2 * H], ln2w=tv[2 * H:3 * H], ln2b=tv[3 * H:4 * H], bqkv=tv[4 * H:7 * H],
                      bo=tv[7 * H:8 * H], bfc1=tv[8 * H:8 * H + F1], bfc2=self.rawb["fc2"])
             if self.family == "opt":
@@ -303,6 +342,7 @@ class BlockEngine:
                      strideA=T * T, strideB=d, strideC=d, causal=2 * cz)
         Oq = self._aq(O, "Oq")
         h1 = B("h1", (M, H))
+        self._join()                # o / fc1 / fc2 operands of this step come from the side stream
         ops.linear_fwd(Oq, W["o"], h1, bias=ws["bo"], residual=x)
         a2 = B("a2", (M, H))
         self.st2 = (B("mean2", (M,), F32), B("rstd2", (M,), F32))
@@ -353,6 +393,7 @@ class BlockEngine:
         dmq = B("dmq", (M, F_))
         ops.linear_dgrad(dout, W["fc2"], dmq)
         ops.linear_wgrad(dout, sv["mq"], dW["fc2"])
+        self._unit_backward_side("fc2", dW, None)
         dm = self._aq_bwd(sv["m"], dmq, "dm")
         df1 = B("df1", sv["f1"].shape)
         if self.glu:
@@ -362,6 +403,7 @@ class BlockEngine:
         da2q = B("da2q", (M, H))
         ops.linear_dgrad(df1, W["fc1"], da2q)
         ops.linear_wgrad(df1, sv["a2q"], dW["fc1"])
+        self._unit_backward_side("fc1", dW, df1)
         da2 = self._aq_bwd(sv["a2"], da2q, "da2")
         dh1 = B("dh1", (M, H))
         ops.norm_bwd(sv["h1"], ws["ln2w"], self.norm_kind, self.st2[0], self.st2[1], da2, dx=dh1, dx_add=dout,
@@ -370,6 +412,7 @@ class BlockEngine:
         dOq = B("dOq", (M, H))
         ops.linear_dgrad(dh1, W["o"], dOq)
         ops.linear_wgrad(dh1, sv["Oq"], dW["o"])
+        self._unit_backward_side("o", dW, dh1)
         dO = self._aq_bwd(sv["O"], dOq, "dO")
         # attention
         qkv, qkvq, alpha = self.qkv, self.qkvq, self.att_alpha
@@ -429,38 +472,51 @@ class BlockEngine:
                          db_acc=self._acc["db1"])
         self._weight_backward(dW, dqkv, dh1, df1)
 
+    def _unit_bwd(self, u, dW, e_row):
+        """Quantiser + LET-fold backward of one weight (csrc/weight_quant*.cu)."""
+        q, p, g, acc = self.q, self.p, self.g, self._acc
+        if q.wbits >= 16:
+            return
+        colacc = {"qkv_s": acc["dcol_qkv"], "out_s": acc["dcol_out"], "fc1_s": acc["dcol_fc1"]}
+        shacc = {"qkv_d": acc["dsh_qkv"], "out_d": acc["dsh_out"], "fc1_d": acc["dsh_fc1"]}
+        up, low = self.lwc(u)
+        st = self.qstat[u.name]
+        ops.weight_quant_bwd(self.wview(u, self.W), self.wview(u, dW), st["xmin"], st["xmax"], n_bits=q.wbits,
+                             symmetric=q.symmetric, group_size=q.group_size, up=up, low=low,
+                             col_scale=p.get(u.col) if u.col else None, row_scale=p.get(u.row) if u.row else None,
+                             row_op=u.row_op, recip_div=q.recip_div, e_row=e_row if u.shift else None,
+                             d_up=g.get(f"{u.name}.up"), d_low=g.get(f"{u.name}.low"),
+                             dcol_acc=colacc[u.col] if u.col else None, drow=self._drow[u.name] if u.row else None,
+                             dshift_acc=shacc[u.shift] if u.shift else None, scale=st["scale"], zp=st["zp"])
+
+    def _unit_backward_side(self, name, dW, dy):
+        """Backward of the o / fc1 / fc2 weight on the side stream, as soon as its wgrad GEMM has been issued:
+        it overlaps the remaining GEMMs of the main stream.  dy: the linear's output gradient (for the bias /
+        shift path), None when the weight carries no LET shift."""
+        u = next(x for x in self.units if x.name == name)
+        self._fork()
+        with self._on_side():
+            e = None
+            if self.q.let and u.shift and dy is not None:
+                e = self.buf(f"db_{name}", (dy.shape[1],), F32)
+                ops.colsum(dy, e)
+            self._unit_bwd(u, dW, e)
+
     def _weight_backward(self, dW, dqkv, dh1, df1):
-        """Quantiser + fold backward per weight, then the LET gradient assembly."""
-        q, p, g, H = self.q, self.p, self.g, self.H
+        """q / k / v weights on the main stream, then join the side stream and assemble the LET gradients."""
+        q, H = self.q, self.H
         let = q.let
         e = {}
         if let:
             dbqkv = self.buf("dbqkv", (3 * H,), F32)
             ops.colsum(dqkv, dbqkv)
-            dbo = self.buf("dbo", (H,), F32)
-            ops.colsum(dh1, dbo)
-            dbf = self.buf("dbf", (df1.shape[1],), F32)
-            ops.colsum(df1, dbf)
             ev = self.buf("e_qkv", (3 * H,), F32)
             ops.let_prep_bwd(H, self.params[:7 * H], dbqkv, self._qscale, ev)
-            e = {"q": ev[:H], "k": ev[H:2 * H], "v": ev[2 * H:], "o": dbo, "fc1": dbf}
-        acc = self._acc
-        colacc = {"qkv_s": acc["dcol_qkv"], "out_s": acc["dcol_out"], "fc1_s": acc["dcol_fc1"]}
-        shacc = {"qkv_d": acc["dsh_qkv"], "out_d": acc["dsh_out"], "fc1_d": acc["dsh_fc1"]}
+            e = {"q": ev[:H], "k": ev[H:2 * H], "v": ev[2 * H:]}
         for u in self.units:
-            if q.wbits >= 16:
-                continue
-            up, low = self.lwc(u)
-            st = self.qstat[u.name]
-            er = e.get(u.name)
-            ops.weight_quant_bwd(self.wview(u, self.W), self.wview(u, dW), st["xmin"], st["xmax"], n_bits=q.wbits,
-                                 symmetric=q.symmetric, group_size=q.group_size, up=up, low=low,
-                                 col_scale=p.get(u.col) if u.col else None, row_scale=p.get(u.row) if u.row else None,
-                                 row_op=u.row_op, recip_div=q.recip_div,
-                                 e_row=er if (er is not None and u.shift) else None,
-                                 d_up=g.get(f"{u.name}.up"), d_low=g.get(f"{u.name}.low"),
-                                 dcol_acc=colacc[u.col] if u.col else None, drow=self._drow[u.name] if u.row else None,
-                                 dshift_acc=shacc[u.shift] if u.shift else None, scale=st["scale"], zp=st["zp"])
+            if u.group == "qkv":
+                self._unit_bwd(u, dW, e.get(u.name))
+        self._join()
         if let:
             ops.let_grad_vec(H, self.F1, self.params[:7 * H], self._tmpv, self._accbuf, self._drowbuf, dbqkv, self._qscale,
                              self.grads[:7 * H])

@@ -242,9 +242,9 @@ def transpose(x, out):
 
 
 # ------------------------------------------------------------------ LET vector folds
-def let_fold_vec(H, F1, let_params, ln1w, ln1b, ln2w, ln2b, rawb_qkv, rawb_o, rawb_fc1, mv, q_bias_scale, tmpv):
+def let_fold_vec(H, F1, let_params, ln1w, ln1b, ln2w, ln2b, rawb_qkv, rawb_o, rawb_fc1, mv, q_bias_scale, tmpv, part=0):
     lib().call("oq_let_fold_vec", H, F1, _p(let_params), _p(ln1w), _p(ln1b), _p(ln2w), _p(ln2b), _p(rawb_qkv), _p(rawb_o),
-               _p(rawb_fc1), _p(mv), float(q_bias_scale), _p(tmpv), _stream())
+               _p(rawb_fc1), _p(mv), float(q_bias_scale), _p(tmpv), int(part), _stream())
 
 
 def let_prep_bwd(H, let_params, dbqkv, q_bias_scale, e):
