@@ -607,8 +607,8 @@ def train(eng: BlockEngine, fp_inps, quant_inps, *, epochs: int, fp_inps_2=None,
                         graph = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(graph):
                             eng.train_step(sx, st, st2)
-                    elif graph is not None:
-                        graph.replay()
+                    if graph is not None:
+                        graph.replay()                # (capturing does not execute: the captured step runs here)
                     else:
                         eng.train_step(sx, st, st2)
                     loss = eng.loss_slot

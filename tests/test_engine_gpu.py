@@ -193,3 +193,26 @@ def test_engine_vs_oracle_16bit_emulation(family, wbits, abits, group):
     print("  fp_out rel", e_fp, "quant_out rel", e_q)
     assert e_fp < 5e-3
     assert not bad, bad
+
+
+def test_cuda_graph_step_equals_eager():
+    """The CUDA-graph replay of the optimiser step (engine.train(use_graph=True)) must run exactly as many steps
+    and land on the same parameters as eager stepping (atomics make the last bits differ)."""
+    from omniquant_b200.engine import BlockEngine, QuantConfig, fp_pass, train
+    H, F_, heads, T, n = 256, 512, 2, 128, 8
+    W, x, act = _synthetic_block("llama", H, F_, heads, T, n)
+    q = QuantConfig(wbits=4, abits=16, group_size=64, lwc=True, let=True, recip_div=True)
+    res = []
+    for use_graph in (False, True):
+        eng = BlockEngine("llama", W, n_heads=heads, seq_len=T, qcfg=q, eps=1e-6,
+                          let_init={"qkv_s": act["qkv"], "out_s": act["out"], "fc1_s": act["fc1"]})
+        xb = x.cuda().to(torch.bfloat16)
+        fp, qi = xb.clone(), xb.clone()
+        fp_pass(eng, fp)
+        losses, _ = train(eng, fp, qi, epochs=2, use_graph=use_graph)
+        torch.cuda.synchronize()
+        res.append((losses.cpu(), eng.params.clone().cpu(), int(eng.step_dev.item())))
+    assert res[0][2] == res[1][2] == 16
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=2e-3, atol=0)
+    # AdamW amplifies the last-bit noise of the atomic reductions on near-zero gradients: compare on average
+    assert float((res[0][1] - res[1][1]).abs().mean()) < 5e-4
