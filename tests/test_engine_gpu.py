@@ -213,6 +213,6 @@ def test_cuda_graph_step_equals_eager():
         torch.cuda.synchronize()
         res.append((losses.cpu(), eng.params.clone().cpu(), int(eng.step_dev.item())))
     assert res[0][2] == res[1][2] == 16
-    torch.testing.assert_close(res[0][0], res[1][0], rtol=2e-3, atol=0)
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=1e-2, atol=0)
     # AdamW amplifies the last-bit noise of the atomic reductions on near-zero gradients: compare on average
     assert float((res[0][1] - res[1][1]).abs().mean()) < 5e-4
