@@ -191,6 +191,7 @@ def run_ours(a):
 
     # ---- roofline of the dominant kernel (gemm_kernel<256>: the QuantLinear fwd/dgrad/wgrad GEMMs), timed live
     eng = new_engine()
+    eng.overlap = False      # time the GEMM launches alone on the stream (no quantiser kernels co-running beside them)
     xs, ts = x_dev[0], x_dev[1 % n_local]
     for _ in range(2):
         eng.train_step(xs, ts)
@@ -216,6 +217,7 @@ def run_ours(a):
                 "traffic_note": "mean DRAM read+write bytes per QuantLinear launch, ncu --set full (profiles/r1_gemm_ncu_full_summary.csv); "
                                 "algorithmic operand+result bytes per launch average 1.7e8",
                 "peak_source": f"bf16_tflops_sustained, {which}", "launches_timed": len(lin),
+                "timing": "CUDA events around each launch on the launching stream, 3 eager optimiser steps after the timed region, side-stream overlap off",
                 "avg_launch_ms": round(lin_ms / max(len(lin), 1), 4),
                 "attention_gemm_tflops": round(sum(f for _, f in att) / (sum(t for t, _ in att) * 1e-3) / 1e12, 1) if att else None}
     # whole-step tensor utilisation: algorithmic flops of one step (causal attention) / step time

@@ -17,6 +17,7 @@ Data layout in HBM (M = batch*T token rows, bf16 activations, fp32 masters):
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -164,7 +165,7 @@ class BlockEngine:
         self._drowbuf = z(3 * H)
         self._drow = {k: self._drowbuf[i * H:(i + 1) * H] for i, k in enumerate(("q", "k", "v"))}
         self._qscale = self.d ** -0.5 if family == "opt" else 1.0
-        self.overlap = overlap and self.dev.type == "cuda"
+        self.overlap = overlap and self.dev.type == "cuda" and os.environ.get("OQ_OVERLAP", "1") != "0"
         self.side = torch.cuda.Stream(device=self.dev) if self.overlap else None
         self._pending = False
 
