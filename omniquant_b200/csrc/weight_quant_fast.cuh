@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(256) wq_pc_bwd(WqArgs a) {
     const float rmul = rop == 1 ? rs : (rop == 2 ? 1.0f / rs : 1.0f);
     const float tie_tol_max = 2.4e-7f * fabsf(xmax), tie_tol_min = 2.4e-7f * fabsf(xmin);
     const bool tie_all = !(lwc && xmax > 0.0f && xmin < 0.0f) || a.symmetric;
+    const float qmid = 0.5f * q.qmax, qhalf_m1 = 0.5f * q.qmax - 1.0f;   // |t - Q/2| >= Q/2 - 1  <=>  t <= 1 or t >= Q-1
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int idx = tid + i * 256;
@@ -232,11 +233,11 @@ __global__ void __launch_bounds__(256) wq_pc_bwd(WqArgs a) {
           const float f = w1 * rmul;          // (W*col) {*,/} row with the division as a reciprocal multiply
           const float qa = f * inv;
           const float t = rintf(qa) + q.zp;
-          const bool inr = (t >= 0.0f) && (t <= q.qmax);
-          const float c = oq_clampf(t, 0.0f, q.qmax);
+          const float c = fminf(fmaxf(t, 0.0f), q.qmax);      // (NaN rows are not representable here; the forward owns them)
+          const bool inr = (c == t);
           const float gk = f4(g[i], j);
           acc[0] += gk * ((c - q.zp) - (inr ? qa : 0.0f));
-          if (tie_all || t >= q.qmax - 1.0f || t <= 1.0f) {   // with an LWC clip (sigmoid < 1) the extrema land on the outermost codes (+-1 from the double rounding of scale and zero point)
+          if (tie_all || fabsf(t - qmid) >= qhalf_m1) {   // with an LWC clip (sigmoid < 1) the extrema land on the outermost codes (+-1 from the double rounding of scale and zero point)
             const bool ismax = fabsf(f - xmax) <= tie_tol_max, ismin = fabsf(f - xmin) <= tie_tol_min;
             if (ismax) { acc[1] += 1.0f; acc[4] += w1; }
             if (ismin) { acc[2] += 1.0f; acc[5] += w1; }

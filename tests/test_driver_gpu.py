@@ -39,3 +39,23 @@ def test_main_synthetic(tmp_path, net, flags):
             assert all(len(torch.unique(r)) <= 16 for r in w.reshape(-1, g)[:8])      # 4-bit levels per row / group
     for v in ck[1].values():
         assert torch.isfinite(v.float()).all()
+
+
+def test_resume_reproduces_quantised_weights(tmp_path):
+    """--resume with --epochs 0 (the reference's way of re-applying saved LWC/LET parameters, quantize/omniquant.py:
+    150-153,199-200): loading omni_parameters.pth and folding/quantising without training reproduces the weights
+    of the run that produced the checkpoint."""
+    from omniquant_b200.main import main
+    from omniquant_b200.quantize.int_linear import QuantLinear
+    common = ["--model", "llama-tiny", "--synthetic", "--nsamples", "4", "--seqlen", "128", "--wbits", "4", "--abits", "4",
+              "--lwc", "--let", "--cache_dir", str(tmp_path / "cache")]
+    out1, out2 = str(tmp_path / "a"), str(tmp_path / "b")
+    m1 = main(common + ["--epochs", "2", "--output_dir", out1])
+    m2 = main(common + ["--epochs", "0", "--output_dir", out2, "--resume", os.path.join(out1, "omni_parameters.pth")])
+    for l1, l2 in zip(m1.model.layers, m2.model.layers):
+        w1 = {n: m.weight for n, m in l1.named_modules() if isinstance(m, QuantLinear)}
+        w2 = {n: m.weight for n, m in l2.named_modules() if isinstance(m, QuantLinear)}
+        assert w1.keys() == w2.keys() and len(w1) == 7
+        for n in w1:
+            assert torch.equal(w1[n], w2[n]), n
+        assert torch.equal(l1.input_layernorm.weight, l2.input_layernorm.weight)
