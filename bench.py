@@ -132,10 +132,12 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line (rank 0): everything libraries print (NCCL's version banner ...) goes to stderr
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
     assert NSAMPLES % world == 0
@@ -156,7 +158,7 @@ def run_ours(a):
 
     def one_block(eng):
         fp, qi = x_dev.clone(), x_dev.clone()
-        return calibrate_block(eng, fp, qi, epochs=EPOCHS, allreduce=allreduce, use_graph=(world == 1))
+        return calibrate_block(eng, fp, qi, epochs=EPOCHS, allreduce=allreduce, use_graph=True)
 
     def sync():
         torch.cuda.synchronize()
@@ -246,9 +248,10 @@ def run_ours(a):
                           "l2": "working set per optimiser step (weights 1.2 GB fp32 + activations) exceeds the 126 MB L2"},
                "optimizer_step_ms_eager_instrumented": round(step_ms_eager, 3), "launches_per_optimizer_step": launches_per_step,
                "loss_mean": loss_mean, "loss_first_epoch": loss_first_epoch, "loss_last_epoch": loss_last_epoch, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-               "gpu_launches": int(launches_eager + (a.steps * max(steps_per_block - 3, 0) * launches_per_step if world == 1 else 0)),
+               "gpu_launches": int(launches_eager + a.steps * max(steps_per_block - 3, 0) * launches_per_step),
                "clocks": clocks}
-        print(json.dumps(out), flush=True)
+        json_out.write(json.dumps(out) + "\n")
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
@@ -316,7 +319,7 @@ def run_e2e(a, W, x_host, dev, world, rank):
     args = SimpleNamespace(net="llama-7b", nsamples=x_host.shape[0] * world, batch_size=world, epochs=EPOCHS, let=True,
                            lwc=True, aug_loss=False, alpha=0.5, let_lr=5e-3, lwc_lr=1e-2, wd=0.0, wbits=WBITS, abits=ABITS,
                            group_size=None, symmetric=False, w_dynamic_method="per_channel", a_dynamic_method="per_token",
-                           resume=None, real_quant=False, output_dir=None, cuda_graph=(world == 1))
+                           resume=None, real_quant=False, output_dir=None, cuda_graph=True)
     quant_param_dicts(args)
 
     # omniquant() shards `inps` by rank itself and only touches this rank's rows: hand it a pinned host view of the

@@ -584,7 +584,8 @@ def train(eng: BlockEngine, fp_inps, quant_inps, *, epochs: int, fp_inps_2=None,
     grads0 = None
     k = 0
     graph = None
-    if use_graph and steps > 3 and allreduce is None:
+    graph_ok = use_graph and steps > 3 and (allreduce is None or os.environ.get("OQ_GRAPH_NCCL", "1") == "1")
+    if graph_ok:
         sx = torch.empty(b * T, H, device=eng.dev, dtype=BF16)
         st = torch.empty_like(sx)
         st2 = torch.empty_like(sx) if fp_inps_2 is not None else None
@@ -599,7 +600,7 @@ def train(eng: BlockEngine, fp_inps, quant_inps, *, epochs: int, fp_inps_2=None,
                     out = eng.forward(x, eng.tmp, act_quant=True)
                     eng.backward(eng.loss_and_grad(out, tgt, tgt2))
                     grads0 = eng.grads.clone()
-                if use_graph and steps > 3 and allreduce is None:
+                if graph_ok:
                     sx.copy_(x)
                     st.copy_(tgt)
                     if st2 is not None:
@@ -607,11 +608,11 @@ def train(eng: BlockEngine, fp_inps, quant_inps, *, epochs: int, fp_inps_2=None,
                     if graph is None and k >= 2:      # two eager steps warm every buffer, then capture
                         graph = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(graph):
-                            eng.train_step(sx, st, st2)
+                            eng.train_step(sx, st, st2, allreduce=allreduce)   # NCCL all-reduce is captured with the step
                     if graph is not None:
                         graph.replay()                # (capturing does not execute: the captured step runs here)
                     else:
-                        eng.train_step(sx, st, st2)
+                        eng.train_step(sx, st, st2, allreduce=allreduce)
                     loss = eng.loss_slot
                 else:
                     loss = eng.train_step(x, tgt, tgt2, allreduce=allreduce)
