@@ -97,12 +97,15 @@ int oq_norm_bwd(const void* x, long rows, int C, long ldx, const float* w, int k
  *   b_mn=0: B[n,k] at B + b*strideB + n*ldb + k     b_mn=1: B[n,k] at B + b*strideB + k*ldb + n
  * c_dtype: 0 bf16, 1 fp32, 2 fp16 (the attention scores, as the reference's fp16 autocast stores them).  causal: 0 none; 1 skip output tiles strictly above the diagonal (QK^T, dP);
  * 2 reduce only k < m0+128 (P.V, dS.K); 3 reduce only k >= m0 (P^T.dO, dS^T.Q).  tile_n 0 = auto.
+ * batch > 1 with strideA (strideB) == 0: that operand is shared by every batch entry (grouped-query attention:
+ * one K/V head serves several Q heads, models/int_llama_layer.py:138-139 repeat_kv).  accumulate (fp32 C only):
+ * C += result (sums the K/V gradients over the Q heads of a group).
  * Replaces F.linear in QuantLinear.forward (quantize/int_linear.py:62) + its autograd dgrad/wgrad, and
  * torch.matmul/bmm in QuantMatMul.forward (quantize/int_matmul.py:41-43). */
 int oq_gemm_bf16(const void* A, int a_mn, long lda, long strideA, const void* B, int b_mn, long ldb, long strideB,
                  void* C, int c_dtype, long ldc, long strideC, int M, int N, int K, int batch, const float* bias,
-                 const void* residual, long ldr, long strideR, float alpha, int causal, int tile_n, int max_ctas,
-                 oq_stream_t stream);
+                 const void* residual, long ldr, long strideR, float alpha, int causal, int accumulate, int tile_n,
+                 int max_ctas, oq_stream_t stream);
 
 /* ---- elementwise / reductions ----------------------------------------------
  * SwiGLU of QuantLlamaMLP.forward (models/int_llama_layer.py:44-45): gu = [gate | up] [rows, 2F]. */

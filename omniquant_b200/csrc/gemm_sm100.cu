@@ -42,6 +42,8 @@ struct GemmParams {
   long ldr, strideR;
   float alpha;
   int num_m, num_n;
+  int a_bcast, b_bcast;  // operand shared by all batch entries (GQA: one K/V head serves several Q heads)
+  int accumulate;        // fp32 output only: C += result
   int causal;  // 0 none; 1 skip tiles with n0 > m0+BM-1; 2 k < m0+BM; 3 k >= m0 (rounded to BK)
 };
 
@@ -209,16 +211,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_expect_tx(&full[stage], C::STAGE_BYTES);
           const int k0 = kb * BK;
           if (!p.a_mn) {
-            tma_load_3d(sa, &tmA, &full[stage], k0, m0, b);
+            tma_load_3d(sa, &tmA, &full[stage], k0, m0, p.a_bcast ? 0 : b);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_3d(sa + j * (64 * BK * 2), &tmA, &full[stage], m0 + 64 * j, k0, b);
+            for (int j = 0; j < BM / 64; ++j) tma_load_3d(sa + j * (64 * BK * 2), &tmA, &full[stage], m0 + 64 * j, k0, p.a_bcast ? 0 : b);
           }
           if (!p.b_mn) {
-            tma_load_3d(sb, &tmB, &full[stage], k0, n0, b);
+            tma_load_3d(sb, &tmB, &full[stage], k0, n0, p.b_bcast ? 0 : b);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * (64 * BK * 2), &tmB, &full[stage], n0 + 64 * j, k0, b);
+            for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * (64 * BK * 2), &tmB, &full[stage], n0 + 64 * j, k0, p.b_bcast ? 0 : b);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -315,6 +317,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (p.c_dtype == 1) {
             float* cr = reinterpret_cast<float*>(p.C) + (long)b * p.strideC + (long)row * p.ldc + nc;
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < valid) v[j] += cr[j];
+            }
             if (valid == 32 && vec_ok) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -433,7 +440,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int max_c
 extern "C" int oq_gemm_bf16(const void* A, int a_mn, long lda, long strideA, const void* B, int b_mn, long ldb,
                             long strideB, void* C, int c_dtype, long ldc, long strideC, int M, int N, int K, int batch,
                             const float* bias, const void* residual, long ldr, long strideR, float alpha, int causal,
-                            int tile_n, int max_ctas, cudaStream_t stream) {
+                            int accumulate, int tile_n, int max_ctas, cudaStream_t stream) {
   OQ_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "oq_gemm_bf16: null pointer or bad shape M=%d N=%d K=%d batch=%d",
              M, N, K, batch);
   OQ_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && strideA % 8 == 0 && strideB % 8 == 0,
@@ -452,11 +459,16 @@ extern "C" int oq_gemm_bf16(const void* A, int a_mn, long lda, long strideA, con
   p.M = M; p.N = N; p.K = K; p.batch = batch; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
   p.C = C; p.c_dtype = c_dtype; p.ldc = ldc; p.strideC = strideC; p.bias = bias; p.res = (const bf16*)residual;
   p.ldr = ldr; p.strideR = strideR; p.alpha = alpha; p.causal = causal;
+  OQ_REQUIRE(!accumulate || c_dtype == 1, "oq_gemm_bf16: accumulate needs an fp32 output");
+  p.accumulate = accumulate ? 1 : 0;
+  p.a_bcast = (batch > 1 && strideA == 0) ? 1 : 0;   // stride 0 = the operand is shared by every batch entry
+  p.b_bcast = (batch > 1 && strideB == 0) ? 1 : 0;
+  const int batchA = p.a_bcast ? 1 : batch, batchB = p.b_bcast ? 1 : batch;
   CUtensorMap ta, tb;
   // K-major: inner = K, rows = M|N, box rows = BM|BN.   MN-major: inner = M|N, rows = K, box = 64 x 64.
-  if (!p.a_mn) { if (make_map(&ta, A, K, M, batch, lda, strideA, BM)) return -1; }
-  else         { if (make_map(&ta, A, M, K, batch, lda, strideA, BK)) return -1; }
-  if (!p.b_mn) { if (make_map(&tb, B, K, N, batch, ldb, strideB, tile_n)) return -1; }
-  else         { if (make_map(&tb, B, N, K, batch, ldb, strideB, BK)) return -1; }
+  if (!p.a_mn) { if (make_map(&ta, A, K, M, batchA, lda, strideA, BM)) return -1; }
+  else         { if (make_map(&ta, A, M, K, batchA, lda, strideA, BK)) return -1; }
+  if (!p.b_mn) { if (make_map(&tb, B, K, N, batchB, ldb, strideB, tile_n)) return -1; }
+  else         { if (make_map(&tb, B, N, K, batchB, ldb, strideB, BK)) return -1; }
   return tile_n == 256 ? launch<256>(ta, tb, p, max_ctas, stream) : launch<128>(ta, tb, p, max_ctas, stream);
 }

@@ -60,7 +60,7 @@ class BlockEngine:
     def __init__(self, family: str, weights: Dict[str, torch.Tensor], *, n_heads: int, seq_len: int, qcfg: QuantConfig,
                  eps: float, device="cuda", batch: int = 1, let_init: Optional[Dict[str, torch.Tensor]] = None,
                  let_lr=5e-3, lwc_lr=1e-2, wd=0.0, world_size=1, causal=True, mask: Optional[torch.Tensor] = None,
-                 overlap: bool = True):
+                 overlap: bool = True, n_kv_heads: Optional[int] = None):
         assert family in ("llama", "opt")
         self.family, self.q, self.eps, self.dev = family, qcfg, float(eps), torch.device(device)
         self.h, self.T, self.b = n_heads, seq_len, batch
@@ -70,6 +70,17 @@ class BlockEngine:
         f = lambda t: t.detach().to(self.dev, F32).contiguous()
         H = weights["q"].shape[1]
         self.H, self.d = H, H // n_heads
+        # grouped-query attention (Llama-2-70B): n_kv_heads K/V heads, each shared by `rep` Q heads (repeat_kv,
+        # models/int_llama_layer.py:138-139); the k / v projections are then [Hkv, H] with Hkv = n_kv_heads * d
+        self.hkv = n_kv_heads or n_heads
+        assert n_heads % self.hkv == 0
+        self.rep = n_heads // self.hkv
+        self.Hkv = self.hkv * self.d
+        self.QW = H + 2 * self.Hkv
+        if self.rep > 1 and (qcfg.let or family != "llama"):
+            raise NotImplementedError("grouped-query attention is supported for LLaMA blocks without LET (the reference's "
+                                      "smooth_q_k / smooth_fc_fc do not support it either)")
+        assert weights["k"].shape[0] == self.Hkv and weights["v"].shape[0] == self.Hkv
         self.M = batch * seq_len
         glu = family == "llama"
         self.glu = glu
@@ -100,8 +111,8 @@ class BlockEngine:
         let = qcfg.let
         U = [
             _Unit("q", "qkv", 0, H, H, "qkv_s", "qkt_s", 2, "qkv_d"),
-            _Unit("k", "qkv", H, 2 * H, H, "qkv_s", "qkt_s", 1, "qkv_d"),
-            _Unit("v", "qkv", 2 * H, 3 * H, H, "qkv_s", "out_s", 2, "qkv_d"),
+            _Unit("k", "qkv", H, H + self.Hkv, H, "qkv_s", "qkt_s", 1, "qkv_d"),
+            _Unit("v", "qkv", H + self.Hkv, self.QW, H, "qkv_s", "out_s", 2, "qkv_d"),
             _Unit("o", "o", 0, H, H, "out_s", None, 0, "out_d"),
             _Unit("fc1", "fc1", 0, self.W["fc1"].shape[0], H, "fc1_s", None, 0, "fc1_d"),
             _Unit("fc2", "fc2", 0, H, F_, None, None, 0, None),
@@ -297,35 +308,37 @@ class BlockEngine:
         self.st1 = (B("mean1", (M,), F32), B("rstd1", (M,), F32))
         ops.norm_fwd(x, ws["ln1w"], ws["ln1b"], self.eps, self.norm_kind, a1, *self.st1)
         a1q = self._aq(a1, "a1q")
-        qkv = B("qkv", (M, 3 * H))
+        QW, Hkv, hkv, rep = self.QW, self.Hkv, self.hkv, self.rep
+        ok, ov = H, H + Hkv                     # column offsets of k and v in the [M, QW] qkv buffers
+        qkv = B("qkv", (M, QW))
         W = ws["W"]
         if self.family == "llama":
             ops.linear_fwd(a1q, W["qkv"], qkv, bias=ws["bqkv"])
         else:
             sc = d ** -0.5
-            ops.gemm(a1q, W["qkv"], qkv, M=M, N=H, K=H, lda=H, ldb=H, ldc=3 * H, bias=ws["bq_scaled"], alpha=sc)
-            ops.gemm(a1q, W["qkv"][H:], qkv[:, H:], M=M, N=2 * H, K=H, lda=H, ldb=H, ldc=3 * H,
+            ops.gemm(a1q, W["qkv"], qkv, M=M, N=H, K=H, lda=H, ldb=H, ldc=QW, bias=ws["bq_scaled"], alpha=sc)
+            ops.gemm(a1q, W["qkv"][H:], qkv[:, H:], M=M, N=2 * H, K=H, lda=H, ldb=H, ldc=QW,
                      bias=None if ws["bqkv"] is None else ws["bqkv"][H:])
         # ---- Q/K/V operands of QuantMatMul
         abits = self.q.abits if self._act_quant else 16
+        parts = ((0, H, h), (ok, ov, hkv), (ov, QW, hkv))     # (column range, heads) of q, k, v
         if self.family == "llama":
-            qkvq = B("qkvq", (M, 3 * H))
+            qkvq = B("qkvq", (M, QW))
             cos, sin = self.rope()
-            for i in range(2):      # rotary + per-(token, head) quant of q and k (int_llama_layer.py:124-125,141-142)
-                ops.act_quant_fwd(qkv[:, i * H:(i + 1) * H].view(M, h, d), qkvq[:, i * H:(i + 1) * H].view(M, h, d),
-                                  n_bits=abits, recip_div=self.q.recip_div, cos=cos, sin=sin, seq_len=T)
-            if abits < 16:          # v quantised per (token, head) (:162)
-                ops.act_quant_fwd(qkv[:, 2 * H:].view(M, h, d), qkvq[:, 2 * H:].view(M, h, d), n_bits=abits,
+            for c0, c1, nh in parts[:2]:   # rotary + per-(token, head) quant of q and k (int_llama_layer.py:124-125,141-142)
+                ops.act_quant_fwd(qkv[:, c0:c1].view(M, nh, d), qkvq[:, c0:c1].view(M, nh, d), n_bits=abits,
+                                  recip_div=self.q.recip_div, cos=cos, sin=sin, seq_len=T)
+            if abits < 16:                 # v quantised per (token, head) (:162)
+                ops.act_quant_fwd(qkv[:, ov:].view(M, hkv, d), qkvq[:, ov:].view(M, hkv, d), n_bits=abits,
                                   recip_div=self.q.recip_div)
             else:
-                qkvq[:, 2 * H:].copy_(qkv[:, 2 * H:])
+                qkvq[:, ov:].copy_(qkv[:, ov:])
             alpha = 1.0 / math.sqrt(d)
         else:
             if abits < 16:          # per token over the full hidden dim, before the head split (int_opt_layer.py:97,125,129)
-                qkvq = B("qkvq", (M, 3 * H))
-                for i in range(3):
-                    ops.act_quant_fwd(qkv[:, i * H:(i + 1) * H], qkvq[:, i * H:(i + 1) * H], n_bits=abits,
-                                      recip_div=self.q.recip_div)
+                qkvq = B("qkvq", (M, QW))
+                for c0, c1, _ in parts:
+                    ops.act_quant_fwd(qkv[:, c0:c1], qkvq[:, c0:c1], n_bits=abits, recip_div=self.q.recip_div)
             else:
                 qkvq = qkv
             alpha = 1.0
@@ -334,13 +347,19 @@ class BlockEngine:
         S = B("S", (h, T, T), torch.float16)     # scores in fp16 like the reference's autocast (int_llama_layer.py:143)
         O = B("O", (M, H))
         cz = 1 if self.causal else 0
+        # one launch over all heads, or (GQA) one per K/V head with that head shared by its `rep` query heads
+        groups = [(0, h, d)] if rep == 1 else [(g * rep, rep, 0) for g in range(hkv)]
         for s in range(nb):
             r = slice(s * T, (s + 1) * T)
-            ops.gemm(qkvq[r, :H], qkvq[r, H:2 * H], S, M=T, N=T, K=d, lda=3 * H, ldb=3 * H, ldc=T, batch=h, strideA=d,
-                     strideB=d, strideC=T * T, alpha=alpha, causal=cz)
+            for h0, nh, sb in groups:
+                kv0 = (h0 // rep) * d
+                ops.gemm(qkvq[r, h0 * d:], qkvq[r, ok + kv0:], S[h0:], M=T, N=T, K=d, lda=QW, ldb=QW, ldc=T, batch=nh,
+                         strideA=d, strideB=sb, strideC=T * T, alpha=alpha, causal=cz)
             ops.softmax_fwd(S, P[s], mask=self.mask, causal=self.causal)
-            ops.gemm(P[s], qkvq[r, 2 * H:], O[r], M=T, N=d, K=T, lda=T, ldb=3 * H, b_mn=True, ldc=H, batch=h,
-                     strideA=T * T, strideB=d, strideC=d, causal=2 * cz)
+            for h0, nh, sb in groups:
+                kv0 = (h0 // rep) * d
+                ops.gemm(P[s, h0:], qkvq[r, ov + kv0:], O[r, h0 * d:], M=T, N=d, K=T, lda=T, ldb=QW, b_mn=True, ldc=H,
+                         batch=nh, strideA=T * T, strideB=sb, strideC=d, causal=2 * cz)
         Oq = self._aq(O, "Oq")
         h1 = B("h1", (M, H))
         self._join()                # o / fc1 / fc2 operands of this step come from the side stream
@@ -417,40 +436,60 @@ class BlockEngine:
         dO = self._aq_bwd(sv["O"], dOq, "dO")
         # attention
         qkv, qkvq, alpha = self.qkv, self.qkvq, self.att_alpha
-        dqkvq = B("dqkvq", (M, 3 * H))
+        QW, Hkv, hkv, rep = self.QW, self.Hkv, self.hkv, self.rep
+        ok, ov = H, H + Hkv
+        dqkvq = B("dqkvq", (M, QW))
         dP = B("S", (h, T, T), torch.float16).view(BF16)   # same scratch storage as the scores
         cz = 1 if self.causal else 0
+        groups = [(0, h, d)] if rep == 1 else [(g * rep, rep, 0) for g in range(hkv)]
+        dkv32 = B("dkv32", (T, 2 * Hkv), F32) if rep > 1 else None     # K/V gradients summed over the group's Q heads
         for s in range(nb):
             r = slice(s * T, (s + 1) * T)
             P = sv["P"][s]
-            ops.gemm(dO[r], qkvq[r, 2 * H:], dP, M=T, N=T, K=d, lda=H, ldb=3 * H, ldc=T, batch=h, strideA=d, strideB=d,
-                     strideC=T * T, causal=cz)
-            ops.gemm(P, dO[r], dqkvq[r, 2 * H:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=H, ldc=3 * H, batch=h,
-                     strideA=T * T, strideB=d, strideC=d, causal=3 * cz)
-            ops.softmax_bwd(P, dP, P, causal=self.causal)      # dS overwrites P
-            ops.gemm(P, qkvq[r, H:2 * H], dqkvq[r, :H], M=T, N=d, K=T, lda=T, b_mn=True, ldb=3 * H, ldc=3 * H, batch=h,
-                     strideA=T * T, strideB=d, strideC=d, alpha=alpha, causal=2 * cz)
-            ops.gemm(P, qkvq[r, :H], dqkvq[r, H:2 * H], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=3 * H,
-                     ldc=3 * H, batch=h, strideA=T * T, strideB=d, strideC=d, alpha=alpha, causal=3 * cz)
-        abits = q.abits if self._act_quant else 16
-        if self.family == "llama":
-            dqkv = B("dqkv", (M, 3 * H))
-            cos, sin = self.rope()
-            for i in range(2):
-                ops.act_quant_bwd(qkv[:, i * H:(i + 1) * H].view(M, h, d), dqkvq[:, i * H:(i + 1) * H].view(M, h, d),
-                                  dqkv[:, i * H:(i + 1) * H].view(M, h, d), n_bits=abits, recip_div=q.recip_div, cos=cos,
-                                  sin=sin, seq_len=T)
-            if abits < 16:
-                ops.act_quant_bwd(qkv[:, 2 * H:].view(M, h, d), dqkvq[:, 2 * H:].view(M, h, d),
-                                  dqkv[:, 2 * H:].view(M, h, d), n_bits=abits, recip_div=q.recip_div)
+            for h0, nh, sb in groups:
+                kv0 = (h0 // rep) * d
+                ops.gemm(dO[r, h0 * d:], qkvq[r, ov + kv0:], dP[h0:], M=T, N=T, K=d, lda=H, ldb=QW, ldc=T, batch=nh,
+                         strideA=d, strideB=sb, strideC=T * T, causal=cz)
+            if rep == 1:
+                ops.gemm(P, dO[r], dqkvq[r, ov:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=H, ldc=QW, batch=h,
+                         strideA=T * T, strideB=d, strideC=d, causal=3 * cz)
             else:
-                dqkv[:, 2 * H:].copy_(dqkvq[:, 2 * H:])
+                for hh in range(h):     # dV_g = sum over the group's heads of P_h^T dO_h
+                    kv0 = (hh // rep) * d
+                    ops.gemm(P[hh], dO[r, hh * d:], dkv32[:, Hkv + kv0:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True,
+                             ldb=H, ldc=2 * Hkv, causal=3 * cz, accumulate=(hh % rep != 0))
+            ops.softmax_bwd(P, dP, P, causal=self.causal)      # dS overwrites P
+            for h0, nh, sb in groups:
+                kv0 = (h0 // rep) * d
+                ops.gemm(P[h0:], qkvq[r, ok + kv0:], dqkvq[r, h0 * d:], M=T, N=d, K=T, lda=T, b_mn=True, ldb=QW, ldc=QW,
+                         batch=nh, strideA=T * T, strideB=sb, strideC=d, alpha=alpha, causal=2 * cz)
+            if rep == 1:
+                ops.gemm(P, qkvq[r, :H], dqkvq[r, ok:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=QW, ldc=QW,
+                         batch=h, strideA=T * T, strideB=d, strideC=d, alpha=alpha, causal=3 * cz)
+            else:
+                for hh in range(h):     # dK_g = sum over the group's heads of dS_h^T Q_h
+                    kv0 = (hh // rep) * d
+                    ops.gemm(P[hh], qkvq[r, hh * d:], dkv32[:, kv0:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=QW,
+                             ldc=2 * Hkv, alpha=alpha, causal=3 * cz, accumulate=(hh % rep != 0))
+                dqkvq[r, ok:].copy_(dkv32)
+        abits = q.abits if self._act_quant else 16
+        parts = ((0, H, h), (ok, ov, hkv), (ov, QW, hkv))
+        if self.family == "llama":
+            dqkv = B("dqkv", (M, QW))
+            cos, sin = self.rope()
+            for c0, c1, nh in parts[:2]:
+                ops.act_quant_bwd(qkv[:, c0:c1].view(M, nh, d), dqkvq[:, c0:c1].view(M, nh, d), dqkv[:, c0:c1].view(M, nh, d),
+                                  n_bits=abits, recip_div=q.recip_div, cos=cos, sin=sin, seq_len=T)
+            if abits < 16:
+                ops.act_quant_bwd(qkv[:, ov:].view(M, hkv, d), dqkvq[:, ov:].view(M, hkv, d), dqkv[:, ov:].view(M, hkv, d),
+                                  n_bits=abits, recip_div=q.recip_div)
+            else:
+                dqkv[:, ov:].copy_(dqkvq[:, ov:])
         else:
             if abits < 16:
-                dqkv = B("dqkv", (M, 3 * H))
-                for i in range(3):
-                    ops.act_quant_bwd(qkv[:, i * H:(i + 1) * H], dqkvq[:, i * H:(i + 1) * H], dqkv[:, i * H:(i + 1) * H],
-                                      n_bits=abits, recip_div=q.recip_div)
+                dqkv = B("dqkv", (M, QW))
+                for c0, c1, _ in parts:
+                    ops.act_quant_bwd(qkv[:, c0:c1], dqkvq[:, c0:c1], dqkv[:, c0:c1], n_bits=abits, recip_div=q.recip_div)
             else:
                 dqkv = dqkvq
         # qkv projections
@@ -458,15 +497,15 @@ class BlockEngine:
             ops.linear_wgrad(dqkv, sv["a1q"], dW["qkv"])
         else:
             sc = d ** -0.5   # q = sc * (x W^T + b)
-            ops.gemm(dqkv, sv["a1q"], dW["qkv"], M=H, N=H, K=M, a_mn=True, lda=3 * H, b_mn=True, ldb=H, ldc=H, alpha=sc)
-            ops.gemm(dqkv[:, H:], sv["a1q"], dW["qkv"][H:], M=2 * H, N=H, K=M, a_mn=True, lda=3 * H, b_mn=True, ldb=H, ldc=H)
+            ops.gemm(dqkv, sv["a1q"], dW["qkv"], M=H, N=H, K=M, a_mn=True, lda=QW, b_mn=True, ldb=H, ldc=H, alpha=sc)
+            ops.gemm(dqkv[:, H:], sv["a1q"], dW["qkv"][H:], M=2 * H, N=H, K=M, a_mn=True, lda=QW, b_mn=True, ldb=H, ldc=H)
         if let:
             da1q = B("da1q", (M, H))
             if self.family == "llama":
                 ops.linear_dgrad(dqkv, W["qkv"], da1q)
             else:
-                ops.gemm(dqkv[:, H:], W["qkv"][H:], da1q, M=M, N=H, K=2 * H, lda=3 * H, b_mn=True, ldb=H, ldc=H)
-                ops.gemm(dqkv, W["qkv"], da1q, M=M, N=H, K=H, lda=3 * H, b_mn=True, ldb=H, ldc=H, alpha=d ** -0.5,
+                ops.gemm(dqkv[:, H:], W["qkv"][H:], da1q, M=M, N=H, K=2 * H, lda=QW, b_mn=True, ldb=H, ldc=H)
+                ops.gemm(dqkv, W["qkv"], da1q, M=M, N=H, K=H, lda=QW, b_mn=True, ldb=H, ldc=H, alpha=d ** -0.5,
                          residual=da1q, ldr=H)
             da1 = self._aq_bwd(sv["a1"], da1q, "da1")
             ops.norm_bwd(self.x, ws["ln1w"], self.norm_kind, self.st1[0], self.st1[1], da1, dw_acc=self._acc["dw1"],

@@ -52,8 +52,8 @@ class QuantDecoderLayerBase(nn.Module):
     norm_names = ()        # (first norm attr, second norm attr)
 
     # ------------------------------------------------------------------ plumbing
-    def _init_common(self, args, n_heads, eps):
-        self._args, self._n_heads, self._eps = args, n_heads, eps
+    def _init_common(self, args, n_heads, eps, n_kv_heads=None):
+        self._args, self._n_heads, self._eps, self._n_kv_heads = args, n_heads, eps, n_kv_heads
         self._eng = None
         self._final_ws = None
         self.use_weight_quant = False
@@ -96,7 +96,8 @@ class QuantDecoderLayerBase(nn.Module):
             a = self._args
             self._eng = BlockEngine(self.family, self._raw_weights(), n_heads=self._n_heads, seq_len=seq_len, qcfg=q,
                                     eps=self._eps, device=dev, batch=batch, let_lr=getattr(a, "let_lr", 5e-3),
-                                    lwc_lr=getattr(a, "lwc_lr", 1e-2), wd=getattr(a, "wd", 0.0), mask=mask)
+                                    lwc_lr=getattr(a, "lwc_lr", 1e-2), wd=getattr(a, "wd", 0.0), mask=mask,
+                                    n_kv_heads=self._n_kv_heads)
             self._push_params()
         return self._eng
 
@@ -171,7 +172,8 @@ class QuantDecoderLayerBase(nn.Module):
         H = eng.H
         lin = self._linears()
         t = eng.tmp
-        slices = {"q": ("qkv", 0, H), "k": ("qkv", H, 2 * H), "v": ("qkv", 2 * H, 3 * H), "o": ("o", 0, H)}
+        kv = eng.Hkv
+        slices = {"q": ("qkv", 0, H), "k": ("qkv", H, H + kv), "v": ("qkv", H + kv, H + 2 * kv), "o": ("o", 0, H)}
         if self.family == "llama":
             slices.update(gate=("fc1", 0, eng.F), up=("fc1", eng.F, 2 * eng.F), down=("fc2", 0, H))
         else:
@@ -208,7 +210,8 @@ class QuantDecoderLayerBase(nn.Module):
         t = eng.tmp
         fc1 = ["gate", "up"] if self.family == "llama" else ["fc1"]
         fc2 = "down" if self.family == "llama" else "fc2"
-        parts = {"q": ("q", 0, "bqkv", 0), "k": ("k", 0, "bqkv", H), "v": ("v", 0, "bqkv", 2 * H), "o": ("o", 0, "bo", 0),
+        kv = eng.Hkv
+        parts = {"q": ("q", 0, "bqkv", 0), "k": ("k", 0, "bqkv", H), "v": ("v", 0, "bqkv", H + kv), "o": ("o", 0, "bo", 0),
                  fc2: ("fc2", 0, "bfc2", 0)}
         r = 0
         for nme in fc1:

@@ -72,16 +72,14 @@ class QuantLlamaDecoderLayer(QuantDecoderLayerBase):
     def __init__(self, config, ori_layer, args):
         super().__init__()
         self.hidden_size = config.hidden_size
-        if getattr(config, "num_key_value_heads", config.num_attention_heads) != config.num_attention_heads:
-            raise NotImplementedError("grouped-query attention (num_key_value_heads < num_attention_heads) is not wired "
-                                      "into the block engine yet")
         self.self_attn = QuantLlamaAttention(org_module=ori_layer.self_attn, config=config, args=args)
         self.mlp = QuantLlamaMLP(org_module=ori_layer.mlp, hidden_size=self.hidden_size,
                                  intermediate_size=config.intermediate_size, hidden_act=config.hidden_act, args=args)
         eps = getattr(ori_layer.input_layernorm, "variance_epsilon", getattr(config, "rms_norm_eps", 1e-6))
         self.input_layernorm = OmniLlamaRMSNorm(ori_layer.input_layernorm, eps=eps)
         self.post_attention_layernorm = OmniLlamaRMSNorm(ori_layer.post_attention_layernorm, eps=eps)
-        self._init_common(args, config.num_attention_heads, eps)
+        self._init_common(args, config.num_attention_heads, eps,
+                          getattr(config, "num_key_value_heads", config.num_attention_heads))
 
     def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
                 output_attentions=False, use_cache=False, **kwargs):

@@ -130,7 +130,8 @@ def launch_count() -> int:
 
 
 def gemm(A, B, C, *, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=None, batch=1, strideA=0, strideB=0,
-         strideC=0, bias=None, residual=None, ldr=0, strideR=0, alpha=1.0, causal=0, tile_n=0, max_ctas=0):
+         strideC=0, bias=None, residual=None, ldr=0, strideR=0, alpha=1.0, causal=0, tile_n=0, max_ctas=0,
+         accumulate=False):
     """C[b] = alpha * A[b] @ B[b]^T (+bias) (+residual); raw strided form (see the header)."""
     _chk(A, BF16, "A"); _chk(B, BF16, "B"); _chk(bias, F32, "bias"); _chk(residual, BF16, "residual")
     if C.dtype not in _CDT:
@@ -140,7 +141,7 @@ def gemm(A, B, C, *, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=No
         e0.record()
     lib().call("oq_gemm_bf16", _p(A), int(a_mn), lda, strideA, _p(B), int(b_mn), ldb, strideB, _p(C),
                _CDT[C.dtype], ldc, strideC, M, N, K, batch, _p(bias), _p(residual), ldr, strideR, float(alpha),
-               causal, tile_n, max_ctas, _stream())
+               causal, int(accumulate), tile_n, max_ctas, _stream())
     if GEMM_TIMER is not None:
         e1.record()
         GEMM_TIMER.append((e0, e1, 2.0 * M * N * K * batch * (0.5 if causal else 1.0), batch > 1))

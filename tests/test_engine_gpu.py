@@ -216,3 +216,48 @@ def test_cuda_graph_step_equals_eager():
     torch.testing.assert_close(res[0][0], res[1][0], rtol=1e-2, atol=0)
     # AdamW amplifies the last-bit noise of the atomic reductions on near-zero gradients: compare on average
     assert float((res[0][1] - res[1][1]).abs().mean()) < 5e-4
+
+
+def test_grouped_query_attention_lwc():
+    """Llama-2-70B style GQA (8 query heads on 2 K/V heads), weight-only LWC (the reference supports GQA only without
+    LET): engine vs the oracle with 16-bit storage emulation, gradients included."""
+    from omniquant_b200.engine import BlockEngine, QuantConfig, calibrate_block
+    from oracle import oq_oracle as orc
+    H, F_, heads, kvh, T, n = 1024, 1536, 8, 2, 128, 4
+    d = H // heads
+    g = torch.Generator().manual_seed(3)
+    r = lambda *s, sc=0.03: (torch.randn(*s, generator=g) * sc).half().float()
+    W = {"q": r(H, H), "k": r(kvh * d, H), "v": r(kvh * d, H), "o": r(H, H), "gate": r(F_, H), "up": r(F_, H), "down": r(H, F_),
+         "ln1": 1 + r(H, sc=0.1), "ln2": 1 + r(H, sc=0.1)}
+    x = r(n, T, H, sc=1.0)
+    for wbits, abits, group in ((2, 16, 64), (4, 4, 0)):
+        cfg = orc.QCfg(wbits, abits, group or None, False, True, False, emu16=torch.bfloat16)
+        Wc = {k: v.cuda() for k, v in W.items()}
+        P = {k: v.cuda() for k, v in orc.init_lwc({k: W[k] for k in orc.LLAMA_LINEARS}, cfg).items()}
+        P0 = {k: v.clone() for k, v in P.items()}
+        xb = x.cuda().to(torch.bfloat16)
+        ref = orc.calibrate_block("llama", Wc, P, cfg, xb.float(), heads, epochs=1, record_grads=True, n_kv_heads=kvh)
+        eng = BlockEngine("llama", W, n_heads=heads, n_kv_heads=kvh, seq_len=T, eps=1e-6,
+                          qcfg=QuantConfig(wbits=wbits, abits=abits, group_size=group, lwc=True, let=False, recip_div=True))
+        fp, qi = xb.clone(), xb.clone()
+        res = calibrate_block(eng, fp, qi, epochs=1, record_grads=True)
+        torch.cuda.synchronize()
+        losses, rl = res["losses"].cpu().numpy(), np.array(ref["losses"])
+        print("gqa", wbits, abits, group, losses, rl)
+        assert float((fp.float() - ref["fp_out"]).norm() / ref["fp_out"].norm()) < 5e-3
+        assert abs(losses[0] - rl[0]) / rl[0] < 2e-3
+        assert np.abs(losses - rl).max() / rl.mean() < 3e-2
+
+        def to_eng(Pd, k):
+            if k.startswith("fc1."):
+                sfx = k.split(".")[1]
+                return torch.cat([Pd[f"gate.{sfx}"].reshape(-1), Pd[f"up.{sfx}"].reshape(-1)])
+            if k.startswith("fc2."):
+                return Pd[f"down.{k.split('.')[1]}"].reshape(-1)
+            return Pd[k].reshape(-1)
+        gmax = max(float(v.norm()) for v in ref["grads"].values())
+        for k in eng.layout:
+            o, c = eng.layout[k]
+            ours, rr = res["grads0"][o:o + c], to_eng(ref["grads"], k)
+            err = float((ours - rr).norm() / max(float(rr.norm()), 2e-2 * gmax))
+            assert err < 5e-2, (k, err)
