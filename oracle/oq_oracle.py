@@ -442,6 +442,53 @@ def opt_forward(x, T, n_heads, mask, cfg: QCfg, act_quant=True, eps=1e-5):
 
 
 # --------------------------------------------------------------------------
+# Falcon block, new decoder architecture (models/int_falcon_layer.py) -- LWC only (:329-331,:344-346 raise on LET)
+# --------------------------------------------------------------------------
+FALCON_LINEARS = ("qkv", "dense", "fc1", "fc2")
+
+
+def falcon_prepare(Wt, P, cfg: QCfg, quant=True):
+    """smooth_and_quant_temporary, models/int_falcon_layer.py:344-360.  Wt: qkv, dense, fc1, fc2 weights
+    (+ optional '<n>.bias'), ln1/ln1.bias (ln_attn), ln2/ln2.bias (ln_mlp)."""
+    T = dict(ln1w=Wt["ln1"], ln1b=Wt["ln1.bias"], ln2w=Wt["ln2"], ln2b=Wt["ln2.bias"])
+    for n in FALCON_LINEARS:
+        T[f"{n}.w"] = wq(Wt[n], n, P, cfg) if quant else Wt[n]
+        T[f"{n}.b"] = Wt.get(f"{n}.bias")
+    return T
+
+
+def falcon_forward(x, T, n_heads, n_kv, cos, sin, cfg: QCfg, act_quant=True, eps=1e-5):
+    """QuantFalconDecoderLayer.forward with new_decoder_architecture (models/int_falcon_layer.py:261-316) and
+    QuantFalconAttention.forward (:122-180): fused QKV laid out per K/V group as [rep query heads | k | v] (:76-86),
+    rotary on q and k, causal softmax(q k^T / sqrt(d)) v without any Q/K/V quantisation, attention and MLP in
+    parallel on two LayerNorms of the block input, exact (erf) GELU."""
+    b, L, H = x.shape
+    d = H // n_heads
+    rep = n_heads // n_kv
+    S = lambda t: st(t, cfg)
+    lin = lambda t, n, res=None: S(F.linear(S(aq(t, cfg, act_quant)), S(T[f"{n}.w"]), T[f"{n}.b"]) if res is None else
+                                   res + F.linear(S(aq(t, cfg, act_quant)), S(T[f"{n}.w"]), T[f"{n}.b"]))
+    a1 = S(layer_norm(x, T["ln1w"], T["ln1b"], eps))
+    a2 = S(layer_norm(x, T["ln2w"], T["ln2b"], eps))
+    qkv = lin(a1, "qkv").view(b, L, n_kv, rep + 2, d)
+    q = qkv[:, :, :, :-2].reshape(b, L, n_heads, d).transpose(1, 2)
+    k = qkv[:, :, :, -2].transpose(1, 2)                     # [b, n_kv, L, d]
+    v = qkv[:, :, :, -1].transpose(1, 2)
+    q, k = apply_rope(q, k, cos[:L], sin[:L])
+    q, k = S(q), S(k)
+    k = k[:, :, None].expand(b, n_kv, rep, L, d).reshape(b, n_heads, L, d)
+    v = v[:, :, None].expand(b, n_kv, rep, L, d).reshape(b, n_heads, L, d)
+    s = st_scores(torch.matmul(q, k.transpose(2, 3)) / math.sqrt(d), cfg)
+    causal = torch.triu(torch.ones(L, L, dtype=torch.bool, device=x.device), diagonal=1)
+    s = s + torch.zeros_like(s).masked_fill(causal, -1e9)
+    p = S(F.softmax(s, dim=-1))
+    o = S(torch.matmul(p, v).transpose(1, 2).reshape(b, L, H))
+    h1 = lin(o, "dense", x)
+    m = S(F.gelu(lin(a2, "fc1")))
+    return lin(m, "fc2", h1)
+
+
+# --------------------------------------------------------------------------
 # calibration loop  (quantize/omniquant.py:157-250)
 # --------------------------------------------------------------------------
 def calibrate_block(family: str, Wt, P, cfg: QCfg, inps, n_heads, *, epochs, batch_size=1,
@@ -461,6 +508,12 @@ def calibrate_block(family: str, Wt, P, cfg: QCfg, inps, n_heads, *, epochs, bat
         eps = 1e-6 if eps is None else eps
         prep = llama_prepare
         fwd = lambda x, T, aqf: llama_forward(x, T, n_heads, cos, sin, mask, cfg, aqf, eps, n_kv_heads)
+    elif family == "falcon":
+        cos, sin = rope_tables(d, L)
+        cos, sin = cos.to(dev), sin.to(dev)
+        eps = 1e-5 if eps is None else eps
+        prep = falcon_prepare
+        fwd = lambda x, T, aqf: falcon_forward(x, T, n_heads, n_kv_heads or n_heads, cos, sin, cfg, aqf, eps)
     else:
         eps = 1e-5 if eps is None else eps
         prep = opt_prepare

@@ -34,9 +34,11 @@ from quantize.quantizer import UniformAffineQuantizer  # noqa: E402
 from quantize.int_linear import QuantLinear  # noqa: E402
 import models.int_llama_layer as L  # noqa: E402
 import models.int_opt_layer as O  # noqa: E402
+import models.int_falcon_layer as FA  # noqa: E402
 from transformers import LlamaConfig, OPTConfig  # noqa: E402
 from transformers.models.llama.modeling_llama import LlamaDecoderLayer, rotate_half  # noqa: E402
 from transformers.models.opt.modeling_opt import OPTDecoderLayer  # noqa: E402
+from transformers.models.falcon.modeling_falcon import FalconConfig, FalconDecoderLayer  # noqa: E402
 
 
 def f16r(t):
@@ -350,6 +352,83 @@ def opt_block(tag, H, F_, heads, T, nsamples, args, epochs, batch_size=1, seed=0
     _dump(os.path.join(OUT, f"opt_{tag}.npz"), inputs, res, qlayer, lin)
 
 
+class LegacyFalconRotary(torch.nn.Module):
+    """transformers-4.31 style FalconRotaryEmbedding the reference calls as maybe_rotary(q, k, past_len)
+    (models/int_falcon_layer.py:52,148): q,k [batch*heads, T, d]."""
+
+    def __init__(self, dim, base=10000):
+        super().__init__()
+        self.register_buffer("inv_freq", 1.0 / (base ** (torch.arange(0, dim, 2).float() / dim)), persistent=False)
+
+    def forward(self, q, k, past_len=0):
+        T = q.shape[1]
+        t = torch.arange(past_len, past_len + T).float()
+        emb = torch.cat((torch.outer(t, self.inv_freq),) * 2, dim=-1)
+        cos, sin = emb.cos()[None], emb.sin()[None]
+        return q * cos + rotate_half(q) * sin, k * cos + rotate_half(k) * sin
+
+
+def falcon_block(tag, H, heads, kvh, T, nsamples, args, epochs, seed=0):
+    torch.manual_seed(seed)
+    cfg = FalconConfig(hidden_size=H, num_attention_heads=heads, num_kv_heads=kvh, num_hidden_layers=1, vocab_size=64,
+                       new_decoder_architecture=True, bias=False, parallel_attn=True, hidden_dropout=0.0, attention_dropout=0.0)
+    cfg._attn_implementation = "eager"
+    hf = FalconDecoderLayer(cfg, 0).half().float().eval()
+    with torch.no_grad():
+        for ln in (hf.ln_attn, hf.ln_mlp):
+            ln.weight.copy_(f16r(1 + 0.1 * torch.randn(H)))
+            ln.bias.copy_(f16r(0.05 * torch.randn(H)))
+    hf.self_attention.maybe_rotary = LegacyFalconRotary(H // heads)
+    raw = {n: p.detach().clone() for n, p in hf.named_parameters()}
+    _plain_linear_tensors(hf)
+    g = torch.Generator().manual_seed(1234)
+    inps = f16r(torch.randn(nsamples, T, H, generator=g))
+    inps[:, :, 3] *= 6.0
+    mask = torch.triu(torch.ones(T, T, dtype=torch.bool), diagonal=1)[None, None]     # True = masked (:164)
+    qlayer = FA.QuantFalconDecoderLayer(cfg, hf, args)
+    # the per-block loop of omniquant.py for the falcon family (no position_ids, no LET)
+    quant_inps, fp_inps = inps.clone(), inps.clone()
+    qlayer.set_quant_state(weight_quant=False, act_quant=False)
+    with torch.no_grad():
+        for j in range(nsamples):
+            fp_inps[j] = qlayer(fp_inps[j].unsqueeze(0), attention_mask=mask)[0]
+    qlayer.set_quant_state(weight_quant=False, act_quant=True)
+    qlayer.let = False
+    init = {k: v.detach().clone() for k, v in qlayer.omni_state_dict().items()}
+    with torch.no_grad():
+        qlayer.float()
+    opt = torch.optim.AdamW([{"params": qlayer.let_parameters(True), "lr": 5e-3}, {"params": qlayer.lwc_parameters(), "lr": 1e-2}],
+                            weight_decay=0)
+    loss_fn = torch.nn.MSELoss()
+    losses, grads0 = [], None
+    for _ in range(epochs):
+        for j in range(nsamples):
+            qlayer.smooth_and_quant_temporary()
+            out = qlayer(quant_inps[j:j + 1], attention_mask=mask)[0]
+            loss = loss_fn(fp_inps[j:j + 1], out)
+            losses.append(float(loss.detach()))
+            opt.zero_grad()
+            loss.backward()
+            if grads0 is None:
+                grads0 = {k: v.grad.detach().clone() for k, v in qlayer.omni_state_dict(keep_vars=True).items() if v.grad is not None}
+            opt.step()
+    qlayer.clear_temp_variable()
+    qlayer.smooth_and_quant_inplace()
+    with torch.no_grad():
+        for j in range(nsamples):
+            quant_inps[j] = qlayer(quant_inps[j].unsqueeze(0), attention_mask=mask)[0]
+    qlayer.register_scales_and_zeros()
+    res = dict(fp_out=fp_inps, quant_out=quant_inps, losses=losses, grads0=grads0, init=init,
+               final={k: v.detach().clone() for k, v in qlayer.omni_state_dict().items()})
+    inputs = dict(inps=inps, H=H, F=4 * H, heads=heads, kv_heads=kvh, T=T, nsamples=nsamples, epochs=epochs, batch_size=1,
+                  wbits=args.wbits, abits=args.abits, group_size=args.group_size or 0, lwc=1, let=0, aug_loss=0)
+    for n, p in raw.items():
+        inputs[f"w/{n}"] = p.half()
+    lin = {"qkv": qlayer.self_attention.query_key_value, "dense": qlayer.self_attention.dense,
+           "fc1": qlayer.mlp.dense_h_to_4h, "fc2": qlayer.mlp.dense_4h_to_h}
+    _dump(os.path.join(OUT, f"falcon_{tag}.npz"), inputs, res, qlayer, lin)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     quantizer_cases()
@@ -361,3 +440,4 @@ if __name__ == "__main__":
     opt_block("w4a16g64_lwc", 128, 256, 2, 32, 4, make_args(4, 16, 64, True, False), epochs=2)
     opt_block("w4a16_lwc_let", 128, 256, 2, 32, 4, make_args(4, 16, None, True, True), epochs=2)
     opt_block("w4a4_lwc_let", 128, 256, 2, 32, 4, make_args(4, 4, None, True, True), epochs=2)
+    falcon_block("w3a16g64_lwc", 256, 4, 2, 32, 4, make_args(3, 16, 64, True, False), epochs=2)

@@ -15,6 +15,8 @@ LLAMA_MAP = {"q": "self_attn.q_proj", "k": "self_attn.k_proj", "v": "self_attn.v
              "gate": "mlp.gate_proj", "up": "mlp.up_proj", "down": "mlp.down_proj"}
 OPT_MAP = {"q": "self_attn.q_proj", "k": "self_attn.k_proj", "v": "self_attn.v_proj", "o": "self_attn.out_proj",
            "fc1": "fc1", "fc2": "fc2"}
+FALCON_MAP = {"qkv": "self_attention.query_key_value", "dense": "self_attention.dense", "fc1": "mlp.dense_h_to_4h",
+              "fc2": "mlp.dense_4h_to_h"}
 LET_MAP = {"qkv_s": "qkv_smooth_scale", "qkv_d": "qkv_smooth_shift", "out_s": "out_smooth_scale",
            "out_d": "out_smooth_shift", "fc1_s": "fc1_smooth_scale", "fc1_d": "fc1_smooth_shift",
            "qkt_s": "qkt_smooth_scale"}
@@ -34,14 +36,15 @@ class BlockFixture:
     def __init__(self, fname):
         z = load(fname)
         self.z = z
-        self.family = "llama" if fname.startswith("llama") else "opt"
-        self.lmap = LLAMA_MAP if self.family == "llama" else OPT_MAP
+        self.family = fname.split("_")[0]
+        self.lmap = {"llama": LLAMA_MAP, "opt": OPT_MAP, "falcon": FALCON_MAP}[self.family]
         g = lambda k: int(z[f"in/{k}"])
         self.H, self.F, self.heads, self.T = g("H"), g("F"), g("heads"), g("T")
         self.nsamples, self.epochs, self.batch_size = g("nsamples"), g("epochs"), g("batch_size")
         self.wbits, self.abits, self.group_size = g("wbits"), g("abits"), g("group_size") or None
         self.lwc, self.let, self.aug_loss = bool(g("lwc")), bool(g("let")), bool(g("aug_loss"))
         self.inps = t(z["in/inps"])
+        self.kv_heads = int(z["in/kv_heads"]) if "in/kv_heads" in z else self.heads
 
     # raw weights in the oracle's short naming
     def weights(self):
@@ -53,6 +56,9 @@ class BlockFixture:
         if self.family == "llama":
             W["ln1"] = t(z["in/w/input_layernorm.weight"])
             W["ln2"] = t(z["in/w/post_attention_layernorm.weight"])
+        elif self.family == "falcon":
+            W["ln1"], W["ln1.bias"] = t(z["in/w/ln_attn.weight"]), t(z["in/w/ln_attn.bias"])
+            W["ln2"], W["ln2.bias"] = t(z["in/w/ln_mlp.weight"]), t(z["in/w/ln_mlp.bias"])
         else:
             W["ln1"], W["ln1.bias"] = t(z["in/w/self_attn_layer_norm.weight"]), t(z["in/w/self_attn_layer_norm.bias"])
             W["ln2"], W["ln2.bias"] = t(z["in/w/final_layer_norm.weight"]), t(z["in/w/final_layer_norm.bias"])
