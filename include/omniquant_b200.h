@@ -112,6 +112,9 @@ int oq_gemm_bf16(const void* A, int a_mn, long lda, long strideA, const void* B,
 int oq_swiglu_fwd(const void* gu, long ldgu, void* m, long ldm, long rows, int F, oq_stream_t stream);
 int oq_swiglu_bwd(const void* gu, long ldgu, const void* dm, long lddm, void* dgu, long lddgu, long rows, int F,
                   oq_stream_t stream);
+/* exact (erf) GELU of QuantFalconMLP.forward (nn.GELU(), models/int_falcon_layer.py:25,29) and its derivative. */
+int oq_gelu_fwd(const void* x, void* y, long n, oq_stream_t stream);
+int oq_gelu_bwd(const void* x, const void* dy, void* dx, long n, oq_stream_t stream);
 /* ReLU of QuantOPTDecoderLayer.forward (models/int_opt_layer.py:318). */
 int oq_relu_fwd(const void* x, void* y, long n, oq_stream_t stream);
 int oq_relu_bwd(const void* x, const void* dy, void* dx, long n, oq_stream_t stream);

@@ -53,6 +53,31 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* gu, long ld
   }
 }
 
+// ---------------------------------------------------------------- exact (erf) GELU of QuantFalconMLP (nn.GELU(), models/int_falcon_layer.py:25)
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const bf16* x, bf16* y, long n8) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    float v[8];
+    load_bf8(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
+    store_bf8(y + i * 8, v);
+  }
+}
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const bf16* x, const bf16* dy, bf16* dx, long n8) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    float v[8], g[8];
+    load_bf8(x + i * 8, v);
+    load_bf8(dy + i * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float cdf = 0.5f * (1.0f + erff(v[j] * 0.70710678118654752f));
+      const float pdf = 0.3989422804014327f * __expf(-0.5f * v[j] * v[j]);
+      g[j] *= cdf + v[j] * pdf;
+    }
+    store_bf8(dx + i * 8, g);
+  }
+}
+
 // ---------------------------------------------------------------- ReLU (OPT)
 __global__ void __launch_bounds__(256) relu_fwd_kernel(const bf16* x, bf16* y, long n8) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
@@ -542,4 +567,16 @@ extern "C" int oq_let_grad_vec(int H, int F1, const float* let_params, const flo
   OQ_REQUIRE(H > 0 && let_params && tmpv && acc && drow && dbqkv && let_grads, "oq_let_grad_vec: bad arguments");
   let_grad_vec_kernel<<<(H + 255) / 256, 256, 0, stream>>>(H, F1, let_params, tmpv, acc, drow, dbqkv, q_bias_scale, let_grads);
   return oq_check_launch("oq_let_grad_vec");
+}
+
+extern "C" int oq_gelu_fwd(const void* x, void* y, long n, cudaStream_t stream) {
+  OQ_REQUIRE(x && y && n > 0 && n % 8 == 0 && al16(x) && al16(y), "oq_gelu_fwd: n %% 8 and 16-byte alignment required");
+  gelu_fwd_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const bf16*)x, (bf16*)y, n / 8);
+  return oq_check_launch("oq_gelu_fwd");
+}
+extern "C" int oq_gelu_bwd(const void* x, const void* dy, void* dx, long n, cudaStream_t stream) {
+  OQ_REQUIRE(x && dy && dx && n > 0 && n % 8 == 0 && al16(x) && al16(dy) && al16(dx),
+             "oq_gelu_bwd: n %% 8 and 16-byte alignment required");
+  gelu_bwd_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, n / 8);
+  return oq_check_launch("oq_gelu_bwd");
 }

@@ -61,33 +61,40 @@ class BlockEngine:
                  eps: float, device="cuda", batch: int = 1, let_init: Optional[Dict[str, torch.Tensor]] = None,
                  let_lr=5e-3, lwc_lr=1e-2, wd=0.0, world_size=1, causal=True, mask: Optional[torch.Tensor] = None,
                  overlap: bool = True, n_kv_heads: Optional[int] = None):
-        assert family in ("llama", "opt")
+        assert family in ("llama", "opt", "falcon")
         self.family, self.q, self.eps, self.dev = family, qcfg, float(eps), torch.device(device)
         self.h, self.T, self.b = n_heads, seq_len, batch
         self.let_lr, self.lwc_lr, self.wd, self.world = let_lr, lwc_lr, wd, world_size
         self.causal = causal and mask is None
         self.mask = None if mask is None else mask.to(self.dev, F32).contiguous()
         f = lambda t: t.detach().to(self.dev, F32).contiguous()
-        H = weights["q"].shape[1]
+        falcon = family == "falcon"
+        H = weights["qkv" if falcon else "q"].shape[1]
         self.H, self.d = H, H // n_heads
-        # grouped-query attention (Llama-2-70B): n_kv_heads K/V heads, each shared by `rep` Q heads (repeat_kv,
-        # models/int_llama_layer.py:138-139); the k / v projections are then [Hkv, H] with Hkv = n_kv_heads * d
+        # grouped-query attention (Llama-2-70B, Falcon): n_kv_heads K/V heads, each shared by `rep` Q heads (repeat_kv,
+        # models/int_llama_layer.py:138-139; models/int_falcon_layer.py:76-86); Hkv = n_kv_heads * d
         self.hkv = n_kv_heads or n_heads
         assert n_heads % self.hkv == 0
         self.rep = n_heads // self.hkv
         self.Hkv = self.hkv * self.d
         self.QW = H + 2 * self.Hkv
-        if self.rep > 1 and (qcfg.let or family != "llama"):
-            raise NotImplementedError("grouped-query attention is supported for LLaMA blocks without LET (the reference's "
+        if falcon and qcfg.let:
+            raise ValueError("falcon not yet support let")          # models/int_falcon_layer.py:329-331,:344-346
+        if self.rep > 1 and (qcfg.let or family == "opt"):
+            raise NotImplementedError("grouped-query attention is supported without LET only (the reference's "
                                       "smooth_q_k / smooth_fc_fc do not support it either)")
-        assert weights["k"].shape[0] == self.Hkv and weights["v"].shape[0] == self.Hkv
         self.M = batch * seq_len
         glu = family == "llama"
         self.glu = glu
         # ---- fp32 masters, concatenated by consumer
         self.W = {}
-        self.W["qkv"] = torch.cat([f(weights["q"]), f(weights["k"]), f(weights["v"])], 0)
-        self.W["o"] = f(weights["o"])
+        if falcon:      # fused QKV, per K/V group [rep query heads | k | v] (models/int_falcon_layer.py:76-86)
+            self.W["qkv"], self.W["o"] = f(weights["qkv"]), f(weights["dense"])
+            assert self.W["qkv"].shape[0] == self.QW
+        else:
+            assert weights["k"].shape[0] == self.Hkv and weights["v"].shape[0] == self.Hkv
+            self.W["qkv"] = torch.cat([f(weights["q"]), f(weights["k"]), f(weights["v"])], 0)
+            self.W["o"] = f(weights["o"])
         if glu:
             self.W["fc1"] = torch.cat([f(weights["gate"]), f(weights["up"])], 0)
             self.W["fc2"] = f(weights["down"])
@@ -101,22 +108,26 @@ class BlockEngine:
         self.ln = {"ln1w": f(weights["ln1"]), "ln2w": f(weights["ln2"]),
                    "ln1b": f(weights["ln1.bias"]) if "ln1.bias" in weights else None,
                    "ln2b": f(weights["ln2.bias"]) if "ln2.bias" in weights else None}
-        # raw linear biases (OPT), concatenated like the weights
+        # raw linear biases (OPT, Falcon with bias=True), concatenated like the weights
         def rawb(names):
             if all(f"{n}.bias" in weights for n in names):
                 return torch.cat([f(weights[f"{n}.bias"]) for n in names], 0)
             return None
-        self.rawb = {"qkv": rawb(["q", "k", "v"]), "o": rawb(["o"]),
+        self.rawb = {"qkv": rawb(["qkv"] if falcon else ["q", "k", "v"]), "o": rawb(["dense"] if falcon else ["o"]),
                      "fc1": rawb(["gate", "up"]) if glu else rawb(["fc1"]), "fc2": rawb(["down"] if glu else ["fc2"])}
         let = qcfg.let
-        U = [
-            _Unit("q", "qkv", 0, H, H, "qkv_s", "qkt_s", 2, "qkv_d"),
-            _Unit("k", "qkv", H, H + self.Hkv, H, "qkv_s", "qkt_s", 1, "qkv_d"),
-            _Unit("v", "qkv", H + self.Hkv, self.QW, H, "qkv_s", "out_s", 2, "qkv_d"),
-            _Unit("o", "o", 0, H, H, "out_s", None, 0, "out_d"),
-            _Unit("fc1", "fc1", 0, self.W["fc1"].shape[0], H, "fc1_s", None, 0, "fc1_d"),
-            _Unit("fc2", "fc2", 0, H, F_, None, None, 0, None),
-        ]
+        if falcon:
+            U = [_Unit("qkv", "qkv", 0, self.QW, H), _Unit("o", "o", 0, H, H),
+                 _Unit("fc1", "fc1", 0, self.W["fc1"].shape[0], H), _Unit("fc2", "fc2", 0, H, F_)]
+        else:
+            U = [
+                _Unit("q", "qkv", 0, H, H, "qkv_s", "qkt_s", 2, "qkv_d"),
+                _Unit("k", "qkv", H, H + self.Hkv, H, "qkv_s", "qkt_s", 1, "qkv_d"),
+                _Unit("v", "qkv", H + self.Hkv, self.QW, H, "qkv_s", "out_s", 2, "qkv_d"),
+                _Unit("o", "o", 0, H, H, "out_s", None, 0, "out_d"),
+                _Unit("fc1", "fc1", 0, self.W["fc1"].shape[0], H, "fc1_s", None, 0, "fc1_d"),
+                _Unit("fc2", "fc2", 0, H, F_, None, None, 0, None),
+            ]
         if not let:
             for u in U:
                 u.col = u.row = u.shift = None
@@ -165,7 +176,7 @@ class BlockEngine:
         mvv = {"q": self._mvbuf[:H], "k": self._mvbuf[H:2 * H], "v": self._mvbuf[2 * H:3 * H], "o": self._mvbuf[3 * H:4 * H],
                "fc1": self._mvbuf[4 * H:], "fc2": z(H)}
         self.qstat = {u.name: dict(xmin=z(u.N * G(u.K)), xmax=z(u.N * G(u.K)), scale=z(u.N * G(u.K)), zp=z(u.N * G(u.K)),
-                                    mv=mvv[u.name]) for u in U}
+                                    mv=mvv.get(u.name)) for u in U}
         self._tmpv = z(9 * H + F1)
         self.tmp = {}     # folded vectors of the current step
         self.bufs = {}
@@ -304,15 +315,16 @@ class BlockEngine:
         self._act_quant = act_quant and self.q.act_quant
         B = self.buf
         self.x = x
+        falcon = self.family == "falcon"
         a1 = B("a1", (M, H))
         self.st1 = (B("mean1", (M,), F32), B("rstd1", (M,), F32))
         ops.norm_fwd(x, ws["ln1w"], ws["ln1b"], self.eps, self.norm_kind, a1, *self.st1)
         a1q = self._aq(a1, "a1q")
         QW, Hkv, hkv, rep = self.QW, self.Hkv, self.hkv, self.rep
-        ok, ov = H, H + Hkv                     # column offsets of k and v in the [M, QW] qkv buffers
+        ok, ov = H, H + Hkv                     # column offsets of k and v in the [M, QW] qkv buffers (LLaMA / OPT)
         qkv = B("qkv", (M, QW))
         W = ws["W"]
-        if self.family == "llama":
+        if self.family in ("llama", "falcon"):
             ops.linear_fwd(a1q, W["qkv"], qkv, bias=ws["bqkv"])
         else:
             sc = d ** -0.5
@@ -334,6 +346,15 @@ class BlockEngine:
             else:
                 qkvq[:, ov:].copy_(qkv[:, ov:])
             alpha = 1.0 / math.sqrt(d)
+        elif falcon:
+            # rotary on the q and k heads of every group, v untouched; no Q/K/V quantisation in the Falcon block
+            # (plain scaled_dot_product_attention, models/int_falcon_layer.py:148,170-176)
+            qkvq = B("qkvq", (M, QW))
+            cos, sin = self.rope()
+            ops.act_quant_fwd(qkv.view(M, hkv * (rep + 2), d), qkvq.view(M, hkv * (rep + 2), d), n_bits=16, cos=cos, sin=sin,
+                              seq_len=T)
+            qkvq.view(M, hkv, rep + 2, d)[:, :, -1].copy_(qkv.view(M, hkv, rep + 2, d)[:, :, -1])
+            alpha = 1.0 / math.sqrt(d)
         else:
             if abits < 16:          # per token over the full hidden dim, before the head split (int_opt_layer.py:97,125,129)
                 qkvq = B("qkvq", (M, QW))
@@ -347,32 +368,32 @@ class BlockEngine:
         S = B("S", (h, T, T), torch.float16)     # scores in fp16 like the reference's autocast (int_llama_layer.py:143)
         O = B("O", (M, H))
         cz = 1 if self.causal else 0
-        # one launch over all heads, or (GQA) one per K/V head with that head shared by its `rep` query heads
-        groups = [(0, h, d)] if rep == 1 else [(g * rep, rep, 0) for g in range(hkv)]
+        groups = self._att_layout()
         for s in range(nb):
             r = slice(s * T, (s + 1) * T)
-            for h0, nh, sb in groups:
-                kv0 = (h0 // rep) * d
-                ops.gemm(qkvq[r, h0 * d:], qkvq[r, ok + kv0:], S[h0:], M=T, N=T, K=d, lda=QW, ldb=QW, ldc=T, batch=nh,
-                         strideA=d, strideB=sb, strideC=T * T, alpha=alpha, causal=cz)
+            for h0, nh, cq, ck, cv, sb in groups:
+                ops.gemm(qkvq[r, cq:], qkvq[r, ck:], S[h0:], M=T, N=T, K=d, lda=QW, ldb=QW, ldc=T, batch=nh, strideA=d,
+                         strideB=sb, strideC=T * T, alpha=alpha, causal=cz)
             ops.softmax_fwd(S, P[s], mask=self.mask, causal=self.causal)
-            for h0, nh, sb in groups:
-                kv0 = (h0 // rep) * d
-                ops.gemm(P[s, h0:], qkvq[r, ov + kv0:], O[r, h0 * d:], M=T, N=d, K=T, lda=T, ldb=QW, b_mn=True, ldc=H,
-                         batch=nh, strideA=T * T, strideB=sb, strideC=d, causal=2 * cz)
+            for h0, nh, cq, ck, cv, sb in groups:
+                ops.gemm(P[s, h0:], qkvq[r, cv:], O[r, h0 * d:], M=T, N=d, K=T, lda=T, ldb=QW, b_mn=True, ldc=H, batch=nh,
+                         strideA=T * T, strideB=sb, strideC=d, causal=2 * cz)
         Oq = self._aq(O, "Oq")
         h1 = B("h1", (M, H))
         self._join()                # o / fc1 / fc2 operands of this step come from the side stream
         ops.linear_fwd(Oq, W["o"], h1, bias=ws["bo"], residual=x)
         a2 = B("a2", (M, H))
         self.st2 = (B("mean2", (M,), F32), B("rstd2", (M,), F32))
-        ops.norm_fwd(h1, ws["ln2w"], ws["ln2b"], self.eps, self.norm_kind, a2, *self.st2)
+        # Falcon: ln_mlp acts on the block input, attention and MLP run in parallel (int_falcon_layer.py:272-301)
+        ops.norm_fwd(x if falcon else h1, ws["ln2w"], ws["ln2b"], self.eps, self.norm_kind, a2, *self.st2)
         a2q = self._aq(a2, "a2q")
         f1 = B("f1", (M, W["fc1"].shape[0]))
         ops.linear_fwd(a2q, W["fc1"], f1, bias=ws["bfc1"])
         m = B("m", (M, F_))
         if self.glu:
             ops.swiglu_fwd(f1, m)
+        elif falcon:
+            ops.gelu_fwd(f1, m)
         else:
             ops.relu_fwd(f1, m)
         mq = self._aq(m, "mq")
@@ -381,6 +402,18 @@ class BlockEngine:
         ops.linear_fwd(mq, W["fc2"], out, bias=ws["bfc2"], residual=h1)
         self.saved = dict(a1=a1, a1q=a1q, O=O, Oq=Oq, h1=h1, a2=a2, a2q=a2q, f1=f1, m=m, mq=mq, P=P, ws=ws)
         return out
+
+    def _att_layout(self):
+        """Launch groups of the attention GEMMs: (first head, heads in the launch, q / k / v column offsets in the
+        [M, QW] qkv buffers, batch stride of the K/V operand -- 0 = shared by the launch's heads).
+        LLaMA / OPT store [q | k | v]; Falcon stores per K/V group [rep q heads | k | v]."""
+        h, d, H, hkv, rep, Hkv = self.h, self.d, self.H, self.hkv, self.rep, self.Hkv
+        if self.family == "falcon":
+            gw = (rep + 2) * d
+            return [(g * rep, rep, g * gw, g * gw + rep * d, g * gw + (rep + 1) * d, 0 if rep > 1 else d) for g in range(hkv)]
+        if rep == 1:
+            return [(0, h, 0, H, H + Hkv, d)]
+        return [(g * rep, rep, g * rep * d, H + g * d, H + Hkv + g * d, 0) for g in range(hkv)]
 
     def rope(self):
         if not hasattr(self, "_rope"):
@@ -416,18 +449,24 @@ class BlockEngine:
         self._unit_backward_side("fc2", dW, None)
         dm = self._aq_bwd(sv["m"], dmq, "dm")
         df1 = B("df1", sv["f1"].shape)
+        falcon = self.family == "falcon"
         if self.glu:
             ops.swiglu_bwd(sv["f1"], dm, df1)
+        elif falcon:
+            ops.gelu_bwd(sv["f1"], dm, df1)
         else:
             ops.relu_bwd(sv["f1"], dm, df1)
-        da2q = B("da2q", (M, H))
-        ops.linear_dgrad(df1, W["fc1"], da2q)
         ops.linear_wgrad(df1, sv["a2q"], dW["fc1"])
         self._unit_backward_side("fc1", dW, df1)
-        da2 = self._aq_bwd(sv["a2"], da2q, "da2")
-        dh1 = B("dh1", (M, H))
-        ops.norm_bwd(sv["h1"], ws["ln2w"], self.norm_kind, self.st2[0], self.st2[1], da2, dx=dh1, dx_add=dout,
-                     dw_acc=self._acc["dw2"] if let else None, db_acc=self._acc["db2"] if let else None)
+        if falcon:
+            dh1 = dout      # parallel block, LWC only: the MLP branch does not feed the attention branch
+        else:
+            da2q = B("da2q", (M, H))
+            ops.linear_dgrad(df1, W["fc1"], da2q)
+            da2 = self._aq_bwd(sv["a2"], da2q, "da2")
+            dh1 = B("dh1", (M, H))
+            ops.norm_bwd(sv["h1"], ws["ln2w"], self.norm_kind, self.st2[0], self.st2[1], da2, dx=dh1, dx_add=dout,
+                         dw_acc=self._acc["dw2"] if let else None, db_acc=self._acc["db2"] if let else None)
         # out projection
         dOq = B("dOq", (M, H))
         ops.linear_dgrad(dh1, W["o"], dOq)
@@ -441,37 +480,44 @@ class BlockEngine:
         dqkvq = B("dqkvq", (M, QW))
         dP = B("S", (h, T, T), torch.float16).view(BF16)   # same scratch storage as the scores
         cz = 1 if self.causal else 0
-        groups = [(0, h, d)] if rep == 1 else [(g * rep, rep, 0) for g in range(hkv)]
-        dkv32 = B("dkv32", (T, 2 * Hkv), F32) if rep > 1 else None     # K/V gradients summed over the group's Q heads
+        groups = self._att_layout()
+        shared = rep > 1
+        dkv32 = B("dkv32", (T, 2 * Hkv), F32) if shared else None     # K/V gradients summed over the group's Q heads
         for s in range(nb):
             r = slice(s * T, (s + 1) * T)
             P = sv["P"][s]
-            for h0, nh, sb in groups:
-                kv0 = (h0 // rep) * d
-                ops.gemm(dO[r, h0 * d:], qkvq[r, ov + kv0:], dP[h0:], M=T, N=T, K=d, lda=H, ldb=QW, ldc=T, batch=nh,
-                         strideA=d, strideB=sb, strideC=T * T, causal=cz)
-            if rep == 1:
-                ops.gemm(P, dO[r], dqkvq[r, ov:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=H, ldc=QW, batch=h,
-                         strideA=T * T, strideB=d, strideC=d, causal=3 * cz)
+            for h0, nh, cq, ck, cv, sb in groups:
+                ops.gemm(dO[r, h0 * d:], qkvq[r, cv:], dP[h0:], M=T, N=T, K=d, lda=H, ldb=QW, ldc=T, batch=nh, strideA=d,
+                         strideB=sb, strideC=T * T, causal=cz)
+            if not shared:
+                for h0, nh, cq, ck, cv, sb in groups:
+                    ops.gemm(P[h0:], dO[r, h0 * d:], dqkvq[r, cv:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=H, ldc=QW,
+                             batch=nh, strideA=T * T, strideB=d, strideC=d, causal=3 * cz)
             else:
                 for hh in range(h):     # dV_g = sum over the group's heads of P_h^T dO_h
                     kv0 = (hh // rep) * d
                     ops.gemm(P[hh], dO[r, hh * d:], dkv32[:, Hkv + kv0:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True,
                              ldb=H, ldc=2 * Hkv, causal=3 * cz, accumulate=(hh % rep != 0))
             ops.softmax_bwd(P, dP, P, causal=self.causal)      # dS overwrites P
-            for h0, nh, sb in groups:
-                kv0 = (h0 // rep) * d
-                ops.gemm(P[h0:], qkvq[r, ok + kv0:], dqkvq[r, h0 * d:], M=T, N=d, K=T, lda=T, b_mn=True, ldb=QW, ldc=QW,
-                         batch=nh, strideA=T * T, strideB=sb, strideC=d, alpha=alpha, causal=2 * cz)
-            if rep == 1:
-                ops.gemm(P, qkvq[r, :H], dqkvq[r, ok:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=QW, ldc=QW,
-                         batch=h, strideA=T * T, strideB=d, strideC=d, alpha=alpha, causal=3 * cz)
+            for h0, nh, cq, ck, cv, sb in groups:
+                ops.gemm(P[h0:], qkvq[r, ck:], dqkvq[r, cq:], M=T, N=d, K=T, lda=T, b_mn=True, ldb=QW, ldc=QW, batch=nh,
+                         strideA=T * T, strideB=sb, strideC=d, alpha=alpha, causal=2 * cz)
+            if not shared:
+                for h0, nh, cq, ck, cv, sb in groups:
+                    ops.gemm(P[h0:], qkvq[r, cq:], dqkvq[r, ck:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=QW, ldc=QW,
+                             batch=nh, strideA=T * T, strideB=d, strideC=d, alpha=alpha, causal=3 * cz)
             else:
                 for hh in range(h):     # dK_g = sum over the group's heads of dS_h^T Q_h
                     kv0 = (hh // rep) * d
-                    ops.gemm(P[hh], qkvq[r, hh * d:], dkv32[:, kv0:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=QW,
+                    cq = groups[hh // rep][2] + (hh % rep) * d
+                    ops.gemm(P[hh], qkvq[r, cq:], dkv32[:, kv0:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=QW,
                              ldc=2 * Hkv, alpha=alpha, causal=3 * cz, accumulate=(hh % rep != 0))
-                dqkvq[r, ok:].copy_(dkv32)
+                if falcon:
+                    gv = dqkvq[r].view(T, hkv, rep + 2, d)
+                    gv[:, :, -2].copy_(dkv32[:, :Hkv].view(T, hkv, d))
+                    gv[:, :, -1].copy_(dkv32[:, Hkv:].view(T, hkv, d))
+                else:
+                    dqkvq[r, ok:].copy_(dkv32)
         abits = q.abits if self._act_quant else 16
         parts = ((0, H, h), (ok, ov, hkv), (ov, QW, hkv))
         if self.family == "llama":
@@ -485,6 +531,13 @@ class BlockEngine:
                                   n_bits=abits, recip_div=q.recip_div)
             else:
                 dqkv[:, ov:].copy_(dqkvq[:, ov:])
+        elif falcon:
+            dqkv = B("dqkv", (M, QW))
+            cos, sin = self.rope()
+            nhh = hkv * (rep + 2)
+            ops.act_quant_bwd(qkv.view(M, nhh, d), dqkvq.view(M, nhh, d), dqkv.view(M, nhh, d), n_bits=16, cos=cos, sin=sin,
+                              seq_len=T)
+            dqkv.view(M, hkv, rep + 2, d)[:, :, -1].copy_(dqkvq.view(M, hkv, rep + 2, d)[:, :, -1])     # v: no rotary
         else:
             if abits < 16:
                 dqkv = B("dqkv", (M, QW))
@@ -493,7 +546,7 @@ class BlockEngine:
             else:
                 dqkv = dqkvq
         # qkv projections
-        if self.family == "llama":
+        if self.family in ("llama", "falcon"):
             ops.linear_wgrad(dqkv, sv["a1q"], dW["qkv"])
         else:
             sc = d ** -0.5   # q = sc * (x W^T + b)

@@ -28,7 +28,8 @@ ARCH = {  # hidden, ffn, heads, layers
     "opt-125m": (768, 3072, 12, 12), "opt-1.3b": (2048, 8192, 32, 24), "opt-6.7b": (4096, 16384, 32, 32),
     "llama-7b": (4096, 11008, 32, 32), "Llama-2-7b": (4096, 11008, 32, 32), "llama-13b": (5120, 13824, 40, 40),
     "Llama-2-13b": (5120, 13824, 40, 40),
-    "llama-tiny": (256, 512, 2, 2), "opt-tiny": (256, 1024, 4, 2),       # smoke-test sizes
+    "llama-tiny": (256, 512, 2, 2), "opt-tiny": (256, 1024, 4, 2), "falcon-tiny": (256, 1024, 4, 2),   # smoke-test sizes
+    "falcon-180b": (14848, 59392, 232, 80), "Llama-2-70b": (8192, 28672, 64, 80),
 }
 
 
@@ -93,12 +94,19 @@ def synthetic_model(net, num_layers=None, seed=0):
     H, F_, heads, L = ARCH[net]
     L = num_layers or L
     torch.manual_seed(seed)
-    if "opt" in net.lower():
+    if "falcon" in net.lower():
+        from transformers import FalconConfig, FalconForCausalLM
+        cfg = FalconConfig(hidden_size=H, num_attention_heads=heads, num_kv_heads=8 if H >= 768 else 2, num_hidden_layers=L,
+                           vocab_size=65024 if H >= 768 else 512, new_decoder_architecture=True, bias=False,
+                           parallel_attn=True, ffn_hidden_size=F_)
+        model = FalconForCausalLM(cfg)
+    elif "opt" in net.lower():
         cfg = OPTConfig(hidden_size=H, ffn_dim=F_, num_attention_heads=heads, num_hidden_layers=L,
                         vocab_size=50272 if H >= 768 else 512, max_position_embeddings=2048, word_embed_proj_dim=H)
         model = OPTForCausalLM(cfg)
     else:
-        cfg = LlamaConfig(hidden_size=H, intermediate_size=F_, num_attention_heads=heads, num_key_value_heads=heads,
+        cfg = LlamaConfig(hidden_size=H, intermediate_size=F_, num_attention_heads=heads,
+                          num_key_value_heads=8 if net == "Llama-2-70b" else heads,
                           num_hidden_layers=L, vocab_size=32000 if H >= 768 else 512, max_position_embeddings=2048)
         model = LlamaForCausalLM(cfg)
     return model.half().eval()

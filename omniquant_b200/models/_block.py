@@ -101,6 +101,26 @@ class QuantDecoderLayerBase(nn.Module):
             self._push_params()
         return self._eng
 
+    def _unit_table(self):
+        """[(engine quantisation unit, engine weight group, [linear short names stacked in that unit])]."""
+        if self.family == "falcon":
+            return [("qkv", "qkv", ["qkv"]), ("o", "o", ["dense"]), ("fc1", "fc1", ["fc1"]), ("fc2", "fc2", ["fc2"])]
+        fc1 = ["gate", "up"] if self.family == "llama" else ["fc1"]
+        fc2 = "down" if self.family == "llama" else "fc2"
+        return [("q", "qkv", ["q"]), ("k", "qkv", ["k"]), ("v", "qkv", ["v"]), ("o", "o", ["o"]), ("fc1", "fc1", fc1),
+                ("fc2", "fc2", [fc2])]
+
+    def _placement(self):
+        """linear short name -> (unit, group, row offset in the unit, row offset in the group buffer)."""
+        lin, out, goff = self._linears(), {}, {}
+        for unit, group, members in self._unit_table():
+            uoff = 0
+            for m in members:
+                out[m] = (unit, group, uoff, goff.get(group, 0))
+                uoff += lin[m].out_features
+                goff[group] = goff.get(group, 0) + lin[m].out_features
+        return out
+
     def _param_map(self):
         """[(engine name, [module parameters concatenated in engine order])]."""
         out = []
@@ -110,9 +130,7 @@ class QuantDecoderLayerBase(nn.Module):
                 out.append((k, [getattr(self, long)]))
         if eng.q.lwc:
             lin = self._linears()
-            fc1 = ["gate", "up"] if self.family == "llama" else ["fc1"]
-            fc2 = "down" if self.family == "llama" else "fc2"
-            groups = [("q", ["q"]), ("k", ["k"]), ("v", ["v"]), ("o", ["o"]), ("fc1", fc1), ("fc2", [fc2])]
+            groups = [(unit, members) for unit, _, members in self._unit_table()]
             for unit, members in groups:
                 for s, attr in (("up", "upbound_factor"), ("low", "lowbound_factor")):
                     out.append((f"{unit}.{s}", [getattr(lin[m].weight_quantizer, attr) for m in members]))
@@ -169,21 +187,14 @@ class QuantDecoderLayerBase(nn.Module):
         self._publish_temp(eng)
 
     def _publish_temp(self, eng):
-        H = eng.H
         lin = self._linears()
         t = eng.tmp
-        kv = eng.Hkv
-        slices = {"q": ("qkv", 0, H), "k": ("qkv", H, H + kv), "v": ("qkv", H + kv, H + 2 * kv), "o": ("o", 0, H)}
-        if self.family == "llama":
-            slices.update(gate=("fc1", 0, eng.F), up=("fc1", eng.F, 2 * eng.F), down=("fc2", 0, H))
-        else:
-            slices.update(fc1=("fc1", 0, eng.F), fc2=("fc2", 0, H))
         bias_of = {"qkv": "bqkv", "o": "bo", "fc1": "bfc1", "fc2": "bfc2"}
-        for k, (g, r0, r1) in slices.items():
+        for k, (unit, g, _, r0) in self._placement().items():
             m = lin[k]
-            m.temp_weight = eng.Wq[g][r0:r1]
+            m.temp_weight = eng.Wq[g][r0:r0 + m.out_features]
             bb = t[bias_of[g]]
-            m.temp_bias = None if bb is None else bb[r0:r1]
+            m.temp_bias = None if bb is None else bb[r0:r0 + m.out_features]
             m.use_temporary_parameter = True
         for n, (w, b) in zip(self.norm_names, (("ln1w", "ln1b"), ("ln2w", "ln2b"))):
             nm = self._mod(n)
@@ -205,21 +216,13 @@ class QuantDecoderLayerBase(nn.Module):
         self._push_params()
         extra = eng.prepare(final=True)
         self._pull_params()       # truncate_number acted on the smooth scales
-        H = eng.H
         lin = self._linears()
         t = eng.tmp
-        fc1 = ["gate", "up"] if self.family == "llama" else ["fc1"]
-        fc2 = "down" if self.family == "llama" else "fc2"
-        kv = eng.Hkv
-        parts = {"q": ("q", 0, "bqkv", 0), "k": ("k", 0, "bqkv", H), "v": ("v", 0, "bqkv", H + kv), "o": ("o", 0, "bo", 0),
-                 fc2: ("fc2", 0, "bfc2", 0)}
-        r = 0
-        for nme in fc1:
-            parts[nme] = ("fc1", r, "bfc1", r)
-            r += lin[nme].out_features
-        for k, (unit, r0, bkey, b0) in parts.items():
+        bias_of = {"qkv": "bqkv", "o": "bo", "fc1": "bfc1", "fc2": "bfc2"}
+        for k, (unit, g, r0, b0) in self._placement().items():
             m = lin[k]
             N = m.out_features
+            bkey = bias_of[g]
             if unit in extra:
                 G = extra[unit]["scales"].numel() // extra[unit]["weight"].shape[0]
                 m.weight = extra[unit]["weight"][r0:r0 + N].to(m.weight.dtype)

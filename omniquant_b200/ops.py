@@ -181,6 +181,14 @@ def swiglu_bwd(gu, dm, dgu):
                dm.shape[0], dm.shape[1], _stream())
 
 
+def gelu_fwd(x, y):
+    lib().call("oq_gelu_fwd", _p(x), _p(y), x.numel(), _stream())
+
+
+def gelu_bwd(x, dy, dx):
+    lib().call("oq_gelu_bwd", _p(x), _p(dy), _p(dx), x.numel(), _stream())
+
+
 def relu_fwd(x, y):
     lib().call("oq_relu_fwd", _p(x), _p(y), x.numel(), _stream())
 

@@ -20,6 +20,7 @@ from .. import engine as E
 from ..parallel import make_allreduce, shard_indices, world_info
 from ..models.int_llama_layer import QuantLlamaDecoderLayer
 from ..models.int_opt_layer import QuantOPTDecoderLayer
+from ..models.int_falcon_layer import QuantFalconDecoderLayer
 from .int_linear import QuantLinear
 
 
@@ -46,7 +47,8 @@ def _family(model, net):
         return dict(name="opt", layers=dec.layers, cls=QuantOPTDecoderLayer, embed=embed, prefix="model.decoder.layers",
                     pairs={"q_proj": "qkv", "out_proj": "out", "fc1": "fc1"})
     if "falcon" in net:
-        raise NotImplementedError("Falcon blocks (LWC-only, no QuantMatMul) are the next family to be wired in")
+        return dict(name="falcon", layers=model.transformer.h, cls=QuantFalconDecoderLayer,
+                    embed=[model.transformer.word_embeddings, model.transformer.ln_f], prefix="model.transformer.h", pairs={})
     raise ValueError("Only support for opt/llama/Llama-2/falcon now")
 
 

@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
     ("llama-tiny", ["--wbits", "4", "--abits", "4", "--lwc", "--let"]),
     ("opt-tiny", ["--wbits", "4", "--abits", "16", "--group_size", "128", "--lwc"]),
     ("opt-tiny", ["--wbits", "4", "--abits", "4", "--lwc", "--let", "--aug_loss", "--batch_size", "2"]),
+    ("falcon-tiny", ["--wbits", "4", "--abits", "16", "--group_size", "128", "--lwc"]),
 ])
 def test_main_synthetic(tmp_path, net, flags):
     from omniquant_b200.main import main
@@ -25,11 +26,13 @@ def test_main_synthetic(tmp_path, net, flags):
     keys = set(ck[0].keys())
     if "--let" in flags:
         assert {"qkv_smooth_scale", "qkv_smooth_shift", "out_smooth_scale", "fc1_smooth_shift", "qkt_smooth_scale"} <= keys
-    assert any(k.endswith("q_proj.weight_quantizer.upbound_factor") for k in keys)
-    layers = model.model.layers if "llama" in net else model.model.decoder.layers
+    first = "query_key_value" if "falcon" in net else "q_proj"
+    assert any(k.endswith(first + ".weight_quantizer.upbound_factor") for k in keys)
+    layers = (model.model.layers if "llama" in net else model.transformer.h if "falcon" in net
+              else model.model.decoder.layers)
     for layer in layers:
         lin = [m for m in layer.modules() if isinstance(m, QuantLinear)]
-        assert len(lin) == (7 if "llama" in net else 6)
+        assert len(lin) == {"llama-tiny": 7, "opt-tiny": 6, "falcon-tiny": 4}[net]
         for m in lin:
             assert m.weight.device.type == "cpu" and m.weight.dtype == torch.float16
             assert torch.isfinite(m.weight.float()).all()

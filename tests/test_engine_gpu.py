@@ -11,7 +11,8 @@ from golden_util import BlockFixture
 pytestmark = pytest.mark.gpu
 
 FIXTURES = ["llama_w4a4_lwc_let.npz", "llama_w4a4_lwc_let_bs2.npz", "llama_w3a16g64_lwc.npz", "llama_w6a6_lwc_let_aug.npz",
-            "llama_w4a16g64_lwc_let.npz", "opt_w4a16g64_lwc.npz", "opt_w4a4_lwc_let.npz", "opt_w4a16_lwc_let.npz"]
+            "llama_w4a16g64_lwc_let.npz", "opt_w4a16g64_lwc.npz", "opt_w4a4_lwc_let.npz", "opt_w4a16_lwc_let.npz",
+            "falcon_w3a16g64_lwc.npz"]
 
 
 def build_engine(fx, recip_div=False):
@@ -19,12 +20,15 @@ def build_engine(fx, recip_div=False):
     q = QuantConfig(wbits=fx.wbits, abits=fx.abits, group_size=fx.group_size or 0, lwc=fx.lwc, let=fx.let,
                     recip_div=recip_div)
     eng = BlockEngine(fx.family, fx.weights(), n_heads=fx.heads, seq_len=fx.T, qcfg=q,
-                      eps=1e-6 if fx.family == "llama" else 1e-5, batch=fx.batch_size)
+                      eps=1e-6 if fx.family == "llama" else 1e-5, batch=fx.batch_size, n_kv_heads=fx.kv_heads)
     init = fx.init_params()
     name = lambda k: k.replace("gate.", "G.").replace("up.", "U.")
     for k, v in init.items():
         if k in eng.p:
             eng.p[k].copy_(v.reshape(-1).cuda())
+    if fx.family == "falcon":
+        for s in ("up", "low"):
+            eng.p[f"o.{s}"].copy_(init[f"dense.{s}"].reshape(-1).cuda())
     if fx.family == "llama" and fx.lwc:   # gate|up share one launch: [gate rows | up rows]
         for s in ("up", "low"):
             eng.p[f"fc1.{s}"].copy_(torch.cat([init[f"gate.{s}"].reshape(-1), init[f"up.{s}"].reshape(-1)]).cuda())
@@ -34,6 +38,8 @@ def build_engine(fx, recip_div=False):
 
 def ref_param(fx, P, key):
     """reference-named parameter dict -> the engine's flat naming."""
+    if fx.family == "falcon" and key.startswith("o."):
+        return P[f"dense.{key.split('.')[1]}"].reshape(-1)
     if fx.family == "llama" and key.startswith("fc1.") and key.endswith((".up", ".low")):
         s = key.split(".")[1]
         return torch.cat([P[f"gate.{s}"].reshape(-1), P[f"up.{s}"].reshape(-1)])
@@ -192,6 +198,60 @@ def test_engine_vs_oracle_16bit_emulation(family, wbits, abits, group):
     e_q = float((qi.float() - ref["quant_out"]).norm() / ref["quant_out"].norm())
     print("  fp_out rel", e_fp, "quant_out rel", e_q)
     assert e_fp < 5e-3
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("wbits,abits,group,kv", [(3, 16, 128, 2), (4, 8, 0, 2), (4, 16, 0, 4)])
+def test_falcon_engine_vs_oracle_16bit_emulation(wbits, abits, group, kv):
+    """Falcon new-decoder block (fused grouped QKV, rotary, parallel attention/MLP, GELU), LWC only: engine against
+    the oracle with the same 16-bit storage points."""
+    from omniquant_b200.engine import BlockEngine, QuantConfig, calibrate_block
+    from oracle import oq_oracle as orc
+    H, F_, heads, T, n = 512, 1024, 4, 128, 4
+    d = H // heads
+    g = torch.Generator().manual_seed(5)
+    r = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).half().float()
+    W = {"qkv": r((heads + 2 * kv) * d, H, sc=0.03), "dense": r(H, H, sc=0.03), "fc1": r(F_, H, sc=0.03),
+         "fc2": r(H, F_, sc=0.03), "ln1": 1 + r(H, sc=0.1), "ln2": 1 + r(H, sc=0.1), "ln1.bias": r(H, sc=0.05),
+         "ln2.bias": r(H, sc=0.05)}
+    x = r(n, T, H)
+    x[:, :, 3] *= 8.0
+    cfg = orc.QCfg(wbits, abits, group or None, False, True, False, emu16=torch.bfloat16)
+    Wc = {k: v.cuda() for k, v in W.items()}
+    P = {k: v.cuda() for k, v in orc.init_lwc({k: W[k] for k in orc.FALCON_LINEARS}, cfg).items()}
+    P0 = {k: v.clone() for k, v in P.items()}
+    xb = x.cuda().to(torch.bfloat16)
+    ref = orc.calibrate_block("falcon", Wc, P, cfg, xb.float(), heads, epochs=1, record_grads=True, n_kv_heads=kv)
+    q = QuantConfig(wbits=wbits, abits=abits, group_size=group, lwc=True, let=False, recip_div=True)
+    eng = BlockEngine("falcon", W, n_heads=heads, seq_len=T, qcfg=q, eps=1e-5, n_kv_heads=kv)
+    to_eng = lambda Pd, k: Pd[k.replace("o.", "dense.")].reshape(-1)
+    for k in eng.layout:
+        eng.p[k].copy_(to_eng(P0, k))
+    fp, qi = xb.clone(), xb.clone()
+    res = calibrate_block(eng, fp, qi, epochs=1, record_grads=True)
+    torch.cuda.synchronize()
+    losses, rl = res["losses"].cpu().numpy(), np.array(ref["losses"])
+    print("falcon", wbits, abits, group, kv, "losses", losses, rl)
+    bad = []
+    if abs(losses[0] - rl[0]) / rl[0] > 1e-3:
+        bad.append(("loss step 0", losses[0], rl[0]))
+    if np.abs(losses - rl).max() / rl.mean() > 3e-2:
+        bad.append(("loss", losses, rl))
+    gmax = max(float(v.norm()) for v in ref["grads"].values())
+    for k in eng.layout:
+        o, c = eng.layout[k]
+        ours, rr_ = res["grads0"][o:o + c], to_eng(ref["grads"], k)
+        err = float((ours - rr_).norm() / max(float(rr_.norm()), 2e-2 * gmax))
+        print(f"  grad {k}: rel err {err:.4f} (|ref| {float(rr_.norm()):.3e})")
+        if err > 5e-2:
+            bad.append(("grad", k, err))
+        dv = float((eng.p[k] - to_eng(ref["P"], k).detach()).abs().mean())
+        if dv > 5e-3:
+            bad.append(("param", k, dv))
+    e_fp = float((fp.float() - ref["fp_out"]).norm() / ref["fp_out"].norm())
+    e_q = float((qi.float() - ref["quant_out"]).norm() / ref["quant_out"].norm())
+    print("  fp_out rel", e_fp, "quant_out rel", e_q)
+    assert e_fp < 5e-3 and e_q < 2e-2
     assert not bad, bad
 
 

@@ -145,3 +145,70 @@ def test_standalone_operators():
     rn = SimpleNamespace(weight=torch.nn.Parameter(torch.rand(256, device="cuda") + 0.5))
     torch.testing.assert_close(OmniLlamaRMSNorm(rn, eps=1e-6).cuda()(xs), orc.rms_norm(xs, rn.weight.detach(), None, 1e-6),
                                rtol=2e-2, atol=2e-2)
+
+
+def test_falcon_block_wrapper_matches_reference_fixture():
+    """QuantFalconDecoderLayer (new decoder architecture, LWC only) built from a HF FalconDecoderLayer holding the
+    fixture's weights: FP targets, the module-level training loop and the in-place quantised weights."""
+    from transformers import FalconConfig
+    from transformers.models.falcon.modeling_falcon import FalconDecoderLayer
+    from golden_util import FALCON_MAP
+    from omniquant_b200.models.int_falcon_layer import QuantFalconDecoderLayer
+    from omniquant_b200.quantize.int_linear import QuantLinear
+    fx = BlockFixture("falcon_w3a16g64_lwc.npz")
+    args = make_args(fx)
+    cfg = FalconConfig(hidden_size=fx.H, num_attention_heads=fx.heads, num_kv_heads=fx.kv_heads, num_hidden_layers=1,
+                       vocab_size=64, new_decoder_architecture=True, bias=False, parallel_attn=True, ffn_hidden_size=fx.F)
+    cfg._attn_implementation = "eager"
+    layer = FalconDecoderLayer(cfg, 0)
+    W = fx.weights()
+    with torch.no_grad():
+        for s, long in FALCON_MAP.items():
+            m = layer
+            for p in long.split("."):
+                m = getattr(m, p)
+            m.weight.copy_(W[s])
+        layer.ln_attn.weight.copy_(W["ln1"]); layer.ln_attn.bias.copy_(W["ln1.bias"])
+        layer.ln_mlp.weight.copy_(W["ln2"]); layer.ln_mlp.bias.copy_(W["ln2.bias"])
+    qlayer = QuantFalconDecoderLayer(cfg, layer.half().cuda(), args).cuda()
+    x = fx.inps.cuda().to(torch.bfloat16)
+    T = fx.T
+    qlayer.set_quant_state(weight_quant=False, act_quant=False)
+    with torch.no_grad():
+        fp = torch.stack([qlayer(x[j:j + 1])[0][0] for j in range(fx.nsamples)])
+    assert float((fp.float().cpu() - fx.fp_out).norm() / fx.fp_out.norm()) < 1e-2
+    qlayer.set_quant_state(weight_quant=False, act_quant=True)
+    qlayer.let = False
+    qlayer.float()
+    assert len(list(qlayer.let_parameters(True))) == 0 and len(list(qlayer.lwc_parameters())) == 8
+    opt = torch.optim.AdamW([{"params": qlayer.lwc_parameters(), "lr": 1e-2}], weight_decay=0)
+    loss_fn = torch.nn.MSELoss()
+    losses = []
+    for _ in range(fx.epochs):
+        for j in range(fx.nsamples):
+            qlayer.smooth_and_quant_temporary(seq_len=T, batch=1)
+            out = qlayer(x[j:j + 1])[0]
+            loss = loss_fn(fp[j:j + 1].float(), out.float())
+            losses.append(float(loss))
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+    ref = fx.losses
+    rel = np.abs(np.array(losses) - ref) / ref
+    print("falcon module-loop losses", losses[:4], "ref", ref[:4], "max rel", rel.max())
+    assert rel.max() < 8e-2 and abs(np.mean(losses) - ref.mean()) / ref.mean() < 3e-2
+    qlayer.clear_temp_variable()
+    qlayer.smooth_and_quant_inplace()
+    qlayer.register_scales_and_zeros()
+    lin = {n: m for n, m in qlayer.named_modules() if isinstance(m, QuantLinear)}
+    assert sorted(lin) == sorted(FALCON_MAP.values())
+    Q = fx.quantized()
+    for s, long in FALCON_MAP.items():
+        w = lin[long].weight.float().cpu()
+        assert w.shape == Q[f"{s}.w"].shape
+        assert float((w - Q[f"{s}.w"]).abs().mean() / Q[f"{s}.w"].abs().mean()) < 5e-2
+        assert lin[long].weight_quantizer.scales.shape == Q[f"{s}.scales"].shape
+        assert all(len(torch.unique(row)) <= 2 ** fx.wbits for row in w.reshape(-1, fx.group_size)[:16])
+    qlayer.let = True
+    with pytest.raises(ValueError):
+        qlayer.smooth_and_quant_temporary(seq_len=T, batch=1)
