@@ -321,8 +321,8 @@ extern "C" int oq_weight_quant_fwd(const float* W, int N, int K, const float* co
     if (let ? launch_pc_fwd<true>(a, g, smem, stream) : launch_pc_fwd<false>(a, g, 0, stream))
       return oq_check_launch("oq_weight_quant_fwd");
   }
-  if (fast_al && team_warp && K % group_size == 0) {
-    const long slots = ((long)N * G * (group_size >= 128 ? 32 : group_size / 4) + 31) / 32;
+  if (fast_al && team_warp && K % group_size == 0 && (long)N * G < (1L << 31) - 64 && grp_lpg(group_size, false) >= 1) {
+    const long slots = ((long)N * G * grp_lpg(group_size, false) + 31) / 32;
     const int g = (int)std::max<long>(1, std::min<long>((slots + 7) / 8, (long)oq_num_sms() * 8));
     if (let ? launch_grp<true, false>(a, g, 0, stream) : launch_grp<false, false>(a, g, 0, stream))
       return oq_check_launch("oq_weight_quant_fwd");
@@ -374,9 +374,9 @@ extern "C" int oq_weight_quant_bwd(const float* W, int N, int K, const float* co
         return oq_check_launch("oq_weight_quant_bwd");
     }
   }
-  if (fast_al && team_warp && K % group_size == 0) {
+  if (fast_al && team_warp && K % group_size == 0 && (long)N * G < (1L << 31) - 64 && grp_lpg(group_size, true) >= 1) {
     const size_t sm2 = let ? sizeof(float) * 2 * K : 0;
-    const long slots = ((long)N * G * (group_size >= 128 ? 32 : group_size / 4) + 31) / 32;
+    const long slots = ((long)N * G * grp_lpg(group_size, true) + 31) / 32;
     const int g = (int)std::max<long>(1, std::min<long>((slots + 7) / 8, (long)oq_num_sms() * (let ? 3 : 8)));
     if (sm2 <= 200 * 1024 && (let ? launch_grp<true, true>(a, g, sm2, stream) : launch_grp<false, true>(a, g, 0, stream)))
       return oq_check_launch("oq_weight_quant_bwd");

@@ -338,18 +338,18 @@ __global__ void __launch_bounds__(256) wq_grp_fwd(WqArgs a) {
   constexpr int GSZ = 4 * LPG * VPL;
   const int lane = threadIdx.x & 31, sub = lane / LPG, sl_ = lane % LPG;
   const int G = a.K / GSZ;
-  const long n_groups = (long)a.N * G;
-  const long n_slots = (n_groups + GPS - 1) / GPS;
-  const long wid = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long nw = (long)gridDim.x * (blockDim.x >> 5);
+  const int n_groups = a.N * G;                 // < 2^31 (checked by the dispatcher): 32-bit index arithmetic
+  const int n_slots = (n_groups + GPS - 1) / GPS;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nw = gridDim.x * (blockDim.x >> 5);
   const int lwc = a.up != nullptr;
   const bool has_col = LET && a.col != nullptr, has_shift = LET && a.shift != nullptr;
-  for (long slot = wid; slot < n_slots; slot += nw) {
-    const long item = slot * GPS + sub;
+  for (int slot = wid; slot < n_slots; slot += nw) {
+    const int item = slot * GPS + sub;
     const bool valid = item < n_groups;
-    const long it = valid ? item : n_groups - 1;
-    const int n = (int)(it / G), gi = (int)(it % G);
-    const long base = (long)n * a.K + (long)gi * GSZ;
+    const int it = valid ? item : n_groups - 1;
+    const int n = it / G, gi = it - n * G;
+    const long base = (long)it * GSZ;            // groups tile the rows exactly (K % group == 0)
     const int kb = gi * GSZ;
     float4 w[VPL];
 #pragma unroll
@@ -410,7 +410,9 @@ __global__ void __launch_bounds__(256) wq_grp_fwd(WqArgs a) {
 }
 
 // dynamic smem (LET): colacc[K] | shacc[K] (shared-memory atomics: several warps hit the same columns)
-template <int LPG, int VPL, bool LET>
+// TIE: the arg-max / arg-min bookkeeping (who receives the clip-path gradient) is only needed when a gradient w.r.t. the
+// weights or the LET vectors is produced; the LWC-only step needs just R per group.
+template <int LPG, int VPL, bool LET, bool TIE>
 __global__ void __launch_bounds__(256) wq_grp_bwd(WqArgs a) {
   extern __shared__ float4 dsm4[];
   constexpr int GPS = 32 / LPG;
@@ -425,17 +427,17 @@ __global__ void __launch_bounds__(256) wq_grp_bwd(WqArgs a) {
   }
   const int lane = threadIdx.x & 31, sub = lane / LPG, sl_ = lane % LPG;
   const int G = a.K / GSZ;
-  const long n_groups = (long)a.N * G;
-  const long n_slots = (n_groups + GPS - 1) / GPS;
-  const long wid = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long nw = (long)gridDim.x * (blockDim.x >> 5);
+  const int n_groups = a.N * G;                 // < 2^31 (checked by the dispatcher): 32-bit index arithmetic
+  const int n_slots = (n_groups + GPS - 1) / GPS;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nw = gridDim.x * (blockDim.x >> 5);
   const int lwc = a.up != nullptr;
-  for (long slot = wid; slot < n_slots; slot += nw) {
-    const long item = slot * GPS + sub;
+  for (int slot = wid; slot < n_slots; slot += nw) {
+    const int item = slot * GPS + sub;
     const bool valid = item < n_groups;
-    const long it = valid ? item : n_groups - 1;
-    const int n = (int)(it / G), gi = (int)(it % G);
-    const long base = (long)n * a.K + (long)gi * GSZ;
+    const int it = valid ? item : n_groups - 1;
+    const int n = it / G, gi = it - n * G;
+    const long base = (long)it * GSZ;            // groups tile the rows exactly (K % group == 0)
     const int kb = gi * GSZ;
     float4 w[VPL], g[VPL];
 #pragma unroll
@@ -481,30 +483,31 @@ __global__ void __launch_bounds__(256) wq_grp_bwd(WqArgs a) {
         const float wv = f4(w[v], j);
         const float w1 = has_col ? wv * f4(c4, j) : wv;
         const float f = w1 * rmul;
-        f4(fv[v], j) = f;
+        if (TIE) f4(fv[v], j) = f;
         const float qa = f * inv;
         const float t = rintf(qa) + q.zp;
         const bool inr = (t >= 0.0f) && (t <= q.qmax);
         const float c = oq_clampf(t, 0.0f, q.qmax);
         const float gk = valid ? f4(g[v], j) : 0.0f;
         R += gk * ((c - q.zp) - (inr ? qa : 0.0f));
-        if (tie_all || t >= q.qmax - 1.0f || t <= 1.0f) {
+        if (TIE && (tie_all || t >= q.qmax - 1.0f || t <= 1.0f)) {
           if (fabsf(f - xmax) <= tie_tol_max) { nmax += 1.0f; smax += w1; }
           if (fabsf(f - xmin) <= tie_tol_min) { nmin += 1.0f; smin += w1; }
         }
         const float d2 = inr ? gk : 0.0f;
-        rowdot += d2 * w1;
-        f4(g[v], j) = d2;
+        if (LET) rowdot += d2 * w1;
+        if (TIE) f4(g[v], j) = d2;
         if (valid && want_col) atomicAdd(colacc + k + j, d2 * rfac * wv);
         if (valid && want_sh) atomicAdd(shacc + k + j, wv * en);
       }
     }
-    R = grp_sum<LPG>(R); nmax = grp_sum<LPG>(nmax); nmin = grp_sum<LPG>(nmin);
+    R = grp_sum<LPG>(R);
+    if (TIE) { nmax = grp_sum<LPG>(nmax); nmin = grp_sum<LPG>(nmin); }
     float gmaxp, gminp;
     oq_scale_grad(R, xmin, xmax, su, sl, lwc, a.n_bits, a.symmetric, a.recip_div, &gmaxp, &gminp);
     const float cmax = nmax > 0.f ? gmaxp * su / nmax : 0.0f;
     const float cmin = nmin > 0.f ? gminp * sl / nmin : 0.0f;
-    if (a.drow) {
+    if (LET && a.drow) {
       rowdot = grp_sum<LPG>(rowdot); smax = grp_sum<LPG>(smax); smin = grp_sum<LPG>(smin);
       if (sl_ == 0 && valid) atomicAdd(a.drow + n, rowdot + cmax * smax + cmin * smin);
     }
@@ -512,7 +515,7 @@ __global__ void __launch_bounds__(256) wq_grp_bwd(WqArgs a) {
       if (a.d_up) a.d_up[item] = gmaxp * xmax * su * (1.0f - su);
       if (a.d_low) a.d_low[item] = gminp * xmin * sl * (1.0f - sl);
     }
-    if (valid && (want_col || a.dW)) {
+    if (TIE && valid && (want_col || a.dW)) {
 #pragma unroll
       for (int v = 0; v < VPL; ++v) {
         const int ko = 4 * (sl_ + v * LPG);
@@ -576,24 +579,55 @@ static bool launch_pc_bwd(const WqArgs& a, int grid, size_t smem, cudaStream_t s
 #undef OQ_PC_BWD
   return false;
 }
+// Elements per lane of the grouped kernels.  The per-group scalar work (two sigmoids, the scale / zero-point /
+// reciprocal divisions, the shuffles) is executed by every lane of a group, so few lanes per group amortise it best:
+// measured on B200 (tools/wq_bench.py, g128) forward 2.0 / 3.9 / 4.6 TB/s and backward 1.27 / 2.4 / 2.4 TB/s at
+// 4 / 16 / 32 elements per lane.  OQ_WQ_EPL_FWD / OQ_WQ_EPL_BWD override for experiments.
+static int grp_epl(int group, bool bwd) {
+  static int env_f = [] { const char* e = getenv("OQ_WQ_EPL_FWD"); return e ? atoi(e) : 0; }();
+  static int env_b = [] { const char* e = getenv("OQ_WQ_EPL_BWD"); return e ? atoi(e) : 0; }();
+  int epl = bwd ? (env_b ? env_b : 16) : (env_f ? env_f : 32);
+  if (group == 512 && epl == 4) epl = 16;
+  if (group == 256 && epl == 4) epl = 8;
+  if (epl > group) epl = group;
+  return epl;
+}
+static int grp_lpg(int group, bool bwd) { return group / grp_epl(group, bwd); }
+
 template <bool LET, bool BWD>
 static bool launch_grp(const WqArgs& a, int grid, size_t smem, cudaStream_t s) {
+  const int epl = grp_epl(a.group, BWD);
 #define OQ_GRP(L, V)                                                                                             \
   {                                                                                                              \
     if (BWD) {                                                                                                   \
-      if (smem > 40 * 1024) cudaFuncSetAttribute(wq_grp_bwd<L, V, LET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      wq_grp_bwd<L, V, LET><<<grid, 256, smem, s>>>(a);                                                          \
+      if (LET || a.dW) {                                                                                         \
+        if (smem > 40 * 1024) cudaFuncSetAttribute(wq_grp_bwd<L, V, LET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        wq_grp_bwd<L, V, LET, true><<<grid, 256, smem, s>>>(a);                                                  \
+      } else {                                                                                                   \
+        wq_grp_bwd<L, V, false, false><<<grid, 256, 0, s>>>(a);                                                  \
+      }                                                                                                          \
     } else {                                                                                                     \
       wq_grp_fwd<L, V, LET><<<grid, 256, 0, s>>>(a);                                                             \
     }                                                                                                            \
     return true;                                                                                                 \
   }
-  switch (a.group) {
-    case 32: OQ_GRP(8, 1)
-    case 64: OQ_GRP(16, 1)
-    case 128: OQ_GRP(32, 1)
-    case 256: OQ_GRP(32, 2)
-    case 512: OQ_GRP(32, 4)
+  // elements per lane: 16 (4 float4) -- the per-group scalar work (two sigmoids, scale / zero-point / reciprocal
+  // divisions, the shuffles) is executed by every lane of a group, so few lanes per group amortise it best
+  switch (a.group * 100 + epl) {
+    case 3204: OQ_GRP(8, 1)
+    case 6404: OQ_GRP(16, 1)
+    case 12804: OQ_GRP(32, 1)
+    case 25608: OQ_GRP(32, 2)
+    case 3216: OQ_GRP(2, 4)
+    case 6416: OQ_GRP(4, 4)
+    case 12816: OQ_GRP(8, 4)
+    case 25616: OQ_GRP(16, 4)
+    case 51216: OQ_GRP(32, 4)
+    case 3232: OQ_GRP(1, 8)
+    case 6432: OQ_GRP(2, 8)
+    case 12832: OQ_GRP(4, 8)
+    case 25632: OQ_GRP(8, 8)
+    case 51232: OQ_GRP(16, 8)
     default: return false;
   }
 #undef OQ_GRP
