@@ -46,23 +46,35 @@ __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret
 __device__ __forceinline__ float& f4(float4& v, int j) { return reinterpret_cast<float*>(&v)[j]; }
 
 // ================================================================== per-channel forward
-template <int NV, bool LET>
+// warp-wide fp32 max in ONE instruction (sm_100a: CREDUX.MAX.F32); NaN operands are ignored like fmaxf
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+// Instruction-count notes (ncu, K=4096: the first version executed 50 thread-instructions per weight, 10 % of them
+// branches on run-time-uniform LET options inside the element loops): the row-division fold is a template parameter,
+// absent column scale / shift vectors are read as 1 / 0 from shared memory (w*1 and +w*0 are exact), the sigmoids of
+// all rows a block visits are evaluated once up front (one row per thread), the block-wide min / max is two CREDUX
+// + one barrier, and the bit-exact rounding guard of oq_rint_div is evaluated branch-free with one fallback branch
+// per float4 (the exact IEEE-division path re-does those four elements; probability ~1e-5).
+template <int NV, bool LET, bool ROWDIV>
 __global__ void __launch_bounds__(256) wq_pc_fwd(WqArgs a) {
   extern __shared__ float4 dsm4[];
-  __shared__ float scratch[2 * 3 * 8];
-  const int tid = threadIdx.x, K4 = a.K >> 2;
-  float4* colv = dsm4;            // [K4] when LET && a.col
-  float4* shv = dsm4 + K4;        // [K4] when LET && a.shift
+  __shared__ float red[2][3][8];
+  __shared__ float sig[2][256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, K4 = a.K >> 2;
+  float4* colv = dsm4;            // [K4] (LET)
+  float4* shv = dsm4 + K4;        // [K4] (LET)
+  const bool has_shift = LET && a.shift != nullptr;
   if (LET) {
     for (int i = tid; i < K4; i += 256) {
-      if (a.col) colv[i] = ld4(a.col + 4 * i);
-      if (a.shift) shv[i] = ld4(a.shift + 4 * i);
+      colv[i] = a.col ? ld4(a.col + 4 * i) : make_float4(1.f, 1.f, 1.f, 1.f);
+      shv[i] = a.shift ? ld4(a.shift + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __syncthreads();
   }
   const int lwc = a.up != nullptr;
-  const bool has_col = LET && a.col != nullptr;
-  const bool has_shift = LET && a.shift != nullptr;
   float4 wn[NV];
   int n = blockIdx.x;
   if (n < a.N) {
@@ -72,8 +84,16 @@ __global__ void __launch_bounds__(256) wq_pc_fwd(WqArgs a) {
       wn[i] = idx < K4 ? ld4(a.W + (long)n * a.K + 4 * idx) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  int par = 0;
-  for (; n < a.N; n += gridDim.x, par ^= 1) {
+  int par = 0, k = 0;
+  for (; n < a.N; n += gridDim.x, par ^= 1, ++k) {
+    if ((k & 255) == 0) {   // sigmoids of the next 256 rows of this block, one row per thread
+      __syncthreads();
+      const long r = (long)n + (long)tid * gridDim.x;
+      const bool ok = lwc && r < a.N;
+      sig[0][tid] = ok ? oq_sigmoidf(a.up[r]) : 1.0f;
+      sig[1][tid] = ok ? oq_sigmoidf(a.low[r]) : 1.0f;
+      __syncthreads();
+    }
     float4 w[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) w[i] = wn[i];
@@ -85,58 +105,76 @@ __global__ void __launch_bounds__(256) wq_pc_fwd(WqArgs a) {
         if (idx < K4) wn[i] = ld4(a.W + (long)nn * a.K + 4 * idx);
       }
     }
-    const float rs = (LET && a.row) ? a.row[n] : 1.0f;
-    const int rop = (LET && a.row) ? a.row_op : 0;
-    float sm[1] = {0.f}, mm[2] = {-INFINITY, -INFINITY};
+    const float rs = (LET && a.row && a.row_op != 0) ? a.row[n] : 1.0f;
+    float sm = 0.f, mlo = -INFINITY, mhi = -INFINITY;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int idx = tid + i * 256;
       if (idx < K4) {
-        float4 c4 = has_col ? colv[idx] : make_float4(1.f, 1.f, 1.f, 1.f);
-        if (has_shift) {
-          const float4 s4 = shv[idx];
-          sm[0] += w[i].x * s4.x + w[i].y * s4.y + w[i].z * s4.z + w[i].w * s4.w;
-        }
+        if (LET) {
+          const float4 c4 = colv[idx], s4 = shv[idx];
+          sm += w[i].x * s4.x + w[i].y * s4.y + w[i].z * s4.z + w[i].w * s4.w;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float f = oq_fold(f4(w[i], j), f4(c4, j), has_col, rs, rop);
-          f4(w[i], j) = f;  // keep the folded value
-          mm[0] = fmaxf(mm[0], -f);
-          mm[1] = fmaxf(mm[1], f);
+          for (int j = 0; j < 4; ++j) {
+            const float f1 = OQ_MUL(f4(w[i], j), f4(const_cast<float4&>(c4), j));
+            f4(w[i], j) = ROWDIV ? OQ_DIV(f1, rs) : OQ_MUL(f1, rs);  // (W * col) {*,/} row; a factor 1 is exact
+          }
         }
+        mlo = fmaxf(mlo, fmaxf(fmaxf(-w[i].x, -w[i].y), fmaxf(-w[i].z, -w[i].w)));
+        mhi = fmaxf(mhi, fmaxf(fmaxf(w[i].x, w[i].y), fmaxf(w[i].z, w[i].w)));
       }
     }
-    block_reduce_1sync<1, 2>(sm, mm, scratch, par);
-    const float xmin = -mm[0], xmax = mm[1];
-    const float su = lwc ? oq_sigmoidf(a.up[n]) : 1.0f;
-    const float sl = lwc ? oq_sigmoidf(a.low[n]) : 1.0f;
-    const OqQParams q = oq_qparams(xmin, xmax, su, sl, lwc, a.n_bits, a.symmetric, a.recip_div);
+    mlo = warp_max_f32(mlo);
+    mhi = warp_max_f32(mhi);
+    if (has_shift) sm = warp_reduce(sm, OpSum());
+    if (lane == 0) {
+      red[par][0][warp] = mlo;
+      red[par][1][warp] = mhi;
+      red[par][2][warp] = sm;
+    }
+    __syncthreads();
+    const float xmin = -warp_max_f32(lane < 8 ? red[par][0][lane] : -INFINITY);
+    const float xmax = warp_max_f32(lane < 8 ? red[par][1][lane] : -INFINITY);
+    const OqQParams q = oq_qparams(xmin, xmax, sig[0][k & 255], sig[1][k & 255], lwc, a.n_bits, a.symmetric, a.recip_div);
     if (tid == 0) {
       if (a.scale_out) a.scale_out[n] = q.scale;
       if (a.zp_out) a.zp_out[n] = q.zp;
       if (a.xmin_out) a.xmin_out[n] = xmin;
       if (a.xmax_out) a.xmax_out[n] = xmax;
-      if (has_shift && a.mv) a.mv[n] = sm[0];
+      if (has_shift && a.mv) {
+        float t = 0.f;
+#pragma unroll
+        for (int x = 0; x < 8; ++x) t += red[par][2][x];
+        a.mv[n] = t;
+      }
     }
     const float inv = OQ_DIV(1.0f, q.scale);
-    const int inv_ok = oq_inv_ok(inv);
+    const bool inv_bad = !oq_inv_ok(inv);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int idx = tid + i * 256;
       if (idx < K4) {
-        float y[4], c[4];
+        float4 c;
+        bool redo = inv_bad;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float t = OQ_ADD(oq_rint_div(f4(w[i], j), q.scale, inv, inv_ok), q.zp);
-          c[j] = oq_clampf(t, 0.0f, q.qmax);
-          y[j] = oq_dequant(c[j], q);
+          const float qa = OQ_MUL(f4(w[i], j), inv);
+          const float r = rintf(qa);
+          redo |= !(fabsf(fabsf(qa - r) - 0.5f) > fabsf(qa) * 2.4e-7f + 1e-30f);   // oq_rint_div's guard
+          f4(c, j) = fminf(fmaxf(OQ_ADD(r, q.zp), 0.0f), q.qmax);    // finite here: scale is normal, weights finite
         }
+        if (redo) {   // exact IEEE division (and NaN-preserving clamp) for this float4
+#pragma unroll
+          for (int j = 0; j < 4; ++j) f4(c, j) = oq_code(f4(w[i], j), q);
+        }
+        float y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = oq_dequant(f4(c, j), q);
         const long o = (long)n * a.K + 4 * idx;
         if (a.q_bf) store_bf4(a.q_bf + (long)n * a.ld_bf + 4 * idx, y);
         if (a.q_f32) *reinterpret_cast<float4*>(a.q_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
         if (a.codes)
-          *reinterpret_cast<uchar4*>(a.codes + o) =
-              make_uchar4((unsigned char)c[0], (unsigned char)c[1], (unsigned char)c[2], (unsigned char)c[3]);
+          *reinterpret_cast<uchar4*>(a.codes + o) = make_uchar4((unsigned char)c.x, (unsigned char)c.y, (unsigned char)c.z, (unsigned char)c.w);
       }
     }
   }
@@ -543,13 +581,13 @@ __global__ void __launch_bounds__(256) wq_grp_bwd(WqArgs a) {
 }
 
 // ------------------------------------------------------------------ dispatch helpers
-template <bool LET>
-static bool launch_pc_fwd(const WqArgs& a, int grid, size_t smem, cudaStream_t s) {
+template <bool LET, bool ROWDIV>
+static bool launch_pc_fwd2(const WqArgs& a, int grid, size_t smem, cudaStream_t s) {
   const int nv = (a.K / 4 + 255) / 256;
 #define OQ_PC_FWD(NVV)                                                                                          \
   {                                                                                                             \
-    if (smem > 40 * 1024) cudaFuncSetAttribute(wq_pc_fwd<NVV, LET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    wq_pc_fwd<NVV, LET><<<grid, 256, smem, s>>>(a);                                                             \
+    if (smem > 40 * 1024) cudaFuncSetAttribute(wq_pc_fwd<NVV, LET, ROWDIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    wq_pc_fwd<NVV, LET, ROWDIV><<<grid, 256, smem, s>>>(a);                                                     \
     return true;                                                                                                \
   }
   if (nv <= 1) OQ_PC_FWD(1)
@@ -560,6 +598,11 @@ static bool launch_pc_fwd(const WqArgs& a, int grid, size_t smem, cudaStream_t s
   if (nv <= 16) OQ_PC_FWD(16)
 #undef OQ_PC_FWD
   return false;
+}
+template <bool LET>
+static bool launch_pc_fwd(const WqArgs& a, int grid, size_t smem, cudaStream_t s) {
+  if (LET && a.row && a.row_op == 2) return launch_pc_fwd2<LET, true>(a, grid, smem, s);
+  return launch_pc_fwd2<LET, false>(a, grid, smem, s);
 }
 template <bool LET>
 static bool launch_pc_bwd(const WqArgs& a, int grid, size_t smem, cudaStream_t s) {
