@@ -158,6 +158,20 @@ int oq_let_prep_bwd(int H, const float* let_params, const float* dbqkv, float q_
 int oq_let_grad_vec(int H, int F1, const float* let_params, const float* tmpv, const float* acc, const float* drow,
                     const float* dbqkv, float q_bias_scale, float* let_grads, oq_stream_t stream);
 
+/* ---- activation statistics for the LET initialisation (next row f3 of SURVEY.md section 8)
+ * Replaces generate_act_scale_shift.py:25-58 (get_act_scales: per-channel running max of |x| over samples) and :60-94
+ * (get_act_shifts: (max+min)/2 of the first sample, then 0.99*prev + 0.01*(max+min)/2 per sample) for the input of
+ * one linear layer.  oq_act_stats reduces ONE sample x[rows, C] (bf16, row stride ld) to absmax[C] and mid[C]
+ * (either may be NULL); workspace of *bytes_out bytes as reported by
+ * oq_act_stats_workspace(rows, C, &bytes).  oq_act_stats_fold folds the vectors of
+ * n samples (absmax[n, C], mid[n, C], sample order) into scale_io[C] / shift_io[C]; first != 0 starts the
+ * recursion from sample 0 (the reference's `name not in act_scales` branch), otherwise the running values continue. */
+int oq_act_stats_workspace(int rows, int C, long* bytes_out);
+int oq_act_stats(const void* x, int rows, int C, long ld, float* absmax, float* mid, float* workspace, long workspace_bytes,
+                 oq_stream_t stream);
+int oq_act_stats_fold(const float* absmax, const float* mid, int n, int C, int first, float* scale_io, float* shift_io,
+                      oq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

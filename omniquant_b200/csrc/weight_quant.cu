@@ -367,14 +367,13 @@ extern "C" int oq_weight_quant_bwd(const float* W, int N, int K, const float* co
   const bool let = col_scale || row_scale || e_row || dcol_acc || dshift_acc;
   const bool fast_al = (K % 4 == 0) && (group_size % 4 == 0) && (a.ld_g % 4 == 0) && al(W, 16) && al(grad_wq, 16) &&
                        al(col_scale, 16) && al(dW_full, 16);
-  static const int stream_mode = [] { const char* e = getenv("OQ_WQ_STREAM"); return e ? atoi(e) : 3; }();   // bit 0: lwc, bit 1: pipe
-  if (fast_al && !team_warp && !let && !dW_full && (stream_mode & 1)) {
+  if (fast_al && !team_warp && !let && !dW_full) {       // LWC only: R per row, one warp per row
     const int g = (int)std::min<long>((N + 7) / 8, (long)oq_num_sms() * 8);
     wq_pc_bwd_lwc<4><<<g, 256, 0, stream>>>(a);
     return oq_check_launch("oq_weight_quant_bwd");
   }
-  if (fast_al && !team_warp && let && (stream_mode & 2) && K % 8 == 0 && a.ld_g % 8 == 0) {
-    if (launch_pc_bwd_pipe(a, stream)) return oq_check_launch("oq_weight_quant_bwd");
+  if (fast_al && !team_warp && let && !dW_full && K % 8 == 0 && a.ld_g % 8 == 0) {   // bulk copies: 16-byte rows
+    if (launch_pc_bwd_ws(a, stream)) return oq_check_launch("oq_weight_quant_bwd");
   }
   if (fast_al && !team_warp && K <= 16384) {
     const size_t sm2 = let ? sizeof(float) * 3 * K : 0;

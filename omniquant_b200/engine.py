@@ -645,9 +645,42 @@ class BlockEngine:
 
 
 # ---------------------------------------------------------------------- per-block calibration loop
-def fp_pass(eng: BlockEngine, fp_inps: torch.Tensor, quant_inps: Optional[torch.Tensor] = None, aug_loss: bool = False):
+ACT_STAT_SITES = ("qkv", "out", "fc1", "fc2")     # inputs of q/k/v, the attention output projection, fc1 (gate/up), fc2 (down)
+
+
+def new_act_stats(eng: BlockEngine, n_samples: int):
+    """Per-sample buffers {site: (absmax [n, C], mid [n, C])} filled by ``fp_pass(..., stats=...)``."""
+    C = {"qkv": eng.H, "out": eng.H, "fc1": eng.H, "fc2": eng.F}
+    return {k: (torch.zeros(n_samples, C[k], device=eng.dev), torch.zeros(n_samples, C[k], device=eng.dev))
+            for k in ACT_STAT_SITES}
+
+
+def fold_act_stats(stats, sample_index=None, nsamples: Optional[int] = None, allreduce=None):
+    """{site: (act_scale [C], act_shift [C])} from the per-sample vectors, folded in GLOBAL sample order like
+    generate_act_scale_shift.py:34-37,69-72.  With several ranks every rank scatters its rows into a zero
+    [nsamples, C] matrix and the matrices are summed (x + 0 is exact), so all ranks fold identical inputs."""
+    out = {}
+    for site, (am, md) in stats.items():
+        if allreduce is not None:
+            idx = torch.as_tensor(sample_index, device=am.device)
+            full_a = torch.zeros(nsamples, am.shape[1], device=am.device)
+            full_m = torch.zeros_like(full_a)
+            full_a[idx], full_m[idx] = am, md
+            allreduce(full_a)
+            allreduce(full_m)
+            am, md = full_a, full_m
+        scale, shift = torch.empty(am.shape[1], device=am.device), torch.empty(am.shape[1], device=am.device)
+        ops.act_stats_fold(am.contiguous(), md.contiguous(), scale, shift, first=True)
+        out[site] = (scale, shift)
+    return out
+
+
+def fp_pass(eng: BlockEngine, fp_inps: torch.Tensor, quant_inps: Optional[torch.Tensor] = None, aug_loss: bool = False,
+            stats=None):
     """Full-precision targets (quantize/omniquant.py:165-172): fp_inps <- block(fp_inps) in place; with
-    ``aug_loss`` also returns block_fp(quant_inps) (the reference's fp_inps_2)."""
+    ``aug_loss`` also returns block_fp(quant_inps) (the reference's fp_inps_2).  ``stats`` (new_act_stats) additionally
+    records the per-channel statistics of the linear-layer inputs of every sample -- the activations of the unquantised
+    model that generate_act_scale_shift.py collects in a separate run."""
     n, T, H = fp_inps.shape
     b = eng.b
     fpw = eng.fp_weights()
@@ -660,6 +693,11 @@ def fp_pass(eng: BlockEngine, fp_inps: torch.Tensor, quant_inps: Optional[torch.
         tmp = torch.empty(b * T, H, device=eng.dev, dtype=BF16)
         for j in range(0, n, b):
             eng.forward(fp_inps[j:j + b].view(b * T, H), fpw, act_quant=False, out=tmp)
+            if stats is not None:
+                sv = eng.saved
+                for site, act in (("qkv", sv["a1"]), ("out", sv["O"]), ("fc1", sv["a2"]), ("fc2", sv["m"])):
+                    for i in range(b):
+                        ops.act_stats(act[i * T:(i + 1) * T], stats[site][0][j + i], stats[site][1][j + i])
             fp_inps[j:j + b].view(b * T, H).copy_(tmp)
     return fp2
 

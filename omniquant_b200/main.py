@@ -71,6 +71,9 @@ def build_parser():
     # additions of this implementation
     p.add_argument("--synthetic", action="store_true", help="random-init model of --net and synthetic tokens")
     p.add_argument("--num_layers", type=int, default=None, help="calibrate only the first N blocks (synthetic runs)")
+    p.add_argument("--online_act_stats", action="store_true",
+                   help="collect the LET activation statistics in the FP pass of each block instead of loading "
+                        "--act-scales / --act-shifts (generate_act_scale_shift.py); also used when those files are absent")
     p.add_argument("--seqlen", type=int, default=2048)
     return p
 
@@ -149,14 +152,20 @@ def main(argv=None):
         model = synthetic_model(args.net, args.num_layers)
         prefix = "model.layers" if "llama" in args.net.lower() else "model.decoder.layers"
         act_scales, act_shifts = synthetic_statistics(model, args.net, prefix)
+        if args.online_act_stats:
+            act_scales = act_shifts = None
         g = torch.Generator().manual_seed(1234)
         dataloader = [(torch.randint(0, model.config.vocab_size, (1, args.seqlen), generator=g), None)
                       for _ in range(args.nsamples)]
     else:
         from transformers import AutoModelForCausalLM
         model = AutoModelForCausalLM.from_pretrained(args.model, torch_dtype=torch.float16).eval()
-        act_scales = torch.load(args.act_scales or f"./act_scales/{args.net}.pt") if args.let else None
-        act_shifts = torch.load(args.act_shifts or f"./act_shifts/{args.net}.pt") if args.let else None
+        sc_path, sh_path = args.act_scales or f"./act_scales/{args.net}.pt", args.act_shifts or f"./act_shifts/{args.net}.pt"
+        act_scales = act_shifts = None
+        if args.let and not args.online_act_stats and os.path.exists(sc_path) and os.path.exists(sh_path):
+            act_scales, act_shifts = torch.load(sc_path), torch.load(sh_path)
+        elif args.let:
+            logger.info("LET activation statistics: collected online in the FP pass of each block")
         cache = f"{args.cache_dir}/dataloader_{args.model_family}_{args.calib_dataset}_{args.nsamples}.cache"
         if not os.path.exists(cache):
             raise FileNotFoundError(f"{cache}: calibration tokens must be prepared offline (datautils is out of scope)")

@@ -263,3 +263,37 @@ def let_prep_bwd(H, let_params, dbqkv, q_bias_scale, e):
 def let_grad_vec(H, F1, let_params, tmpv, acc, drow, dbqkv, q_bias_scale, let_grads):
     lib().call("oq_let_grad_vec", H, F1, _p(let_params), _p(tmpv), _p(acc), _p(drow), _p(dbqkv), float(q_bias_scale),
                _p(let_grads), _stream())
+
+
+# ------------------------------------------------------------------ activation statistics (LET initialisation)
+_STATS_WS = {}
+
+
+def act_stats(x: torch.Tensor, absmax: torch.Tensor = None, mid: torch.Tensor = None):
+    """Per-channel max|x| and (max+min)/2 over the rows of one sample x [rows, C] (bf16)
+    (generate_act_scale_shift.py:30-33 and :64-72)."""
+    import ctypes
+    _chk(x, BF16, "x")
+    _chk(absmax, F32, "absmax")
+    _chk(mid, F32, "mid")
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise OqError("act_stats: x must be a 2-D view with contiguous channels")
+    rows, C = x.shape
+    key = (rows, C, x.device)
+    ws = _STATS_WS.get(key)
+    if ws is None:
+        nbytes = ctypes.c_long(0)
+        lib().call("oq_act_stats_workspace", rows, C, ctypes.addressof(nbytes))
+        ws = _STATS_WS[key] = torch.empty(nbytes.value // 4, device=x.device, dtype=F32)
+    lib().call("oq_act_stats", _p(x), rows, C, x.stride(0), _p(absmax), _p(mid), _p(ws), ws.numel() * 4, _stream())
+
+
+def act_stats_fold(absmax, mid, scale_io=None, shift_io=None, first=True):
+    """Fold per-sample vectors (absmax [n, C], mid [n, C], sample order) into the running max / EMA of the reference."""
+    t = absmax if absmax is not None else mid
+    n, C = t.shape
+    for name, v in (("absmax", absmax), ("mid", mid), ("scale_io", scale_io), ("shift_io", shift_io)):
+        _chk(v, F32, name)
+        if v is not None and not v.is_contiguous():
+            raise OqError(f"act_stats_fold: {name} must be contiguous")
+    lib().call("oq_act_stats_fold", _p(absmax), _p(mid), n, C, int(first), _p(scale_io), _p(shift_io), _stream())

@@ -105,6 +105,16 @@ def init_let_parameters(qlayer, layer_idx, fam, args, act_scales, act_shifts, de
                 qlayer.register_parameter(f"{tag}_smooth_scale", nn.Parameter(scale))
 
 
+def _stat_names(qlayer, layer_idx, fam):
+    """{reference key 'prefix.i.linear_name': LET tag} of the linears whose input statistics initialise LET."""
+    out = {}
+    for name in get_named_linears(qlayer):
+        for key, tag in fam["pairs"].items():
+            if key in name:
+                out[f"{fam['prefix']}.{layer_idx}.{name}"] = tag
+    return out
+
+
 def omniquant(lm, args, dataloader, act_scales, act_shifts, logger=None, inps=None):
     """Calibrate every decoder block of ``lm.model``.  ``inps`` (optional, [nsamples, seqlen, H]) bypasses the
     embedding capture for synthetic runs."""
@@ -145,15 +155,34 @@ def omniquant(lm, args, dataloader, act_scales, act_shifts, logger=None, inps=No
         qlayer = fam["cls"](model.config, layer, args).to(dev)
         qlayer.set_quant_state(weight_quant=False, act_quant=True)
         qlayer.let = args.let
+        online = args.let and act_scales is None      # no statistics file: collect them in the FP pass of this block
         if args.let:
-            init_let_parameters(qlayer, i, fam, args, act_scales, act_shifts, dev)
+            if online:
+                H = model.config.hidden_size
+                names = _stat_names(qlayer, i, fam)
+                init_let_parameters(qlayer, i, fam, args, {k: torch.ones(H) for k in names},
+                                    {k: torch.zeros(H) for k in names}, dev)      # placeholders until the FP pass ran
+            else:
+                init_let_parameters(qlayer, i, fam, args, act_scales, act_shifts, dev)
         if getattr(args, "resume", None):
             qlayer.load_state_dict(omni_parameters[i], strict=False)
         qlayer.float()
         eng = qlayer._ensure_engine(T, b_local)
         eng.world = world
         if args.epochs > 0:
-            fp2 = E.fp_pass(eng, fp_inps, quant_inps, args.aug_loss)
+            collect = online and not getattr(args, "resume", None)
+            stats = E.new_act_stats(eng, fp_inps.shape[0]) if collect else None
+            fp2 = E.fp_pass(eng, fp_inps, quant_inps, args.aug_loss, stats=stats)
+            if collect:
+                folded = E.fold_act_stats(stats, idx, args.nsamples, allreduce)
+                names = _stat_names(qlayer, i, fam)
+                init_let_parameters(qlayer, i, fam, args, {k: folded[t][0] for k, t in names.items()},
+                                    {k: folded[t][1] for k, t in names.items()}, dev)
+                qlayer.float()
+                qlayer._push_params()
+                if getattr(args, "save_act_stats", None) is not None:
+                    args.save_act_stats[0].update({k: folded[t][0].cpu() for k, t in names.items()})
+                    args.save_act_stats[1].update({k: folded[t][1].cpu() for k, t in names.items()})
 
             def epoch_log(ep, ls, i=i):
                 if logger is not None:

@@ -561,3 +561,23 @@ def calibrate_block(family: str, Wt, P, cfg: QCfg, inps, n_heads, *, epochs, bat
     for k in let_keys + lwc_keys:
         P[k].requires_grad_(False)
     return dict(losses=losses, P=P, T_final=T_final, quant_out=qout, fp_out=fp_out, grads=grads0)
+
+
+# ---------------------------------------------------------------- activation statistics (LET initialisation inputs)
+def act_stats_sample(x):
+    """One sample's per-channel statistics of a linear layer's input x [..., C]: (max|x|, (max+min)/2), both fp32
+    (generate_act_scale_shift.py:30-33 stat_tensor of get_act_scales; :64-67,70,72 of get_act_shifts)."""
+    t = x.reshape(-1, x.shape[-1])
+    absmax = t.abs().max(dim=0)[0].float()
+    mid = (t.max(dim=0)[0].float() + t.min(dim=0)[0].float()) / 2
+    return absmax, mid
+
+
+def act_stats_fold(absmaxs, mids):
+    """Fold per-sample vectors in sample order: running max (generate_act_scale_shift.py:34-37) and the EMA
+    0.99*prev + 0.01*mid started from the first sample (:69-72)."""
+    scale, shift = absmaxs[0].clone(), mids[0].clone()
+    for i in range(1, len(absmaxs)):
+        scale = torch.max(scale, absmaxs[i])
+        shift = 0.99 * shift + 0.01 * mids[i]
+    return scale, shift

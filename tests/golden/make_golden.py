@@ -429,8 +429,48 @@ def falcon_block(tag, H, heads, kvh, T, nsamples, args, epochs, seed=0):
     _dump(os.path.join(OUT, f"falcon_{tag}.npz"), inputs, res, qlayer, lin)
 
 
+
+# ---------------------------------------------------------------- activation statistics (generate_act_scale_shift.py)
+def act_stats_fixture():
+    """get_act_scales / get_act_shifts of the reference on a two-linear toy model; the first linear sees the
+    (bf16-representable) inputs themselves, the second arbitrary fp32 activations."""
+    for n in ("datasets", "datautils", "tqdm"):
+        if n not in sys.modules:
+            try:
+                __import__(n)
+            except Exception:
+                sys.modules[n] = types.ModuleType(n)
+    if not hasattr(sys.modules["datasets"], "load_dataset"):
+        sys.modules["datasets"].load_dataset = None
+    if not hasattr(sys.modules["datautils"], "get_loaders"):
+        sys.modules["datautils"].get_loaders = None
+    if not hasattr(sys.modules["tqdm"], "tqdm"):
+        sys.modules["tqdm"].tqdm = lambda it, *a, **k: it
+    import generate_act_scale_shift as G
+    g = torch.Generator().manual_seed(77)
+    nsamples, T, C, C2 = 6, 48, 200, 72
+    model = torch.nn.Sequential(torch.nn.Linear(C, C2), torch.nn.Tanh(), torch.nn.Linear(C2, 16))
+    xs = (torch.randn(nsamples, 1, T, C, generator=g) * (1 + 3 * torch.rand(C, generator=g)) +
+          torch.randn(C, generator=g)).bfloat16().float()
+    dataloader = [(xs[i],) for i in range(nsamples)]
+    with torch.no_grad():
+        scales = G.get_act_scales(model, dataloader, nsamples)
+        shifts = G.get_act_shifts(model, dataloader, nsamples)
+        h = torch.stack([torch.tanh(model[0](xs[i])) for i in range(nsamples)])
+    out = {"in/x0": xs.numpy(), "in/x2": h.numpy()}
+    for k, v in scales.items():
+        out[f"out/scale/{k}"] = v.numpy()
+    for k, v in shifts.items():
+        out[f"out/shift/{k}"] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "act_stats.npz"), **out)
+    print("act_stats.npz", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if sys.argv[1:] == ["act_stats"]:
+        act_stats_fixture()
+        sys.exit(0)
     quantizer_cases()
     llama_block("w4a4_lwc_let", 256, 384, 2, 32, 4, make_args(4, 4, None, True, True), epochs=2)
     llama_block("w4a4_lwc_let_bs2", 256, 384, 2, 32, 4, make_args(4, 4, None, True, True), epochs=2, batch_size=2)
@@ -441,3 +481,4 @@ if __name__ == "__main__":
     opt_block("w4a16_lwc_let", 128, 256, 2, 32, 4, make_args(4, 16, None, True, True), epochs=2)
     opt_block("w4a4_lwc_let", 128, 256, 2, 32, 4, make_args(4, 4, None, True, True), epochs=2)
     falcon_block("w3a16g64_lwc", 256, 4, 2, 32, 4, make_args(3, 16, 64, True, False), epochs=2)
+    act_stats_fixture()

@@ -14,6 +14,8 @@ pytestmark = pytest.mark.gpu
     ("opt-tiny", ["--wbits", "4", "--abits", "16", "--group_size", "128", "--lwc"]),
     ("opt-tiny", ["--wbits", "4", "--abits", "4", "--lwc", "--let", "--aug_loss", "--batch_size", "2"]),
     ("falcon-tiny", ["--wbits", "4", "--abits", "16", "--group_size", "128", "--lwc"]),
+    ("opt-tiny", ["--wbits", "4", "--abits", "4", "--lwc", "--let", "--online_act_stats"]),
+    ("llama-tiny", ["--wbits", "4", "--abits", "16", "--lwc", "--let", "--online_act_stats", "--batch_size", "2"]),
 ])
 def test_main_synthetic(tmp_path, net, flags):
     from omniquant_b200.main import main

@@ -255,6 +255,35 @@ def test_falcon_engine_vs_oracle_16bit_emulation(wbits, abits, group, kv):
     assert not bad, bad
 
 
+def test_fp_pass_collects_act_stats():
+    """The FP pass records, per sample, the per-channel statistics of the linear-layer inputs
+    (generate_act_scale_shift.py); checked exactly against the engine's own activations of the last sample and within
+    bf16 tolerance against the oracle's fp32 activations folded with the reference's running max / EMA."""
+    from omniquant_b200 import engine as E
+    from oracle import oq_oracle as orc
+    fx = BlockFixture("opt_w4a4_lwc_let.npz")
+    eng = build_engine(fx)
+    x = fx.inps.cuda().to(torch.bfloat16)
+    fp = x.clone()
+    stats = E.new_act_stats(eng, fx.nsamples)
+    E.fp_pass(eng, fp, stats=stats)
+    torch.cuda.synchronize()
+    sv = eng.saved
+    for site, key in (("qkv", "a1"), ("out", "O"), ("fc1", "a2"), ("fc2", "m")):
+        a = sv[key][-fx.T:].float()
+        assert torch.equal(stats[site][0][-1], a.abs().amax(0)), site
+        assert torch.equal(stats[site][1][-1], (a.amax(0) + a.amin(0)) / 2), site
+    folded = E.fold_act_stats(stats)
+    W = fx.weights()
+    per = []
+    for i in range(fx.nsamples):
+        a1 = orc.layer_norm(x[i].float().cpu(), W["ln1"], W["ln1.bias"], 1e-5)
+        per.append(orc.act_stats_sample(a1))
+    sc, sh = orc.act_stats_fold([p[0] for p in per], [p[1] for p in per])
+    assert float((folded["qkv"][0].cpu() - sc).abs().max() / sc.abs().max()) < 1e-2
+    assert float((folded["qkv"][1].cpu() - sh).abs().max() / sc.abs().max()) < 1e-2
+
+
 def test_cuda_graph_step_equals_eager():
     """The CUDA-graph replay of the optimiser step (engine.train(use_graph=True)) must run exactly as many steps
     and land on the same parameters as eager stepping (atomics make the last bits differ)."""

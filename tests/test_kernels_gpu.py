@@ -525,3 +525,46 @@ def test_mse_adamw_colsum_truncate_transpose(ops):
     Xt = torch.empty(520, 300, device="cuda", dtype=torch.bfloat16)
     ops.transpose(X.cuda(), Xt)
     assert torch.equal(Xt.cpu(), X.t())
+
+
+# ------------------------------------------------------------------ activation statistics (LET initialisation inputs)
+@pytest.mark.parametrize("rows,C,pad", [(48, 200, 0), (2048, 4096, 0), (333, 1000, 8), (7, 8, 0), (129, 4100, 4)])
+def test_act_stats_bit_exact(ops, rows, C, pad):
+    """oq_act_stats / oq_act_stats_fold against the oracle (generate_act_scale_shift.py arithmetic), bit-exact;
+    ragged channel counts and strided rows included."""
+    from oracle import oq_oracle as orc
+    g = torch.Generator().manual_seed(rows * 7 + C)
+    n = 5
+    xs = (torch.randn(n, rows, C + pad, generator=g) * (1 + 3 * torch.rand(C + pad, generator=g)) +
+          torch.randn(C + pad, generator=g)).bfloat16()
+    xd = xs.cuda()
+    am = torch.empty(n, C, device="cuda")
+    md = torch.empty(n, C, device="cuda")
+    for i in range(n):
+        ops.act_stats(xd[i, :, :C], am[i], md[i])
+    per = [orc.act_stats_sample(xs[i, :, :C].float()) for i in range(n)]
+    for i in range(n):
+        assert torch.equal(am[i].cpu(), per[i][0]) and torch.equal(md[i].cpu(), per[i][1])
+    scale, shift = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.act_stats_fold(am, md, scale, shift, first=True)
+    rs, rsh = orc.act_stats_fold([p[0] for p in per], [p[1] for p in per])
+    assert torch.equal(scale.cpu(), rs) and torch.equal(shift.cpu(), rsh)
+    # continuing a running state in two calls gives the same result as one call
+    s2, h2 = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.act_stats_fold(am[:2], md[:2], s2, h2, first=True)
+    ops.act_stats_fold(am[2:].contiguous(), md[2:].contiguous(), s2, h2, first=False)
+    assert torch.equal(s2, scale) and torch.equal(h2, shift)
+
+
+def test_act_stats_matches_reference_fixture(ops):
+    from golden_util import load
+    z = load("act_stats.npz")
+    xs = torch.from_numpy(z["in/x0"]).squeeze(1).bfloat16().cuda()      # bf16-representable by construction
+    n, rows, C = xs.shape
+    am, md = torch.empty(n, C, device="cuda"), torch.empty(n, C, device="cuda")
+    for i in range(n):
+        ops.act_stats(xs[i], am[i], md[i])
+    scale, shift = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.act_stats_fold(am, md, scale, shift)
+    assert np.array_equal(scale.cpu().numpy(), z["out/scale/0"])
+    assert np.array_equal(shift.cpu().numpy(), z["out/shift/0"])

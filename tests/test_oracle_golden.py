@@ -138,3 +138,16 @@ def test_block_trajectory(fname):
         frac = np.mean(np.abs(w_or - w_ref) > 1e-6)
         assert frac < 5e-3, (n, frac)      # a handful of codes may flip from 1e-7 differences in trained factors
     np.testing.assert_allclose(res["quant_out"].numpy(), fx.quant_out.numpy(), rtol=0, atol=5e-2)
+
+
+def test_act_stats_oracle_matches_reference():
+    """get_act_scales / get_act_shifts of the reference (generate_act_scale_shift.py) on a toy model: the oracle's
+    per-sample statistics folded in sample order reproduce them bit for bit."""
+    from golden_util import load
+    z = load("act_stats.npz")
+    for site, key in (("0", "in/x0"), ("2", "in/x2")):
+        xs = torch.from_numpy(z[key])
+        per = [orc.act_stats_sample(xs[i]) for i in range(xs.shape[0])]
+        scale, shift = orc.act_stats_fold([p[0] for p in per], [p[1] for p in per])
+        assert np.array_equal(scale.numpy(), z[f"out/scale/{site}"])
+        assert np.array_equal(shift.numpy(), z[f"out/shift/{site}"])
