@@ -172,6 +172,16 @@ int oq_act_stats(const void* x, int rows, int C, long ld, float* absmax, float* 
 int oq_act_stats_fold(const float* absmax, const float* mid, int n, int C, int first, float* scale_io, float* shift_io,
                       oq_stream_t stream);
 
+/* ---- real-quant export (next row f1 of SURVEY.md section 8)
+ * Replaces `qlinear_cuda.QuantLinear(wbits, group_size, in, out, bias).pack(module, scales, zeros)` at
+ * quantize/omniquant.py:255-265 (AutoGPTQ wire format; see oracle/gptq_pack.py for the restated algorithm and what is
+ * unpinned).  W[N, K] is the fake-quantised fp32 weight, scales / zeros [N, G] (G = K / group_size, group_size 0 =
+ * per channel) as registered by quantizer.py:149-153.  Outputs: qweight int32 [K/32*bits, N], qzeros int32
+ * [G, N/32*bits] (zero - 1, fields masked to `bits` bits), scales_f16 [G, N], g_idx int32 [K].  bits in {2,3,4,8};
+ * N and K multiples of 32. */
+int oq_gptq_pack(const float* W, const float* scales, const float* zeros, int N, int K, int group_size, int n_bits,
+                 int32_t* qweight, int32_t* qzeros, void* scales_f16, int32_t* g_idx, oq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -297,3 +297,29 @@ def act_stats_fold(absmax, mid, scale_io=None, shift_io=None, first=True):
         if v is not None and not v.is_contiguous():
             raise OqError(f"act_stats_fold: {name} must be contiguous")
     lib().call("oq_act_stats_fold", _p(absmax), _p(mid), n, C, int(first), _p(scale_io), _p(shift_io), _stream())
+
+
+# ------------------------------------------------------------------ real-quant export (GPTQ wire format)
+def gptq_pack(W: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor, *, n_bits: int, group_size: int = 0):
+    """(qweight int32 [K/32*bits, N], qzeros int32 [G, N/32*bits], scales fp16 [G, N], g_idx int32 [K]) of a
+    fake-quantised weight W [N, K] with its per-group scales / zero points [N*G(,1)] (quantize/omniquant.py:255-265)."""
+    _chk(W, F32, "W")
+    _chk(scales, F32, "scales")
+    _chk(zeros, F32, "zeros")
+    if not (W.is_contiguous() and scales.is_contiguous() and zeros.is_contiguous()):
+        raise OqError("gptq_pack: contiguous tensors required")
+    N, K = W.shape
+    group = group_size or K
+    if K % group or K % 32 or N % 32:
+        raise OqError(f"gptq_pack: N={N}, K={K} must be multiples of 32 and K a multiple of the group size {group}")
+    G = K // group
+    if scales.numel() != N * G or zeros.numel() != N * G:
+        raise OqError(f"gptq_pack: scales / zeros must hold {N * G} values")
+    dev = W.device
+    qweight = torch.empty(K // 32 * n_bits, N, device=dev, dtype=torch.int32)
+    qzeros = torch.empty(G, N // 32 * n_bits, device=dev, dtype=torch.int32)
+    sc = torch.empty(G, N, device=dev, dtype=torch.float16)
+    g_idx = torch.empty(K, device=dev, dtype=torch.int32)
+    lib().call("oq_gptq_pack", _p(W), _p(scales), _p(zeros), N, K, int(group_size or 0), n_bits, _p(qweight), _p(qzeros),
+               _p(sc), _p(g_idx), _stream())
+    return qweight, qzeros, sc, g_idx

@@ -202,14 +202,17 @@ def omniquant(lm, args, dataloader, act_scales, act_shifts, logger=None, inps=No
         qlayer.register_scales_and_zeros()
         qlayer._eng = None                         # drop the fp32 masters / workspaces of this block
         qlayer._final_ws = None
+        saved = None
+        if getattr(args, "real_quant", False):     # pack before the fp16 cast: same integer codes, on the GPU (:255-278)
+            from .real_quant import pack_block
+            saved = {k: v.detach().half().cpu() for k, v in qlayer.omni_state_dict().items()}   # LWC factors leave with the QuantLinears
+            pack_block(qlayer, args.wbits)
         qlayer.half()
         layers[i] = qlayer.to("cpu")
         if args.epochs > 0:
-            omni_parameters[i] = qlayer.omni_state_dict()
+            omni_parameters[i] = saved if saved is not None else qlayer.omni_state_dict()
             if rank == 0 and getattr(args, "output_dir", None):
                 torch.save(omni_parameters, os.path.join(args.output_dir, "omni_parameters.pth"))
-        if getattr(args, "real_quant", False):
-            raise NotImplementedError("--real_quant (AutoGPTQ packing) is out of scope of the calibration hot path")
         del layer, eng
 
     del quant_inps, fp_inps

@@ -67,3 +67,29 @@ def test_resume_reproduces_quantised_weights(tmp_path):
             a, b = w1[n].float(), w2[n].float()
             assert float((a - b).norm() / a.norm()) < 5e-2, n
         torch.testing.assert_close(l1.input_layernorm.weight.float(), l2.input_layernorm.weight.float(), rtol=2e-3, atol=1e-3)
+
+
+def test_real_quant_packs_blocks(tmp_path):
+    """--real_quant (quantize/omniquant.py:255-278): every linear of a calibrated block becomes a packed module with
+    AutoGPTQ's buffer names; unpacking gives back integer codes whose dequantisation is the fake-quantised weight."""
+    import numpy as np
+    from omniquant_b200.main import main
+    from omniquant_b200.quantize.real_quant import PackedQuantLinear
+    from oracle import gptq_pack as gp
+    out = str(tmp_path / "log")
+    common = ["--model", "llama-tiny", "--synthetic", "--nsamples", "4", "--seqlen", "128", "--epochs", "1", "--wbits", "3",
+              "--abits", "16", "--group_size", "128", "--lwc", "--cache_dir", str(tmp_path / "cache")]
+    fake = main(common + ["--output_dir", out])
+    real = main(common + ["--output_dir", str(tmp_path / "log2"), "--real_quant"])
+    ck = torch.load(os.path.join(str(tmp_path / "log2"), "omni_parameters.pth"))
+    assert any(k.endswith("q_proj.weight_quantizer.upbound_factor") for k in ck[0])
+    for lf, lr in zip(fake.model.layers, real.model.layers):
+        packed = {n: m for n, m in lr.named_modules() if isinstance(m, PackedQuantLinear)}
+        assert len(packed) == 7
+        for n, m in packed.items():
+            assert set(dict(m.named_buffers())) == {"qweight", "qzeros", "scales", "g_idx"}
+            N, K = m.outfeatures, m.infeatures
+            p = {k: v.numpy() for k, v in m.named_buffers()}
+            dq = gp.dequant(p, 3, N, K)
+            ref = dict(lf.named_modules())[n].weight.float().numpy()
+            assert np.abs(dq - ref).max() <= 2e-3 * np.abs(ref).max()

@@ -568,3 +568,35 @@ def test_act_stats_matches_reference_fixture(ops):
     ops.act_stats_fold(am, md, scale, shift)
     assert np.array_equal(scale.cpu().numpy(), z["out/scale/0"])
     assert np.array_equal(shift.cpu().numpy(), z["out/shift/0"])
+
+
+# ------------------------------------------------------------------ real-quant export (GPTQ wire format)
+@pytest.mark.parametrize("bits,group,N,K", [(4, 128, 64, 256), (3, 128, 96, 384), (2, 64, 64, 256), (8, 0, 32, 128),
+                                            (3, 0, 64, 160), (4, 0, 4096, 4096), (3, 512, 128, 1024)])
+def test_gptq_pack_bit_exact(ops, bits, group, N, K):
+    """oq_gptq_pack against the numpy restatement of AutoGPTQ's QuantLinear.pack (oracle/gptq_pack.py), bit-exact, and
+    the round trip packed -> codes / zero points -> dequantised weights."""
+    from oracle import gptq_pack as gp
+    g = torch.Generator().manual_seed(bits * 100 + N)
+    W = (torch.randn(N, K, generator=g) * 0.02).cuda()
+    G = K // group if group else 1
+    up = torch.full((N * G,), 3.0, device="cuda")
+    wq = torch.empty(N, K, device="cuda")
+    sc, zp = torch.empty(N * G, device="cuda"), torch.empty(N * G, device="cuda")
+    codes = torch.empty(N, K, device="cuda", dtype=torch.uint8)
+    ops.weight_quant_fwd(W, n_bits=bits, group_size=group, up=up, low=up.clone(), wq_f32=wq, codes=codes, scale_out=sc,
+                         zp_out=zp, recip_div=False)
+    qw, qz, sh, gi = ops.gptq_pack(wq, sc, zp, n_bits=bits, group_size=group)
+    ref = gp.pack(wq.cpu().numpy(), sc.cpu().numpy().reshape(N, G), zp.cpu().numpy().reshape(N, G), bits, group)
+    assert np.array_equal(qw.cpu().numpy(), ref["qweight"])
+    assert np.array_equal(qz.cpu().numpy(), ref["qzeros"])
+    assert np.array_equal(sh.cpu().numpy(), ref["scales"])
+    assert np.array_equal(gi.cpu().numpy(), ref["g_idx"])
+    packed = dict(qweight=qw.cpu().numpy(), qzeros=qz.cpu().numpy(), scales=sh.cpu().numpy(), g_idx=gi.cpu().numpy())
+    c2, z2 = gp.unpack(packed, bits, N, K)
+    assert np.array_equal(c2, codes.cpu().numpy().astype(np.int64))            # the calibration's integer codes
+    assert np.array_equal(z2, zp.cpu().numpy().reshape(N, G).astype(np.int64) & ((1 << bits) - 1))
+    dq = gp.dequant(packed, bits, N, K)
+    ok = (zp.cpu().numpy().reshape(N, G) >= 0).all()
+    if ok:
+        assert np.abs(dq - wq.cpu().numpy()).max() <= 6e-4 * np.abs(wq.cpu().numpy()).max() + 1e-8   # fp16 scales

@@ -151,3 +151,27 @@ def test_act_stats_oracle_matches_reference():
         scale, shift = orc.act_stats_fold([p[0] for p in per], [p[1] for p in per])
         assert np.array_equal(scale.numpy(), z[f"out/scale/{site}"])
         assert np.array_equal(shift.numpy(), z[f"out/shift/{site}"])
+
+
+@pytest.mark.parametrize("bits,group", [(4, 128), (3, 128), (2, 64), (8, 0), (3, 0)])
+def test_gptq_pack_oracle_round_trip(bits, group):
+    """The packer restatement (unpinned third-party format, see oracle/gptq_pack.py): unpack(pack(x)) returns the integer
+    codes / zero points of the reference quantiser, and the 3-bit words follow AutoGPTQ's 10+1|10+1|10 split."""
+    from oracle import gptq_pack as gp
+    rng = np.random.default_rng(bits)
+    N, K = 64, 256
+    W = torch.from_numpy(rng.standard_normal((N, K)).astype(np.float32) * 0.02)
+    up = torch.full((orc.lwc_shape(W, group or None), 1), 4.0)
+    deq, s, z, codes = orc.fake_quant(W, bits, False, group or None, up, up.clone(), return_all=True)
+    p = gp.pack(deq.numpy(), s.numpy().reshape(N, -1), z.numpy().reshape(N, -1), bits, group)
+    c2, z2 = gp.unpack(p, bits, N, K)
+    assert np.array_equal(c2, codes.numpy().reshape(N, K).astype(np.int64))
+    assert np.array_equal(z2, z.numpy().reshape(N, -1).astype(np.int64))
+    assert p["qweight"].shape == (K // 32 * bits, N) and p["qzeros"].shape == (s.numel() // N, N // 32 * bits)
+    if bits == 3:      # literal transcription of the published loop for the first 32 input features of column 0
+        iw = codes.numpy().reshape(N, K).astype(np.uint32)[0, :32]
+        w0 = sum(int(iw[j]) << (3 * j) for j in range(10)) | (int(iw[10]) << 30)
+        w1 = ((int(iw[10]) >> 2) & 1) | sum(int(iw[11 + j]) << (3 * j + 1) for j in range(10)) | (int(iw[21]) << 31)
+        w2 = ((int(iw[21]) >> 1) & 3) | sum(int(iw[22 + j]) << (3 * j + 2) for j in range(10))
+        got = p["qweight"][:3, 0].astype(np.uint32)
+        assert [int(x) for x in got] == [w0 & 0xFFFFFFFF, w1 & 0xFFFFFFFF, w2 & 0xFFFFFFFF]
