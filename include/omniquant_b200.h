@@ -71,21 +71,40 @@ int oq_weight_quant_bwd(const float* W, int N, int K, const float* col_scale, co
  * Row r lives at x + (r / rows_inner)*ld_outer + (r % rows_inner)*ld_inner, C contiguous bf16 elements.
  * rope_cos/sin ([seq_len, C] fp32, or NULL): rotary embedding applied before quantisation
  * (models/int_llama_layer.py:124-125), position = (r / rows_inner) % seq_len; needs C in {64,128}.
- * n_bits >= 16 with rope = rotary only. */
+ * Only the inner rows [0, rope_inner) are rotated (rope_inner <= 0: all of them) -- one launch covers the fused
+ * [q heads | k heads | v heads] buffer of a token, V un-rotated (:162).  n_bits >= 16 with rope = rotary only
+ * (un-rotated rows are copied). */
 int oq_act_quant_fwd(const void* x, long rows, int C, int rows_inner, long ld_outer, long ld_inner, int n_bits,
-                     int symmetric, int recip_div, const float* rope_cos, const float* rope_sin, int seq_len, void* y,
-                     long ldy_outer, long ldy_inner, float* scale_out, float* zp_out, oq_stream_t stream);
+                     int symmetric, int recip_div, const float* rope_cos, const float* rope_sin, int seq_len,
+                     int rope_inner, void* y, long ldy_outer, long ldy_inner, float* scale_out, float* zp_out,
+                     oq_stream_t stream);
 /* Backward: gx = d/dx [ fake_quant(rope(x)) ] . gy   (x is the forward INPUT, re-quantised on the fly). */
 int oq_act_quant_bwd(const void* x, long rows, int C, int rows_inner, long ld_outer, long ld_inner, int n_bits,
                      int symmetric, int recip_div, const float* rope_cos, const float* rope_sin, int seq_len,
-                     const void* gy, long ldg_outer, long ldg_inner, void* gx, long ldgx_outer, long ldgx_inner,
-                     oq_stream_t stream);
+                     int rope_inner, const void* gy, long ldg_outer, long ldg_inner, void* gx, long ldgx_outer,
+                     long ldgx_inner, oq_stream_t stream);
+
+/* SwiGLU fused with the per-token quantiser of down_proj's input: mq = fake_quant(bf16(silu(gate) * up)) for
+ * gu = [gate | up] [rows, 2F] (LlamaMLP, models/int_llama_layer.py:44-45, feeding QuantLinear.act_quantizer,
+ * quantize/int_linear.py:59-60).  The un-quantised product is never written; the backward re-derives it from gu and
+ * returns dgu = d/dgu of the same composition.  Bit-identical to oq_swiglu_fwd + oq_act_quant_fwd (and their
+ * backwards) run one after the other. */
+int oq_swiglu_act_quant_fwd(const void* gu, long ldgu, long rows, int F, int n_bits, int symmetric, int recip_div,
+                            void* mq, long ldmq, oq_stream_t stream);
+int oq_swiglu_act_quant_bwd(const void* gu, long ldgu, long rows, int F, int n_bits, int symmetric, int recip_div,
+                            const void* gy, long ldgy, void* dgu, long lddgu, oq_stream_t stream);
 
 /* ---- K7: norms with temporary (folded) weight / bias ------------------------
  * kind 0: OmniLlamaRMSNorm.forward quantize/omni_norm.py:52-63; kind 1: OmniLayerNorm.forward :26-33.
  * w/b are the temp_weight/temp_bias of the step (b may be NULL). */
 int oq_norm_fwd(const void* x, long rows, int C, long ldx, const float* w, const float* b, float eps, int kind, void* y,
                 long ldy, float* mean_out, float* rstd_out, oq_stream_t stream);
+/* oq_norm_fwd plus yq = per-token fake-quant of the (bf16-rounded) norm output in the same pass: the norm feeding
+ * QuantLinear.act_quantizer of q/k/v or gate/up (quantize/int_linear.py:59-60).  y may be NULL.  Bit-identical to
+ * oq_norm_fwd followed by oq_act_quant_fwd. */
+int oq_norm_act_quant_fwd(const void* x, long rows, int C, long ldx, const float* w, const float* b, float eps, int kind,
+                          void* y, long ldy, float* mean_out, float* rstd_out, int n_bits, int symmetric, int recip_div,
+                          void* yq, long ldyq, oq_stream_t stream);
 /* dx = norm'(x).dy (+ dx_add);  dw_acc[c] += sum_r dy*xhat, db_acc[c] += sum_r dy (atomic adds; NULL to skip). */
 int oq_norm_bwd(const void* x, long rows, int C, long ldx, const float* w, int kind, const float* mean,
                 const float* rstd, const void* dy, long lddy, void* dx, long lddx, const void* dx_add, long ldadd,

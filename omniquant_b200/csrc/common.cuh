@@ -100,4 +100,15 @@ __device__ __forceinline__ void store_bf8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// ---- SwiGLU (LlamaMLP: down(silu(gate) * up), models/int_llama_layer.py:44-45); one definition shared by the
+// stand-alone and the act-quant-fused kernels so both produce the same bits
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float swiglu_val(float g, float u) { return __fmul_rn(__fmul_rn(g, sigmoid_fast(g)), u); }
+__device__ __forceinline__ void swiglu_grad(float g, float u, float d, float& dg, float& du) {
+  const float s = sigmoid_fast(g);
+  dg = __fmul_rn(__fmul_rn(__fmul_rn(d, u), s), __fmaf_rn(g, 1.0f - s, 1.0f));
+  du = __fmul_rn(__fmul_rn(d, g), s);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
 static inline int ceil_div_i(long a, long b) { return (int)((a + b - 1) / b); }

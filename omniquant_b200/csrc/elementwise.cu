@@ -13,8 +13,6 @@
 
 namespace {
 
-__device__ __forceinline__ float sigmoid_fast(float x) { return 1.0f / (1.0f + __expf(-x)); }
-
 // ---------------------------------------------------------------- SwiGLU
 // gu: [rows, 2F] = [gate | up];  m = silu(gate) * up
 __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* gu, long ldgu, bf16* m, long ldm, long rows, int F) {
@@ -26,7 +24,7 @@ __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* gu, long ld
     load_bf8(gu + r * ldgu + c, g);
     load_bf8(gu + r * ldgu + F + c, u);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = g[j] * sigmoid_fast(g[j]) * u[j];
+    for (int j = 0; j < 8; ++j) g[j] = swiglu_val(g[j], u[j]);
     store_bf8(m + r * ldm + c, g);
   }
 }
@@ -42,9 +40,8 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* gu, long ld
     load_bf8(dm + r * lddm + c, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float s = sigmoid_fast(g[j]);
-      const float dg = d[j] * u[j] * s * (1.0f + g[j] * (1.0f - s));
-      const float du = d[j] * g[j] * s;
+      float dg, du;
+      swiglu_grad(g[j], u[j], d[j], dg, du);
       g[j] = dg;
       u[j] = du;
     }
@@ -286,6 +283,166 @@ __global__ void __launch_bounds__(256) softmax_bwd_reg(const bf16* P, const void
   }
 }
 
+// ---- warp-per-row softmax for 16-bit scores (Tk <= 256*NC, Tk % 8 == 0): 16-byte accesses, NC independent loads in
+// flight per lane, no block barrier; causal rows stop at the diagonal as above.
+template <int DT>   // 2 fp16, 0 bf16
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  if constexpr (DT == 2) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+  } else {
+    unpack_bf2(u.x, v[0], v[1]); unpack_bf2(u.y, v[2], v[3]); unpack_bf2(u.z, v[4], v[5]); unpack_bf2(u.w, v[6], v[7]);
+  }
+}
+
+// Two warps per row, four rows per 256-thread block: a lane holds NC 16-byte chunks (Tk <= 512*NC), the two halves of
+// a row meet through shared memory.  Few registers per thread -> 32+ resident warps per SM to cover the HBM latency.
+template <int NC, int DT>
+__global__ void __launch_bounds__(256, 4) softmax_fwd_warp(const void* S, bf16* P, const float* mask, long mask_bstride,
+                                                           long rows, int Tq, int Tk, int causal) {
+  __shared__ float red[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = warp & 1;
+  long row = (long)blockIdx.x * 4 + (warp >> 1);
+  const bool live = row < rows;
+  if (!live) row = rows - 1;
+  const int i = (int)(row % Tq);
+  const long b = row / Tq;
+  const uint16_t* s = reinterpret_cast<const uint16_t*>(S) + row * (long)Tk;
+  bf16* p = P + row * (long)Tk;
+  const float* mk = mask ? mask + b * mask_bstride + (long)i * Tk : nullptr;
+  const int lim = causal ? min(Tk, i + (Tk - Tq) + 1) : Tk;
+  const int wlim = causal ? min(Tk, (lim + 127) & ~127) : Tk;
+  const int nc = (lim + 511) >> 9, ncw = (wlim + 511) >> 9;   // 512-column chunks with data / to be written (row-uniform)
+  const int j0 = (half * 32 + lane) * 8;
+  uint4 raw[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    if (c < nc && c * 512 + j0 < lim) raw[c] = *reinterpret_cast<const uint4*>(s + c * 512 + j0);
+  float v[NC][8];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c < nc) {
+      const int j = c * 512 + j0;
+      if (j < lim) {
+        unpack8<DT>(raw[c], v[c]);
+        if (mk) {
+          const float4 m0 = *reinterpret_cast<const float4*>(mk + j), m1 = *reinterpret_cast<const float4*>(mk + j + 4);
+          const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[c][e] = fmaxf(v[c][e] + m[e], -3.4028234663852886e38f);
+        }
+        if (j + 8 > lim) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (j + e >= lim) v[c][e] = -INFINITY;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mx = fmaxf(mx, v[c][e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[c][e] = -INFINITY;
+      }
+    }
+  }
+  mx = warp_reduce(mx, OpMax());
+  if (lane == 0) red[0][warp] = mx;
+  __syncthreads();
+  mx = fmaxf(mx, red[0][warp ^ 1]);
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c < nc) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[c][e] = __expf(v[c][e] - mx);
+      sum += ((v[c][0] + v[c][1]) + (v[c][2] + v[c][3])) + ((v[c][4] + v[c][5]) + (v[c][6] + v[c][7]));
+    }
+  }
+  sum = warp_reduce(sum, OpSum());
+  if (lane == 0) red[1][warp] = sum;
+  __syncthreads();
+  sum = red[1][warp & ~1] + red[1][warp | 1];
+  const float inv = 1.0f / sum;
+  if (!live) return;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c < ncw) {
+      const int j = c * 512 + j0;
+      if (j < wlim) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = c < nc ? v[c][e] * inv : 0.f;
+        store_bf8(p + j, o);
+      }
+    }
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256, 3) softmax_bwd_warp(const bf16* P, const bf16* dP, bf16* dS, long rows, int Tq, int Tk,
+                                                           int causal) {
+  __shared__ float red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = warp & 1;
+  long row = (long)blockIdx.x * 4 + (warp >> 1);
+  const bool live = row < rows;
+  if (!live) row = rows - 1;
+  const int i = (int)(row % Tq);
+  const int lim = causal ? min(Tk, i + (Tk - Tq) + 1) : Tk;
+  const int wlim = causal ? min(Tk, (lim + 127) & ~127) : Tk;
+  const int nc = (lim + 511) >> 9, ncw = (wlim + 511) >> 9;
+  const int j0 = (half * 32 + lane) * 8;
+  const bf16* p = P + row * (long)Tk;
+  const bf16* g = dP + row * (long)Tk;
+  bf16* ds = dS + row * (long)Tk;
+  uint4 pr[NC], gr[NC];      // the row stays packed in registers between the two passes
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    pr[c] = make_uint4(0u, 0u, 0u, 0u);
+    gr[c] = make_uint4(0u, 0u, 0u, 0u);
+    if (c < nc && c * 512 + j0 < lim) {
+      pr[c] = *reinterpret_cast<const uint4*>(p + c * 512 + j0);
+      gr[c] = *reinterpret_cast<const uint4*>(g + c * 512 + j0);
+    }
+  }
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c < nc) {
+      const int j = c * 512 + j0;
+      float pv[8], gv[8];
+      unpack8<0>(pr[c], pv);
+      unpack8<0>(gr[c], gv);
+      if (j + 8 > lim) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (j + e >= lim) pv[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc += pv[e] * gv[e];
+    }
+  }
+  acc = warp_reduce(acc, OpSum());
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  acc = red[warp & ~1] + red[warp | 1];
+  if (!live) return;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c < ncw) {
+      const int j = c * 512 + j0;
+      if (j < wlim) {
+        float pv[8], gv[8];
+        unpack8<0>(pr[c], pv);
+        unpack8<0>(gr[c], gv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pv[e] = (j + e < lim) ? pv[e] * (gv[e] - acc) : 0.f;
+        store_bf8(ds + j, pv);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- MSE
 // loss += inv_numel * sum((out-target)^2 [+ (out-target2)^2]);  dout = 2*inv_numel*((out-target) [+ (out-target2)])
 __global__ void __launch_bounds__(256) mse_kernel(const bf16* out, const bf16* tgt, const bf16* tgt2, long n8,
@@ -478,7 +635,12 @@ extern "C" int oq_softmax_fwd(const void* S, int s_dtype, void* P, const float* 
     if (s_dtype == 1) softmax_fwd_reg<NV, 1><<<grid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal); \
     else softmax_fwd_reg<NV, 2><<<grid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, Tq, Tk, causal);          \
   }
-  if (fast && Tk <= 1024) OQ_SMF(1)
+  const bool wrow = s_dtype == 2 && Tk % 8 == 0 && Tk <= 2048 && al16(S) && al16(P) && al16(mask);
+  const long rows = batch * Tq;
+  const unsigned wgrid = (unsigned)((rows + 3) / 4);
+  if (wrow && Tk <= 1024) softmax_fwd_warp<2, 2><<<wgrid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, rows, Tq, Tk, causal);
+  else if (wrow) softmax_fwd_warp<4, 2><<<wgrid, 256, 0, stream>>>(S, (bf16*)P, mask, mask_bstride, rows, Tq, Tk, causal);
+  else if (fast && Tk <= 1024) OQ_SMF(1)
   else if (fast && Tk <= 2048) OQ_SMF(2)
   else if (fast && Tk <= 4096) OQ_SMF(4)
   else if (fast) OQ_SMF(8)
@@ -498,7 +660,12 @@ extern "C" int oq_softmax_bwd(const void* P, const void* dP, int dp_dtype, void*
     if (dp_dtype == 1) softmax_bwd_reg<NV, 1><<<grid, 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal); \
     else softmax_bwd_reg<NV, 0><<<grid, 256, 0, stream>>>((const bf16*)P, dP, (bf16*)dS, Tq, Tk, causal);           \
   }
-  if (fast && Tk <= 1024) OQ_SMB(1)
+  const bool wrow = dp_dtype == 0 && Tk % 8 == 0 && Tk <= 2048 && al16(dP) && al16(P) && al16(dS);
+  const long rows = batch * Tq;
+  const unsigned wgrid = (unsigned)((rows + 3) / 4);
+  if (wrow && Tk <= 1024) softmax_bwd_warp<2><<<wgrid, 256, 0, stream>>>((const bf16*)P, (const bf16*)dP, (bf16*)dS, rows, Tq, Tk, causal);
+  else if (wrow) softmax_bwd_warp<4><<<wgrid, 256, 0, stream>>>((const bf16*)P, (const bf16*)dP, (bf16*)dS, rows, Tq, Tk, causal);
+  else if (fast && Tk <= 1024) OQ_SMB(1)
   else if (fast && Tk <= 2048) OQ_SMB(2)
   else if (fast && Tk <= 4096) OQ_SMB(4)
   else if (fast) OQ_SMB(8)

@@ -25,6 +25,8 @@ struct NormArgs {
   bf16* dx; long lddx;
   const bf16* dx_add; long ldadd;
   float* dw_acc; float* db_acc;
+  bf16* yq; long ldyq;      // optional fused per-token fake-quant of y (n_bits < 16)
+  int n_bits, symmetric, recip_div;
 };
 
 template <bool VEC>
@@ -75,6 +77,101 @@ __global__ void __launch_bounds__(256) norm_fwd_kernel(NormArgs a) {
     }
     if constexpr (VEC) store_bf8(yr + c, v);
     else yr[c] = f2bf(v[0]);
+  }
+}
+
+// Register-resident forward (C <= TPB*8*NV, C % 8 == 0): one read of x, one write of y; optionally also writes
+// yq = per-token fake-quant of the bf16-rounded y (QuantLinear.act_quantizer on the norm output,
+// quantize/int_linear.py:59-60) -- bit-identical to oq_act_quant_fwd run on y afterwards.
+template <int NV, int TPB>
+__global__ void __launch_bounds__(TPB) norm_fwd_reg(NormArgs a) {
+  __shared__ float scratch[2 * 32];
+  const long r = blockIdx.x;
+  const bf16* xr = a.x + r * a.ldx;
+  float v[NV][8];
+  float s[2] = {0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (threadIdx.x + i * TPB) * 8;
+    if (c < a.C) {
+      load_bf8(xr + c, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[0] += v[i][j]; s[1] += v[i][j] * v[i][j]; }
+    }
+  }
+  block_reduce<2>(s, scratch, OpSum(), 0.0f);
+  float mean = 0.f, rstd;
+  if (a.kind == 1) {
+    mean = s[0] / a.C;
+    float vs[1] = {0.f};
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (threadIdx.x + i * TPB) * 8;
+      if (c < a.C) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; vs[0] += d * d; }
+      }
+    }
+    block_reduce<1>(vs, scratch, OpSum(), 0.0f);
+    rstd = rsqrtf(vs[0] / a.C + a.eps);
+  } else {
+    rstd = rsqrtf(s[1] / a.C + a.eps);
+  }
+  if (threadIdx.x == 0) {
+    if (a.mean) a.mean[r] = mean;
+    if (a.rstd) a.rstd[r] = rstd;
+  }
+  float mm[2] = {-INFINITY, -INFINITY};   // -min, max of the bf16-rounded output
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (threadIdx.x + i * TPB) * 8;
+    if (c < a.C) {
+      const float4 w0 = *reinterpret_cast<const float4*>(a.w + c), w1 = *reinterpret_cast<const float4*>(a.w + c + 4);
+      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (a.b) {
+        const float4 b0 = *reinterpret_cast<const float4*>(a.b + c), b1 = *reinterpret_cast<const float4*>(a.b + c + 4);
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float h = (v[i][j] - mean) * rstd;
+        v[i][j] = w[j] * h + b[j];
+      }
+      if (a.y) store_bf8(a.y + r * a.ldy + c, v[i]);
+      if (a.yq) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[i][j] = bf16_round(v[i][j]);
+          mm[0] = fmaxf(mm[0], -v[i][j]);
+          mm[1] = fmaxf(mm[1], v[i][j]);
+        }
+      }
+    }
+  }
+  if (!a.yq) return;
+  block_reduce<2>(mm, scratch, OpMax(), -INFINITY);
+  const OqQParams q = oq_qparams(-mm[0], mm[1], 1.f, 1.f, 0, a.n_bits, a.symmetric, a.recip_div);
+  const float inv = OQ_DIV(1.0f, q.scale);
+  const bool fast = oq_inv_ok(inv);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (threadIdx.x + i * TPB) * 8;
+    if (c < a.C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x = v[i][j];
+        float t;
+        if (fast) {   // same arithmetic as the stand-alone quantiser (csrc/act_quant.cu aq_t)
+          const float qa = __fmul_rn(x, inv);
+          t = OQ_ADD(rintf(__fmaf_rn(__fmaf_rn(-qa, q.scale, x), inv, qa)), q.zp);
+        } else {
+          t = OQ_ADD(rintf(OQ_DIV(x, q.scale)), q.zp);
+        }
+        v[i][j] = oq_dequant(oq_clampf(t, 0.0f, q.qmax), q);
+      }
+      store_bf8(a.yq + r * a.ldyq + c, v[i]);
+    }
   }
 }
 
@@ -142,6 +239,117 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(NormArgs a) {
   }
 }
 
+// Register-resident variant (C <= 2048*NV, C % 8 == 0): a thread owns the same 8*NV columns for every row its block
+// visits, so the per-channel sums dL/dw', dL/db' accumulate in registers (the shared-memory accumulators of the kernel
+// above serialise on 8-way bank conflicts) and x / dy are read once.  Flushed with 16-byte vector atomics.
+template <int NV, bool ACC, int TPB>
+__global__ void __launch_bounds__(TPB, (NV == 1 ? 1024 : 512) / TPB) norm_bwd_reg(NormArgs a) {
+  __shared__ float scratch[2 * 32];
+  float wv[NV][8], dw[ACC ? NV : 1][8], db[ACC ? NV : 1][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (threadIdx.x + i * TPB) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      wv[i][j] = c < a.C ? a.w[c + j] : 0.f;
+      if constexpr (ACC) { dw[i][j] = 0.f; db[i][j] = 0.f; }
+    }
+  }
+  for (long r = blockIdx.x; r < a.rows; r += gridDim.x) {
+    const bf16* xr = a.x + r * a.ldx;
+    const bf16* gr = a.dy + r * a.lddy;
+    const float mean = a.kind == 1 ? a.mean[r] : 0.f, rstd = a.rstd[r];
+    float h[NV][8], dh[NV][8], ad[NV][8];
+    float s[2] = {0.f, 0.f};  // sum(dxhat*xhat), sum(dxhat)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (threadIdx.x + i * TPB) * 8;
+      if (c < a.C) {
+        load_bf8(xr + c, h[i]);
+        load_bf8(gr + c, dh[i]);
+        if (a.dx && a.dx_add) load_bf8(a.dx_add + r * a.ldadd + c, ad[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (threadIdx.x + i * TPB) * 8;
+      if (c < a.C) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float hh = (h[i][j] - mean) * rstd, g = dh[i][j];
+          const float d = g * wv[i][j];
+          s[0] += d * hh;
+          s[1] += d;
+          if constexpr (ACC) { dw[i][j] += g * hh; db[i][j] += g; }
+          h[i][j] = hh;
+          dh[i][j] = d;
+        }
+      }
+    }
+    if (a.dx) {
+      block_reduce<2>(s, scratch, OpSum(), 0.0f);
+      const float m1 = s[0] / a.C, m2 = a.kind == 1 ? s[1] / a.C : 0.f;
+      bf16* dr = a.dx + r * a.lddx;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (threadIdx.x + i * TPB) * 8;
+        if (c < a.C) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dh[i][j] = rstd * (dh[i][j] - m2 - h[i][j] * m1) + (a.dx_add ? ad[i][j] : 0.f);
+          store_bf8(dr + c, dh[i]);
+        }
+      }
+    }
+  }
+  if constexpr (ACC) {
+    const bool v4 = ((uintptr_t)a.dw_acc % 16 == 0) && ((uintptr_t)a.db_acc % 16 == 0);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (threadIdx.x + i * TPB) * 8;
+      if (c < a.C) {
+        if (v4) {
+          if (a.dw_acc) {
+            atomicAdd(reinterpret_cast<float4*>(a.dw_acc + c), make_float4(dw[i][0], dw[i][1], dw[i][2], dw[i][3]));
+            atomicAdd(reinterpret_cast<float4*>(a.dw_acc + c + 4), make_float4(dw[i][4], dw[i][5], dw[i][6], dw[i][7]));
+          }
+          if (a.db_acc) {
+            atomicAdd(reinterpret_cast<float4*>(a.db_acc + c), make_float4(db[i][0], db[i][1], db[i][2], db[i][3]));
+            atomicAdd(reinterpret_cast<float4*>(a.db_acc + c + 4), make_float4(db[i][4], db[i][5], db[i][6], db[i][7]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (a.dw_acc) atomicAdd(a.dw_acc + c + j, dw[i][j]);
+            if (a.db_acc) atomicAdd(a.db_acc + c + j, db[i][j]);
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+namespace {
+int norm_fwd_launch(const char* fn, NormArgs a, cudaStream_t stream) {
+  const bool al = (uintptr_t)a.x % 16 == 0 && (uintptr_t)a.y % 16 == 0 && (uintptr_t)a.yq % 16 == 0 &&
+                  (uintptr_t)a.w % 16 == 0 && (uintptr_t)a.b % 16 == 0;
+  const bool vec = a.C % 8 == 0 && a.ldx % 8 == 0 && (!a.y || a.ldy % 8 == 0) && (!a.yq || a.ldyq % 8 == 0) && al;
+  const unsigned g = (unsigned)a.rows;
+  if (vec && a.C <= 2048) norm_fwd_reg<1, 256><<<g, 256, 0, stream>>>(a);
+  else if (vec && a.C <= 4096) norm_fwd_reg<1, 512><<<g, 512, 0, stream>>>(a);
+  else if (vec && a.C <= 8192) norm_fwd_reg<2, 512><<<g, 512, 0, stream>>>(a);
+  else if (vec && a.C <= 16384) norm_fwd_reg<4, 512><<<g, 512, 0, stream>>>(a);
+  else {
+    if (a.yq) {
+      oq_set_error("%s: the fused quantiser needs C %% 8 == 0, C <= 16384, strides multiples of 8, 16-byte aligned pointers", fn);
+      return -1;
+    }
+    if (vec) norm_fwd_kernel<true><<<g, 256, 0, stream>>>(a);
+    else norm_fwd_kernel<false><<<g, 256, 0, stream>>>(a);
+  }
+  return oq_check_launch(fn);
+}
 }  // namespace
 
 extern "C" int oq_norm_fwd(const void* x, long rows, int C, long ldx, const float* w, const float* b, float eps,
@@ -152,10 +360,21 @@ extern "C" int oq_norm_fwd(const void* x, long rows, int C, long ldx, const floa
   NormArgs a = {};
   a.x = (const bf16*)x; a.ldx = ldx; a.rows = rows; a.C = C; a.w = w; a.b = b; a.eps = eps; a.kind = kind;
   a.y = (bf16*)y; a.ldy = ldy; a.mean = mean_out; a.rstd = rstd_out;
-  const bool vec = C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0;
-  if (vec) norm_fwd_kernel<true><<<(unsigned)rows, 256, 0, stream>>>(a);
-  else norm_fwd_kernel<false><<<(unsigned)rows, 256, 0, stream>>>(a);
-  return oq_check_launch("oq_norm_fwd");
+  return norm_fwd_launch("oq_norm_fwd", a, stream);
+}
+
+extern "C" int oq_norm_act_quant_fwd(const void* x, long rows, int C, long ldx, const float* w, const float* b, float eps,
+                                     int kind, void* y, long ldy, float* mean_out, float* rstd_out, int n_bits,
+                                     int symmetric, int recip_div, void* yq, long ldyq, cudaStream_t stream) {
+  OQ_REQUIRE(x && yq && w && rows > 0 && C > 0, "oq_norm_act_quant_fwd: null pointer or bad shape");
+  OQ_REQUIRE(kind == 0 || kind == 1, "oq_norm_act_quant_fwd: kind must be 0 (rms) or 1 (layernorm)");
+  OQ_REQUIRE(rows < (1L << 31), "oq_norm_act_quant_fwd: too many rows");
+  OQ_REQUIRE(n_bits >= 2 && n_bits <= 8, "oq_norm_act_quant_fwd: n_bits %d unsupported", n_bits);
+  NormArgs a = {};
+  a.x = (const bf16*)x; a.ldx = ldx; a.rows = rows; a.C = C; a.w = w; a.b = b; a.eps = eps; a.kind = kind;
+  a.y = (bf16*)y; a.ldy = ldy; a.mean = mean_out; a.rstd = rstd_out;
+  a.yq = (bf16*)yq; a.ldyq = ldyq; a.n_bits = n_bits; a.symmetric = symmetric; a.recip_div = recip_div;
+  return norm_fwd_launch("oq_norm_act_quant_fwd", a, stream);
 }
 
 extern "C" int oq_norm_bwd(const void* x, long rows, int C, long ldx, const float* w, int kind, const float* mean,
@@ -174,7 +393,16 @@ extern "C" int oq_norm_bwd(const void* x, long rows, int C, long ldx, const floa
                    (uintptr_t)x % 16 == 0 && (uintptr_t)dy % 16 == 0 && (uintptr_t)dx % 16 == 0 &&
                    (uintptr_t)dx_add % 16 == 0;
   const int grid = (int)std::min<long>(rows, smem ? (long)oq_num_sms() * 2 : rows);
-  if (vec) {
+  if (vec && C <= 8192) {
+    const bool acc = dw_acc || db_acc;
+#define OQ_NB(NV, TPB)                                                     \
+  {                                                                        \
+    if (acc) norm_bwd_reg<NV, true, TPB><<<grid, TPB, 0, stream>>>(a);     \
+    else norm_bwd_reg<NV, false, TPB><<<grid, TPB, 0, stream>>>(a);        \
+  }
+    if (C <= 2048) OQ_NB(1, 256) else if (C <= 4096) OQ_NB(1, 512) else OQ_NB(2, 512)
+#undef OQ_NB
+  } else if (vec) {
     if (smem > 40 * 1024) cudaFuncSetAttribute(norm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     norm_bwd_kernel<true><<<grid, 256, smem, stream>>>(a);
   } else {

@@ -308,6 +308,16 @@ class BlockEngine:
         ops.act_quant_fwd(x, y, n_bits=self.q.abits, recip_div=self.q.recip_div)
         return y
 
+    def _norm_aq(self, x, w, b, y, name, stats):
+        """y = norm(x) and, when activations are quantised, its per-token fake-quant in the same pass."""
+        if not self._act_quant:
+            ops.norm_fwd(x, w, b, self.eps, self.norm_kind, y, *stats)
+            return y
+        yq = self.buf(name, y.shape)
+        ops.norm_act_quant_fwd(x, w, b, self.eps, self.norm_kind, y, yq, n_bits=self.q.abits, recip_div=self.q.recip_div,
+                               mean_out=stats[0], rstd_out=stats[1])
+        return yq
+
     def forward(self, x: torch.Tensor, ws: dict, act_quant: bool, out: Optional[torch.Tensor] = None):
         """Block forward on x [M,H] bf16 (models/int_llama_layer.py:213-267 / int_opt_layer.py:268-346)."""
         M, H, F_, h, d, T = x.shape[0], self.H, self.F, self.h, self.d, self.T
@@ -318,8 +328,7 @@ class BlockEngine:
         falcon = self.family == "falcon"
         a1 = B("a1", (M, H))
         self.st1 = (B("mean1", (M,), F32), B("rstd1", (M,), F32))
-        ops.norm_fwd(x, ws["ln1w"], ws["ln1b"], self.eps, self.norm_kind, a1, *self.st1)
-        a1q = self._aq(a1, "a1q")
+        a1q = self._norm_aq(x, ws["ln1w"], ws["ln1b"], a1, "a1q", self.st1)
         QW, Hkv, hkv, rep = self.QW, self.Hkv, self.hkv, self.rep
         ok, ov = H, H + Hkv                     # column offsets of k and v in the [M, QW] qkv buffers (LLaMA / OPT)
         qkv = B("qkv", (M, QW))
@@ -337,14 +346,11 @@ class BlockEngine:
         if self.family == "llama":
             qkvq = B("qkvq", (M, QW))
             cos, sin = self.rope()
-            for c0, c1, nh in parts[:2]:   # rotary + per-(token, head) quant of q and k (int_llama_layer.py:124-125,141-142)
-                ops.act_quant_fwd(qkv[:, c0:c1].view(M, nh, d), qkvq[:, c0:c1].view(M, nh, d), n_bits=abits,
-                                  recip_div=self.q.recip_div, cos=cos, sin=sin, seq_len=T)
-            if abits < 16:                 # v quantised per (token, head) (:162)
-                ops.act_quant_fwd(qkv[:, ov:].view(M, hkv, d), qkvq[:, ov:].view(M, hkv, d), n_bits=abits,
-                                  recip_div=self.q.recip_div)
-            else:
-                qkvq[:, ov:].copy_(qkv[:, ov:])
+            # one launch over the [q heads | k heads | v heads] of every token: rotary on q and k, per-(token, head)
+            # quantisation of all three (int_llama_layer.py:124-125,141-142,162); abits >= 16: rotary only, v copied
+            nh3 = h + 2 * hkv
+            ops.act_quant_fwd(qkv.view(M, nh3, d), qkvq.view(M, nh3, d), n_bits=abits, recip_div=self.q.recip_div,
+                              cos=cos, sin=sin, seq_len=T, rope_inner=h + hkv)
             alpha = 1.0 / math.sqrt(d)
         elif falcon:
             # rotary on the q and k heads of every group, v untouched; no Q/K/V quantisation in the Falcon block
@@ -385,18 +391,23 @@ class BlockEngine:
         a2 = B("a2", (M, H))
         self.st2 = (B("mean2", (M,), F32), B("rstd2", (M,), F32))
         # Falcon: ln_mlp acts on the block input, attention and MLP run in parallel (int_falcon_layer.py:272-301)
-        ops.norm_fwd(x if falcon else h1, ws["ln2w"], ws["ln2b"], self.eps, self.norm_kind, a2, *self.st2)
-        a2q = self._aq(a2, "a2q")
+        a2q = self._norm_aq(x if falcon else h1, ws["ln2w"], ws["ln2b"], a2, "a2q", self.st2)
         f1 = B("f1", (M, W["fc1"].shape[0]))
         ops.linear_fwd(a2q, W["fc1"], f1, bias=ws["bfc1"])
-        m = B("m", (M, F_))
-        if self.glu:
-            ops.swiglu_fwd(f1, m)
-        elif falcon:
-            ops.gelu_fwd(f1, m)
+        if self.glu and self._act_quant:
+            # SwiGLU and down_proj's input quantiser in one pass; m itself is re-derived in the backward
+            m = None
+            mq = B("mq", (M, F_))
+            ops.swiglu_act_quant_fwd(f1, mq, n_bits=self.q.abits, recip_div=self.q.recip_div)
         else:
-            ops.relu_fwd(f1, m)
-        mq = self._aq(m, "mq")
+            m = B("m", (M, F_))
+            if self.glu:
+                ops.swiglu_fwd(f1, m)
+            elif falcon:
+                ops.gelu_fwd(f1, m)
+            else:
+                ops.relu_fwd(f1, m)
+            mq = self._aq(m, "mq")
         if out is None:
             out = B("out", (M, H))
         ops.linear_fwd(mq, W["fc2"], out, bias=ws["bfc2"], residual=h1)
@@ -447,10 +458,13 @@ class BlockEngine:
         ops.linear_dgrad(dout, W["fc2"], dmq)
         ops.linear_wgrad(dout, sv["mq"], dW["fc2"])
         self._unit_backward_side("fc2", dW, None)
-        dm = self._aq_bwd(sv["m"], dmq, "dm")
         df1 = B("df1", sv["f1"].shape)
         falcon = self.family == "falcon"
-        if self.glu:
+        fused_glu = self.glu and self._act_quant
+        dm = None if fused_glu else self._aq_bwd(sv["m"], dmq, "dm")
+        if fused_glu:
+            ops.swiglu_act_quant_bwd(sv["f1"], dmq, df1, n_bits=q.abits, recip_div=q.recip_div)
+        elif self.glu:
             ops.swiglu_bwd(sv["f1"], dm, df1)
         elif falcon:
             ops.gelu_bwd(sv["f1"], dm, df1)
@@ -523,14 +537,9 @@ class BlockEngine:
         if self.family == "llama":
             dqkv = B("dqkv", (M, QW))
             cos, sin = self.rope()
-            for c0, c1, nh in parts[:2]:
-                ops.act_quant_bwd(qkv[:, c0:c1].view(M, nh, d), dqkvq[:, c0:c1].view(M, nh, d), dqkv[:, c0:c1].view(M, nh, d),
-                                  n_bits=abits, recip_div=q.recip_div, cos=cos, sin=sin, seq_len=T)
-            if abits < 16:
-                ops.act_quant_bwd(qkv[:, ov:].view(M, hkv, d), dqkvq[:, ov:].view(M, hkv, d), dqkv[:, ov:].view(M, hkv, d),
-                                  n_bits=abits, recip_div=q.recip_div)
-            else:
-                dqkv[:, ov:].copy_(dqkvq[:, ov:])
+            nh3 = h + 2 * hkv
+            ops.act_quant_bwd(qkv.view(M, nh3, d), dqkvq.view(M, nh3, d), dqkv.view(M, nh3, d), n_bits=abits,
+                              recip_div=q.recip_div, cos=cos, sin=sin, seq_len=T, rope_inner=h + hkv)
         elif falcon:
             dqkv = B("dqkv", (M, QW))
             cos, sin = self.rope()

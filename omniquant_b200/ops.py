@@ -86,24 +86,43 @@ def _rows2(x: torch.Tensor, name: str):
     raise OqError(f"{name}: expected 2-D or 3-D view, got {tuple(x.shape)}")
 
 
-def act_quant_fwd(x, y, *, n_bits, symmetric=False, recip_div=True, cos=None, sin=None, seq_len=0, scale_out=None,
-                  zp_out=None):
+def act_quant_fwd(x, y, *, n_bits, symmetric=False, recip_div=True, cos=None, sin=None, seq_len=0, rope_inner=0,
+                  scale_out=None, zp_out=None):
     rows, C, ri, lo, li = _rows2(x, "x")
     rows2, C2, ri2, lo2, li2 = _rows2(y, "y")
     if (rows, C, ri) != (rows2, C2, ri2):
         raise OqError("act_quant_fwd: x / y shape mismatch")
     lib().call("oq_act_quant_fwd", _p(x), rows, C, ri, lo, li, n_bits, int(symmetric), int(recip_div), _p(cos), _p(sin),
-               seq_len, _p(y), lo2, li2, _p(scale_out), _p(zp_out), _stream())
+               seq_len, rope_inner, _p(y), lo2, li2, _p(scale_out), _p(zp_out), _stream())
 
 
-def act_quant_bwd(x, gy, gx, *, n_bits, symmetric=False, recip_div=True, cos=None, sin=None, seq_len=0):
+def act_quant_bwd(x, gy, gx, *, n_bits, symmetric=False, recip_div=True, cos=None, sin=None, seq_len=0, rope_inner=0):
     rows, C, ri, lo, li = _rows2(x, "x")
     r2, c2, ri2, glo, gli = _rows2(gy, "gy")
     r3, c3, ri3, xlo, xli = _rows2(gx, "gx")
     if (rows, C, ri) != (r2, c2, ri2) or (rows, C, ri) != (r3, c3, ri3):
         raise OqError("act_quant_bwd: shape mismatch")
     lib().call("oq_act_quant_bwd", _p(x), rows, C, ri, lo, li, n_bits, int(symmetric), int(recip_div), _p(cos), _p(sin),
-               seq_len, _p(gy), glo, gli, _p(gx), xlo, xli, _stream())
+               seq_len, rope_inner, _p(gy), glo, gli, _p(gx), xlo, xli, _stream())
+
+
+def swiglu_act_quant_fwd(gu, mq, *, n_bits, symmetric=False, recip_div=True):
+    """mq = fake_quant(silu(gate) * up) for gu = [gate | up]; the product itself is not stored."""
+    _chk(gu, BF16, "gu"); _chk(mq, BF16, "mq")
+    rows, F = mq.shape
+    if gu.shape != (rows, 2 * F):
+        raise OqError("swiglu_act_quant_fwd: gu must be [rows, 2F]")
+    lib().call("oq_swiglu_act_quant_fwd", _p(gu), _rowmajor(gu, "gu"), rows, F, n_bits, int(symmetric), int(recip_div),
+               _p(mq), _rowmajor(mq, "mq"), _stream())
+
+
+def swiglu_act_quant_bwd(gu, gy, dgu, *, n_bits, symmetric=False, recip_div=True):
+    _chk(gu, BF16, "gu"); _chk(gy, BF16, "gy"); _chk(dgu, BF16, "dgu")
+    rows, F = gy.shape
+    if gu.shape != (rows, 2 * F) or dgu.shape != (rows, 2 * F):
+        raise OqError("swiglu_act_quant_bwd: gu / dgu must be [rows, 2F]")
+    lib().call("oq_swiglu_act_quant_bwd", _p(gu), _rowmajor(gu, "gu"), rows, F, n_bits, int(symmetric), int(recip_div),
+               _p(gy), _rowmajor(gy, "gy"), _p(dgu), _rowmajor(dgu, "dgu"), _stream())
 
 
 # ------------------------------------------------------------------ norms
@@ -111,6 +130,14 @@ def norm_fwd(x, w, b, eps, kind, y, mean_out=None, rstd_out=None):
     _chk(x, BF16, "x"); _chk(y, BF16, "y"); _chk(w, F32, "w"); _chk(b, F32, "b")
     lib().call("oq_norm_fwd", _p(x), x.shape[0], x.shape[1], _rowmajor(x, "x"), _p(w), _p(b), float(eps), kind, _p(y),
                _rowmajor(y, "y"), _p(mean_out), _p(rstd_out), _stream())
+
+
+def norm_act_quant_fwd(x, w, b, eps, kind, y, yq, *, n_bits, symmetric=False, recip_div=True, mean_out=None, rstd_out=None):
+    """y = norm(x) (optional) and yq = fake_quant(y) per token, one pass."""
+    _chk(x, BF16, "x"); _chk(y, BF16, "y"); _chk(yq, BF16, "yq"); _chk(w, F32, "w"); _chk(b, F32, "b")
+    lib().call("oq_norm_act_quant_fwd", _p(x), x.shape[0], x.shape[1], _rowmajor(x, "x"), _p(w), _p(b), float(eps), kind,
+               _p(y), _rowmajor(y, "y") if y is not None else 0, _p(mean_out), _p(rstd_out), n_bits, int(symmetric),
+               int(recip_div), _p(yq), _rowmajor(yq, "yq"), _stream())
 
 
 def norm_bwd(x, w, kind, mean, rstd, dy, dx=None, dx_add=None, dw_acc=None, db_acc=None):

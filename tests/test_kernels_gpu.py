@@ -286,6 +286,84 @@ def test_act_quant_rope_heads(ops):
         torch.testing.assert_close(y2.cpu().float(), qr.detach()[0].transpose(0, 1), rtol=1e-2, atol=1e-2)
 
 
+def test_act_quant_fused_qkv_launch(ops):
+    """One launch over [q heads | k heads | v heads] of a token (rope_inner = rotated heads) must equal the three
+    separate launches bit for bit, forward and backward, for MHA and GQA head counts (chunk tails included) and for
+    the rotary-only (n_bits=16) mode, where the V heads are copied."""
+    gen = torch.Generator().manual_seed(11)
+    for d, h, hkv, T in ((128, 5, 5, 37), (64, 12, 3, 29), (128, 32, 32, 16)):
+        nh = h + 2 * hkv
+        qkv = torch.randn(T, nh * d, generator=gen).to(torch.bfloat16).cuda()
+        gy = torch.randn(T, nh * d, generator=gen).to(torch.bfloat16).cuda()
+        cos, sin = (v.cuda() for v in orc.rope_tables(d, T))
+        for nb in (4, 16):
+            y1, y3 = torch.zeros_like(qkv), torch.zeros_like(qkv)
+            g1, g3 = torch.zeros_like(qkv), torch.zeros_like(qkv)
+            sc1, sc3 = torch.zeros(T * nh, device="cuda"), torch.zeros(T, nh, device="cuda")
+            v3 = lambda t_: t_.view(T, nh, d)
+            kw = dict(scale_out=sc1) if nb < 16 else {}
+            ops.act_quant_fwd(v3(qkv), v3(y1), n_bits=nb, recip_div=True, cos=cos, sin=sin, seq_len=T, rope_inner=h + hkv, **kw)
+            ops.act_quant_bwd(v3(qkv), v3(gy), v3(g1), n_bits=nb, recip_div=True, cos=cos, sin=sin, seq_len=T,
+                              rope_inner=h + hkv)
+            for a, b, rope in ((0, h + hkv, True), (h + hkv, nh, False)):
+                if not rope and nb >= 16:
+                    v3(y3)[:, a:b].copy_(v3(qkv)[:, a:b])
+                    v3(g3)[:, a:b].copy_(v3(gy)[:, a:b])
+                    continue
+                rk = dict(cos=cos, sin=sin, seq_len=T) if rope else {}
+                sc_part = torch.zeros(T * (b - a), device="cuda")
+                fk = dict(scale_out=sc_part) if nb < 16 else {}
+                ops.act_quant_fwd(v3(qkv)[:, a:b], v3(y3)[:, a:b], n_bits=nb, recip_div=True, **rk, **fk)
+                ops.act_quant_bwd(v3(qkv)[:, a:b], v3(gy)[:, a:b], v3(g3)[:, a:b], n_bits=nb, recip_div=True, **rk)
+                sc3[:, a:b] = sc_part.view(T, b - a)
+            torch.cuda.synchronize()
+            assert torch.equal(y1, y3) and torch.equal(g1, g3)
+            if nb < 16:
+                assert torch.equal(sc1.view(T, nh), sc3)
+
+
+@pytest.mark.parametrize("F", [11008, 3072, 256, 16384])
+def test_swiglu_act_quant_fused_equals_unfused(ops, F):
+    """oq_swiglu_act_quant_fwd/bwd == oq_swiglu_fwd -> oq_act_quant_fwd (and the two backwards) bit for bit."""
+    gen = torch.Generator().manual_seed(F)
+    rows = 19
+    gu = (torch.randn(rows, 2 * F, generator=gen) * 1.5).to(torch.bfloat16).cuda()
+    gy = torch.randn(rows, F, generator=gen).to(torch.bfloat16).cuda()
+    for nb in (4, 6):
+        m, mq, mq2 = (torch.empty(rows, F, device="cuda", dtype=torch.bfloat16) for _ in range(3))
+        ops.swiglu_fwd(gu, m)
+        ops.act_quant_fwd(m, mq, n_bits=nb, recip_div=True)
+        ops.swiglu_act_quant_fwd(gu, mq2, n_bits=nb, recip_div=True)
+        dm = torch.empty_like(m)
+        d1, d2 = torch.empty_like(gu), torch.empty_like(gu)
+        ops.act_quant_bwd(m, gy, dm, n_bits=nb, recip_div=True)
+        ops.swiglu_bwd(gu, dm, d1)
+        ops.swiglu_act_quant_bwd(gu, gy, d2, n_bits=nb, recip_div=True)
+        torch.cuda.synchronize()
+        assert torch.equal(mq, mq2)
+        assert torch.equal(d1, d2)
+
+
+@pytest.mark.parametrize("C,kind", [(4096, 0), (768, 1), (8192, 0), (14848, 1), (256, 0)])
+def test_norm_act_quant_fused_equals_unfused(ops, C, kind):
+    """oq_norm_act_quant_fwd == oq_norm_fwd -> oq_act_quant_fwd bit for bit (y, yq, row statistics)."""
+    gen = torch.Generator().manual_seed(C + kind)
+    rows = 21
+    x = (torch.randn(rows, C, generator=gen) * 2).to(torch.bfloat16).cuda()
+    w = (1 + 0.1 * torch.randn(C, generator=gen)).cuda()
+    b = (0.1 * torch.randn(C, generator=gen)).cuda() if kind == 1 else None
+    y1, y2, q1, q2 = (torch.empty_like(x) for _ in range(4))
+    st = [torch.zeros(rows, device="cuda") for _ in range(4)]
+    ops.norm_fwd(x, w, b, 1e-5, kind, y1, st[0], st[1])
+    ops.act_quant_fwd(y1, q1, n_bits=4, recip_div=True)
+    ops.norm_act_quant_fwd(x, w, b, 1e-5, kind, y2, q2, n_bits=4, recip_div=True, mean_out=st[2], rstd_out=st[3])
+    q3 = torch.empty_like(x)
+    ops.norm_act_quant_fwd(x, w, b, 1e-5, kind, None, q3, n_bits=4, recip_div=True)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2) and torch.equal(q1, q2) and torch.equal(q1, q3)
+    assert torch.equal(st[0], st[2]) and torch.equal(st[1], st[3])
+
+
 def test_act_quant_large_rows(ops):
     gen = torch.Generator().manual_seed(9)
     for C in (4096, 11008, 768, 100):
