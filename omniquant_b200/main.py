@@ -178,6 +178,19 @@ def main(argv=None):
         tick = time.time()
         omniquant(lm, args, dataloader, act_scales, act_shifts, logger)
         logger.info(time.time() - tick)
+    if args.eval_ppl:
+        # main.py:97-148 on a caller-supplied / synthetic token stream (dataset loaders are out of scope)
+        from .evaluate import evaluate_ppl
+        if args.synthetic or not os.path.isdir(args.model or ""):
+            g = torch.Generator().manual_seed(4321)
+            testenc = torch.randint(0, model.config.vocab_size, (1, args.seqlen * max(1, args.limit if args.limit > 0 else 4)), generator=g)
+        else:
+            path = f"{args.cache_dir}/testloader_{args.model_family}_wikitext2_all.cache"
+            if not os.path.exists(path):
+                raise FileNotFoundError(f"{path}: evaluation tokens must be prepared offline (datautils is out of scope)")
+            testenc = torch.load(path)
+            testenc = testenc.input_ids if hasattr(testenc, "input_ids") else testenc
+        args.ppl = evaluate_ppl(lm, args, testenc, logger, limit=args.limit)
     if args.save_dir:
         model.save_pretrained(args.save_dir)
     return model

@@ -149,9 +149,13 @@ def omniquant(lm, args, dataloader, act_scales, act_shifts, logger=None, inps=No
     T = lm.seqlen
     use_graph = getattr(args, "cuda_graph", True)
 
+    from ..streaming import BlockStreamer
+    streamer = BlockStreamer(layers, dev, enabled=getattr(args, "prefetch_blocks", True))
+
     for i in range(len(layers)):
         log(f"=== Start quantize layer {i} ===")
-        layer = layers[i].to(dev)
+        layer = streamer.fetch(i)                  # :159, already resident when block i-1 prefetched it
+        streamer.prefetch(i + 1)                   # next block's H2D copy overlaps this block's calibration
         qlayer = fam["cls"](model.config, layer, args).to(dev)
         qlayer.set_quant_state(weight_quant=False, act_quant=True)
         qlayer.let = args.let

@@ -93,3 +93,68 @@ def test_real_quant_packs_blocks(tmp_path):
             dq = gp.dequant(p, 3, N, K)
             ref = dict(lf.named_modules())[n].weight.float().numpy()
             assert np.abs(dq - ref).max() <= 2e-3 * np.abs(ref).max()
+
+
+def _tiny_args(tmp_path, extra=(), epochs=2):
+    return ["--model", "llama-tiny", "--synthetic", "--nsamples", "4", "--seqlen", "128", "--epochs", str(epochs), "--wbits", "4",
+            "--abits", "4", "--lwc", "--let", "--output_dir", str(tmp_path / "log"), "--cache_dir", str(tmp_path / "cache"),
+            "--num_layers", "3"] + list(extra)
+
+
+def test_block_prefetch_is_transparent(tmp_path):
+    """Blocks streamed from pinned host memory on the copy stream (streaming.BlockStreamer) give exactly the model
+    the synchronous layer.to(dev) path gives (--epochs 0: fold + round-to-nearest only, so the comparison is bit for
+    bit; the optimiser steps accumulate gradients with atomics and are not run-to-run deterministic)."""
+    from omniquant_b200 import main as M
+    a = M.main(_tiny_args(tmp_path / "a", epochs=0))
+    import unittest.mock as mock
+    from omniquant_b200 import streaming
+    with mock.patch.object(streaming.BlockStreamer, "prefetch", lambda self, i: None):
+        b = M.main(_tiny_args(tmp_path / "b", epochs=0))
+    sa, sb = a.state_dict(), b.state_dict()
+    assert sa.keys() == sb.keys()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+
+
+def test_eval_path_matches_oracle_block_chain(tmp_path):
+    """Post-calibration inference (evaluate.block_chain / evaluate_ppl, reference main.py:97-148): the calibrated blocks
+    run with in-place quantised weights + dynamic activation quantisation; hidden states are compared with the CPU oracle
+    forward (16-bit storage emulation) fed the same quantised weights, the perplexity with the one computed from them."""
+    from types import SimpleNamespace
+    from oracle import oq_oracle as orc
+    from omniquant_b200 import main as M
+    from omniquant_b200.evaluate import block_chain, evaluate_ppl
+    argv = _tiny_args(tmp_path)
+    model = M.main(argv)
+    args = M.build_parser().parse_args(argv)
+    args.net = "llama-tiny"
+    M.quant_param_dicts(args)
+    T = 128
+    lm = SimpleNamespace(model=model, device=torch.device("cuda"), _device=torch.device("cuda"), seqlen=T)
+    g = torch.Generator().manual_seed(99)
+    toks = torch.randint(0, model.config.vocab_size, (2, T), generator=g)
+    hs = block_chain(lm, args, toks).float().cpu()
+    # oracle chain on the same (already folded + fake-quantised) weights
+    cfg = orc.QCfg(16, 4, None, False, False, False, recip_div=True, emu16=torch.bfloat16)
+    heads = model.config.num_attention_heads
+    cos, sin = orc.rope_tables(model.config.hidden_size // heads, T)
+    x = model.model.embed_tokens(toks).to(torch.bfloat16).float()
+    for layer in model.model.layers:
+        Tw = {}
+        for n, path in layer.linear_names.items():
+            m = layer._mod(path)
+            Tw[f"{n}.w"] = m.weight.float()
+            Tw[f"{n}.b"] = m.bias.float() if getattr(m, "bias", None) is not None else None
+        for key, nm in zip(("ln1", "ln2"), layer.norm_names):
+            mod = layer._mod(nm)
+            Tw[f"{key}w"] = mod.weight.float()
+            Tw[f"{key}b"] = mod.bias.float() if getattr(mod, "bias", None) is not None else None
+        x = orc.llama_forward(x, Tw, heads, cos, sin, orc.causal_mask(T), cfg, act_quant=True,
+                              eps=model.config.rms_norm_eps)
+    rel = (hs - x).norm() / x.norm()
+    assert rel < 3e-2, rel          # a few 4-bit activation codes re-drawn by bf16 rounding differences
+    ppl = evaluate_ppl(lm, args, toks)
+    logits = model.lm_head(model.model.norm(x.to(model.lm_head.weight.dtype)).to(model.lm_head.weight.dtype)).float()
+    nll = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]), toks[:, 1:].reshape(-1))
+    assert abs(ppl - float(torch.exp(nll))) / float(torch.exp(nll)) < 2e-2
