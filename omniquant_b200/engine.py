@@ -371,19 +371,21 @@ class BlockEngine:
             alpha = 1.0
         self.qkv, self.qkvq, self.att_alpha = qkv, qkvq, alpha
         P = B("P", (nb, h, T, T))
-        S = B("S", (h, T, T), torch.float16)     # scores in fp16 like the reference's autocast (int_llama_layer.py:143)
+        passes = self._att_passes()
+        hmax = max(c1 - c0 for c0, c1, _ in passes)
+        S = B("S", (hmax, T, T), torch.float16)     # scores in fp16 like the reference's autocast (int_llama_layer.py:143)
         O = B("O", (M, H))
         cz = 1 if self.causal else 0
-        groups = self._att_layout()
         for s in range(nb):
             r = slice(s * T, (s + 1) * T)
-            for h0, nh, cq, ck, cv, sb in groups:
-                ops.gemm(qkvq[r, cq:], qkvq[r, ck:], S[h0:], M=T, N=T, K=d, lda=QW, ldb=QW, ldc=T, batch=nh, strideA=d,
-                         strideB=sb, strideC=T * T, alpha=alpha, causal=cz)
-            ops.softmax_fwd(S, P[s], mask=self.mask, causal=self.causal)
-            for h0, nh, cq, ck, cv, sb in groups:
-                ops.gemm(P[s, h0:], qkvq[r, cv:], O[r, h0 * d:], M=T, N=d, K=T, lda=T, ldb=QW, b_mn=True, ldc=H, batch=nh,
-                         strideA=T * T, strideB=sb, strideC=d, causal=2 * cz)
+            for c0, c1, groups in passes:       # a few heads at a time: scores + probabilities of a pass stay in L2
+                for h0, nh, cq, ck, cv, sb in groups:
+                    ops.gemm(qkvq[r, cq:], qkvq[r, ck:], S[h0 - c0:], M=T, N=T, K=d, lda=QW, ldb=QW, ldc=T, batch=nh, strideA=d,
+                             strideB=sb, strideC=T * T, alpha=alpha, causal=cz)
+                ops.softmax_fwd(S[:c1 - c0], P[s, c0:c1], mask=self.mask, causal=self.causal)
+                for h0, nh, cq, ck, cv, sb in groups:
+                    ops.gemm(P[s, h0:], qkvq[r, cv:], O[r, h0 * d:], M=T, N=d, K=T, lda=T, ldb=QW, b_mn=True, ldc=H, batch=nh,
+                             strideA=T * T, strideB=sb, strideC=d, causal=2 * cz)
         Oq = self._aq(O, "Oq")
         h1 = B("h1", (M, H))
         self._join()                # o / fc1 / fc2 operands of this step come from the side stream
@@ -425,6 +427,35 @@ class BlockEngine:
         if rep == 1:
             return [(0, h, 0, H, H + Hkv, d)]
         return [(g * rep, rep, g * rep * d, H + g * d, H + Hkv + g * d, 0) for g in range(hkv)]
+
+    def _att_passes(self):
+        """[(first head, end head, launch groups)]: optionally the attention runs over a few heads at a time so that the
+        fp16 scores and bf16 probabilities of one pass (causal: half of heads*T*T*4 bytes) fit the 126 MB L2 between the
+        QK^T GEMM, the softmax and the P.V GEMM.  OQ_ATT_PASS_MB sets the budget; default 0 = all heads in one pass:
+        measured on B200 at LLaMA-7B shapes the split is SLOWER (3.49 ms/step single pass, 3.56 ms at 72 MB, 3.81 ms at
+        40 MB) -- the extra launches and partial waves cost more than the HBM trips they save."""
+        if getattr(self, "_passes", None) is not None:
+            return self._passes
+        import os
+        budget = float(os.environ.get("OQ_ATT_PASS_MB", "0")) * 1e6
+        per_head = self.T * self.T * 4 * (0.5 if self.causal else 1.0)
+        hc = self.h if budget <= 0 else max(1, min(self.h, int(budget // per_head)))
+        groups = self._att_layout()
+        if len(groups) == 1 and groups[0][1] == self.h and self.rep == 1:      # MHA: one launch group, split by heads
+            h0, nh, cq, ck, cv, sb = groups[0]
+            d = self.d
+            n_pass = -(-self.h // hc)
+            hc = -(-self.h // n_pass)
+            groups = [(a, min(hc, self.h - a), cq + a * d, ck + a * d, cv + a * d, sb) for a in range(0, self.h, hc)]
+        passes, cur = [], []
+        for g in groups:                          # whole launch groups (K/V groups under GQA) per pass
+            if cur and (g[0] + g[1] - cur[0][0]) > hc:
+                passes.append((cur[0][0], cur[-1][0] + cur[-1][1], cur))
+                cur = []
+            cur.append(g)
+        passes.append((cur[0][0], cur[-1][0] + cur[-1][1], cur))
+        self._passes = passes
+        return passes
 
     def rope(self):
         if not hasattr(self, "_rope"):
@@ -492,40 +523,44 @@ class BlockEngine:
         QW, Hkv, hkv, rep = self.QW, self.Hkv, self.hkv, self.rep
         ok, ov = H, H + Hkv
         dqkvq = B("dqkvq", (M, QW))
-        dP = B("S", (h, T, T), torch.float16).view(BF16)   # same scratch storage as the scores
+        passes = self._att_passes()
+        hmax = max(c1 - c0 for c0, c1, _ in passes)
+        dP = B("S", (hmax, T, T), torch.float16).view(BF16)   # same scratch storage as the scores
         cz = 1 if self.causal else 0
-        groups = self._att_layout()
         shared = rep > 1
         dkv32 = B("dkv32", (T, 2 * Hkv), F32) if shared else None     # K/V gradients summed over the group's Q heads
         for s in range(nb):
             r = slice(s * T, (s + 1) * T)
             P = sv["P"][s]
-            for h0, nh, cq, ck, cv, sb in groups:
-                ops.gemm(dO[r, h0 * d:], qkvq[r, cv:], dP[h0:], M=T, N=T, K=d, lda=H, ldb=QW, ldc=T, batch=nh, strideA=d,
-                         strideB=sb, strideC=T * T, causal=cz)
-            if not shared:
+            for c0, c1, groups in passes:
                 for h0, nh, cq, ck, cv, sb in groups:
-                    ops.gemm(P[h0:], dO[r, h0 * d:], dqkvq[r, cv:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=H, ldc=QW,
-                             batch=nh, strideA=T * T, strideB=d, strideC=d, causal=3 * cz)
-            else:
-                for hh in range(h):     # dV_g = sum over the group's heads of P_h^T dO_h
-                    kv0 = (hh // rep) * d
-                    ops.gemm(P[hh], dO[r, hh * d:], dkv32[:, Hkv + kv0:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True,
-                             ldb=H, ldc=2 * Hkv, causal=3 * cz, accumulate=(hh % rep != 0))
-            ops.softmax_bwd(P, dP, P, causal=self.causal)      # dS overwrites P
-            for h0, nh, cq, ck, cv, sb in groups:
-                ops.gemm(P[h0:], qkvq[r, ck:], dqkvq[r, cq:], M=T, N=d, K=T, lda=T, b_mn=True, ldb=QW, ldc=QW, batch=nh,
-                         strideA=T * T, strideB=sb, strideC=d, alpha=alpha, causal=2 * cz)
-            if not shared:
+                    ops.gemm(dO[r, h0 * d:], qkvq[r, cv:], dP[h0 - c0:], M=T, N=T, K=d, lda=H, ldb=QW, ldc=T, batch=nh, strideA=d,
+                             strideB=sb, strideC=T * T, causal=cz)
+                if not shared:
+                    for h0, nh, cq, ck, cv, sb in groups:
+                        ops.gemm(P[h0:], dO[r, h0 * d:], dqkvq[r, cv:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=H, ldc=QW,
+                                 batch=nh, strideA=T * T, strideB=d, strideC=d, causal=3 * cz)
+                else:
+                    for hh in range(c0, c1):     # dV_g = sum over the group's heads of P_h^T dO_h
+                        kv0 = (hh // rep) * d
+                        ops.gemm(P[hh], dO[r, hh * d:], dkv32[:, Hkv + kv0:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True,
+                                 ldb=H, ldc=2 * Hkv, causal=3 * cz, accumulate=(hh % rep != 0))
+                ops.softmax_bwd(P[c0:c1], dP[:c1 - c0], P[c0:c1], causal=self.causal)      # dS overwrites P
                 for h0, nh, cq, ck, cv, sb in groups:
-                    ops.gemm(P[h0:], qkvq[r, cq:], dqkvq[r, ck:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=QW, ldc=QW,
-                             batch=nh, strideA=T * T, strideB=d, strideC=d, alpha=alpha, causal=3 * cz)
-            else:
-                for hh in range(h):     # dK_g = sum over the group's heads of dS_h^T Q_h
-                    kv0 = (hh // rep) * d
-                    cq = groups[hh // rep][2] + (hh % rep) * d
-                    ops.gemm(P[hh], qkvq[r, cq:], dkv32[:, kv0:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=QW,
-                             ldc=2 * Hkv, alpha=alpha, causal=3 * cz, accumulate=(hh % rep != 0))
+                    ops.gemm(P[h0:], qkvq[r, ck:], dqkvq[r, cq:], M=T, N=d, K=T, lda=T, b_mn=True, ldb=QW, ldc=QW, batch=nh,
+                             strideA=T * T, strideB=sb, strideC=d, alpha=alpha, causal=2 * cz)
+                if not shared:
+                    for h0, nh, cq, ck, cv, sb in groups:
+                        ops.gemm(P[h0:], qkvq[r, cq:], dqkvq[r, ck:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=QW, ldc=QW,
+                                 batch=nh, strideA=T * T, strideB=d, strideC=d, alpha=alpha, causal=3 * cz)
+                else:
+                    allg = self._att_layout()
+                    for hh in range(c0, c1):     # dK_g = sum over the group's heads of dS_h^T Q_h
+                        kv0 = (hh // rep) * d
+                        cq = allg[hh // rep][2] + (hh % rep) * d
+                        ops.gemm(P[hh], qkvq[r, cq:], dkv32[:, kv0:], M=T, N=d, K=T, a_mn=True, lda=T, b_mn=True, ldb=QW,
+                                 ldc=2 * Hkv, alpha=alpha, causal=3 * cz, accumulate=(hh % rep != 0))
+            if shared:
                 if falcon:
                     gv = dqkvq[r].view(T, hkv, rep + 2, d)
                     gv[:, :, -2].copy_(dkv32[:, :Hkv].view(T, hkv, d))

@@ -350,3 +350,31 @@ def test_grouped_query_attention_lwc():
             ours, rr = res["grads0"][o:o + c], to_eng(ref["grads"], k)
             err = float((ours - rr).norm() / max(float(rr.norm()), 2e-2 * gmax))
             assert err < 5e-2, (k, err)
+
+
+@pytest.mark.parametrize("kv_heads", [4, 2])
+def test_attention_head_passes_equal_single_pass(monkeypatch, kv_heads):
+    """Running the attention a few heads at a time (scores kept in L2, engine._att_passes) is the same computation as
+    one pass over all heads: same loss and gradients after one step, for MHA (4/4 heads) and GQA (4 query / 2 K/V heads)."""
+    from omniquant_b200.engine import BlockEngine, QuantConfig
+    H, F_, heads, T = 256, 512, 4, 128
+    W, x, act = _synthetic_block("llama", H, F_, heads, T, 1)
+    if kv_heads != heads:
+        Hkv = kv_heads * (H // heads)
+        W["k"], W["v"] = W["k"][:Hkv].contiguous(), W["v"][:Hkv].contiguous()
+    let = kv_heads == heads
+    q = QuantConfig(wbits=4, abits=4 if let else 16, group_size=0, lwc=True, let=let, recip_div=True)
+    out = []
+    for budget, npass in (("0", 1), (str(2 * T * T * 4 * 0.5 / 1e6), 2)):
+        monkeypatch.setenv("OQ_ATT_PASS_MB", budget)
+        kw = dict(let_init={"qkv_s": act["qkv"], "out_s": act["out"], "fc1_s": act["fc1"]}) if let else {}
+        eng = BlockEngine("llama", W, n_heads=heads, seq_len=T, qcfg=q, eps=1e-6,
+                          **({"n_kv_heads": kv_heads} if kv_heads != heads else {}), **kw)
+        assert len(eng._att_passes()) == npass
+        xb = x[0].cuda().to(torch.bfloat16)
+        tgt = torch.roll(xb, 1, 0)
+        loss = eng.train_step(xb, tgt).clone()
+        torch.cuda.synchronize()
+        out.append((float(loss), eng.grads.clone().cpu()))
+    assert abs(out[0][0] - out[1][0]) <= 1e-6 * abs(out[0][0])
+    torch.testing.assert_close(out[0][1], out[1][1], rtol=1e-3, atol=1e-6)
