@@ -158,17 +158,19 @@ __global__ void __launch_bounds__(TPB) norm_fwd_reg(NormArgs a) {
   for (int i = 0; i < NV; ++i) {
     const int c = (threadIdx.x + i * TPB) * 8;
     if (c < a.C) {
+      if (fast) {   // same arithmetic as the stand-alone quantiser (csrc/act_quant.cu aq_t); branch uniform per row
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float x = v[i][j];
-        float t;
-        if (fast) {   // same arithmetic as the stand-alone quantiser (csrc/act_quant.cu aq_t)
-          const float qa = __fmul_rn(x, inv);
-          t = OQ_ADD(rintf(__fmaf_rn(__fmaf_rn(-qa, q.scale, x), inv, qa)), q.zp);
-        } else {
-          t = OQ_ADD(rintf(OQ_DIV(x, q.scale)), q.zp);
+        for (int j = 0; j < 8; ++j) {
+          const float x = v[i][j], qa = __fmul_rn(x, inv);
+          const float t = OQ_ADD(rintf(__fmaf_rn(__fmaf_rn(-qa, q.scale, x), inv, qa)), q.zp);
+          v[i][j] = oq_dequant(oq_clampf(t, 0.0f, q.qmax), q);
         }
-        v[i][j] = oq_dequant(oq_clampf(t, 0.0f, q.qmax), q);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = OQ_ADD(rintf(OQ_DIV(v[i][j], q.scale)), q.zp);
+          v[i][j] = oq_dequant(oq_clampf(t, 0.0f, q.qmax), q);
+        }
       }
       store_bf8(a.yq + r * a.ldyq + c, v[i]);
     }
@@ -337,7 +339,7 @@ int norm_fwd_launch(const char* fn, NormArgs a, cudaStream_t stream) {
   const bool vec = a.C % 8 == 0 && a.ldx % 8 == 0 && (!a.y || a.ldy % 8 == 0) && (!a.yq || a.ldyq % 8 == 0) && al;
   const unsigned g = (unsigned)a.rows;
   if (vec && a.C <= 2048) norm_fwd_reg<1, 256><<<g, 256, 0, stream>>>(a);
-  else if (vec && a.C <= 4096) norm_fwd_reg<1, 512><<<g, 512, 0, stream>>>(a);
+  else if (vec && a.C <= 4096) norm_fwd_reg<2, 256><<<g, 256, 0, stream>>>(a);   // 16 elements per thread amortise the reductions
   else if (vec && a.C <= 8192) norm_fwd_reg<2, 512><<<g, 512, 0, stream>>>(a);
   else if (vec && a.C <= 16384) norm_fwd_reg<4, 512><<<g, 512, 0, stream>>>(a);
   else {
