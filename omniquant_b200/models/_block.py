@@ -8,6 +8,9 @@ HF decoder-layer signature -- and runs all of it on the B200 block engine (omniq
 The sub-modules (QuantLinear, Omni*Norm, QuantMatMul) carry the reference's buffers, parameters
 and checkpoint key names; the wrapper synchronises them with the engine's flat buffers.
 """
+import dataclasses
+import os
+import weakref
 from collections import OrderedDict
 
 import torch
@@ -44,6 +47,9 @@ class _BlockFn(torch.autograd.Function):
         eng.backward(g2)
         grads = layer._pull_grads()
         return (None, None, None, None) + tuple(grads)
+
+
+_ENGINES = {}      # shape key -> the resident BlockEngine (see _ensure_engine)
 
 
 class QuantDecoderLayerBase(nn.Module):
@@ -94,10 +100,24 @@ class QuantDecoderLayerBase(nn.Module):
         if e is None or e.T != seq_len or e.b != batch or e.q != q:
             dev = next(iter(self._linears().values())).weight.device
             a = self._args
-            self._eng = BlockEngine(self.family, self._raw_weights(), n_heads=self._n_heads, seq_len=seq_len, qcfg=q,
-                                    eps=self._eps, device=dev, batch=batch, let_lr=getattr(a, "let_lr", 5e-3),
-                                    lwc_lr=getattr(a, "lwc_lr", 1e-2), wd=getattr(a, "wd", 0.0), mask=mask,
-                                    n_kv_heads=self._n_kv_heads)
+            W = self._raw_weights()
+            lrs = (getattr(a, "let_lr", 5e-3), getattr(a, "lwc_lr", 1e-2), getattr(a, "wd", 0.0))
+            # decoder blocks of one model share shapes: the previous block's engine (device buffers + the captured CUDA
+            # graph of its optimiser step) is re-loaded with this block's weights instead of being rebuilt
+            key = (self.family, str(dev), seq_len, batch, dataclasses.astuple(q), self._n_heads, self._n_kv_heads, self._eps,
+                   lrs, tuple(sorted((k, tuple(v.shape)) for k, v in W.items())))
+            cached = _ENGINES.get(key) if (mask is None and os.environ.get("OQ_ENGINE_CACHE", "1") == "1") else None
+            owner = cached._owner() if cached is not None and getattr(cached, "_owner", None) is not None else None
+            if cached is not None and (owner is None or owner._eng is not cached):
+                self._eng = cached.reload(W)
+            else:
+                self._eng = BlockEngine(self.family, W, n_heads=self._n_heads, seq_len=seq_len, qcfg=q,
+                                        eps=self._eps, device=dev, batch=batch, let_lr=lrs[0], lwc_lr=lrs[1], wd=lrs[2],
+                                        mask=mask, n_kv_heads=self._n_kv_heads)
+                if mask is None:
+                    _ENGINES.clear()           # one resident engine: a new shape replaces the old one
+                    _ENGINES[key] = self._eng
+            self._eng._owner = weakref.ref(self)
             self._push_params()
         return self._eng
 

@@ -378,3 +378,35 @@ def test_attention_head_passes_equal_single_pass(monkeypatch, kv_heads):
         out.append((float(loss), eng.grads.clone().cpu()))
     assert abs(out[0][0] - out[1][0]) <= 1e-6 * abs(out[0][0])
     torch.testing.assert_close(out[0][1], out[1][1], rtol=1e-3, atol=1e-6)
+
+
+def test_engine_reload_reuses_graph_and_matches_fresh_engine():
+    """BlockEngine.reload(): the next block's weights go into the same device buffers and the optimiser-step graph captured
+    for the previous block is replayed (no second capture); the result equals a freshly built engine's (last-bit noise
+    from the atomic reductions aside), the AdamW step counter restarts, the in-place quantised weights are those of block B."""
+    from omniquant_b200.engine import BlockEngine, QuantConfig, calibrate_block
+    H, F_, heads, T, n = 256, 512, 2, 128, 8
+    WA, xA, actA = _synthetic_block("llama", H, F_, heads, T, n, seed=0)
+    WB, xB, actB = _synthetic_block("llama", H, F_, heads, T, n, seed=1)
+    q = QuantConfig(wbits=4, abits=4, group_size=0, lwc=True, let=True, recip_div=True)
+    li = lambda act: {"qkv_s": act["qkv"], "out_s": act["out"], "fc1_s": act["fc1"]}
+    run = lambda eng, x: calibrate_block(eng, x.cuda().to(torch.bfloat16), x.cuda().to(torch.bfloat16), epochs=2, use_graph=True)
+    eng = BlockEngine("llama", WA, n_heads=heads, seq_len=T, qcfg=q, eps=1e-6, let_init=li(actA))
+    run(eng, xA)
+    g0 = eng._graph_state["graph"]
+    assert g0 is not None
+    eng.reload(WB, li(actB))
+    assert int(eng.step_dev.item()) == 0 and float(eng.adam_m.abs().max()) == 0.0
+    rB = run(eng, xB)
+    assert eng._graph_state["graph"] is g0                  # replayed, not re-captured
+    assert int(eng.step_dev.item()) == 2 * n
+    fresh = BlockEngine("llama", WB, n_heads=heads, seq_len=T, qcfg=q, eps=1e-6, let_init=li(actB))
+    rF = run(fresh, xB)
+    torch.cuda.synchronize()
+    lb, lf = rB["losses"].cpu(), rF["losses"].cpu()
+    torch.testing.assert_close(lb[:n], lf[:n], rtol=1e-2, atol=0)         # first epoch: nothing left over from block A
+    torch.testing.assert_close(lb, lf, rtol=5e-2, atol=0)                 # W4A4 codes amplify the atomics' last-bit noise later
+    assert float((eng.params - fresh.params).abs().mean()) < 5e-3      # AdamW moves lr per step whatever the gradient size: sign noise on ~0 gradients
+    for u in ("q", "fc1", "fc2"):
+        a, b = rB["final"][u]["weight"], rF["final"][u]["weight"]
+        assert float((a - b).abs().mean() / b.abs().mean()) < 2e-2   # scales differ in the last bits, a few codes flip
