@@ -262,8 +262,24 @@ def run_ours(a):
                "clocks": clocks}
         json_out.write(json.dumps(out) + "\n")
         json_out.flush()
+    # teardown: the captured step graphs hold the NCCL all-reduce kernel; release them BEFORE the communicator goes away
+    # (destroying the process group under a live graph blocks), and never let teardown outlive the measurement
+    import gc
+    for e in resident.values():
+        e._graph_state = None
+    resident.clear()
+    from omniquant_b200.models._block import release_engines
+    release_engines()
+    eng = last = None
+    gc.collect()
+    torch.cuda.synchronize()
     if world > 1:
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        dist.barrier()
         dist.destroy_process_group()
+        watchdog.cancel()
 
 
 class _StridedHostInputs:

@@ -52,6 +52,14 @@ class _BlockFn(torch.autograd.Function):
 _ENGINES = {}      # shape key -> the resident BlockEngine (see _ensure_engine)
 
 
+def release_engines():
+    """Drop the resident engine(s) and with them the captured CUDA graphs.  Must run before the NCCL process group is
+    destroyed: tearing down a communicator while a live graph still holds its all-reduce kernel blocks at exit."""
+    for e in _ENGINES.values():
+        e._graph_state = None
+    _ENGINES.clear()
+
+
 class QuantDecoderLayerBase(nn.Module):
     family = None          # "llama" | "opt"
     linear_names = {}      # engine short name -> attribute path of the QuantLinear

@@ -220,5 +220,8 @@ def omniquant(lm, args, dataloader, act_scales, act_shifts, logger=None, inps=No
         del layer, eng
 
     del quant_inps, fp_inps
+    from ..models._block import release_engines
+    release_engines()              # the resident engine + its step graph (holds the NCCL all-reduce under DP)
+    torch.cuda.synchronize()
     model.config.use_cache = use_cache
     return model
