@@ -266,9 +266,11 @@ def _dump(path, inputs, res, qlayer, linears):
           res["losses"][-1])
 
 
-def llama_block(tag, H, F_, heads, T, nsamples, args, epochs, batch_size=1, aug_loss=False, seed=0):
+def llama_block(tag, H, F_, heads, T, nsamples, args, epochs, batch_size=1, aug_loss=False, seed=0, kv_heads=None):
+    """kv_heads < heads: grouped-query attention (Llama-2-70B); the reference supports it without LET only."""
     torch.manual_seed(seed)
-    cfg = LlamaConfig(hidden_size=H, intermediate_size=F_, num_attention_heads=heads, num_key_value_heads=heads,
+    kv_heads = kv_heads or heads
+    cfg = LlamaConfig(hidden_size=H, intermediate_size=F_, num_attention_heads=heads, num_key_value_heads=kv_heads,
                       num_hidden_layers=1, vocab_size=64, max_position_embeddings=2048, rms_norm_eps=1e-6)
     hf = LlamaDecoderLayer(cfg, 0).half().float().eval()
     with torch.no_grad():   # non-trivial norm weights
@@ -291,6 +293,8 @@ def llama_block(tag, H, F_, heads, T, nsamples, args, epochs, batch_size=1, aug_
     inputs = dict(inps=inps, H=H, F=F_, heads=heads, T=T, nsamples=nsamples, epochs=epochs, batch_size=batch_size,
                   wbits=args.wbits, abits=args.abits, group_size=args.group_size or 0, lwc=int(args.lwc),
                   let=int(args.let), aug_loss=int(aug_loss))
+    if kv_heads != heads:
+        inputs["kv_heads"] = kv_heads
     for n, p in raw.items():
         inputs[f"w/{n}"] = p.half()
     for n, s in act_scales.items():
@@ -471,6 +475,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["act_stats"]:
         act_stats_fixture()
         sys.exit(0)
+    if sys.argv[1:] == ["gqa"]:      # BASELINE config 4's quantisation (W2A16g64 LWC) on a 4-query / 2-K/V-head block
+        llama_block("gqa_w2a16g64_lwc", 256, 384, 4, 32, 4, make_args(2, 16, 64, True, False), epochs=2, kv_heads=2)
+        sys.exit(0)
     quantizer_cases()
     llama_block("w4a4_lwc_let", 256, 384, 2, 32, 4, make_args(4, 4, None, True, True), epochs=2)
     llama_block("w4a4_lwc_let_bs2", 256, 384, 2, 32, 4, make_args(4, 4, None, True, True), epochs=2, batch_size=2)
@@ -481,4 +488,5 @@ if __name__ == "__main__":
     opt_block("w4a16_lwc_let", 128, 256, 2, 32, 4, make_args(4, 16, None, True, True), epochs=2)
     opt_block("w4a4_lwc_let", 128, 256, 2, 32, 4, make_args(4, 4, None, True, True), epochs=2)
     falcon_block("w3a16g64_lwc", 256, 4, 2, 32, 4, make_args(3, 16, 64, True, False), epochs=2)
+    llama_block("gqa_w2a16g64_lwc", 256, 384, 4, 32, 4, make_args(2, 16, 64, True, False), epochs=2, kv_heads=2)
     act_stats_fixture()

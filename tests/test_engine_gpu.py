@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 FIXTURES = ["llama_w4a4_lwc_let.npz", "llama_w4a4_lwc_let_bs2.npz", "llama_w3a16g64_lwc.npz", "llama_w6a6_lwc_let_aug.npz",
             "llama_w4a16g64_lwc_let.npz", "opt_w4a16g64_lwc.npz", "opt_w4a4_lwc_let.npz", "opt_w4a16_lwc_let.npz",
-            "falcon_w3a16g64_lwc.npz"]
+            "falcon_w3a16g64_lwc.npz", "llama_gqa_w2a16g64_lwc.npz"]
 
 
 def build_engine(fx, recip_div=False):

@@ -106,7 +106,8 @@ def _oracle_setup(fx):
 
 FIXTURES = ["llama_w4a4_lwc_let.npz", "llama_w4a4_lwc_let_bs2.npz", "llama_w3a16g64_lwc.npz",
             "llama_w6a6_lwc_let_aug.npz", "llama_w4a16g64_lwc_let.npz", "opt_w4a16g64_lwc.npz", "opt_w4a4_lwc_let.npz",
-            "opt_w4a16_lwc_let.npz", "falcon_w3a16g64_lwc.npz"]
+            "opt_w4a16_lwc_let.npz", "falcon_w3a16g64_lwc.npz",
+            "llama_gqa_w2a16g64_lwc.npz"]      # grouped-query attention (Llama-2-70B layout), BASELINE config 4's W2A16g64 LWC
 
 
 @pytest.mark.parametrize("fname", FIXTURES)
