@@ -70,3 +70,29 @@ def test_fused_entry_points_are_declared_and_exported():
     assert sig is not None
     hdr = open(os.path.join(os.path.dirname(_lib.__file__), "..", "include", "omniquant_b200.h")).read()
     assert "int rope_inner" in hdr                            # one launch covers q | k (rotated) | v (not rotated)
+
+
+def test_integer_forward_gemm_identity():
+    """DESIGN.md section 9, item 1 (numerics of the planned exact-integer forward GEMM): with both operands fake-quantised,
+    Y = s_a[m] * s_w[n] * sum_k (c_a - z_a)(c_w - z_w) with the integer sum accumulated exactly; it reproduces the fp64 product
+    of the oracle's dequantised operands to fp32 round-off and is closer to it than the product of bf16-rounded operands."""
+    from oracle import oq_oracle as orc
+    g = torch.Generator().manual_seed(3)
+    M, K, N = 24, 512, 40
+    x = torch.randn(M, K, generator=g) * 2
+    W = torch.randn(N, K, generator=g) * 0.02
+    for bits in (4, 6):
+        xq, sa, za, ca = orc.fake_quant(x, bits, return_all=True)                     # per token
+        up = torch.full((N, 1), 4.0)
+        wq, sw, zw, cw = orc.fake_quant(W, bits, False, None, up, up.clone(), return_all=True)   # per channel + LWC
+        ia = (ca.reshape(M, K) - za.reshape(M, 1)).to(torch.int64)
+        iw = (cw.reshape(N, K) - zw.reshape(N, 1)).to(torch.int64)
+        assert int(ia.abs().max()) < 128 and int(iw.abs().max()) < 128               # s8 operands
+        acc = ia @ iw.t()                                                             # exact
+        assert int(acc.abs().max()) < 2 ** 24                                         # also exact in an fp32 accumulator
+        y_int = acc.double() * sa.reshape(M, 1).double() * sw.reshape(1, N).double()
+        y_ref = xq.double() @ wq.double().t()
+        y_bf = (xq.bfloat16().double()) @ (wq.bfloat16().double()).t()
+        e_int = float((y_int - y_ref).abs().max() / y_ref.abs().max())
+        e_bf = float((y_bf - y_ref).abs().max() / y_ref.abs().max())
+        assert e_int < 1e-6 and e_int < e_bf / 50, (bits, e_int, e_bf)
