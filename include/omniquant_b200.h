@@ -94,6 +94,20 @@ int oq_swiglu_act_quant_fwd(const void* gu, long ldgu, long rows, int F, int n_b
 int oq_swiglu_act_quant_bwd(const void* gu, long ldgu, long rows, int F, int n_bits, int symmetric, int recip_div,
                             const void* gy, long ldgy, void* dgu, long lddgu, oq_stream_t stream);
 
+/* EXPERIMENTAL (round 1: validated by a kernel-level bit-exactness test on B200, not used by the engine yet -- DESIGN.md
+ * section 9 item 1).
+ * Exact-integer forward contraction of QuantLinear when BOTH operands are quantised (W4A4 / W6A6,
+ * quantize/int_linear.py:48-65 with quantize/quantizer.py:93-100): A [M,K], B [N,K] hold the signed 8-bit codes
+ * (code - zero point) K-major, the K sum is exact (tcgen05.mma kind::i8, s32 accumulators),
+ *   C[m,n] = row_scale[m]*col_scale[n]*sum_k A[m,k]*B[n,k]
+ *            (+ row_t[m]*col_beta[n] + row_beta[m]*col_t[n] + K*row_beta[m]*col_beta[n]) (+ bias[n]) (+ residual[m,n]).
+ * The four correction vectors (all or none) carry zero points that fall outside the code range: beta = (z0 - z)*scale,
+ * t = scale * sum_k (code - z0).  lda / ldb in bytes (= elements), multiples of 16. */
+int oq_gemm_s8(const void* A, long lda, const void* B, long ldb, void* C, int c_dtype, long ldc, int M, int N, int K,
+               const float* row_scale, const float* col_scale, const float* row_t, const float* row_beta,
+               const float* col_t, const float* col_beta, const float* bias, const void* residual, long ldr,
+               oq_stream_t stream);
+
 /* ---- K7: norms with temporary (folded) weight / bias ------------------------
  * kind 0: OmniLlamaRMSNorm.forward quantize/omni_norm.py:52-63; kind 1: OmniLayerNorm.forward :26-33.
  * w/b are the temp_weight/temp_bias of the step (b may be NULL). */

@@ -1,0 +1,317 @@
+// EXPERIMENTAL exact-integer forward contraction of QuantLinear for configurations that quantise BOTH operands
+// (W4A4 / W6A6): the operands are the signed integer codes (code - zero point) of the fake-quantised activations and
+// weights, the sum over K is exact (tcgen05.mma kind::i8 = UTCIMMA, s32 accumulators in TMEM), the per-token and
+// per-channel scales are applied in the epilogue:
+//
+//   C[m,n] = rs[m]*cs[n] * sum_k A[m,k]*B[n,k]
+//            (+ rt[m]*cbeta[n] + rbeta[m]*ct[n] + K*rbeta[m]*cbeta[n])  (+ bias[n]) (+ residual[m,n])
+//
+// Reference: QuantLinear.forward, quantize/int_linear.py:48-65 (F.linear on the two fake-quantised tensors):
+// x_q[m,k] = (c_a - z_a[m])*s_a[m], w_q[n,k] = (c_w - z_w[n])*s_w[n]  (quantize/quantizer.py:93-100), so
+// F.linear(x_q, w_q)[m,n] = s_a[m]*s_w[n]*sum_k (c_a - z_a)(c_w - z_w).  With |c - z| <= 127 and K*127^2 < 2^31 the integer
+// sum has no rounding at all, unlike the bf16 path which rounds every dequantised operand to 8 mantissa bits.  A zero point
+// outside the code range (a row that does not straddle zero) is split as z = z0 + (z - z0) with z0 clamped into range: the
+// caller passes beta = (z0 - z)*s and t = s*sum_k(c - z0) per row / column and the epilogue adds the cross terms.
+//
+// STATUS (round 1): validated at kernel level on B200 (tests/test_kernels_gpu.py::test_gemm_s8_exact: bit for bit equal to
+// the same expression evaluated by torch, ragged shapes, K up to 11008); not wired into the engine yet -- DESIGN.md
+// section 9 item 1.  The epilogue still stores element-wise (fine behind a K >= 4096 main loop).  Same pipeline as gemm_sm100.cu:
+// warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue, two TMEM accumulator stages.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "mbar.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BKB = 128;   // bytes (= s8 elements) per smem row: one 128-byte swizzle row
+constexpr int UMMA_KB = 32;  // bytes per MMA k-step (32 s8 elements)
+constexpr int NUM_THREADS = 256;
+
+struct S8Params {
+  int M, N, K;
+  void* C;
+  int c_dtype;  // 0 bf16, 1 fp32, 2 fp16
+  long ldc;
+  const float* bias;
+  const bf16* res;
+  long ldr;
+  const float* rs; const float* cs;
+  const float* rt; const float* rbeta; const float* ct; const float* cbeta;
+  int num_m, num_n;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_s8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 64-bit shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart (SBO)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;               // LBO (unused for K-major swizzled) = 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;     // SBO
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int A_BYTES = BM * BKB;
+  static constexpr int B_BYTES = BN * BKB;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const S8Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m * p.num_n;
+  const int num_kb = (p.K + BKB - 1) / BKB;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.num_m) * BM, n0 = (tile / p.num_m) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full[stage], kb * BKB, m0);           // out-of-range rows / K tail are zero-filled
+          tma_load_2d(sa + C::A_BYTES, &tmB, &full[stage], kb * BKB, n0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D = s32 (2), A = B = int8 (1), both K-major, N>>3, M>>4
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BKB / UMMA_KB; ++k)
+            tc_mma_s8(d_tmem, make_desc(sa + k * UMMA_KB), make_desc(sb + k * UMMA_KB), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&empty[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const float fK = (float)p.K;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile % p.num_m) * BM, n0 = (tile / p.num_m) * BN;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const bool live = row < p.M;
+      const float rs = live ? p.rs[row] : 0.f;
+      const float rt = (live && p.rt) ? p.rt[row] : 0.f, rb = (live && p.rt) ? p.rbeta[row] : 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tc_ld32(taddr + c0, r);
+        tc_wait_ld();
+        if (live) {
+          const int nc = n0 + c0;
+          const int valid = min(32, p.N - nc);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < valid) {
+              float y = __fmul_rn(__fmul_rn(__int2float_rn((int)r[j]), rs), p.cs[nc + j]);
+              if (p.rt) {
+                const float cb = p.cbeta[nc + j];
+                y += rt * cb + rb * p.ct[nc + j] + fK * rb * cb;
+              }
+              if (p.bias) y += p.bias[nc + j];
+              if (p.res) y += bf2f(p.res[(long)row * p.ldr + nc + j]);
+              if (p.c_dtype == 1) reinterpret_cast<float*>(p.C)[(long)row * p.ldc + nc + j] = y;
+              else if (p.c_dtype == 2) reinterpret_cast<__half*>(p.C)[(long)row * p.ldc + nc + j] = __float2half_rn(y);
+              else reinterpret_cast<bf16*>(p.C)[(long)row * p.ldc + nc + j] = f2bf(y);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D s8 tensor map: dims (K, rows), row stride ld bytes; box (128, box_rows)
+int make_map_s8(CUtensorMap* map, const void* base, long K, long rows, long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  OQ_REQUIRE(enc, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld};
+  cuuint32_t box[2] = {(cuuint32_t)BKB, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  OQ_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (s8) failed (%d): base=%p K=%ld rows=%ld ld=%ld", (int)r, base, K, rows, ld);
+  return 0;
+}
+
+template <int BN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, S8Params p, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_s8_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      oq_set_error("oq_gemm_s8: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  p.num_m = (p.M + BM - 1) / BM;
+  p.num_n = (p.N + BN - 1) / BN;
+  const long tiles = (long)p.num_m * p.num_n;
+  const int grid = (int)std::min<long>(tiles, oq_num_sms());
+  gemm_s8_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  return oq_check_launch("oq_gemm_s8");
+}
+
+}  // namespace
+
+extern "C" int oq_gemm_s8(const void* A, long lda, const void* B, long ldb, void* C, int c_dtype, long ldc, int M, int N, int K,
+                          const float* row_scale, const float* col_scale, const float* row_t, const float* row_beta,
+                          const float* col_t, const float* col_beta, const float* bias, const void* residual, long ldr,
+                          cudaStream_t stream) {
+  OQ_REQUIRE(A && B && C && row_scale && col_scale && M > 0 && N > 0 && K > 0, "oq_gemm_s8: null pointer or bad shape");
+  OQ_REQUIRE(lda % 16 == 0 && ldb % 16 == 0 && (uintptr_t)A % 16 == 0 && (uintptr_t)B % 16 == 0,
+             "oq_gemm_s8: operand strides and base pointers must be multiples of 16 bytes (TMA)");
+  OQ_REQUIRE(c_dtype >= 0 && c_dtype <= 2, "oq_gemm_s8: c_dtype must be 0 (bf16), 1 (fp32) or 2 (fp16)");
+  const bool corr = row_t || row_beta || col_t || col_beta;
+  OQ_REQUIRE(!corr || (row_t && row_beta && col_t && col_beta), "oq_gemm_s8: the zero-point correction needs all four vectors");
+  OQ_REQUIRE((long)K * 127 * 127 < (1L << 31), "oq_gemm_s8: K too large for an exact s32 sum");
+  S8Params p = {};
+  p.M = M; p.N = N; p.K = K; p.C = C; p.c_dtype = c_dtype; p.ldc = ldc; p.bias = bias;
+  p.res = (const bf16*)residual; p.ldr = ldr;
+  p.rs = row_scale; p.cs = col_scale; p.rt = row_t; p.rbeta = row_beta; p.ct = col_t; p.cbeta = col_beta;
+  const long t256 = (long)((M + BM - 1) / BM) * ((N + 255) / 256);
+  const int tile_n = (N <= 128 || t256 < oq_num_sms()) ? 128 : 256;
+  CUtensorMap ta, tb;
+  if (make_map_s8(&ta, A, K, M, lda, BM)) return -1;
+  if (make_map_s8(&tb, B, K, N, ldb, tile_n)) return -1;
+  return tile_n == 256 ? launch<256>(ta, tb, p, stream) : launch<128>(ta, tb, p, stream);
+}

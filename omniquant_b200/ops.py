@@ -152,6 +152,21 @@ _CDT = {BF16: 0, F32: 1, torch.float16: 2}
 GEMM_TIMER = None   # bench.py sets this to a list to collect (event0, event1, flops, tile) per GEMM launch
 
 
+def gemm_s8(A, B, C, row_scale, col_scale, *, corr=None, bias=None, residual=None):
+    """EXPERIMENTAL: C = row_scale[:, None] * col_scale[None, :] * (A.int() @ B.int().T) for int8 code matrices A [M, K],
+    B [N, K] (exact integer sum on the tensor cores); corr = (row_t, row_beta, col_t, col_beta) or None."""
+    if A.dtype != torch.int8 or B.dtype != torch.int8 or A.dim() != 2 or B.dim() != 2 or A.shape[1] != B.shape[1]:
+        raise OqError("gemm_s8: A [M, K] and B [N, K] must be int8")
+    if A.stride(1) != 1 or B.stride(1) != 1 or C.stride(1) != 1:
+        raise OqError("gemm_s8: last dims must be contiguous")
+    M, K = A.shape
+    N = B.shape[0]
+    rt, rb, ct, cb = corr if corr is not None else (None, None, None, None)
+    lib().call("oq_gemm_s8", _p(A), A.stride(0), _p(B), B.stride(0), _p(C), _CDT[C.dtype], C.stride(0), M, N, K,
+               _p(row_scale), _p(col_scale), _p(rt), _p(rb), _p(ct), _p(cb), _p(bias), _p(residual),
+               residual.stride(0) if residual is not None else 0, _stream())
+
+
 def launch_count() -> int:
     return lib().launches
 

@@ -678,3 +678,31 @@ def test_gptq_pack_bit_exact(ops, bits, group, N, K):
     ok = (zp.cpu().numpy().reshape(N, G) >= 0).all()
     if ok:
         assert np.abs(dq - wq.cpu().numpy()).max() <= 6e-4 * np.abs(wq.cpu().numpy()).max() + 1e-8   # fp16 scales
+
+
+def test_gemm_s8_exact(ops):
+    """oq_gemm_s8: the integer K sum is exact, the scaled fp32 result equals the same expression evaluated by torch bit for
+    bit; zero-point correction terms, bias and residual, ragged M / N / K."""
+    gen = torch.Generator().manual_seed(17)
+    for (M, N, K) in [(256, 512, 4096), (200, 300, 1008), (2048, 4096, 11008), (130, 96, 64)]:
+        A = torch.randint(-63, 64, (M, K), generator=gen, dtype=torch.int8).cuda()
+        B = torch.randint(-63, 64, (N, K), generator=gen, dtype=torch.int8).cuda()
+        rs = (torch.rand(M, generator=gen) + 0.5).cuda()
+        cs = (torch.rand(N, generator=gen) * 0.01 + 0.001).cuda()
+        acc = (A.double() @ B.double().t())                      # exact: |acc| < 2^53
+        assert float(acc.abs().max()) < 2 ** 24
+        ref = acc.float() * rs[:, None] * cs[None, :]
+        C = torch.empty(M, N, device="cuda")
+        ops.gemm_s8(A, B, C, rs, cs)
+        torch.cuda.synchronize()
+        assert torch.equal(C, ref), (M, N, K, float((C - ref).abs().max()))
+        # correction terms + bias + residual, bf16 output
+        rt, rb = torch.randn(M, generator=gen).cuda(), (torch.randn(M, generator=gen) * 0.1).cuda()
+        ct, cb = torch.randn(N, generator=gen).cuda(), (torch.randn(N, generator=gen) * 0.1).cuda()
+        bias = torch.randn(N, generator=gen).cuda()
+        res = torch.randn(M, N, generator=gen).to(torch.bfloat16).cuda()
+        Cb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ops.gemm_s8(A, B, Cb, rs, cs, corr=(rt, rb, ct, cb), bias=bias, residual=res)
+        torch.cuda.synchronize()
+        full = ref + rt[:, None] * cb[None, :] + rb[:, None] * ct[None, :] + K * rb[:, None] * cb[None, :] + bias + res.float()
+        torch.testing.assert_close(Cb.float(), full, rtol=1e-2, atol=1e-2 * float(full.abs().max()))
