@@ -15,7 +15,7 @@
 //
 // STATUS (round 1): validated at kernel level on B200 (tests/test_kernels_gpu.py::test_gemm_s8_exact: bit for bit equal to
 // the same expression evaluated by torch, ragged shapes, K up to 11008); not wired into the engine yet -- DESIGN.md
-// section 9 item 1.  The epilogue still stores element-wise (fine behind a K >= 4096 main loop).  Same pipeline as gemm_sm100.cu:
+// section 9 item 1.  Same pipeline as gemm_sm100.cu:
 // warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue, two TMEM accumulator stages.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -208,19 +208,63 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (live) {
           const int nc = n0 + c0;
           const int valid = min(32, p.N - nc);
+          float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            if (j < valid) {
-              float y = __fmul_rn(__fmul_rn(__int2float_rn((int)r[j]), rs), p.cs[nc + j]);
-              if (p.rt) {
-                const float cb = p.cbeta[nc + j];
-                y += rt * cb + rb * p.ct[nc + j] + fK * rb * cb;
+            const int c = nc + (j < valid ? j : 0);      // clamped column: loads stay in bounds, the value is not stored
+            float y = __fmul_rn(__fmul_rn(__int2float_rn((int)r[j]), rs), p.cs[c]);
+            if (p.rt) {
+              const float cb = p.cbeta[c];
+              y += rt * cb + rb * p.ct[c] + fK * rb * cb;
+            }
+            if (p.bias) y += p.bias[c];
+            v[j] = y;
+          }
+          if (p.res) {
+            const bf16* resr = p.res + (long)row * p.ldr + nc;
+            if (valid == 32 && p.ldr % 8 == 0 && ((uintptr_t)p.res % 16) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float t[8];
+                load_bf8(resr + j, t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[j + e] += t[e];
               }
-              if (p.bias) y += p.bias[nc + j];
-              if (p.res) y += bf2f(p.res[(long)row * p.ldr + nc + j]);
-              if (p.c_dtype == 1) reinterpret_cast<float*>(p.C)[(long)row * p.ldc + nc + j] = y;
-              else if (p.c_dtype == 2) reinterpret_cast<__half*>(p.C)[(long)row * p.ldc + nc + j] = __float2half_rn(y);
-              else reinterpret_cast<bf16*>(p.C)[(long)row * p.ldc + nc + j] = f2bf(y);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < valid) v[j] += bf2f(resr[j]);
+            }
+          }
+          if (p.c_dtype == 1) {
+            float* cr = reinterpret_cast<float*>(p.C) + (long)row * p.ldc + nc;
+            if (valid == 32 && p.ldc % 4 == 0 && ((uintptr_t)p.C % 16) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < valid) cr[j] = v[j];
+            }
+          } else if (p.c_dtype == 2) {
+            __half* cr = reinterpret_cast<__half*>(p.C) + (long)row * p.ldc + nc;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < valid) cr[j] = __float2half_rn(v[j]);
+          } else {
+            bf16* cr = reinterpret_cast<bf16*>(p.C) + (long)row * p.ldc + nc;
+            if (valid == 32 && p.ldc % 8 == 0 && ((uintptr_t)p.C % 16) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float t[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) t[e] = v[j + e];
+                store_bf8(cr + j, t);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < valid) cr[j] = f2bf(v[j]);
             }
           }
         }
