@@ -295,6 +295,8 @@ def llama_block(tag, H, F_, heads, T, nsamples, args, epochs, batch_size=1, aug_
                   let=int(args.let), aug_loss=int(aug_loss))
     if kv_heads != heads:
         inputs["kv_heads"] = kv_heads
+    if getattr(args, "symmetric", False):
+        inputs["symmetric"] = 1
     for n, p in raw.items():
         inputs[f"w/{n}"] = p.half()
     for n, s in act_scales.items():
@@ -475,6 +477,10 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["act_stats"]:
         act_stats_fixture()
         sys.exit(0)
+    if sys.argv[1:] == ["extra"]:    # symmetric weights (main.py --symmetric) and a W6A6 OPT block
+        llama_block("sym_w4a16g64_lwc", 256, 384, 2, 32, 4, make_args(4, 16, 64, True, False, sym=True), epochs=2)
+        opt_block("w6a6_lwc_let", 128, 256, 2, 32, 4, make_args(6, 6, None, True, True), epochs=2)
+        sys.exit(0)
     if sys.argv[1:] == ["gqa"]:      # BASELINE config 4's quantisation (W2A16g64 LWC) on a 4-query / 2-K/V-head block
         llama_block("gqa_w2a16g64_lwc", 256, 384, 4, 32, 4, make_args(2, 16, 64, True, False), epochs=2, kv_heads=2)
         sys.exit(0)
@@ -489,4 +495,6 @@ if __name__ == "__main__":
     opt_block("w4a4_lwc_let", 128, 256, 2, 32, 4, make_args(4, 4, None, True, True), epochs=2)
     falcon_block("w3a16g64_lwc", 256, 4, 2, 32, 4, make_args(3, 16, 64, True, False), epochs=2)
     llama_block("gqa_w2a16g64_lwc", 256, 384, 4, 32, 4, make_args(2, 16, 64, True, False), epochs=2, kv_heads=2)
+    llama_block("sym_w4a16g64_lwc", 256, 384, 2, 32, 4, make_args(4, 16, 64, True, False, sym=True), epochs=2)
+    opt_block("w6a6_lwc_let", 128, 256, 2, 32, 4, make_args(6, 6, None, True, True), epochs=2)
     act_stats_fixture()

@@ -45,6 +45,7 @@ class BlockFixture:
         self.lwc, self.let, self.aug_loss = bool(g("lwc")), bool(g("let")), bool(g("aug_loss"))
         self.inps = t(z["in/inps"])
         self.kv_heads = int(z["in/kv_heads"]) if "in/kv_heads" in z else self.heads
+        self.symmetric = bool(int(z["in/symmetric"])) if "in/symmetric" in z else False
 
     # raw weights in the oracle's short naming
     def weights(self):

@@ -89,7 +89,7 @@ def test_survey_kat():
 
 
 def _oracle_setup(fx):
-    cfg = orc.QCfg(fx.wbits, fx.abits, fx.group_size, False, fx.lwc, fx.let)
+    cfg = orc.QCfg(fx.wbits, fx.abits, fx.group_size, fx.symmetric, fx.lwc, fx.let)
     Wt = fx.weights()
     lin = {"llama": orc.LLAMA_LINEARS, "opt": orc.OPT_LINEARS, "falcon": orc.FALCON_LINEARS}[fx.family]
     P = orc.init_lwc({n: Wt[n] for n in lin}, cfg)
@@ -107,7 +107,9 @@ def _oracle_setup(fx):
 FIXTURES = ["llama_w4a4_lwc_let.npz", "llama_w4a4_lwc_let_bs2.npz", "llama_w3a16g64_lwc.npz",
             "llama_w6a6_lwc_let_aug.npz", "llama_w4a16g64_lwc_let.npz", "opt_w4a16g64_lwc.npz", "opt_w4a4_lwc_let.npz",
             "opt_w4a16_lwc_let.npz", "falcon_w3a16g64_lwc.npz",
-            "llama_gqa_w2a16g64_lwc.npz"]      # grouped-query attention (Llama-2-70B layout), BASELINE config 4's W2A16g64 LWC
+            "llama_gqa_w2a16g64_lwc.npz",      # grouped-query attention (Llama-2-70B layout), BASELINE config 4's W2A16g64 LWC
+            "llama_sym_w4a16g64_lwc.npz",      # symmetric weight quantiser (main.py --symmetric)
+            "opt_w6a6_lwc_let.npz"]
 
 
 @pytest.mark.parametrize("fname", FIXTURES)
