@@ -85,3 +85,30 @@ def test_truncate_and_fold(hostlib):
     hostlib.host_truncate.argtypes = [ctypes.c_float, ctypes.c_float]
     tr = lambda x: hostlib.host_truncate(x, 1e-2)
     assert tr(0.5) == 0.5 and tr(-0.004) == np.float32(-1e-2) and tr(0.0) == 0.0 and tr(0.003) == np.float32(1e-2)
+
+
+def test_header_signatures_match_the_definitions():
+    """ctypes binds from include/omniquant_b200.h; a parameter added in a .cu definition but not in the header (or the other
+    way round) would be silent undefined behaviour.  Compare the parameter TYPE lists of every extern "C" definition under
+    csrc/ with the declaration (cudaStream_t == oq_stream_t)."""
+    import re
+    from omniquant_b200 import _lib
+    decl = _lib.declared_functions()
+    norm = lambda t: " ".join(t.replace("cudaStream_t", "oq_stream_t").replace("const ", "const ").split())
+    seen = {}
+    for src in _lib.sources():
+        text = open(src).read()
+        text = re.sub(r"//[^\n]*", "", text)
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        for m in re.finditer(r'extern\s+"C"\s+(int|const char\*)\s+(oq_\w+)\s*\(([^)]*)\)\s*\{', text):
+            ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+            types = []
+            if args and args != "void":
+                for a in args.split(","):
+                    a = " ".join(a.split())
+                    types.append(norm(re.match(r"(.*?)(\w+)$", a).group(1).strip()))
+            seen[name] = (ret, types)
+    assert set(seen) == set(decl), sorted(set(seen) ^ set(decl))
+    for name, (ret, params) in decl.items():
+        assert seen[name][0] == ret, name
+        assert seen[name][1] == [norm(t) for t, _ in params], (name, seen[name][1], [t for t, _ in params])
