@@ -1,22 +1,28 @@
 #!/usr/bin/env python
-"""Benchmark of the calibration hot path: LLaMA-7B W4A4 LWC+LET, seconds per decoder block.
+"""Benchmark of the calibration hot path: seconds per decoder block (default: LLaMA-7B W4A4 LWC+LET, BASELINE config 3).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1..5]
 
-A "step" is the calibration of ONE decoder block exactly as quantize/omniquant.py:157-250 does it:
-FP pass over the 128 calibration samples, 20 epochs of AdamW steps on the LWC+LET parameters (global
-batch = N, one sample per GPU per step, 128/N steps per epoch), in-place fold + quantise, and the
-re-quantised forward pass over the 128 samples.  Random-init LLaMA-7B block weights (fp16 values),
-synthetic calibration activations and LET statistics (no network in this environment).
+A "step" is the calibration of ONE decoder block exactly as quantize/omniquant.py:157-250 does it: FP pass over the
+calibration samples, `epochs` epochs of AdamW steps on the LWC(+LET) parameters (global batch = N, one sample per GPU per
+step, nsamples/N steps per epoch), in-place fold + quantise, and the re-quantised forward pass over the samples.
+Random-init block weights of the named architecture (fp16 values), synthetic calibration activations and LET statistics
+(no network in this environment).
 
-`value` is device-timed (CUDA events, max over ranks) with weights and calibration activations already
-resident in HBM; `e2e` is the same block through the public API (`omniquant()` on a one-block model)
-with the block weights coming from pinned host memory, the quantised block going back to the host and
-the calibration activations copied from pinned host memory, all inside the timed region.
+`value` is device-timed (CUDA events, max over ranks) with weights and calibration activations already resident in HBM;
+`e2e` is the same work through the public API (`omniquant()` on a several-block model, divided by the block count) with
+every block's weights coming from pinned host memory, the quantised blocks going back to host memory and the calibration
+activations copied from pinned host memory, all inside the timed region.
 
---impl reference: the reference algorithm on the host cores (the oracle port, oracle/oq_oracle.py; the
-reference is Python/PyTorch and cannot travel to the GPU box), a bounded sample of the same workload
-(K optimiser steps + FP forwards at the same shapes) extrapolated to one block and labelled as such.
+Baselines printed beside it (never the measured product): `cpu_baseline` / `--impl reference` = the reference algorithm
+on the host cores (oracle port; the reference is Python/PyTorch and cannot travel to the GPU box), `gpu_eager_baseline` =
+the same port run as eager PyTorch + cuBLAS with bf16 autocast on the same B200 -- the bar the reference itself would
+set on this hardware.  Both are bounded samples (a few optimiser steps + FP forwards at the same shapes) extrapolated
+to one block and labelled as such.
+
+--config selects another BASELINE.json configuration (1: OPT-125m W4A16g128 LWC 16 samples 1 epoch; 2: LLaMA-7B W3A16g128
+LWC; 4: Llama-2-70B W2A16g64 LWC 40 epochs; 5: Falcon-180B W3A16g128 LWC 32 samples 40 epochs, blocks streamed from host
+DRAM in the e2e leg); their lines are kept under profiles/.
 """
 import argparse
 import json
@@ -31,63 +37,104 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, FFN, HEADS, T = 4096, 11008, 32, 2048
-NSAMPLES, EPOCHS = 128, 20
-WBITS, ABITS = 4, 4
-METRIC = "llama7b_w4a4_lwc_let_calib_s_per_block"
-WORKLOAD = "LLaMA-7B decoder block, W4A4 per-channel weights / per-token activations, LWC+LET, 128x2048 synthetic tokens, 20 epochs"
+T = 2048
+CONFIGS = {
+    1: dict(net="opt-125m", family="opt", H=768, F=3072, heads=12, kv=12, nsamples=16, epochs=1, wbits=4, abits=16, group=128,
+            let=False, metric="opt125m_w4a16g128_lwc_calib_s_per_block",
+            workload="OPT-125m decoder block, W4A16g128 LWC, 16x2048 synthetic tokens, 1 epoch"),
+    2: dict(net="llama-7b", family="llama", H=4096, F=11008, heads=32, kv=32, nsamples=128, epochs=20, wbits=3, abits=16, group=128,
+            let=False, metric="llama7b_w3a16g128_lwc_calib_s_per_block",
+            workload="LLaMA-7B decoder block, W3A16g128 LWC, 128x2048 synthetic tokens, 20 epochs"),
+    3: dict(net="llama-7b", family="llama", H=4096, F=11008, heads=32, kv=32, nsamples=128, epochs=20, wbits=4, abits=4, group=0,
+            let=True, metric="llama7b_w4a4_lwc_let_calib_s_per_block",
+            workload="LLaMA-7B decoder block, W4A4 per-channel weights / per-token activations, LWC+LET, 128x2048 synthetic tokens, 20 epochs"),
+    4: dict(net="Llama-2-70b", family="llama", H=8192, F=28672, heads=64, kv=8, nsamples=128, epochs=40, wbits=2, abits=16, group=64,
+            let=False, metric="llama2_70b_w2a16g64_lwc_calib_s_per_block",
+            workload="Llama-2-70B decoder block (GQA 64/8), W2A16g64 LWC, 128x2048 synthetic tokens, 40 epochs"),
+    5: dict(net="falcon-180b", family="falcon", H=14848, F=59392, heads=232, kv=8, nsamples=32, epochs=40, wbits=3, abits=16, group=128,
+            let=False, metric="falcon180b_w3a16g128_lwc_calib_s_per_block",
+            workload="Falcon-180B decoder block (new decoder architecture, 232/8 heads), W3A16g128 LWC, 32x2048 synthetic tokens, 40 epochs"),
+}
+
+
+class Cfg:
+    def __init__(self, idx, epochs=None, nsamples=None):
+        self.idx = idx
+        self.__dict__.update(CONFIGS[idx])
+        self.full_epochs, self.full_nsamples = self.epochs, self.nsamples
+        if epochs:
+            self.epochs = epochs
+        if nsamples:
+            self.nsamples = nsamples
+        self.reduced = (self.epochs, self.nsamples) != (self.full_epochs, self.full_nsamples)
+        self.d = self.H // self.heads
+        self.Hkv = self.kv * self.d
+        self.eps = 1e-6 if self.family == "llama" else 1e-5
+
+    def p_lin(self):
+        if self.family == "llama":
+            return self.H * self.H * 2 + 2 * self.Hkv * self.H + 3 * self.H * self.F
+        return self.H * (self.H + 2 * self.Hkv) + self.H * self.H + 2 * self.H * self.F
+
+    def flops(self):
+        """(F_fwd, F_step) per 2048-token sample, causal attention (c = 1/2); LWC-only runs skip
+        the dgrad of the q/k/v projection (nothing upstream of it is learned)."""
+        lin = 2 * T * self.p_lin()
+        att = 4 * self.heads * T * T * self.d * 0.5
+        f_fwd = lin + att
+        f_step = 3 * f_fwd
+        if not self.let:
+            f_step -= 2 * T * self.H * (self.H + 2 * self.Hkv)
+        return f_fwd, f_step
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", 1388.8), d.get("hbm_gbs", 6539.5), "measured"
-    return 1400.0, 6650.0, "fallback"
+        return d.get("bf16_tflops", 1656.7), d.get("bf16_tflops_sustained", 1388.8), d.get("hbm_gbs", 6539.5), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
 
 
-def gemm_traffic_from_ncu():
-    """Per-launch DRAM bytes (read + write) of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r1_gemm_ncu_full_summary.csv, QuantLinear launches of gemm_kernel<256>), or None."""
-    import csv
-    path = os.path.join(ROOT, "profiles", "r1_gemm_ncu_full_summary.csv")
-    if not os.path.exists(path):
-        return None
-    rows = list(csv.reader(open(path)))
-    hdr = rows[0]
-    name = [i for i, h in enumerate(hdr) if h.startswith("Kernel Name")][0]
-    rd = [i for i, h in enumerate(hdr) if h.startswith("dram__bytes_read.sum")][0]
-    wr = [i for i, h in enumerate(hdr) if h.startswith("dram__bytes_write.sum")][0]
-    vals = [(float(r[rd]) + float(r[wr])) * 1e6 for r in rows[1:] if "gemm_kernel<256>" in r[name] and float(r[wr]) < 200]
-    return round(sum(vals) / len(vals)) if vals else None
+def block_weights(c, device="cpu", seed=0):
+    """fp16 weights of one decoder block in the engine's short naming."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    r = lambda *s: (torch.randn(*s, generator=g, device=device) * 0.02).half()
+    H, F_, Hkv = c.H, c.F, c.Hkv
+    ones = lambda n: torch.ones(n, device=device).half()
+    if c.family == "llama":
+        return {"q": r(H, H), "k": r(Hkv, H), "v": r(Hkv, H), "o": r(H, H), "gate": r(F_, H), "up": r(F_, H), "down": r(H, F_),
+                "ln1": ones(H), "ln2": ones(H)}
+    if c.family == "opt":
+        W = {"q": r(H, H), "k": r(H, H), "v": r(H, H), "o": r(H, H), "fc1": r(F_, H), "fc2": r(H, F_), "ln1": ones(H), "ln2": ones(H)}
+        for n in ("q", "k", "v", "o", "fc2", "ln1", "ln2"):
+            W[f"{n}.bias"] = r(H)
+        W["fc1.bias"] = r(F_)
+        return W
+    return {"qkv": r(H + 2 * Hkv, H), "dense": r(H, H), "fc1": r(F_, H), "fc2": r(H, F_), "ln1": ones(H), "ln2": ones(H),
+            "ln1.bias": r(H), "ln2.bias": r(H)}
 
 
-def block_weights(seed=0):
-    g = torch.Generator().manual_seed(seed)
-    r = lambda *s: (torch.randn(*s, generator=g) * 0.02).half()
-    W = {"q": r(H, H), "k": r(H, H), "v": r(H, H), "o": r(H, H), "gate": r(FFN, H), "up": r(FFN, H), "down": r(H, FFN),
-         "ln1": torch.ones(H).half(), "ln2": torch.ones(H).half()}
-    return W
-
-
-def calib_inputs(indices, seed=1234):
+def calib_inputs(c, indices, device="cpu", seed=1234):
     """Synthetic block inputs for the given global sample indices (one generator per sample, so every rank
     builds only its own shard and the data does not depend on the world size)."""
-    out = torch.empty(len(indices), T, H, dtype=torch.bfloat16)
+    out = torch.empty(len(indices), T, c.H, dtype=torch.bfloat16, device=device)
     for i, j in enumerate(indices):
-        g = torch.Generator().manual_seed(seed + int(j))
-        x = torch.randn(T, H, generator=g, dtype=torch.float32)
+        g = torch.Generator(device=device).manual_seed(seed + int(j))
+        x = torch.randn(T, c.H, generator=g, dtype=torch.float32, device=device)
         x[:, ::512] *= 8.0          # a few outlier channels, what LET exists for
         out[i] = x.to(torch.bfloat16)
     return out
 
 
-def let_init(W, seed=1234):
+def let_init(c, W, seed=1234):
+    if not c.let:
+        return None
     g = torch.Generator().manual_seed(seed)
     out = {}
-    for key, wn in (("qkv", "q"), ("out", "o"), ("fc1", "up")):
-        act = (torch.randn(H, generator=g).abs() * 2 + 1e-5).clamp(min=1e-5)
-        w = W[wn].float().max(dim=0)[0].clamp(min=1e-5)
+    for key, wn in (("qkv", "q"), ("out", "o"), ("fc1", "up" if c.family == "llama" else "fc1")):
+        act = (torch.randn(c.H, generator=g).abs() * 2 + 1e-5).clamp(min=1e-5)
+        w = W[wn].float().cpu().max(dim=0)[0].clamp(min=1e-5)
         out[f"{key}_s"] = (act.pow(0.5) / w.pow(0.5)).clamp(min=1e-5)
     return out
 
@@ -123,12 +170,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def make_engine(c, W, dev, world, batch=1, init=None):
+    from omniquant_b200.engine import BlockEngine, QuantConfig
+    q = QuantConfig(wbits=c.wbits, abits=c.abits, group_size=c.group, lwc=True, let=c.let, recip_div=True)
+    return BlockEngine(c.family, W, n_heads=c.heads, n_kv_heads=c.kv if c.kv != c.heads else None, seq_len=T, qcfg=q, eps=c.eps,
+                       device=dev, batch=batch, let_init=init, world_size=world)
+
+
 # ---------------------------------------------------------------------------------------------- ours
 def run_ours(a):
     import torch.distributed as dist
     from omniquant_b200 import ops
-    from omniquant_b200.engine import BlockEngine, QuantConfig, calibrate_block
+    from omniquant_b200.engine import calibrate_block
 
+    c = Cfg(a.config, a.epochs, a.nsamples)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -140,35 +195,31 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
-    assert NSAMPLES % world == 0
+    assert c.nsamples % world == 0
     allreduce = (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)) if world > 1 else None
 
-    W_host = block_weights()
-    W = {k: v.to(dev) for k, v in W_host.items()}       # resident in HBM before the timed region
-    n_local = NSAMPLES // world
+    big = c.idx in (4, 5)                       # generate the large blocks on the device (a CPU randn of 2.2 G values takes minutes)
+    gen_dev = dev if big else "cpu"
+    W_src = block_weights(c, gen_dev)
+    W = {k: v.to(dev) for k, v in W_src.items()}        # resident in HBM before the timed region
+    n_local = c.nsamples // world
     # rank r owns samples r, r+world, ... (global step j = samples [j*world, (j+1)*world), reference --batch_size world)
-    x_host = calib_inputs(range(rank, NSAMPLES, world)).pin_memory()
-    x_dev = x_host.to(dev)
-    q = QuantConfig(wbits=WBITS, abits=ABITS, group_size=0, lwc=True, let=True, recip_div=True)
-    init = let_init(W_host)
+    x_dev = calib_inputs(c, range(rank, c.nsamples, world), gen_dev).to(dev)
+    init = let_init(c, W_src)
 
     resident = {}
-
-    def fresh_engine():
-        return BlockEngine("llama", W, n_heads=HEADS, seq_len=T, qcfg=q, eps=1e-6, device=dev, batch=1, let_init=init,
-                           world_size=world)
 
     def new_engine():
         """The engine of the next block: like omniquant() on a multi-block model, the resident engine is re-loaded with
         the block's weights (copied + converted inside the timed region) and keeps the captured CUDA graph of the step."""
         if "eng" not in resident:
-            resident["eng"] = fresh_engine()
+            resident["eng"] = make_engine(c, W, dev, world, init=init)
             return resident["eng"]
         return resident["eng"].reload(W, init)
 
     def one_block(eng):
         fp, qi = x_dev.clone(), x_dev.clone()
-        return calibrate_block(eng, fp, qi, epochs=EPOCHS, allreduce=allreduce, use_graph=True)
+        return calibrate_block(eng, fp, qi, epochs=c.epochs, allreduce=allreduce, use_graph=True)
 
     def sync():
         torch.cuda.synchronize()
@@ -196,13 +247,44 @@ def run_ours(a):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_block = float(ms) / a.steps
     launches_eager = ops.launch_count() - l0
-    # the captured step replays its kernels from a CUDA graph: count them per replay
-    steps_per_block = EPOCHS * n_local
+    steps_per_block = c.epochs * n_local
     loss_mean = float(last["losses"].mean())
     loss_first_epoch, loss_last_epoch = float(last["losses"][:n_local].mean()), float(last["losses"][-n_local:].mean())
 
+    # ---- DP correctness beside the number: replicas identical, step-0 loss == one engine stepping on the batch of N
+    dp_check = None
+    if world > 1:
+        eng = resident["eng"]
+        pmax, pmin = eng.params.clone(), eng.params.clone()
+        dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
+        spread = float((pmax - pmin).abs().max())
+        dp_eng = make_engine(c, W, dev, world, init=init)
+        xs = x_dev[0]
+        with torch.no_grad():
+            tgt = torch.empty_like(xs)
+            dp_eng.forward(xs, dp_eng.fp_weights(), act_quant=False, out=tgt)
+            loss0 = dp_eng.train_step(xs, tgt, allreduce=allreduce).clone() / world       # mean over the N ranks' samples
+        gathered = [torch.empty_like(xs) for _ in range(world)] if rank == 0 else None
+        dist.gather(xs.contiguous(), gathered, dst=0)
+        del dp_eng
+        loss_b = None
+        if rank == 0:
+            bN = make_engine(c, W, dev, 1, batch=world, init=init)
+            xb = torch.cat(gathered, 0)
+            with torch.no_grad():
+                tb = torch.empty_like(xb)
+                bN.forward(xb, bN.fp_weights(), act_quant=False, out=tb)
+                loss_b = float(bN.train_step(xb, tb))
+            del bN
+        dp_check = {"param_max_abs_diff_across_ranks": spread, "step0_loss_dp": float(loss0), "step0_loss_single_rank_batchN": loss_b,
+                    "step0_rel_diff": None if loss_b is None else abs(float(loss0) - loss_b) / loss_b,
+                    "semantics": f"N ranks x 1 sample == reference --batch_size {world}: {steps_per_block} optimiser steps per block "
+                                 f"instead of {c.epochs * c.nsamples}, so the optimisation result differs from N=1 (see loss_last_epoch)"}
+        torch.cuda.empty_cache()
+
     # ---- roofline of the dominant kernel (gemm_kernel<256>: the QuantLinear fwd/dgrad/wgrad GEMMs), timed live
-    eng = fresh_engine()
+    eng = make_engine(c, W, dev, 1, init=init)
     eng.overlap = False      # time the GEMM launches alone on the stream (no quantiser kernels co-running beside them)
     xs, ts = x_dev[0], x_dev[1 % n_local]
     for _ in range(2):
@@ -221,45 +303,60 @@ def run_ours(a):
     lin = [(e0_.elapsed_time(e1_), fl) for e0_, e1_, fl, batched in ops.GEMM_TIMER if not batched]
     att = [(e0_.elapsed_time(e1_), fl) for e0_, e1_, fl, batched in ops.GEMM_TIMER if batched]
     ops.GEMM_TIMER = None
-    peak_tf, peak_hbm, which = peaks()
+    peak_burst, peak_sus, peak_hbm, which = peaks()
     lin_ms, lin_fl = sum(t for t, _ in lin), sum(f for _, f in lin)
     achieved = lin_fl / (lin_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm_kernel<256> (QuantLinear fwd/dgrad/wgrad)", "achieved": round(achieved, 1),
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": gemm_traffic_from_ncu(),
-                "traffic_note": "mean DRAM read+write bytes per QuantLinear launch, ncu --set full (profiles/r1_gemm_ncu_full_summary.csv); "
-                                "algorithmic operand+result bytes per launch average 1.7e8",
-                "peak_source": f"bf16_tflops_sustained, {which}", "launches_timed": len(lin),
+    # event-timed single launches are a burst measurement: the burst cuBLAS figure is the denominator; the sustained one is
+    # printed beside it because inside the seconds-long step the same kernel runs under the power cap
+    roofline = {"bound": "tensor", "kernel": "QuantLinear fwd/dgrad/wgrad GEMMs (tcgen05)", "achieved": round(achieved, 1),
+                "peak": peak_burst, "unit": "TFLOP/s", "frac": round(achieved / peak_burst, 4),
+                "frac_of_sustained_peak": round(achieved / peak_sus, 4), "peak_sustained": peak_sus,
+                "traffic": None,
+                "traffic_note": "not measured live; ncu --set full captures of the same kernels are under profiles/ (r1_gemm_ncu_full_summary.csv: "
+                                "174.5 MB DRAM read+write per QuantLinear launch vs 170 MB algorithmic at LLaMA-7B shapes)",
+                "peak_source": f"bf16_tflops (burst), {which}", "launches_timed": len(lin),
                 "timing": "CUDA events around each launch on the launching stream, 3 eager optimiser steps after the timed region, side-stream overlap off",
                 "avg_launch_ms": round(lin_ms / max(len(lin), 1), 4),
                 "attention_gemm_tflops": round(sum(f for _, f in att) / (sum(t for t, _ in att) * 1e-3) / 1e12, 1) if att else None}
-    # whole-step tensor utilisation: algorithmic flops of one step (causal attention) / step time
-    f_step = 3 * 2 * T * (4 * H * H + 3 * H * FFN) + 3 * 4 * HEADS * T * T * (H // HEADS) * 0.5
-    f_block = steps_per_block * world * f_step + 2 * NSAMPLES * (f_step / 3)
+    # whole-step tensor utilisation: algorithmic flops of one block (causal attention) / block time
+    f_fwd, f_step = c.flops()
+    f_block = steps_per_block * world * f_step + 2 * c.nsamples * f_fwd
     roofline["block_tflops"] = round(f_block / (ms_per_block * 1e-3) / 1e12 / world, 1)
-    roofline["block_frac_of_peak"] = round(roofline["block_tflops"] / peak_tf, 4)
+    roofline["block_frac_of_peak"] = round(roofline["block_tflops"] / peak_burst, 4)
+    roofline["block_frac_of_sustained_peak"] = round(roofline["block_tflops"] / peak_sus, 4)
     del eng
 
     # ---- e2e through the public API with host buffers
     e2e = None
     if a.e2e:
-        e2e = run_e2e(a, W_host, x_host, dev, world, rank)
+        W_host = {k: v.cpu() for k, v in W_src.items()}
+        x_host = x_dev.cpu().pin_memory()
+        e2e = run_e2e(a, c, W_host, x_host, dev, world, rank)
 
-    cpu = None
+    cpu = gpu_eager = None
+    if rank == 0 and world == 1 and a.gpu_eager_baseline:
+        gpu_eager = gpu_eager_baseline(c, dev)
     if rank == 0 and world == 1 and a.cpu_baseline:
-        cpu = cpu_baseline(steps=1)
+        cpu = cpu_baseline(c, steps=1)
 
     if rank == 0:
-        out = {"metric": METRIC, "value": round(ms_per_block / 1e3, 4), "unit": "s/block", "n_gpus": world, "steps": a.steps,
+        out = {"metric": c.metric, "value": round(ms_per_block / 1e3, 4), "unit": "s/block", "n_gpus": world, "steps": a.steps,
                "warmup": a.warmup, "ms_per_step": round(ms_per_block, 2), "higher_is_better": False, "scaling": "strong",
                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-               "config": {"workload": WORKLOAD, "step": "one decoder block calibrated (FP pass + 20x128 AdamW steps + requant pass)",
-                          "global_batch": world, "seq_len": T, "nsamples": NSAMPLES, "epochs": EPOCHS,
+               "config": {"workload": c.workload, "baseline_config": c.idx,
+                          "step": f"one decoder block calibrated (FP pass + {c.epochs}x{c.nsamples} sample visits of AdamW steps + requant pass)",
+                          "global_batch": world, "seq_len": T, "nsamples": c.nsamples, "epochs": c.epochs,
+                          "reduced_from_named_config": c.reduced,
                           "parallelism": f"sample-sharded dp{world}",
+                          "scaling_semantics": f"fixed {c.nsamples} samples x {c.epochs} epochs; N ranks == reference --batch_size N, "
+                                               f"i.e. {steps_per_block} optimiser steps per block at N={world}",
                           "engine": "resident across blocks: each block's weights are copied + converted into the same device "
                                     "buffers inside the timed region, the optimiser-step CUDA graph is captured once (warm-up) and replayed",
-                          "l2": "working set per optimiser step (weights 1.2 GB fp32 + activations) exceeds the 126 MB L2"},
+                          "l2": "working set per optimiser step (fp32 master weights + activations) exceeds the 126 MB L2"},
+               "optimizer_steps_per_block": steps_per_block,
                "optimizer_step_ms_eager_instrumented": round(step_ms_eager, 3), "launches_per_optimizer_step": launches_per_step,
-               "loss_mean": loss_mean, "loss_first_epoch": loss_first_epoch, "loss_last_epoch": loss_last_epoch, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+               "loss_mean": loss_mean, "loss_first_epoch": loss_first_epoch, "loss_last_epoch": loss_last_epoch, "roofline": roofline,
+               "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "dp_check": dp_check, "e2e": e2e,
                "gpu_launches": int(launches_eager + a.steps * max(steps_per_block - 3, 0) * launches_per_step),
                "clocks": clocks}
         json_out.write(json.dumps(out) + "\n")
@@ -305,146 +402,252 @@ class _StridedDeviceInputs:
         return self.shard[local]
 
 
-def run_e2e(a, W, x_host, dev, world, rank):
-    """One block through omniquant() (the call a user makes): weights from pinned host memory, calibration
-    activations from pinned host memory, quantised block + learned parameters back on the host."""
-    from types import SimpleNamespace
-    from transformers import LlamaConfig
-    from omniquant_b200.main import quant_param_dicts
-    from omniquant_b200.quantize.omniquant import omniquant
-
-    cfg = LlamaConfig(hidden_size=H, intermediate_size=FFN, num_attention_heads=HEADS, num_key_value_heads=HEADS,
-                      num_hidden_layers=1, vocab_size=32, max_position_embeddings=T, rms_norm_eps=1e-6)
-    cfg.use_cache = False
+def _host_model(c, W, n_blocks):
+    """A bare module tree with the attribute names omniquant() walks, holding `n_blocks` copies of the block in pinned
+    host memory (what a checkpoint loaded with low_cpu_mem_usage looks like to the calibration driver)."""
+    from transformers import FalconConfig, LlamaConfig, OPTConfig
 
     class Lin(torch.nn.Module):
-        def __init__(self, w):
+        def __init__(self, w, b=None):
             super().__init__()
             self.weight = torch.nn.Parameter(w.clone().pin_memory(), requires_grad=False)
-            self.bias = None
+            self.bias = None if b is None else torch.nn.Parameter(b.clone().pin_memory(), requires_grad=False)
             self.out_features, self.in_features = w.shape
 
     class Norm(torch.nn.Module):
-        def __init__(self, w):
+        def __init__(self, w, b=None):
             super().__init__()
             self.weight = torch.nn.Parameter(w.clone().pin_memory(), requires_grad=False)
-            self.variance_epsilon = 1e-6
+            self.bias = None if b is None else torch.nn.Parameter(b.clone().pin_memory(), requires_grad=False)
+            self.variance_epsilon = self.eps = c.eps
+            self.normalized_shape = (w.shape[0],)
 
-    def make_layer():
-        layer = torch.nn.Module()
-        layer.self_attn = torch.nn.Module()
-        for n in ("q", "k", "v", "o"):
-            setattr(layer.self_attn, f"{n}_proj", Lin(W[n]))
-        layer.mlp = torch.nn.Module()
-        for n in ("gate", "up", "down"):
-            setattr(layer.mlp, f"{n}_proj", Lin(W[n]))
-        layer.input_layernorm, layer.post_attention_layernorm = Norm(W["ln1"]), Norm(W["ln2"])
-        return layer
+    lin = lambda n: Lin(W[n], W.get(f"{n}.bias"))
+    norm = lambda n: Norm(W[n], W.get(f"{n}.bias"))
+    M = torch.nn.Module
 
+    def layer():
+        L = M()
+        if c.family == "llama":
+            L.self_attn, L.mlp = M(), M()
+            for n in ("q", "k", "v", "o"):
+                setattr(L.self_attn, f"{n}_proj", lin(n))
+            for n in ("gate", "up", "down"):
+                setattr(L.mlp, f"{n}_proj", lin(n))
+            L.input_layernorm, L.post_attention_layernorm = norm("ln1"), norm("ln2")
+        elif c.family == "opt":
+            L.self_attn = M()
+            for n, attr in (("q", "q_proj"), ("k", "k_proj"), ("v", "v_proj"), ("o", "out_proj")):
+                setattr(L.self_attn, attr, lin(n))
+            L.fc1, L.fc2 = lin("fc1"), lin("fc2")
+            L.self_attn_layer_norm, L.final_layer_norm = norm("ln1"), norm("ln2")
+        else:
+            L.self_attention, L.mlp = M(), M()
+            L.self_attention.query_key_value, L.self_attention.dense = lin("qkv"), lin("dense")
+            L.mlp.dense_h_to_4h, L.mlp.dense_4h_to_h = lin("fc1"), lin("fc2")
+            L.ln_attn, L.ln_mlp = norm("ln1"), norm("ln2")
+        return L
+
+    model = M()
+    layers = torch.nn.ModuleList([layer() for _ in range(n_blocks)])
+    ident = torch.nn.Identity
+    if c.family == "llama":
+        cfg = LlamaConfig(hidden_size=c.H, intermediate_size=c.F, num_attention_heads=c.heads, num_key_value_heads=c.kv,
+                          num_hidden_layers=n_blocks, vocab_size=32, max_position_embeddings=T, rms_norm_eps=c.eps)
+        model.model = M()
+        model.model.layers, model.model.embed_tokens, model.model.norm = layers, ident(), ident()
+        names = ("self_attn.q_proj", "self_attn.o_proj", "mlp.up_proj")
+        prefix = "model.layers"
+    elif c.family == "opt":
+        cfg = OPTConfig(hidden_size=c.H, ffn_dim=c.F, num_attention_heads=c.heads, num_hidden_layers=n_blocks, vocab_size=32,
+                        max_position_embeddings=T, word_embed_proj_dim=c.H)
+        model.model = M()
+        model.model.decoder = M()
+        dec = model.model.decoder
+        dec.layers, dec.embed_tokens, dec.embed_positions, dec.project_out, dec.project_in = layers, ident(), ident(), None, None
+        names = ("self_attn.q_proj", "self_attn.out_proj", "fc1")
+        prefix = "model.decoder.layers"
+    else:
+        cfg = FalconConfig(hidden_size=c.H, num_attention_heads=c.heads, num_kv_heads=c.kv, num_hidden_layers=n_blocks, vocab_size=32,
+                           new_decoder_architecture=True, bias=False, parallel_attn=True, ffn_hidden_size=c.F)
+        model.transformer = M()
+        model.transformer.h, model.transformer.word_embeddings, model.transformer.ln_f = layers, ident(), ident()
+        names, prefix = (), "model.transformer.h"
+    cfg.use_cache = False
+    model.config = cfg
     g = torch.Generator().manual_seed(1234)
-    act = {f"model.layers.0.{n}": torch.randn(H, generator=g).abs() * 2 + 1e-5
-           for n in ("self_attn.q_proj", "self_attn.o_proj", "mlp.up_proj")}
-    args = SimpleNamespace(net="llama-7b", nsamples=x_host.shape[0] * world, batch_size=world, epochs=EPOCHS, let=True,
-                           lwc=True, aug_loss=False, alpha=0.5, let_lr=5e-3, lwc_lr=1e-2, wd=0.0, wbits=WBITS, abits=ABITS,
-                           group_size=None, symmetric=False, w_dynamic_method="per_channel", a_dynamic_method="per_token",
-                           resume=None, real_quant=False, output_dir=None, cuda_graph=True)
-    quant_param_dicts(args)
+    act = {f"{prefix}.{i}.{n}": torch.randn(c.H, generator=g).abs() * 2 + 1e-5 for i in range(n_blocks) for n in names}
+    return model, act, layers
 
+
+def run_e2e(a, c, W, x_host, dev, world, rank):
+    """`n_blocks` decoder blocks through omniquant() (the call a user makes): every block's weights from pinned host
+    memory (the next block's copy overlaps the current block's calibration), calibration activations from pinned host
+    memory, every quantised block + its learned parameters back in host memory.  Reported per block."""
+    from types import SimpleNamespace
+    from omniquant_b200.main import quant_param_dicts
+    from omniquant_b200.quantize.omniquant import omniquant
+    import torch.distributed as dist
+
+    n_blocks = max(1, a.e2e_blocks)
+    args = SimpleNamespace(net=c.net, nsamples=x_host.shape[0] * world, batch_size=world, epochs=c.epochs, let=c.let,
+                           lwc=True, aug_loss=False, alpha=0.5, let_lr=5e-3, lwc_lr=1e-2, wd=0.0, wbits=c.wbits, abits=c.abits,
+                           group_size=c.group or None, symmetric=False, w_dynamic_method="per_channel", a_dynamic_method="per_token",
+                           resume=None, real_quant=False, output_dir=None, cuda_graph=True, deactive_amp=True)
+    quant_param_dicts(args)
     # omniquant() shards `inps` by rank itself and only touches this rank's rows: hand it a pinned host view of the
     # global [nsamples, T, H] tensor in which the rank's own samples sit at stride `world` (other rows unused)
-    if world == 1:
-        inps_view = x_host
-    else:
-        inps_view = _StridedHostInputs(x_host, rank, world)
+    inps_view = x_host if world == 1 else _StridedHostInputs(x_host, rank, world)
 
     def one():
-        model = torch.nn.Module()
-        model.config = cfg
-        model.model = torch.nn.Module()
-        model.model.layers = torch.nn.ModuleList([make_layer()])
-        model.model.embed_tokens = torch.nn.Identity()
-        model.model.norm = torch.nn.Identity()
+        model, act, layers = _host_model(c, W, n_blocks)
         lm = SimpleNamespace(model=model, device=dev, _device=dev, seqlen=T)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        omniquant(lm, args, None, act, None, None, inps=inps_view)
-        w0 = model.model.layers[0].self_attn.q_proj.weight
-        assert w0.device.type == "cpu"
-        torch.cuda.synchronize()
-        return time.perf_counter() - t0
-
-    one()                                       # warm-up
-    n = max(1, a.steps // 2)
-    import torch.distributed as dist
-    ts = []
-    for _ in range(n):
         if world > 1:
             dist.barrier()
-        ts.append(one())
-    t = torch.tensor([sum(ts) / n], device=dev)
+        t0 = time.perf_counter()
+        omniquant(lm, args, None, act if c.let else None, None, None, inps=inps_view)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        w0 = next(iter(layers[0].parameters()), None)
+        w0 = w0 if w0 is not None else next(iter(layers[0].buffers()))
+        assert w0.device.type == "cpu"
+        return dt
+
+    one()                                       # warm-up (captures the step graph, allocates the pinned staging)
+    n_calls = max(1, -(-max(1, a.steps // 2) // n_blocks))
+    ts = [one() for _ in range(n_calls)]
+    t = torch.tensor([sum(ts) / (n_calls * n_blocks)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     wbytes = sum(v.numel() * 2 for v in W.values())
-    return {"value": round(float(t), 4), "unit": "s/block", "h2d_bytes_per_step": int(wbytes + x_host.numel() * 2),
-            "d2h_bytes_per_step": int(wbytes + 4 * (2 * 7 * H + 7 * H)), "steps": n,
-            "api": "omniquant_b200.quantize.omniquant.omniquant() on a one-block model; wall clock, max over ranks"}
+    return {"value": round(float(t), 4), "unit": "s/block", "h2d_bytes_per_step": int(wbytes + x_host.numel() * 2 // n_blocks),
+            "d2h_bytes_per_step": int(wbytes), "steps": n_calls * n_blocks, "blocks_per_call": n_blocks,
+            "api": f"omniquant_b200.quantize.omniquant.omniquant() on a {n_blocks}-block model (weights pinned on the host, next block "
+                   "prefetched on a copy stream, quantised blocks written back asynchronously); wall clock / blocks, max over ranks"}
 
 
-# ---------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_baseline(steps=1):
-    """The oracle port (torch fp32 on the host cores) at the same shapes: `steps` optimiser steps + one FP
-    forward, extrapolated to a block: 2560*t_step + 256*t_fwd."""
+# ---------------------------------------------------------------------------------------------- baselines (oracle port)
+def _oracle_setup(c, device):
+    """Oracle-side block, parameters and closures for `c` on `device` (LLaMA / OPT / Falcon)."""
     from oracle import oq_oracle as orc
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    W = {k: v.float() for k, v in block_weights().items()}
-    cfg = orc.QCfg(WBITS, ABITS, None, False, True, True)
-    P = orc.init_lwc({k: W[k] for k in orc.LLAMA_LINEARS}, cfg)
-    for k, v in let_init(W).items():
-        P[k] = v.clone()
-    for k in ("qkv_d", "out_d", "fc1_d"):
-        P[k] = torch.zeros(H)
-    P["qkt_s"] = torch.ones(H)
-    x = calib_inputs(range(2)).float()
-    cos, sin = orc.rope_tables(H // HEADS, T)
-    mask = orc.causal_mask(T)
-    with torch.no_grad():
-        Tfp = orc.llama_prepare(W, P, orc.QCfg(WBITS, ABITS, None, False, True, False), quant=False)
-        t0 = time.perf_counter()
-        fp = orc.llama_forward(x[:1], Tfp, HEADS, cos, sin, mask, cfg, False)
-        t_fwd = time.perf_counter() - t0
+    W = {k: v.float().to(device) for k, v in block_weights(c).items()}
+    cfg = orc.QCfg(c.wbits, c.abits, c.group or None, False, True, c.let, recip_div=device != "cpu" and str(device) != "cpu")
+    lin = {"llama": orc.LLAMA_LINEARS, "opt": orc.OPT_LINEARS, "falcon": orc.FALCON_LINEARS}[c.family]
+    P = {k: v.to(device) for k, v in orc.init_lwc({k: W[k] for k in lin}, cfg).items()}
+    if c.let:
+        for k, v in let_init(c, block_weights(c)).items():
+            P[k] = v.clone().to(device)
+        for k in ("qkv_d", "out_d", "fc1_d"):
+            P[k] = torch.zeros(c.H, device=device)
+        P["qkt_s"] = torch.ones(c.H, device=device)
+    cos, sin = orc.rope_tables(c.d, T)
+    cos, sin = cos.to(device), sin.to(device)
+    mask = orc.causal_mask(T).to(device)
+    kv = c.kv if c.kv != c.heads else None
+    if c.family == "llama":
+        prep = orc.llama_prepare
+        fwd = lambda x, Tw, aq: orc.llama_forward(x, Tw, c.heads, cos, sin, mask, cfg, aq, c.eps, kv)
+    elif c.family == "opt":
+        prep = orc.opt_prepare
+        fwd = lambda x, Tw, aq: orc.opt_forward(x, Tw, c.heads, mask, cfg, aq, c.eps)
+    else:
+        prep = orc.falcon_prepare
+        fwd = lambda x, Tw, aq: orc.falcon_forward(x, Tw, c.heads, c.kv, cos, sin, cfg, aq, c.eps)
+    no_let = orc.QCfg(c.wbits, c.abits, c.group or None, False, True, False)
     keys = [k for k in P if k.endswith(("_s", "_d", ".up", ".low"))]
+    return orc, W, P, cfg, no_let, prep, fwd, keys
+
+
+def _oracle_sample(c, device, steps, timer, autocast=None):
+    """t_fwd (one FP forward) and t_step (mean of `steps` optimiser steps) of the oracle port at the config's shapes."""
+    import contextlib
+    orc, W, P, cfg, no_let, prep, fwd, keys = _oracle_setup(c, device)
+    x = calib_inputs(c, range(1)).float().to(device)
+    ctx = (lambda: torch.autocast("cuda", dtype=autocast)) if autocast is not None else contextlib.nullcontext
+    with torch.no_grad(), ctx():
+        Tfp = prep(W, P, no_let, quant=False)
+        fwd(x, Tfp, False)                         # warm
+        t_fwd, fp = timer(lambda: fwd(x, Tfp, False))
+    fp = fp.float()
     for k in keys:
         P[k].requires_grad_(True)
-    opt = torch.optim.AdamW([{"params": [P[k] for k in keys if "_" in k and "." not in k], "lr": 5e-3},
+    opt = torch.optim.AdamW([{"params": [P[k] for k in keys if "." not in k], "lr": 5e-3},
                              {"params": [P[k] for k in keys if "." in k], "lr": 1e-2}], weight_decay=0)
-    ts = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        Tq = orc.llama_prepare(W, P, cfg)
-        out = orc.llama_forward(x[:1], Tq, HEADS, cos, sin, mask, cfg, True)
-        loss = torch.nn.functional.mse_loss(fp, out)
+
+    def step():
+        with ctx():
+            Tq = prep(W, P, cfg)
+            out = fwd(x, Tq, True)
+            loss = torch.nn.functional.mse_loss(fp, out.float())
         opt.zero_grad()
         loss.backward()
         opt.step()
-        ts.append(time.perf_counter() - t0)
-    t_step = sum(ts) / len(ts)
-    block = EPOCHS * NSAMPLES * t_step + 2 * NSAMPLES * t_fwd
+        return loss
+
+    if autocast is not None:
+        step()                                     # warm-up step on the GPU (cuBLAS heuristics, allocator)
+    ts = [timer(step)[0] for _ in range(steps)]
+    return t_fwd, sum(ts) / len(ts)
+
+
+def cpu_baseline(c, steps=1):
+    """The oracle port (torch fp32 on the host cores) at the same shapes: `steps` optimiser steps + one FP
+    forward, extrapolated to a block: epochs*nsamples*t_step + 2*nsamples*t_fwd."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+
+    def timer(fn):
+        t0 = time.perf_counter()
+        r = fn()
+        return time.perf_counter() - t0, r
+
+    t_fwd, t_step = _oracle_sample(c, "cpu", steps, timer)
+    block = c.epochs * c.nsamples * t_step + 2 * c.nsamples * t_fwd
     return {"value": round(block, 1), "unit": "s/block", "cores": cores, "kind": "port",
-            "sample": f"{steps} optimiser step(s) ({t_step:.2f} s each) + 1 FP forward ({t_fwd:.2f} s) at LLaMA-7B block shapes, "
-                      f"fp32 torch on the host, extrapolated: {EPOCHS * NSAMPLES}*t_step + {2 * NSAMPLES}*t_fwd"}
+            "sample": f"{steps} optimiser step(s) ({t_step:.2f} s each) + 1 FP forward ({t_fwd:.2f} s) at the block's shapes, "
+                      f"fp32 torch on the host, extrapolated: {c.epochs * c.nsamples}*t_step + {2 * c.nsamples}*t_fwd"}
+
+
+def gpu_eager_baseline(c, dev, steps=3):
+    """The same port as eager PyTorch + cuBLAS on THIS B200 with bf16 autocast (what the reference's own modules do on a
+    GPU, quantize/omniquant.py:211-234 with torch.cuda.amp.autocast): the bar that matters for speed-up claims.  Timed with
+    CUDA events on `steps` optimiser steps + one FP forward, extrapolated to one block like the CPU baseline."""
+    def timer(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3, r
+
+    try:
+        t_fwd, t_step = _oracle_sample(c, dev, steps, timer, autocast=torch.bfloat16)
+    except torch.cuda.OutOfMemoryError as e:
+        return {"unavailable": f"out of memory at these shapes: {str(e)[:80]}"}
+    finally:
+        torch.cuda.empty_cache()
+    block = c.epochs * c.nsamples * t_step + 2 * c.nsamples * t_fwd
+    return {"value": round(block, 2), "unit": "s/block", "kind": "port on CUDA (eager PyTorch + cuBLAS, bf16 autocast, fp32 master weights)",
+            "step_ms": round(t_step * 1e3, 2), "fwd_ms": round(t_fwd * 1e3, 2),
+            "sample": f"{steps} optimiser steps ({t_step * 1e3:.1f} ms each) + 1 FP forward ({t_fwd * 1e3:.1f} ms), extrapolated: "
+                      f"{c.epochs * c.nsamples}*t_step + {2 * c.nsamples}*t_fwd"}
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    c = Cfg(a.config, a.epochs, a.nsamples)
     t0 = time.perf_counter()
-    cpu = cpu_baseline(steps=max(1, a.steps))
-    out = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "s/block", "n_gpus": a.gpus, "steps": a.steps,
+    # bounded: the driver's --steps is the number of BLOCKS of our arm; a CPU optimiser step at 7B shapes takes seconds
+    cpu = cpu_baseline(c, steps=max(1, min(a.steps, 20 if c.idx in (1, 2, 3) else 2)))
+    out = {"impl": "reference", "metric": c.metric, "value": cpu["value"], "unit": "s/block", "n_gpus": a.gpus, "steps": a.steps,
            "warmup": a.warmup, "ms_per_step": round(cpu["value"] * 1e3, 1), "higher_is_better": False, "scaling": "strong",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "note": "reference algorithm on the host cores (oracle port), bounded sample extrapolated to one block"},
+           "config": {"workload": c.workload, "baseline_config": c.idx,
+                      "note": "reference algorithm on the host cores (oracle port), bounded sample extrapolated to one block"},
            "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "s/block", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": round(time.perf_counter() - t0, 1)}
     print(json.dumps(out), flush=True)
@@ -456,8 +659,13 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
+    ap.add_argument("--epochs", type=int, default=None, help="override the config's epochs (marks the line as reduced)")
+    ap.add_argument("--nsamples", type=int, default=None, help="override the config's sample count (marks the line as reduced)")
+    ap.add_argument("--e2e-blocks", dest="e2e_blocks", type=int, default=4)
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-gpu-eager-baseline", dest="gpu_eager_baseline", action="store_false")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -115,9 +115,11 @@ __global__ void __launch_bounds__(256) wq_fwd_kernel(WqArgs a) {
       if (a.shift) Team<TEAM_WARP>::reduce(sm, scratch, OpSum(), 0.0f);
       red[0] = -mm[0]; red[1] = mm[1]; red[2] = sm[0];
     }
+    const bool ident = a.n_bits >= 16;   // fold only: UniformAffineQuantizer.forward returns x (quantizer.py:109)
     const float su = lwc ? oq_sigmoidf(a.up[item]) : 1.0f;
     const float sl = lwc ? oq_sigmoidf(a.low[item]) : 1.0f;
-    const OqQParams q = oq_qparams(red[0], red[1], su, sl, lwc, a.n_bits, a.symmetric, a.recip_div);
+    OqQParams q = {1.0f, 0.0f, 0.0f};
+    if (!ident) q = oq_qparams(red[0], red[1], su, sl, lwc, a.n_bits, a.symmetric, a.recip_div);
     if (tr == 0) {
       if (a.scale_out) a.scale_out[item] = q.scale;
       if (a.zp_out) a.zp_out[item] = q.zp;
@@ -139,8 +141,8 @@ __global__ void __launch_bounds__(256) wq_fwd_kernel(WqArgs a) {
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         float f = oq_fold(w[j], has_col ? a.col[k + j] : 1.0f, has_col, rs, rop);
-        c[j] = oq_code(f, q);
-        y[j] = oq_dequant(c[j], q);
+        c[j] = ident ? 0.0f : oq_code(f, q);
+        y[j] = ident ? f : oq_dequant(c[j], q);
       }
       const long o = (long)n * a.K + k;
       if constexpr (VEC) {
@@ -192,7 +194,9 @@ __global__ void __launch_bounds__(256) wq_bwd_kernel(WqArgs a) {
     const float xmin = a.xmin_in[item], xmax = a.xmax_in[item];
     const float su = lwc ? oq_sigmoidf(a.up[item]) : 1.0f;
     const float sl = lwc ? oq_sigmoidf(a.low[item]) : 1.0f;
-    const OqQParams q = oq_qparams(xmin, xmax, su, sl, lwc, a.n_bits, a.symmetric, a.recip_div);
+    const bool ident = a.n_bits >= 16;   // fold only: dL/dW' = dL/dW_q, no scale path
+    OqQParams q = {1.0f, 0.0f, 0.0f};
+    if (!ident) q = oq_qparams(xmin, xmax, su, sl, lwc, a.n_bits, a.symmetric, a.recip_div);
 
     float acc[4] = {0.f, 0.f, 0.f, 0.f};  // R, #argmax, #argmin, row dot
     bool tie = false;
@@ -200,12 +204,12 @@ __global__ void __launch_bounds__(256) wq_bwd_kernel(WqArgs a) {
       const float w = Wr[k];
       const float w1 = has_col ? OQ_MUL(w, a.col[k]) : w;
       const float f = rop == 1 ? OQ_MUL(w1, rs) : (rop == 2 ? OQ_DIV(w1, rs) : w1);
-      const float t = oq_code_unclamped(f, q);
-      const bool inr = (t >= 0.0f) && (t <= q.qmax);
+      const float t = ident ? 0.0f : oq_code_unclamped(f, q);
+      const bool inr = ident || ((t >= 0.0f) && (t <= q.qmax));
       const float c = oq_clampf(t, 0.0f, q.qmax);
       const float gk = load_g(a, (long)n * a.ld_g + k);
-      acc[0] += gk * ((c - q.zp) - (inr ? f / q.scale : 0.0f));
-      const bool ismax = (f == xmax), ismin = (f == xmin);
+      if (!ident) acc[0] += gk * ((c - q.zp) - (inr ? f / q.scale : 0.0f));
+      const bool ismax = !ident && (f == xmax), ismin = !ident && (f == xmin);
       acc[1] += ismax ? 1.0f : 0.0f;
       acc[2] += ismin ? 1.0f : 0.0f;
       tie |= ismax | ismin;
@@ -229,11 +233,11 @@ __global__ void __launch_bounds__(256) wq_bwd_kernel(WqArgs a) {
     Team<TEAM_WARP>::reduce(acc, scratch, OpSum(), 0.0f);
     const float R = acc[0];
     // dL/dxmax', dL/dxmin' (after the LWC clip); symmetric variant through max(|.|,|.|) and the clamp
-    float gmaxp, gminp;
-    oq_scale_grad(R, xmin, xmax, su, sl, lwc, a.n_bits, a.symmetric, a.recip_div, &gmaxp, &gminp);
+    float gmaxp = 0.0f, gminp = 0.0f;
+    if (!ident) oq_scale_grad(R, xmin, xmax, su, sl, lwc, a.n_bits, a.symmetric, a.recip_div, &gmaxp, &gminp);
     if (tr == 0 && lwc) {
-      if (a.d_up) a.d_up[item] = gmaxp * xmax * su * (1.0f - su);
-      if (a.d_low) a.d_low[item] = gminp * xmin * sl * (1.0f - sl);
+      if (a.d_up) a.d_up[item] = ident ? 0.0f : gmaxp * xmax * su * (1.0f - su);
+      if (a.d_low) a.d_low[item] = ident ? 0.0f : gminp * xmin * sl * (1.0f - sl);
     }
     // gradient through amax/amin, split evenly over ties
     const float cmax = acc[1] > 0.f ? gmaxp * su / acc[1] : 0.0f;
@@ -294,7 +298,8 @@ extern "C" int oq_weight_quant_fwd(const float* W, int N, int K, const float* co
                                    long ld_bf16, float* wq_f32, uint8_t* codes, float* scale_out, float* zp_out,
                                    float* xmin_out, float* xmax_out, cudaStream_t stream) {
   OQ_REQUIRE(W && N > 0 && K > 0, "oq_weight_quant_fwd: bad shape N=%d K=%d", N, K);
-  OQ_REQUIRE(n_bits >= 2 && n_bits <= 8, "oq_weight_quant_fwd: n_bits %d not in [2,8]", n_bits);
+  OQ_REQUIRE((n_bits >= 2 && n_bits <= 8) || n_bits >= 16, "oq_weight_quant_fwd: n_bits %d not in [2,8] or >= 16 (fold only)", n_bits);
+  const bool ident = n_bits >= 16;
   OQ_REQUIRE(group_size >= 0, "oq_weight_quant_fwd: negative group_size");
   OQ_REQUIRE((up == nullptr) == (low == nullptr), "oq_weight_quant_fwd: up/low must both be set or both null");
   OQ_REQUIRE(group_size == 0 || K % group_size == 0 || symmetric,
@@ -316,13 +321,13 @@ extern "C" int oq_weight_quant_fwd(const float* W, int N, int K, const float* co
   // fast register-resident paths (weight_quant_fast.cuh); the generic kernels below cover everything else
   const bool let = col_scale || row_scale || shift;
   const bool fast_al = vec && al(col_scale, 16) && al(shift, 16);
-  if (fast_al && !team_warp && K <= 16384) {
+  if (!ident && fast_al && !team_warp && K <= 16384) {
     const size_t smem = let ? sizeof(float) * 2 * K : 0;
     const int g = (int)std::min<long>(N, (long)oq_num_sms() * (K > 8192 ? 2 : 4));
     if (let ? launch_pc_fwd<true>(a, g, smem, stream) : launch_pc_fwd<false>(a, g, 0, stream))
       return oq_check_launch("oq_weight_quant_fwd");
   }
-  if (fast_al && team_warp && K % group_size == 0 && (long)N * G < (1L << 31) - 64 && grp_lpg(group_size, false) >= 1) {
+  if (!ident && fast_al && team_warp && K % group_size == 0 && (long)N * G < (1L << 31) - 64 && grp_lpg(group_size, false) >= 1) {
     const long slots = ((long)N * G * grp_lpg(group_size, false) + 31) / 32;
     const int g = (int)std::max<long>(1, std::min<long>((slots + 7) / 8, (long)oq_num_sms() * 8));
     if (let ? launch_grp<true, false>(a, g, 0, stream) : launch_grp<false, false>(a, g, 0, stream))
@@ -346,7 +351,8 @@ extern "C" int oq_weight_quant_bwd(const float* W, int N, int K, const float* co
                                    float* d_up, float* d_low, float* dcol_acc, float* drow, float* dshift_acc,
                                    float* dW_full, cudaStream_t stream) {
   OQ_REQUIRE(W && grad_wq && xmin && xmax && N > 0 && K > 0, "oq_weight_quant_bwd: null input or bad shape");
-  OQ_REQUIRE(n_bits >= 2 && n_bits <= 8, "oq_weight_quant_bwd: n_bits %d not in [2,8]", n_bits);
+  OQ_REQUIRE((n_bits >= 2 && n_bits <= 8) || n_bits >= 16, "oq_weight_quant_bwd: n_bits %d not in [2,8] or >= 16 (fold only)", n_bits);
+  const bool ident = n_bits >= 16;
   OQ_REQUIRE((up == nullptr) == (low == nullptr), "oq_weight_quant_bwd: up/low must both be set or both null");
   OQ_REQUIRE(!dshift_acc || e_row, "oq_weight_quant_bwd: dshift needs e_row");
   OQ_REQUIRE((scale_saved == nullptr) == (zp_saved == nullptr), "oq_weight_quant_bwd: scale/zp must both be given or both null");
@@ -365,7 +371,7 @@ extern "C" int oq_weight_quant_bwd(const float* W, int N, int K, const float* co
     if (e != cudaSuccess) return (int)e;
   }
   const bool let = col_scale || row_scale || e_row || dcol_acc || dshift_acc;
-  const bool fast_al = (K % 4 == 0) && (group_size % 4 == 0) && (a.ld_g % 4 == 0) && al(W, 16) && al(grad_wq, 16) &&
+  const bool fast_al = !ident && (K % 4 == 0) && (group_size % 4 == 0) && (a.ld_g % 4 == 0) && al(W, 16) && al(grad_wq, 16) &&
                        al(col_scale, 16) && al(dW_full, 16);
   if (fast_al && !team_warp && !let && !dW_full) {       // LWC only: R per row, one warp per row
     const int g = (int)std::min<long>((N + 7) / 8, (long)oq_num_sms() * 8);

@@ -60,8 +60,9 @@ class BlockEngine:
     def __init__(self, family: str, weights: Dict[str, torch.Tensor], *, n_heads: int, seq_len: int, qcfg: QuantConfig,
                  eps: float, device="cuda", batch: int = 1, let_init: Optional[Dict[str, torch.Tensor]] = None,
                  let_lr=5e-3, lwc_lr=1e-2, wd=0.0, world_size=1, causal=True, mask: Optional[torch.Tensor] = None,
-                 overlap: bool = True, n_kv_heads: Optional[int] = None):
+                 overlap: bool = True, n_kv_heads: Optional[int] = None, rope_theta: float = 10000.0):
         assert family in ("llama", "opt", "falcon")
+        self.rope_theta = float(rope_theta)
         self.family, self.q, self.eps, self.dev = family, qcfg, float(eps), torch.device(device)
         self.h, self.T, self.b = n_heads, seq_len, batch
         self.let_lr, self.lwc_lr, self.wd, self.world = let_lr, lwc_lr, wd, world_size
@@ -293,15 +294,17 @@ class BlockEngine:
             up, low = self.lwc(u)
             st = self.qstat[u.name]
             kw = dict(scale_out=st["scale"], zp_out=st["zp"])
-            if final:
+            if final and q.wbits >= 16:
+                # 16-bit weights: LET fold only, the quantiser is the identity and leaves scale / zero point None
+                # (quantizer.py:109; register_scales_and_zeros then registers None buffers, :149-153)
+                extra[u.name] = dict(weight=torch.empty(u.N, u.K, device=self.dev), scales=None, zeros=None)
+                kw = dict(wq_f32=extra[u.name]["weight"])
+            elif final:
                 G = st["xmin"].numel()
                 extra[u.name] = dict(weight=torch.empty(u.N, u.K, device=self.dev), scales=torch.empty(G, device=self.dev),
                                      zeros=torch.empty(G, device=self.dev))
                 kw = dict(wq_f32=extra[u.name]["weight"], scale_out=extra[u.name]["scales"], zp_out=extra[u.name]["zeros"])
                 st["scale"], st["zp"] = extra[u.name]["scales"], extra[u.name]["zeros"]
-            if q.wbits >= 16:
-                self.wview(u, self.Wq).copy_(self.wview(u, self.W))     # weights left un-quantised
-                return
             ops.weight_quant_fwd(self.wview(u, self.W), n_bits=q.wbits, symmetric=q.symmetric, group_size=q.group_size,
                                  up=up, low=low, col_scale=p.get(u.col) if u.col else None,
                                  row_scale=p.get(u.row) if u.row else None, row_op=u.row_op,
@@ -513,7 +516,9 @@ class BlockEngine:
 
     def rope(self):
         if not hasattr(self, "_rope"):
-            inv = 1.0 / (10000.0 ** (torch.arange(0, self.d, 2, dtype=F32) / self.d))
+            # LlamaRotaryEmbedding (transformers 4.31, deep-copied by the reference at int_llama_layer.py:70): base from
+            # config.rope_theta; scaled variants (linear / NTK / yarn) are rejected by the block wrappers
+            inv = 1.0 / (self.rope_theta ** (torch.arange(0, self.d, 2, dtype=F32) / self.d))
             emb = torch.outer(torch.arange(self.T, dtype=F32), inv)
             emb = torch.cat((emb, emb), -1)
             self._rope = (emb.cos().to(self.dev).contiguous(), emb.sin().to(self.dev).contiguous())
@@ -666,8 +671,8 @@ class BlockEngine:
     def _unit_bwd(self, u, dW, e_row):
         """Quantiser + LET-fold backward of one weight (csrc/weight_quant*.cu)."""
         q, p, g, acc = self.q, self.p, self.g, self._acc
-        if q.wbits >= 16:
-            return
+        if q.wbits >= 16 and not q.let:
+            return          # identity quantiser, nothing folded: no parameter depends on this weight
         colacc = {"qkv_s": acc["dcol_qkv"], "out_s": acc["dcol_out"], "fc1_s": acc["dcol_fc1"]}
         shacc = {"qkv_d": acc["dsh_qkv"], "out_d": acc["dsh_out"], "fc1_d": acc["dsh_fc1"]}
         up, low = self.lwc(u)
@@ -678,7 +683,8 @@ class BlockEngine:
                              row_op=u.row_op, recip_div=q.recip_div, e_row=e_row if u.shift else None,
                              d_up=g.get(f"{u.name}.up"), d_low=g.get(f"{u.name}.low"),
                              dcol_acc=colacc[u.col] if u.col else None, drow=self._drow[u.name] if u.row else None,
-                             dshift_acc=shacc[u.shift] if u.shift else None, scale=st["scale"], zp=st["zp"])
+                             dshift_acc=shacc[u.shift] if u.shift else None,
+                             scale=st["scale"] if q.wbits < 16 else None, zp=st["zp"] if q.wbits < 16 else None)
 
     def _unit_backward_side(self, name, dW, dy):
         """Backward of the o / fc1 / fc2 weight on the side stream, as soon as its wgrad GEMM has been issued:

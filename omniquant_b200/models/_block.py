@@ -25,6 +25,23 @@ LET_NAMES = {"qkv_s": "qkv_smooth_scale", "qkv_d": "qkv_smooth_shift", "out_s": 
              "qkt_s": "qkt_smooth_scale"}
 
 
+def rope_theta_of(config) -> float:
+    """Rotary base of an HF config (``rope_theta``; transformers >= 5 keeps it in ``rope_parameters``).  The reference
+    deep-copies the checkpoint's rotary module (models/int_llama_layer.py:70), so a scaled variant would silently change
+    the tables: anything but the default rotary type is refused here instead of being computed wrongly."""
+    if config is None:
+        return 10000.0
+    rp = getattr(config, "rope_parameters", None) or {}
+    scaling = getattr(config, "rope_scaling", None) or {}
+    kind = (rp.get("rope_type") or scaling.get("rope_type") or scaling.get("type") or "default") if isinstance(rp, dict) else "default"
+    if kind != "default":
+        raise NotImplementedError(f"rotary scaling type {kind!r}: only the default rotary embedding is implemented")
+    theta = rp.get("rope_theta") if isinstance(rp, dict) else None
+    if theta is None:
+        theta = getattr(config, "rope_theta", None)
+    return float(theta if theta is not None else 10000.0)
+
+
 class _BlockFn(torch.autograd.Function):
     """Block forward/backward on the engine, exposed to autograd so the reference's training loop
     (loss.backward(); optimizer.step()) works unchanged on the module parameters."""
@@ -66,8 +83,9 @@ class QuantDecoderLayerBase(nn.Module):
     norm_names = ()        # (first norm attr, second norm attr)
 
     # ------------------------------------------------------------------ plumbing
-    def _init_common(self, args, n_heads, eps, n_kv_heads=None):
+    def _init_common(self, args, n_heads, eps, n_kv_heads=None, config=None):
         self._args, self._n_heads, self._eps, self._n_kv_heads = args, n_heads, eps, n_kv_heads
+        self._rope_theta = rope_theta_of(config)
         self._eng = None
         self._final_ws = None
         self.use_weight_quant = False
@@ -113,7 +131,7 @@ class QuantDecoderLayerBase(nn.Module):
             # decoder blocks of one model share shapes: the previous block's engine (device buffers + the captured CUDA
             # graph of its optimiser step) is re-loaded with this block's weights instead of being rebuilt
             key = (self.family, str(dev), seq_len, batch, dataclasses.astuple(q), self._n_heads, self._n_kv_heads, self._eps,
-                   lrs, tuple(sorted((k, tuple(v.shape)) for k, v in W.items())))
+                   self._rope_theta, lrs, tuple(sorted((k, tuple(v.shape)) for k, v in W.items())))
             cached = _ENGINES.get(key) if (mask is None and os.environ.get("OQ_ENGINE_CACHE", "1") == "1") else None
             owner = cached._owner() if cached is not None and getattr(cached, "_owner", None) is not None else None
             if cached is not None and (owner is None or owner._eng is not cached):
@@ -121,7 +139,7 @@ class QuantDecoderLayerBase(nn.Module):
             else:
                 self._eng = BlockEngine(self.family, W, n_heads=self._n_heads, seq_len=seq_len, qcfg=q,
                                         eps=self._eps, device=dev, batch=batch, let_lr=lrs[0], lwc_lr=lrs[1], wd=lrs[2],
-                                        mask=mask, n_kv_heads=self._n_kv_heads)
+                                        mask=mask, n_kv_heads=self._n_kv_heads, rope_theta=self._rope_theta)
                 if mask is None:
                     _ENGINES.clear()           # one resident engine: a new shape replaces the old one
                     _ENGINES[key] = self._eng
@@ -252,10 +270,13 @@ class QuantDecoderLayerBase(nn.Module):
             N = m.out_features
             bkey = bias_of[g]
             if unit in extra:
-                G = extra[unit]["scales"].numel() // extra[unit]["weight"].shape[0]
                 m.weight = extra[unit]["weight"][r0:r0 + N].to(m.weight.dtype)
-                m.weight_quantizer.scale = extra[unit]["scales"][r0 * G:(r0 + N) * G].view(-1, 1)
-                m.weight_quantizer.round_zero_point = extra[unit]["zeros"][r0 * G:(r0 + N) * G].view(-1, 1)
+                if extra[unit]["scales"] is None:       # 16-bit weights: folded only, the quantiser never ran
+                    m.weight_quantizer.scale = m.weight_quantizer.round_zero_point = None
+                else:
+                    G = extra[unit]["scales"].numel() // extra[unit]["weight"].shape[0]
+                    m.weight_quantizer.scale = extra[unit]["scales"][r0 * G:(r0 + N) * G].view(-1, 1)
+                    m.weight_quantizer.round_zero_point = extra[unit]["zeros"][r0 * G:(r0 + N) * G].view(-1, 1)
             bb = t[bkey]
             if bb is not None:
                 val = bb[b0:b0 + N].clone()

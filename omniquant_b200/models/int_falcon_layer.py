@@ -62,7 +62,7 @@ class QuantFalconDecoderLayer(QuantDecoderLayerBase):
         self.hidden_dropout = config.hidden_dropout
         self.ln_attn = OmniLayerNorm(ori_layer.ln_attn)
         self.ln_mlp = OmniLayerNorm(ori_layer.ln_mlp)
-        self._init_common(args, config.num_attention_heads, ori_layer.ln_attn.eps, config.num_kv_heads)
+        self._init_common(args, config.num_attention_heads, ori_layer.ln_attn.eps, config.num_kv_heads, config=config)
 
     def smooth_and_quant_temporary(self, *a, **k):
         if self.let:

@@ -79,7 +79,7 @@ class QuantLlamaDecoderLayer(QuantDecoderLayerBase):
         self.input_layernorm = OmniLlamaRMSNorm(ori_layer.input_layernorm, eps=eps)
         self.post_attention_layernorm = OmniLlamaRMSNorm(ori_layer.post_attention_layernorm, eps=eps)
         self._init_common(args, config.num_attention_heads, eps,
-                          getattr(config, "num_key_value_heads", config.num_attention_heads))
+                          getattr(config, "num_key_value_heads", config.num_attention_heads), config=config)
 
     def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
                 output_attentions=False, use_cache=False, **kwargs):

@@ -9,7 +9,8 @@ design: bf16 storage instead of fp16 autocast (no GradScaler), losse
 device (no per-step ``.item()``), the step can be replayed as a CUDA graph, and when
 ``torch.distributed`` is initialised the calibration samples are sharded over the ranks with one
 all-reduce of the flat LWC/LET gradient buffer per step (== the reference with
-``--batch_size world_size``).  AutoGPTQ real-quant packing (:255-278) is out of scope.
+``--batch_size world_size``).  ``--real_quant`` packs the calibrated block into the AutoGPTQ wire format on the GPU
+(quantize/real_quant.py, csrc/gptq_pack.cu; reference :255-278).
 """
 import os
 
@@ -94,9 +95,12 @@ def init_let_parameters(qlayer, layer_idx, fam, args, act_scales, act_shifts, de
         for key, tag in fam["pairs"].items():
             if key in name:
                 full = f"{fam['prefix']}.{layer_idx}.{name}"
-                act = act_scales[full].to(device=dev, dtype=torch.float32).clamp(min=1e-5)
-                weight = module.weight.float().max(dim=0)[0].clamp(min=1e-5)       # max, not abs().max() (:190)
-                scale = (act.pow(args.alpha) / weight.pow(1 - args.alpha)).clamp(min=1e-5)
+                # the reference evaluates this in the model's dtype (fp16 under its default autocast path, :189-191; fp32
+                # with --deactive_amp) before the parameter is promoted by qlayer.float(); same rounding here
+                idt = torch.float32 if getattr(args, "deactive_amp", False) else torch.float16
+                act = act_scales[full].to(device=dev, dtype=idt).clamp(min=1e-5)
+                weight = module.weight.to(idt).max(dim=0)[0].clamp(min=1e-5)       # max, not abs().max() (:190)
+                scale = (act.pow(args.alpha) / weight.pow(1 - args.alpha)).clamp(min=1e-5).float()
                 if is_llama:
                     shift = torch.zeros_like(scale)
                 else:
@@ -189,10 +193,12 @@ def omniquant(lm, args, dataloader, act_scales, act_shifts, logger=None, inps=No
                     args.save_act_stats[1].update({k: folded[t][1].cpu() for k, t in names.items()})
 
             def epoch_log(ep, ls, i=i):
+                # the per-step losses were all-reduced with the gradients, so every rank sees the same values and all
+                # ranks abort together (the reference checks `loss.isfinite()` per step, :223-225)
+                ls = ls / world
+                if not bool(torch.isfinite(ls).all()):
+                    raise FloatingPointError(f"layer {i} epoch {ep}: loss is not finite")
                 if logger is not None:
-                    ls = ls / world        # per-step losses were already summed over ranks
-                    if not bool(torch.isfinite(ls).all()):
-                        raise FloatingPointError(f"layer {i} epoch {ep}: loss is not finite")
                     log(f"layer {i} iter {ep} loss:{ls.mean().item()} max memory_allocated "
                         f"{torch.cuda.max_memory_allocated(dev) / 1024 ** 2} ")
 
@@ -212,14 +218,16 @@ def omniquant(lm, args, dataloader, act_scales, act_shifts, logger=None, inps=No
             saved = {k: v.detach().half().cpu() for k, v in qlayer.omni_state_dict().items()}   # LWC factors leave with the QuantLinears
             pack_block(qlayer, args.wbits)
         qlayer.half()
-        layers[i] = qlayer.to("cpu")
+        layers[i] = streamer.writeback(qlayer)     # :248 `qlayer.to("cpu")`, asynchronous: overlaps the next block
         if args.epochs > 0:
             omni_parameters[i] = saved if saved is not None else qlayer.omni_state_dict()
             if rank == 0 and getattr(args, "output_dir", None):
+                streamer.drain()               # the checkpoint reads the host copies
                 torch.save(omni_parameters, os.path.join(args.output_dir, "omni_parameters.pth"))
         del layer, eng
 
     del quant_inps, fp_inps
+    streamer.drain()               # the host copies of the calibrated blocks are complete from here on
     from ..models._block import release_engines
     release_engines()              # the resident engine + its step graph (holds the NCCL all-reduce under DP)
     torch.cuda.synchronize()

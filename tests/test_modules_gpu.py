@@ -212,3 +212,106 @@ def test_falcon_block_wrapper_matches_reference_fixture():
     qlayer.let = True
     with pytest.raises(ValueError):
         qlayer.smooth_and_quant_temporary(seq_len=T, batch=1)
+
+
+class _Holder:
+    """A bare module-like object carrying weight / bias the way QuantLinear / Omni*Norm do for the LET folds."""
+
+    def __init__(self, weight, bias=None):
+        self.weight, self.bias = weight, bias
+        self._buffers = {}
+
+    def register_buffer(self, name, value):
+        setattr(self, name, value)
+
+
+@pytest.mark.parametrize("fname", ["llama_w4a4_lwc_let.npz", "opt_w4a4_lwc_let.npz"])
+def test_smooth_functions_match_the_reference_folds(fname):
+    """The six LET fold functions (models/transformation.py:24-114) on the CUDA fold kernel, against the oracle's
+    restatement of the same algebra evaluated in fp32 on the CPU at the fixture's LEARNED LET parameters: folded weights
+    bit for bit (every element is one or two individually rounded fp32 operations), biases to summation-order round-off;
+    then the folded weights are quantised and compared with the reference's own in-place result (fixture qw/*), and the
+    gradients of the temporary variant w.r.t. scales / shifts are checked against torch autograd of the oracle."""
+    from omniquant_b200 import ops
+    from omniquant_b200.models import transformation as TR
+    from oracle import oq_oracle as orc
+    fx = BlockFixture(fname)
+    W, P = fx.weights(), fx.final_params()
+    llama = fx.family == "llama"
+    fc1s = ["up", "gate"] if llama else ["fc1"]
+    cu = lambda t: None if t is None else t.clone().cuda()
+    bias = lambda n: W.get(f"{n}.bias")
+
+    def modules():
+        lin = {n: _Holder(cu(W[n]), cu(bias(n))) for n in ["q", "k", "v", "o"] + fc1s}
+        ln1, ln2 = _Holder(cu(W["ln1"]), cu(W.get("ln1.bias"))), _Holder(cu(W["ln2"]), cu(W.get("ln2.bias")))
+        return lin, ln1, ln2
+
+    def ref_fold(Pd):
+        pair = lambda n: (W[n], bias(n))
+        ln1w, ln1b, (q, k, v) = orc.fold_ln_fcs(W["ln1"], W.get("ln1.bias"), [pair("q"), pair("k"), pair("v")], Pd["qkv_s"], Pd["qkv_d"])
+        ln2w, ln2b, f1 = orc.fold_ln_fcs(W["ln2"], W.get("ln2.bias"), [pair(n) for n in fc1s], Pd["fc1_s"], Pd["fc1_d"])
+        v, o = orc.fold_fc_fc(v, pair("o"), Pd["out_s"], Pd["out_d"])
+        q, k = orc.fold_q_k(q, k, Pd["qkt_s"])
+        out = dict(q=q, k=k, v=v, o=o, ln1=(ln1w, ln1b), ln2=(ln2w, ln2b))
+        out.update({n: f for n, f in zip(fc1s, f1)})
+        return out
+
+    want = ref_fold(P)
+    Pc = {k: v.clone().cuda() for k, v in P.items()}
+
+    def check(lin, ln1, ln2, wattr, battr):
+        for n in ["q", "k", "v", "o"] + fc1s:
+            w, b = getattr(lin[n], wattr), getattr(lin[n], battr)
+            assert torch.equal(w.detach().cpu(), want[n][0]), f"{n} folded weight"
+            torch.testing.assert_close(b.detach().cpu(), want[n][1], rtol=1e-5, atol=1e-6)
+        for key, ln in (("ln1", ln1), ("ln2", ln2)):
+            assert torch.equal(getattr(ln, wattr).detach().cpu(), want[key][0])
+            torch.testing.assert_close(getattr(ln, battr).detach().cpu(), want[key][1], rtol=1e-6, atol=1e-7)
+
+    # ---- temporary variant (differentiable), in the reference's call order (int_llama_layer.py:285-292)
+    lin, ln1, ln2 = modules()
+    Pg = {k: v.clone().requires_grad_(True) for k, v in Pc.items() if k.endswith(("_s", "_d"))}
+    TR.smooth_ln_fcs_temporary(ln1, [lin["q"], lin["k"], lin["v"]], Pg["qkv_s"], Pg["qkv_d"])
+    TR.smooth_ln_fcs_temporary(ln2, [lin[n] for n in fc1s], Pg["fc1_s"], Pg["fc1_d"])
+    TR.smooth_fc_fc_temporary(lin["v"], lin["o"], Pg["out_s"], Pg["out_d"])
+    TR.smooth_q_k_temporary(lin["q"], lin["k"], Pg["qkt_s"])
+    check(lin, ln1, ln2, "temp_weight", "temp_bias")
+    assert all(m.use_temporary_parameter for m in lin.values())
+    # gradients: a fixed random linear functional of every folded tensor
+    g = torch.Generator().manual_seed(7)
+    coef = {n: (torch.randn(want[n][0].shape, generator=g), torch.randn(want[n][1].shape, generator=g)) for n in lin}
+    loss = sum((lin[n].temp_weight * coef[n][0].cuda()).sum() + (lin[n].temp_bias * coef[n][1].cuda()).sum() for n in lin)
+    loss.backward()
+    Pr = {k: v.clone().requires_grad_(True) for k, v in P.items() if k.endswith(("_s", "_d"))}
+    wr = ref_fold(Pr)
+    sum((wr[n][0] * coef[n][0]).sum() + (wr[n][1] * coef[n][1]).sum() for n in lin).backward()
+    for k in Pr:
+        a, b = Pg[k].grad.cpu(), Pr[k].grad
+        assert float((a - b).norm() / b.norm()) < 1e-4, (k, float((a - b).norm() / b.norm()))
+
+    # ---- in-place variant (int_llama_layer.py:315-327), then the weight quantiser -> the reference's own buffers
+    lin, ln1, ln2 = modules()
+    with torch.no_grad():
+        TR.smooth_ln_fcs_inplace(ln1, [lin["q"], lin["k"], lin["v"]], Pc["qkv_s"], Pc["qkv_d"])
+        TR.smooth_ln_fcs_inplace(ln2, [lin[n] for n in fc1s], Pc["fc1_s"], Pc["fc1_d"])
+        TR.smooth_fc_fc_inplace(lin["v"], lin["o"], Pc["out_s"], Pc["out_d"])
+        TR.smooth_q_k_inplace(lin["q"], lin["k"], Pc["qkt_s"])
+    check(lin, ln1, ln2, "weight", "bias")
+    assert not any(m.use_temporary_parameter for m in lin.values())
+    Q = fx.quantized()
+    for n in ["q", "k", "v", "o"] + fc1s:
+        out = torch.empty_like(lin[n].weight)
+        ops.weight_quant_fwd(lin[n].weight.contiguous(), n_bits=fx.wbits, group_size=fx.group_size or 0,
+                             up=Pc[f"{n}.up"].view(-1).contiguous(), low=Pc[f"{n}.low"].view(-1).contiguous(), recip_div=False,
+                             wq_f32=out)
+        assert torch.equal(out.cpu(), Q[f"{n}.w"]), f"{n}: quantised in-place weight differs from the reference's"
+
+
+def test_smooth_functions_have_no_cpu_path():
+    from omniquant_b200.models import transformation as TR
+    from omniquant_b200._lib import OqError
+    fc = _Holder(torch.randn(8, 8), None)
+    ln = _Holder(torch.ones(8), None)
+    with pytest.raises(OqError):
+        TR.smooth_ln_fcs_temporary(ln, [fc], torch.ones(8), torch.zeros(8))
