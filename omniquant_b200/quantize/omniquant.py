@@ -210,6 +210,9 @@ def omniquant(lm, args, dataloader, act_scales, act_shifts, logger=None, inps=No
         if args.epochs > 0:
             E.requant_pass(eng, quant_inps)        # update input of quantization model (:242-245)
         qlayer.register_scales_and_zeros()
+        if os.environ.get("OQ_DEBUG_STREAMS") == "1":
+            f = lambda t: f"absmax {float(t.float().abs().max()):.3e} rms {float(t.float().pow(2).mean().sqrt()):.3e} finite {bool(torch.isfinite(t).all())}"
+            print(f"[oq debug] after layer {i}: fp stream {f(fp_inps)} | quant stream {f(quant_inps)}", flush=True)
         qlayer._eng = None                         # drop the fp32 masters / workspaces of this block
         qlayer._final_ws = None
         saved = None
