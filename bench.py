@@ -300,15 +300,17 @@ def run_ours(a):
     launches_per_step = (ops.launch_count() - l1) // 3
     torch.cuda.synchronize()
     step_ms_eager = s0.elapsed_time(s1) / 3
-    lin = [(e0_.elapsed_time(e1_), fl) for e0_, e1_, fl, batched in ops.GEMM_TIMER if not batched]
-    att = [(e0_.elapsed_time(e1_), fl) for e0_, e1_, fl, batched in ops.GEMM_TIMER if batched]
+    lin = [(e0_.elapsed_time(e1_), fl) for e0_, e1_, fl, kind in ops.GEMM_TIMER if kind == "lin"]
+    att = [(e0_.elapsed_time(e1_), fl) for e0_, e1_, fl, kind in ops.GEMM_TIMER if kind == "attn"]
+    i8 = [(e0_.elapsed_time(e1_), fl) for e0_, e1_, fl, kind in ops.GEMM_TIMER if kind == "s8"]
     ops.GEMM_TIMER = None
     peak_burst, peak_sus, peak_hbm, which = peaks()
     lin_ms, lin_fl = sum(t for t, _ in lin), sum(f for _, f in lin)
     achieved = lin_fl / (lin_ms * 1e-3) / 1e12
     # event-timed single launches are a burst measurement: the burst cuBLAS figure is the denominator; the sustained one is
     # printed beside it because inside the seconds-long step the same kernel runs under the power cap
-    roofline = {"bound": "tensor", "kernel": "QuantLinear fwd/dgrad/wgrad GEMMs (tcgen05)", "achieved": round(achieved, 1),
+    roofline = {"bound": "tensor", "kernel": "QuantLinear bf16 GEMMs (tcgen05 kind::f16: dgrad + wgrad, and the forward when it is not "
+                                             "the exact-integer kind::i8 GEMM)", "achieved": round(achieved, 1),
                 "peak": peak_burst, "unit": "TFLOP/s", "frac": round(achieved / peak_burst, 4),
                 "frac_of_sustained_peak": round(achieved / peak_sus, 4), "peak_sustained": peak_sus,
                 "traffic": None,
@@ -317,7 +319,9 @@ def run_ours(a):
                 "peak_source": f"bf16_tflops (burst), {which}", "launches_timed": len(lin),
                 "timing": "CUDA events around each launch on the launching stream, 3 eager optimiser steps after the timed region, side-stream overlap off",
                 "avg_launch_ms": round(lin_ms / max(len(lin), 1), 4),
-                "attention_gemm_tflops": round(sum(f for _, f in att) / (sum(t for t, _ in att) * 1e-3) / 1e12, 1) if att else None}
+                "attention_gemm_tflops": round(sum(f for _, f in att) / (sum(t for t, _ in att) * 1e-3) / 1e12, 1) if att else None,
+                "s8_forward_gemm_tops": round(sum(f for _, f in i8) / (sum(t for t, _ in i8) * 1e-3) / 1e12, 1) if i8 else None,
+                "s8_forward_gemm_launches": len(i8)}
     # whole-step tensor utilisation: algorithmic flops of one block (causal attention) / block time
     f_fwd, f_step = c.flops()
     f_block = steps_per_block * world * f_step + 2 * c.nsamples * f_fwd

@@ -44,13 +44,15 @@ int oq_sm_count(void);
  *   codes = clamp(round(W'/s)+z, 0, 2^n-1); W_q = (codes-z)*s   quantizer.py:84-105 (fake_quant)
  * group_size 0 = per output channel.  up/low: LWC factors [N*ceil(K/group)] or both NULL.
  * recip_div: 0 = CPU ATen semantics for `range / (2^n-1)` (true division), 1 = CUDA ATen
- * semantics (multiply by the fp32 reciprocal).  Any of the outputs may be NULL.
+ * semantics (multiply by the fp32 reciprocal).  Any of the outputs may be NULL.  n_bits >= 16: fold only (the quantiser
+ * is the identity, quantize/quantizer.py:109) -- this mode also implements smooth_*_{temporary,inplace} on their own.
+ * codes_s8 / s8_t / s8_beta (all or none; per-channel, needs scale_out): the exact-integer operand of oq_gemm_s8, see there.
  * Replaces models/int_llama_layer.py:285-304 (smooth_and_quant_temporary) per weight. */
 int oq_weight_quant_fwd(const float* W, int N, int K, const float* col_scale, const float* row_scale, int row_op,
                         const float* shift, float* matvec_out, int n_bits, int symmetric, int group_size,
                         const float* up, const float* low, int recip_div, void* wq_bf16, long ld_bf16, float* wq_f32,
                         uint8_t* codes, float* scale_out, float* zp_out, float* xmin_out, float* xmax_out,
-                        oq_stream_t stream);
+                        int8_t* codes_s8, float* s8_t, float* s8_beta, oq_stream_t stream);
 
 /* Backward of the above (autograd of quantizer.py:84-147 + transformation.py folds).
  * grad_wq: dL/dW_q [N,K] (bf16, or fp32 when grad_is_f32).  xmin/xmax: raw group extrema saved by the
@@ -73,11 +75,13 @@ int oq_weight_quant_bwd(const float* W, int N, int K, const float* col_scale, co
  * (models/int_llama_layer.py:124-125), position = (r / rows_inner) % seq_len; needs C in {64,128}.
  * Only the inner rows [0, rope_inner) are rotated (rope_inner <= 0: all of them) -- one launch covers the fused
  * [q heads | k heads | v heads] buffer of a token, V un-rotated (:162).  n_bits >= 16 with rope = rotary only
- * (un-rotated rows are copied). */
+ * (un-rotated rows are copied).
+ * codes_s8 [rows, C] (row stride ld_s8 bytes) + s8_meta [3, rows] (both or neither; plain 2-D rows without rope): the
+ * exact-integer operand of oq_gemm_s8 -- signed codes (code - z0), then scale | t | beta per row, see oq_gemm_s8. */
 int oq_act_quant_fwd(const void* x, long rows, int C, int rows_inner, long ld_outer, long ld_inner, int n_bits,
                      int symmetric, int recip_div, const float* rope_cos, const float* rope_sin, int seq_len,
                      int rope_inner, void* y, long ldy_outer, long ldy_inner, float* scale_out, float* zp_out,
-                     oq_stream_t stream);
+                     int8_t* codes_s8, long ld_s8, float* s8_meta, oq_stream_t stream);
 /* Backward: gx = d/dx [ fake_quant(rope(x)) ] . gy   (x is the forward INPUT, re-quantised on the fly). */
 int oq_act_quant_bwd(const void* x, long rows, int C, int rows_inner, long ld_outer, long ld_inner, int n_bits,
                      int symmetric, int recip_div, const float* rope_cos, const float* rope_sin, int seq_len,
@@ -90,22 +94,23 @@ int oq_act_quant_bwd(const void* x, long rows, int C, int rows_inner, long ld_ou
  * returns dgu = d/dgu of the same composition.  Bit-identical to oq_swiglu_fwd + oq_act_quant_fwd (and their
  * backwards) run one after the other. */
 int oq_swiglu_act_quant_fwd(const void* gu, long ldgu, long rows, int F, int n_bits, int symmetric, int recip_div,
-                            void* mq, long ldmq, oq_stream_t stream);
+                            void* mq, long ldmq, int8_t* codes_s8, long ld_s8, float* s8_meta, oq_stream_t stream);
 int oq_swiglu_act_quant_bwd(const void* gu, long ldgu, long rows, int F, int n_bits, int symmetric, int recip_div,
                             const void* gy, long ldgy, void* dgu, long lddgu, oq_stream_t stream);
 
-/* EXPERIMENTAL (round 1: validated by a kernel-level bit-exactness test on B200, not used by the engine yet -- DESIGN.md
- * section 9 item 1).
- * Exact-integer forward contraction of QuantLinear when BOTH operands are quantised (W4A4 / W6A6,
- * quantize/int_linear.py:48-65 with quantize/quantizer.py:93-100): A [M,K], B [N,K] hold the signed 8-bit codes
- * (code - zero point) K-major, the K sum is exact (tcgen05.mma kind::i8, s32 accumulators),
- *   C[m,n] = row_scale[m]*col_scale[n]*sum_k A[m,k]*B[n,k]
- *            (+ row_t[m]*col_beta[n] + row_beta[m]*col_t[n] + K*row_beta[m]*col_beta[n]) (+ bias[n]) (+ residual[m,n]).
- * The four correction vectors (all or none) carry zero points that fall outside the code range: beta = (z0 - z)*scale,
- * t = scale * sum_k (code - z0).  lda / ldb in bytes (= elements), multiples of 16. */
+/* Exact-integer forward contraction of QuantLinear when BOTH operands are quantised (W4A4 / W6A6,
+ * quantize/int_linear.py:48-65 with quantize/quantizer.py:93-100): A [M,K], B [N,K] hold signed 8-bit codes
+ * (code - z0) K-major, the K sum is exact (tcgen05.mma kind::i8, s32 accumulators),
+ *   C[m,n] = alpha * ( row_scale[m]*col_scale[n]*sum_k A[m,k]*B[n,k]
+ *                      + row_t[m]*col_beta[n] + row_beta[m]*col_t[n] + K*row_beta[m]*col_beta[n] ) (+ bias[n]) (+ residual[m,n]).
+ * z0 is the zero point clamped into the int8-representable range (= the zero point itself whenever the row / channel
+ * straddles zero); the four correction vectors (all or none) carry the remainder: beta = (z0 - z)*scale,
+ * t = scale * sum_k (code - z0).  The quantiser kernels emit codes, scale, t and beta as their "s8 side output"
+ * (oq_act_quant_fwd, oq_norm_act_quant_fwd, oq_swiglu_act_quant_fwd: s8_meta = [scale | t | beta], each [rows];
+ * oq_weight_quant_fwd: scale_out, s8_t, s8_beta).  lda / ldb in bytes (= elements), multiples of 16. */
 int oq_gemm_s8(const void* A, long lda, const void* B, long ldb, void* C, int c_dtype, long ldc, int M, int N, int K,
                const float* row_scale, const float* col_scale, const float* row_t, const float* row_beta,
-               const float* col_t, const float* col_beta, const float* bias, const void* residual, long ldr,
+               const float* col_t, const float* col_beta, float alpha, const float* bias, const void* residual, long ldr,
                oq_stream_t stream);
 
 /* ---- K7: norms with temporary (folded) weight / bias ------------------------
@@ -118,7 +123,7 @@ int oq_norm_fwd(const void* x, long rows, int C, long ldx, const float* w, const
  * oq_norm_fwd followed by oq_act_quant_fwd. */
 int oq_norm_act_quant_fwd(const void* x, long rows, int C, long ldx, const float* w, const float* b, float eps, int kind,
                           void* y, long ldy, float* mean_out, float* rstd_out, int n_bits, int symmetric, int recip_div,
-                          void* yq, long ldyq, oq_stream_t stream);
+                          void* yq, long ldyq, int8_t* codes_s8, long ld_s8, float* s8_meta, oq_stream_t stream);
 /* dx = norm'(x).dy (+ dx_add);  dw_acc[c] += sum_r dy*xhat, db_acc[c] += sum_r dy (atomic adds; NULL to skip). */
 int oq_norm_bwd(const void* x, long rows, int C, long ldx, const float* w, int kind, const float* mean,
                 const float* rstd, const void* dy, long lddy, void* dx, long lddx, const void* dx_add, long ldadd,

@@ -39,6 +39,7 @@ struct AqArgs {
   const float* cos; const float* sin; int seq_len;  // rope tables [seq_len, C] or null
   int rope_inner;  // inner rows [0, rope_inner) are rotated
   float* scale_out; float* zp_out;
+  S8Side s8;   // optional exact-integer side output (plain 2-D rows only)
 };
 
 // ---- element arithmetic shared by the register-resident kernels ---------------------------------------------------
@@ -65,6 +66,21 @@ template <int E>
 __device__ __forceinline__ void aq_quant_elems(float (&v)[E], const OqQParams& q, float inv, int inv_ok) {
   if (inv_ok) aq_quant_elems_t<true, E>(v, q, inv);
   else aq_quant_elems_t<false, E>(v, q, inv);
+}
+// same, also returning the clamped integer codes (for the s8 side output)
+template <bool FAST, int E>
+__device__ __forceinline__ void aq_quant_codes_t(float (&v)[E], float (&c)[E], const OqQParams& q, float inv) {
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    float qa;
+    c[j] = oq_clampf(aq_t<FAST>(v[j], q, inv, qa), 0.0f, q.qmax);
+    v[j] = oq_dequant(c[j], q);
+  }
+}
+template <int E>
+__device__ __forceinline__ void aq_quant_codes(float (&v)[E], float (&c)[E], const OqQParams& q, float inv, int inv_ok) {
+  if (inv_ok) aq_quant_codes_t<true, E>(v, c, q, inv);
+  else aq_quant_codes_t<false, E>(v, c, q, inv);
 }
 // first backward pass over E elements: accumulates R = dL/dscale, the tie counts of the row extrema, and zeroes the
 // gradient of clipped elements (straight-through part); same codes as the forward, ties included
@@ -189,7 +205,7 @@ __global__ void __launch_bounds__(256) aq_bwd_block(AqArgs a) {
 // ---- register-resident block-per-row variants (C <= 2048*NV, C % 8 == 0): one read of x (and gy), one write
 template <int NV>
 __global__ void __launch_bounds__(256) aq_fwd_block_reg(AqArgs a) {
-  __shared__ float scratch[2 * 8];
+  __shared__ float scratch[3 * 8];
   const long r = blockIdx.x;
   const bf16* xr = a.x + a.xi.off(r);
   bf16* yr = a.y + a.yi.off(r);
@@ -219,13 +235,37 @@ __global__ void __launch_bounds__(256) aq_fwd_block_reg(AqArgs a) {
   }
   const float inv = OQ_DIV(1.0f, q.scale);
   const int inv_ok = oq_inv_ok(inv);
+  if (!a.s8.codes) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (threadIdx.x + i * 256) * 8;
+      if (c < a.C) {
+        aq_quant_elems<8>(v[i], q, inv, inv_ok);
+        store_bf8(yr + c, v[i]);
+      }
+    }
+    return;
+  }
+  const float z0 = oq_s8_z0(q.zp, q.qmax);
+  float csum = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (threadIdx.x + i * 256) * 8;
     if (c < a.C) {
-      aq_quant_elems<8>(v[i], q, inv, inv_ok);
+      float cd[8];
+      aq_quant_codes<8>(v[i], cd, q, inv, inv_ok);
       store_bf8(yr + c, v[i]);
+      s8_store8(a.s8.codes + r * a.s8.ld + c, cd, z0, csum);
     }
+  }
+  csum = warp_reduce(csum, OpSum());
+  if (lane == 0) scratch[16 + warp] = csum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += scratch[16 + w];
+    s8_write_meta(a.s8, r, q, z0, t);
   }
 }
 
@@ -318,11 +358,12 @@ struct GluArgs {
   const bf16* gy; long ldgy;     // backward: dL/d mq
   bf16* dgu; long lddgu;         // backward output [rows, 2F]
   int F, n_bits, symmetric, recip_div;
+  S8Side s8;                     // optional exact-integer side output of the forward
 };
 
 template <int NV>
 __global__ void __launch_bounds__(512, 2) swiglu_aq_fwd_kernel(GluArgs a) {
-  __shared__ float scratch[2 * 16];
+  __shared__ float scratch[3 * 16];
   const long r = blockIdx.x;
   const bf16* gr = a.gu + r * a.ldgu;
   uint4 rg[NV], ru[NV];
@@ -355,13 +396,37 @@ __global__ void __launch_bounds__(512, 2) swiglu_aq_fwd_kernel(GluArgs a) {
   const float inv = OQ_DIV(1.0f, q.scale);
   const int inv_ok = oq_inv_ok(inv);
   bf16* yr = a.mq + r * a.ldmq;
+  if (!a.s8.codes) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (threadIdx.x + i * 512) * 8;
+      if (c < a.F) {
+        aq_quant_elems<8>(v[i], q, inv, inv_ok);
+        store_bf8(yr + c, v[i]);
+      }
+    }
+    return;
+  }
+  const float z0 = oq_s8_z0(q.zp, q.qmax);
+  float csum = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (threadIdx.x + i * 512) * 8;
     if (c < a.F) {
-      aq_quant_elems<8>(v[i], q, inv, inv_ok);
+      float cd[8];
+      aq_quant_codes<8>(v[i], cd, q, inv, inv_ok);
       store_bf8(yr + c, v[i]);
+      s8_store8(a.s8.codes + r * a.s8.ld + c, cd, z0, csum);
     }
+  }
+  csum = warp_reduce(csum, OpSum());
+  if ((threadIdx.x & 31) == 0) scratch[32 + (threadIdx.x >> 5)] = csum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) t += scratch[32 + w];
+    s8_write_meta(a.s8, r, q, z0, t);
   }
 }
 
@@ -629,8 +694,13 @@ int check_ix(const char* fn, long rows, int rows_inner, int C) {
 extern "C" int oq_act_quant_fwd(const void* x, long rows, int C, int rows_inner, long ld_outer, long ld_inner,
                                 int n_bits, int symmetric, int recip_div, const float* rope_cos,
                                 const float* rope_sin, int seq_len, int rope_inner, void* y, long ldy_outer,
-                                long ldy_inner, float* scale_out, float* zp_out, cudaStream_t stream) {
+                                long ldy_inner, float* scale_out, float* zp_out, int8_t* codes_s8, long ld_s8,
+                                float* s8_meta, cudaStream_t stream) {
   if (check_ix("oq_act_quant_fwd", rows, rows_inner, C)) return -1;
+  OQ_REQUIRE((codes_s8 == nullptr) == (s8_meta == nullptr), "oq_act_quant_fwd: codes_s8 and s8_meta go together");
+  OQ_REQUIRE(!codes_s8 || (rows_inner == 1 && !rope_cos && n_bits <= 8 && C % 8 == 0 && C <= 12288 && ld_s8 % 8 == 0 &&
+                           aligned(codes_s8, 8) && aligned(x, 16) && aligned(y, 16) && ld_outer % 8 == 0 && ldy_outer % 8 == 0),
+             "oq_act_quant_fwd: the s8 side output needs plain 2-D rows, C %% 8 == 0, C <= 12288, 8-byte aligned code rows");
   OQ_REQUIRE(x && y, "oq_act_quant_fwd: null pointer");
   OQ_REQUIRE((n_bits >= 2 && n_bits <= 8) || n_bits >= 16, "oq_act_quant_fwd: n_bits %d unsupported", n_bits);
   OQ_REQUIRE(n_bits < 16 || rope_cos, "oq_act_quant_fwd: nothing to do (n_bits>=16 and no rope)");
@@ -643,9 +713,10 @@ extern "C" int oq_act_quant_fwd(const void* x, long rows, int C, int rows_inner,
   a.cos = rope_cos; a.sin = rope_sin; a.seq_len = seq_len > 0 ? seq_len : 1;
   a.rope_inner = rope_inner > 0 ? rope_inner : rows_inner;
   a.scale_out = scale_out; a.zp_out = zp_out;
+  a.s8 = {codes_s8, ld_s8, s8_meta, rows};
   const bool al8 = aligned(x, 16) && aligned(y, 16) && ld_outer % 8 == 0 && ld_inner % 8 == 0 && ldy_outer % 8 == 0 &&
                    ldy_inner % 8 == 0;
-  if ((C == 128 || C == 64) && al8) {
+  if ((C == 128 || C == 64) && al8 && !codes_s8) {
     OQ_REQUIRE(rows < (1L << 31), "oq_act_quant_fwd: too many rows");
     const long warps = (rows / rows_inner) * ((rows_inner + AQ_HPW - 1) / AQ_HPW);
     const int grid = (int)std::min<long>((warps + 7) / 8, (long)oq_num_sms() * 32);
@@ -654,6 +725,7 @@ extern "C" int oq_act_quant_fwd(const void* x, long rows, int C, int rows_inner,
   } else {
     OQ_REQUIRE(!rope_cos, "oq_act_quant_fwd: fused rope needs head_dim 64 or 128 and 16-byte aligned rows");
     OQ_REQUIRE(rows < (1L << 31), "oq_act_quant_fwd: too many rows");
+    OQ_REQUIRE(!codes_s8 || al8, "oq_act_quant_fwd: the s8 side output needs 16-byte aligned rows");
     const unsigned g = (unsigned)rows;
     if (C % 8 == 0 && al8 && C <= 2048) aq_fwd_block_reg<1><<<g, 256, 0, stream>>>(a);
     else if (C % 8 == 0 && al8 && C <= 4096) aq_fwd_block_reg<2><<<g, 256, 0, stream>>>(a);
@@ -706,7 +778,10 @@ extern "C" int oq_act_quant_bwd(const void* x, long rows, int C, int rows_inner,
 /* SwiGLU + per-token fake-quant of the result (LlamaMLP act_fn(gate)*up feeding down_proj's act_quantizer,
  * models/int_llama_layer.py:44-45 + quantize/int_linear.py:59-60). */
 extern "C" int oq_swiglu_act_quant_fwd(const void* gu, long ldgu, long rows, int F, int n_bits, int symmetric,
-                                       int recip_div, void* mq, long ldmq, cudaStream_t stream) {
+                                       int recip_div, void* mq, long ldmq, int8_t* codes_s8, long ld_s8, float* s8_meta,
+                                       cudaStream_t stream) {
+  OQ_REQUIRE((codes_s8 == nullptr) == (s8_meta == nullptr), "oq_swiglu_act_quant_fwd: codes_s8 and s8_meta go together");
+  OQ_REQUIRE(!codes_s8 || (ld_s8 % 8 == 0 && aligned(codes_s8, 8)), "oq_swiglu_act_quant_fwd: code rows must be 8-byte aligned");
   OQ_REQUIRE(gu && mq && rows > 0 && rows < (1L << 31) && F > 0, "oq_swiglu_act_quant_fwd: null pointer or bad shape");
   OQ_REQUIRE(n_bits >= 2 && n_bits <= 8, "oq_swiglu_act_quant_fwd: n_bits %d unsupported", n_bits);
   OQ_REQUIRE(F % 8 == 0 && F <= 16384 && ldgu % 8 == 0 && ldmq % 8 == 0 && aligned(gu, 16) && aligned(mq, 16),
@@ -714,6 +789,7 @@ extern "C" int oq_swiglu_act_quant_fwd(const void* gu, long ldgu, long rows, int
   GluArgs a = {};
   a.gu = (const bf16*)gu; a.ldgu = ldgu; a.mq = (bf16*)mq; a.ldmq = ldmq; a.F = F; a.n_bits = n_bits;
   a.symmetric = symmetric; a.recip_div = recip_div;
+  a.s8 = {codes_s8, ld_s8, s8_meta, rows};
   const unsigned g = (unsigned)rows;
   if (F <= 4096) swiglu_aq_fwd_kernel<1><<<g, 512, 0, stream>>>(a);
   else if (F <= 8192) swiglu_aq_fwd_kernel<2><<<g, 512, 0, stream>>>(a);

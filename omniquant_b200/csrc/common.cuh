@@ -111,4 +111,42 @@ __device__ __forceinline__ void swiglu_grad(float g, float u, float d, float& dg
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// ---- s8 side output of the per-token / per-channel quantisers: the operands of oq_gemm_s8 -------------------------
+struct S8Side {
+  int8_t* codes; long ld;   // [rows, C] signed codes (code - z0), row stride ld bytes
+  float* meta;              // [3, rows]: scale | t = scale * sum_k (code - z0) | beta = (z0 - zp) * scale
+  long rows;
+};
+// 8 consecutive codes -> 8 bytes (one 8-byte store); adds sum (code - z0) to `sum`
+__device__ __forceinline__ void s8_store8(int8_t* p, const float (&c)[8], float z0, float& sum) {
+  uint32_t w[2] = {0u, 0u};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float d = c[j] - z0;          // integer valued, |d| <= 128
+    sum += d;
+    w[j >> 2] |= ((uint32_t)(__float2int_rn(d)) & 0xffu) << (8 * (j & 3));
+  }
+  *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
+}
+__device__ __forceinline__ void s8_store4(int8_t* p, const float (&c)[4], float z0, float& sum) {
+  uint32_t w = 0u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float d = c[j] - z0;
+    sum += d;
+    w |= ((uint32_t)(__float2int_rn(d)) & 0xffu) << (8 * j);
+  }
+  *reinterpret_cast<uint32_t*>(p) = w;
+}
+// a degenerate row (constant: scale 0 / zero point NaN) dequantises to NaN in the fake-quant path; the integer path
+// reports a NaN scale so that the GEMM output row is NaN as well
+__device__ __forceinline__ float s8_scale_or_nan(const OqQParams& q) {
+  return (isfinite(q.zp) && isfinite(q.scale)) ? q.scale : __int_as_float(0x7fc00000);
+}
+__device__ __forceinline__ void s8_write_meta(const S8Side& s, long r, const OqQParams& q, float z0, float csum) {
+  s.meta[r] = s8_scale_or_nan(q);
+  s.meta[s.rows + r] = q.scale * csum;
+  s.meta[2 * s.rows + r] = (z0 - q.zp) * q.scale;
+}
+
 static inline int ceil_div_i(long a, long b) { return (int)((a + b - 1) / b); }

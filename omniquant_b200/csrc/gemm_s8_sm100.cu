@@ -1,10 +1,10 @@
-// EXPERIMENTAL exact-integer forward contraction of QuantLinear for configurations that quantise BOTH operands
+// Exact-integer forward contraction of QuantLinear for configurations that quantise BOTH operands
 // (W4A4 / W6A6): the operands are the signed integer codes (code - zero point) of the fake-quantised activations and
 // weights, the sum over K is exact (tcgen05.mma kind::i8 = UTCIMMA, s32 accumulators in TMEM), the per-token and
 // per-channel scales are applied in the epilogue:
 //
-//   C[m,n] = rs[m]*cs[n] * sum_k A[m,k]*B[n,k]
-//            (+ rt[m]*cbeta[n] + rbeta[m]*ct[n] + K*rbeta[m]*cbeta[n])  (+ bias[n]) (+ residual[m,n])
+//   C[m,n] = alpha * ( rs[m]*cs[n] * sum_k A[m,k]*B[n,k]
+//                      (+ rt[m]*cbeta[n] + rbeta[m]*ct[n] + K*rbeta[m]*cbeta[n]) )  (+ bias[n]) (+ residual[m,n])
 //
 // Reference: QuantLinear.forward, quantize/int_linear.py:48-65 (F.linear on the two fake-quantised tensors):
 // x_q[m,k] = (c_a - z_a[m])*s_a[m], w_q[n,k] = (c_w - z_w[n])*s_w[n]  (quantize/quantizer.py:93-100), so
@@ -13,9 +13,9 @@
 // outside the code range (a row that does not straddle zero) is split as z = z0 + (z - z0) with z0 clamped into range: the
 // caller passes beta = (z0 - z)*s and t = s*sum_k(c - z0) per row / column and the epilogue adds the cross terms.
 //
-// STATUS (round 1): validated at kernel level on B200 (tests/test_kernels_gpu.py::test_gemm_s8_exact: bit for bit equal to
-// the same expression evaluated by torch, ragged shapes, K up to 11008); not wired into the engine yet -- DESIGN.md
-// section 9 item 1.  Same pipeline as gemm_sm100.cu:
+// Used by the block engine for the four forward linears of W4A4 / W6A6 runs (engine.py: _lin_fwd); the operands are the s8
+// side outputs of the activation / weight quantiser kernels (common.cuh S8Side).  Validated bit for bit against the same
+// expression evaluated by torch (tests/test_kernels_gpu.py::test_gemm_s8_exact).  Same pipeline as gemm_sm100.cu:
 // warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue, two TMEM accumulator stages.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -42,6 +42,7 @@ struct S8Params {
   long ldr;
   const float* rs; const float* cs;
   const float* rt; const float* rbeta; const float* ct; const float* cbeta;
+  float alpha;
   int num_m, num_n;
 };
 
@@ -217,6 +218,7 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float cb = p.cbeta[c];
               y += rt * cb + rb * p.ct[c] + fK * rb * cb;
             }
+            y *= p.alpha;
             if (p.bias) y += p.bias[c];
             v[j] = y;
           }
@@ -339,8 +341,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, S8Params p, cudaStream_
 
 extern "C" int oq_gemm_s8(const void* A, long lda, const void* B, long ldb, void* C, int c_dtype, long ldc, int M, int N, int K,
                           const float* row_scale, const float* col_scale, const float* row_t, const float* row_beta,
-                          const float* col_t, const float* col_beta, const float* bias, const void* residual, long ldr,
-                          cudaStream_t stream) {
+                          const float* col_t, const float* col_beta, float alpha, const float* bias, const void* residual,
+                          long ldr, cudaStream_t stream) {
   OQ_REQUIRE(A && B && C && row_scale && col_scale && M > 0 && N > 0 && K > 0, "oq_gemm_s8: null pointer or bad shape");
   OQ_REQUIRE(lda % 16 == 0 && ldb % 16 == 0 && (uintptr_t)A % 16 == 0 && (uintptr_t)B % 16 == 0,
              "oq_gemm_s8: operand strides and base pointers must be multiples of 16 bytes (TMA)");
@@ -351,6 +353,7 @@ extern "C" int oq_gemm_s8(const void* A, long lda, const void* B, long ldb, void
   S8Params p = {};
   p.M = M; p.N = N; p.K = K; p.C = C; p.c_dtype = c_dtype; p.ldc = ldc; p.bias = bias;
   p.res = (const bf16*)residual; p.ldr = ldr;
+  p.alpha = alpha;
   p.rs = row_scale; p.cs = col_scale; p.rt = row_t; p.rbeta = row_beta; p.ct = col_t; p.cbeta = col_beta;
   const long t256 = (long)((M + BM - 1) / BM) * ((N + 255) / 256);
   const int tile_n = (N <= 128 || t256 < oq_num_sms()) ? 128 : 256;

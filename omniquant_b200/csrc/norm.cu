@@ -27,6 +27,7 @@ struct NormArgs {
   float* dw_acc; float* db_acc;
   bf16* yq; long ldyq;      // optional fused per-token fake-quant of y (n_bits < 16)
   int n_bits, symmetric, recip_div;
+  S8Side s8;                // optional exact-integer side output of the fused quantiser
 };
 
 template <bool VEC>
@@ -154,26 +155,36 @@ __global__ void __launch_bounds__(TPB) norm_fwd_reg(NormArgs a) {
   const OqQParams q = oq_qparams(-mm[0], mm[1], 1.f, 1.f, 0, a.n_bits, a.symmetric, a.recip_div);
   const float inv = OQ_DIV(1.0f, q.scale);
   const bool fast = oq_inv_ok(inv);
+  const float z0 = oq_s8_z0(q.zp, q.qmax);
+  float csum[1] = {0.f};
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (threadIdx.x + i * TPB) * 8;
     if (c < a.C) {
+      float cd[8];
       if (fast) {   // same arithmetic as the stand-alone quantiser (csrc/act_quant.cu aq_t); branch uniform per row
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float x = v[i][j], qa = __fmul_rn(x, inv);
           const float t = OQ_ADD(rintf(__fmaf_rn(__fmaf_rn(-qa, q.scale, x), inv, qa)), q.zp);
-          v[i][j] = oq_dequant(oq_clampf(t, 0.0f, q.qmax), q);
+          cd[j] = oq_clampf(t, 0.0f, q.qmax);
+          v[i][j] = oq_dequant(cd[j], q);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float t = OQ_ADD(rintf(OQ_DIV(v[i][j], q.scale)), q.zp);
-          v[i][j] = oq_dequant(oq_clampf(t, 0.0f, q.qmax), q);
+          cd[j] = oq_clampf(t, 0.0f, q.qmax);
+          v[i][j] = oq_dequant(cd[j], q);
         }
       }
       store_bf8(a.yq + r * a.ldyq + c, v[i]);
+      if (a.s8.codes) s8_store8(a.s8.codes + r * a.s8.ld + c, cd, z0, csum[0]);
     }
+  }
+  if (a.s8.codes) {
+    block_reduce<1>(csum, scratch, OpSum(), 0.0f);
+    if (threadIdx.x == 0) s8_write_meta(a.s8, r, q, z0, csum[0]);
   }
 }
 
@@ -367,7 +378,10 @@ extern "C" int oq_norm_fwd(const void* x, long rows, int C, long ldx, const floa
 
 extern "C" int oq_norm_act_quant_fwd(const void* x, long rows, int C, long ldx, const float* w, const float* b, float eps,
                                      int kind, void* y, long ldy, float* mean_out, float* rstd_out, int n_bits,
-                                     int symmetric, int recip_div, void* yq, long ldyq, cudaStream_t stream) {
+                                     int symmetric, int recip_div, void* yq, long ldyq, int8_t* codes_s8, long ld_s8,
+                                     float* s8_meta, cudaStream_t stream) {
+  OQ_REQUIRE((codes_s8 == nullptr) == (s8_meta == nullptr), "oq_norm_act_quant_fwd: codes_s8 and s8_meta go together");
+  OQ_REQUIRE(!codes_s8 || (ld_s8 % 8 == 0 && (uintptr_t)codes_s8 % 8 == 0), "oq_norm_act_quant_fwd: code rows must be 8-byte aligned");
   OQ_REQUIRE(x && yq && w && rows > 0 && C > 0, "oq_norm_act_quant_fwd: null pointer or bad shape");
   OQ_REQUIRE(kind == 0 || kind == 1, "oq_norm_act_quant_fwd: kind must be 0 (rms) or 1 (layernorm)");
   OQ_REQUIRE(rows < (1L << 31), "oq_norm_act_quant_fwd: too many rows");
@@ -376,6 +390,7 @@ extern "C" int oq_norm_act_quant_fwd(const void* x, long rows, int C, long ldx, 
   a.x = (const bf16*)x; a.ldx = ldx; a.rows = rows; a.C = C; a.w = w; a.b = b; a.eps = eps; a.kind = kind;
   a.y = (bf16*)y; a.ldy = ldy; a.mean = mean_out; a.rstd = rstd_out;
   a.yq = (bf16*)yq; a.ldyq = ldyq; a.n_bits = n_bits; a.symmetric = symmetric; a.recip_div = recip_div;
+  a.s8 = {codes_s8, ld_s8, s8_meta, rows};
   return norm_fwd_launch("oq_norm_act_quant_fwd", a, stream);
 }
 

@@ -85,6 +85,14 @@ OQ_HD float oq_dequant(float code, const OqQParams& q) { return OQ_MUL(OQ_SUB(co
 
 OQ_HD float oq_fake_quant(float x, const OqQParams& q) { return oq_dequant(oq_code(x, q), q); }
 
+// Exact-integer operand of oq_gemm_s8: the stored signed code is (code - z0) with z0 = the zero point clamped so that
+// every code - z0 fits in int8 (for n <= 7 bits: z0 = clamp(zp, 0, 2^n - 1); for 8 bits z0 = 128).  A zero point outside
+// that range (a row that does not straddle zero) leaves the remainder beta = (z0 - zp) * scale to the GEMM epilogue.
+OQ_HD float oq_s8_z0(float zp, float qmax) {
+  const float lo = fmaxf(0.0f, qmax - 127.0f), hi = fminf(qmax, 128.0f);
+  return fminf(fmaxf(zp, lo), hi);     // NaN zp -> lo (the row's scale is reported as NaN instead)
+}
+
 // LET fold of one weight element: (W * col) {none | * row | / row}
 // (models/transformation.py:41,51,60,66,68).  row_op: 0 none, 1 mul, 2 div.
 OQ_HD float oq_fold(float w, float col, int has_col, float row, int row_op) {

@@ -35,6 +35,7 @@ struct WqArgs {
   bf16* q_bf;  long ld_bf;
   float* q_f32;
   uint8_t* codes;
+  int8_t* codes8; float* s8_t; float* s8_beta;   // exact-integer side output (per-channel fast path): code - z0, t, beta
   float* scale_out; float* zp_out; float* xmin_out; float* xmax_out;
   // backward inputs
   const void* g; int g_is_f32; long ld_g;
@@ -296,7 +297,12 @@ extern "C" int oq_weight_quant_fwd(const float* W, int N, int K, const float* co
                                    int row_op, const float* shift, float* matvec_out, int n_bits, int symmetric,
                                    int group_size, const float* up, const float* low, int recip_div, void* wq_bf16,
                                    long ld_bf16, float* wq_f32, uint8_t* codes, float* scale_out, float* zp_out,
-                                   float* xmin_out, float* xmax_out, cudaStream_t stream) {
+                                   float* xmin_out, float* xmax_out, int8_t* codes_s8, float* s8_t, float* s8_beta,
+                                   cudaStream_t stream) {
+  OQ_REQUIRE((codes_s8 == nullptr) == (s8_t == nullptr) && (codes_s8 == nullptr) == (s8_beta == nullptr),
+             "oq_weight_quant_fwd: codes_s8, s8_t and s8_beta go together");
+  OQ_REQUIRE(!codes_s8 || (group_size == 0 && n_bits <= 8 && scale_out && (uintptr_t)codes_s8 % 4 == 0),
+             "oq_weight_quant_fwd: the s8 side output needs per-channel quantisation, n_bits <= 8 and scale_out");
   OQ_REQUIRE(W && N > 0 && K > 0, "oq_weight_quant_fwd: bad shape N=%d K=%d", N, K);
   OQ_REQUIRE((n_bits >= 2 && n_bits <= 8) || n_bits >= 16, "oq_weight_quant_fwd: n_bits %d not in [2,8] or >= 16 (fold only)", n_bits);
   const bool ident = n_bits >= 16;
@@ -310,6 +316,7 @@ extern "C" int oq_weight_quant_fwd(const float* W, int N, int K, const float* co
   a.n_bits = n_bits; a.symmetric = symmetric; a.group = group_size; a.recip_div = recip_div; a.up = up; a.low = low;
   a.q_bf = (bf16*)wq_bf16; a.ld_bf = ld_bf16 ? ld_bf16 : K; a.q_f32 = wq_f32; a.codes = codes;
   a.scale_out = scale_out; a.zp_out = zp_out; a.xmin_out = xmin_out; a.xmax_out = xmax_out;
+  a.codes8 = codes_s8; a.s8_t = s8_t; a.s8_beta = s8_beta;
   const bool team_warp = group_size > 0;
   const long G = group_size ? (K + group_size - 1) / group_size : 1;
   const bool vec = (K % 4 == 0) && (group_size % 4 == 0) && (a.ld_bf % 4 == 0) && ((uintptr_t)W % 16 == 0) &&
@@ -333,6 +340,8 @@ extern "C" int oq_weight_quant_fwd(const float* W, int N, int K, const float* co
     if (let ? launch_grp<true, false>(a, g, 0, stream) : launch_grp<false, false>(a, g, 0, stream))
       return oq_check_launch("oq_weight_quant_fwd");
   }
+  OQ_REQUIRE(!codes_s8, "oq_weight_quant_fwd: the s8 side output needs the per-channel fast path (K %% 4 == 0, K <= 16384, "
+                        "16-byte aligned W / col_scale / shift)");
   const int grid = pick_grid((long)N * G, team_warp, 8);
   if (team_warp) {
     if (vec) wq_fwd_kernel<true, true><<<grid, 256, 0, stream>>>(a);

@@ -62,7 +62,7 @@ __device__ __forceinline__ float warp_max_f32(float v) {
 template <int NV, bool LET, bool ROWDIV>
 __global__ void __launch_bounds__(256) wq_pc_fwd(WqArgs a) {
   extern __shared__ float4 dsm4[];
-  __shared__ float red[2][3][8];
+  __shared__ float red[2][4][8];
   __shared__ float sig[2][256];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, K4 = a.K >> 2;
   float4* colv = dsm4;            // [K4] (LET)
@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(256) wq_pc_fwd(WqArgs a) {
     }
   }
   int par = 0, k = 0;
+  int pend_n = -1;          // s8 side output: the row whose code sum is still in red[par ^ 1][3] (thread 0 only)
+  float pend_scale = 0.f;
   for (; n < a.N; n += gridDim.x, par ^= 1, ++k) {
     if ((k & 255) == 0) {   // sigmoids of the next 256 rows of this block, one row per thread
       __syncthreads();
@@ -136,7 +138,20 @@ __global__ void __launch_bounds__(256) wq_pc_fwd(WqArgs a) {
     const float xmin = -warp_max_f32(lane < 8 ? red[par][0][lane] : -INFINITY);
     const float xmax = warp_max_f32(lane < 8 ? red[par][1][lane] : -INFINITY);
     const OqQParams q = oq_qparams(xmin, xmax, sig[0][k & 255], sig[1][k & 255], lwc, a.n_bits, a.symmetric, a.recip_div);
+    const float z0 = oq_s8_z0(q.zp, q.qmax);
     if (tid == 0) {
+      if (a.codes8) {
+        if (pend_n >= 0) {     // the previous row's warp sums were published before this row's barrier
+          float t = 0.f;
+#pragma unroll
+          for (int x = 0; x < 8; ++x) t += red[par ^ 1][3][x];
+          a.s8_t[pend_n] = pend_scale * t;
+        }
+        pend_n = n;
+        pend_scale = q.scale;
+        // a degenerate (constant) row dequantises to NaN in the fake-quant path: poison the epilogue term instead
+        a.s8_beta[n] = isfinite(s8_scale_or_nan(q)) && q.scale != 0.0f ? (z0 - q.zp) * q.scale : __int_as_float(0x7fc00000);
+      }
       if (a.scale_out) a.scale_out[n] = q.scale;
       if (a.zp_out) a.zp_out[n] = q.zp;
       if (a.xmin_out) a.xmin_out[n] = xmin;
@@ -150,6 +165,7 @@ __global__ void __launch_bounds__(256) wq_pc_fwd(WqArgs a) {
     }
     const float inv = OQ_DIV(1.0f, q.scale);
     const bool inv_bad = !oq_inv_ok(inv);
+    float csum = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int idx = tid + i * 256;
@@ -175,7 +191,24 @@ __global__ void __launch_bounds__(256) wq_pc_fwd(WqArgs a) {
         if (a.q_f32) *reinterpret_cast<float4*>(a.q_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
         if (a.codes)
           *reinterpret_cast<uchar4*>(a.codes + o) = make_uchar4((unsigned char)c.x, (unsigned char)c.y, (unsigned char)c.z, (unsigned char)c.w);
+        if (a.codes8) {
+          const float cc[4] = {c.x, c.y, c.z, c.w};
+          s8_store4(a.codes8 + o, cc, z0, csum);
+        }
       }
+    }
+    if (a.codes8) {
+      csum = warp_reduce(csum, OpSum());
+      if (lane == 0) red[par][3][warp] = csum;
+    }
+  }
+  if (a.codes8) {
+    __syncthreads();
+    if (tid == 0 && pend_n >= 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int x = 0; x < 8; ++x) t += red[par ^ 1][3][x];
+      a.s8_t[pend_n] = pend_scale * t;
     }
   }
 }

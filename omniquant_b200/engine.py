@@ -170,14 +170,20 @@ class BlockEngine:
                     self.p[n].copy_(v.to(self.dev, F32))
         # ---- per-unit quantiser state + bf16 operands
         self.Wq = {g: torch.empty_like(w, dtype=BF16) for g, w in self.W.items()}
+        # W4A4 / W6A6 with per-channel weights: the four forward linears contract the integer codes of both operands
+        # exactly (oq_gemm_s8, tcgen05 kind::i8) and apply the scales in the epilogue; the bf16 copies stay for dgrad / wgrad
+        self.s8 = (qcfg.act_quant and qcfg.wbits <= 8 and qcfg.abits <= 8 and not qcfg.group_size and H % 16 == 0
+                   and F_ % 16 == 0 and max(H, F_) <= 16384 and (glu or F_ <= 12288) and self.dev.type == "cuda"
+                   and os.environ.get("OQ_S8", "1") != "0")
+        self.W8 = {g: ops.S8Operand(w.shape[0], w.shape[1], self.dev) for g, w in self.W.items()} if self.s8 else None
         self.Wfp = None
         F1 = self.W["fc1"].shape[0]
         self.F1 = F1
         self._mvbuf = z(4 * H + F1)         # packed W@shift outputs (layout: include/omniquant_b200.h, oq_let_fold_vec)
         mvv = {"q": self._mvbuf[:H], "k": self._mvbuf[H:2 * H], "v": self._mvbuf[2 * H:3 * H], "o": self._mvbuf[3 * H:4 * H],
                "fc1": self._mvbuf[4 * H:], "fc2": z(H)}
-        self.qstat = {u.name: dict(xmin=z(u.N * G(u.K)), xmax=z(u.N * G(u.K)), scale=z(u.N * G(u.K)), zp=z(u.N * G(u.K)),
-                                    mv=mvv.get(u.name)) for u in U}
+        self.qstat = {u.name: dict(xmin=z(u.N * G(u.K)), xmax=z(u.N * G(u.K)), zp=z(u.N * G(u.K)), mv=mvv.get(u.name),
+                                    scale=self.W8[u.group].scale[u.r0:u.r1] if self.s8 else z(u.N * G(u.K))) for u in U}
         self._tmpv = z(9 * H + F1)
         self.tmp = {}     # folded vectors of the current step
         self.bufs = {}
@@ -304,13 +310,21 @@ class BlockEngine:
                 extra[u.name] = dict(weight=torch.empty(u.N, u.K, device=self.dev), scales=torch.empty(G, device=self.dev),
                                      zeros=torch.empty(G, device=self.dev))
                 kw = dict(wq_f32=extra[u.name]["weight"], scale_out=extra[u.name]["scales"], zp_out=extra[u.name]["zeros"])
-                st["scale"], st["zp"] = extra[u.name]["scales"], extra[u.name]["zeros"]
+                if self.s8:       # the scale lands in the integer operand and is copied out below
+                    kw["scale_out"] = st["scale"]
+                    st["zp"] = extra[u.name]["zeros"]
+                else:
+                    st["scale"], st["zp"] = extra[u.name]["scales"], extra[u.name]["zeros"]
+            if self.s8 and q.wbits < 16:
+                kw["s8"] = self.W8[u.group].rows(u.r0, u.r1)
             ops.weight_quant_fwd(self.wview(u, self.W), n_bits=q.wbits, symmetric=q.symmetric, group_size=q.group_size,
                                  up=up, low=low, col_scale=p.get(u.col) if u.col else None,
                                  row_scale=p.get(u.row) if u.row else None, row_op=u.row_op,
                                  shift=p.get(u.shift) if u.shift else None, matvec_out=st["mv"] if u.shift else None,
                                  recip_div=q.recip_div, wq_bf16=self.wview(u, self.Wq), xmin_out=st["xmin"],
                                  xmax_out=st["xmax"], **kw)
+            if final and self.s8 and q.wbits < 16:
+                extra[u.name]["scales"].copy_(st["scale"])
 
         t = self.tmp
         H = self.H
@@ -344,6 +358,7 @@ class BlockEngine:
             # q = (x W^T + b) * d^-0.5 is folded into the q GEMM epilogue (models/int_opt_layer.py:96)
             t["bq_scaled"] = None if t["bqkv"] is None else t["bqkv"][:H] * self.d ** -0.5
         t["W"] = self.Wq
+        t["W8"] = self.W8
         return extra
 
     def fp_weights(self):
@@ -357,46 +372,70 @@ class BlockEngine:
         return fp
 
     # ------------------------------------------------------------------ forward
+    def _s8buf(self, name, shape):
+        """Integer twin of an activation operand (None when the exact-integer forward is off for this pass)."""
+        if not self._use_s8:
+            return None
+        key = name + ".s8"
+        t = self.bufs.get(key)
+        if t is None or tuple(t.codes.shape) != tuple(shape):
+            t = self.bufs[key] = ops.S8Operand(shape[0], shape[1], self.dev)
+        return t
+
     def _aq(self, x, name):
-        """per-token fake-quant over the last dim (QuantLinear.act_quantizer)."""
+        """per-token fake-quant over the last dim (QuantLinear.act_quantizer); returns (bf16 operand, integer operand)."""
         if not self._act_quant:
-            return x
+            return x, None
         y = self.buf(name, x.shape)
-        ops.act_quant_fwd(x, y, n_bits=self.q.abits, recip_div=self.q.recip_div)
-        return y
+        x8 = self._s8buf(name, x.shape)
+        ops.act_quant_fwd(x, y, n_bits=self.q.abits, recip_div=self.q.recip_div, s8=x8)
+        return y, x8
 
     def _norm_aq(self, x, w, b, y, name, stats):
         """y = norm(x) and, when activations are quantised, its per-token fake-quant in the same pass."""
         if not self._act_quant:
             ops.norm_fwd(x, w, b, self.eps, self.norm_kind, y, *stats)
-            return y
+            return y, None
         yq = self.buf(name, y.shape)
+        y8 = self._s8buf(name, y.shape)
         ops.norm_act_quant_fwd(x, w, b, self.eps, self.norm_kind, y, yq, n_bits=self.q.abits, recip_div=self.q.recip_div,
-                               mean_out=stats[0], rstd_out=stats[1])
-        return yq
+                               mean_out=stats[0], rstd_out=stats[1], s8=y8)
+        return yq, y8
+
+    def _linear(self, xq, x8, ws, g, out, bias=None, residual=None, rows=None, alpha=1.0):
+        """QuantLinear forward GEMM of weight group g (optionally a row range of it): exact-integer contraction when both
+        operands carry their codes, bf16 tcgen05 GEMM otherwise (quantize/int_linear.py:62)."""
+        r0, r1 = rows if rows is not None else (0, ws["W"][g].shape[0])
+        if x8 is not None:
+            w8 = ws["W8"][g]
+            ops.linear_s8_fwd(x8, w8 if rows is None else w8.rows(r0, r1), out, bias=bias, residual=residual, alpha=alpha)
+            return
+        Wg = ws["W"][g][r0:r1]
+        M, K = xq.shape
+        ops.gemm(xq, Wg, out, M=M, N=r1 - r0, K=K, lda=xq.stride(0), ldb=Wg.stride(0), ldc=out.stride(0), bias=bias,
+                 residual=residual, ldr=residual.stride(0) if residual is not None else 0, alpha=alpha)
 
     def forward(self, x: torch.Tensor, ws: dict, act_quant: bool, out: Optional[torch.Tensor] = None):
         """Block forward on x [M,H] bf16 (models/int_llama_layer.py:213-267 / int_opt_layer.py:268-346)."""
         M, H, F_, h, d, T = x.shape[0], self.H, self.F, self.h, self.d, self.T
         nb = M // T
         self._act_quant = act_quant and self.q.act_quant
+        self._use_s8 = self._act_quant and self.s8 and ws.get("W8") is not None
         B = self.buf
         self.x = x
         falcon = self.family == "falcon"
         a1 = B("a1", (M, H))
         self.st1 = (B("mean1", (M,), F32), B("rstd1", (M,), F32))
-        a1q = self._norm_aq(x, ws["ln1w"], ws["ln1b"], a1, "a1q", self.st1)
+        a1q, a1q8 = self._norm_aq(x, ws["ln1w"], ws["ln1b"], a1, "a1q", self.st1)
         QW, Hkv, hkv, rep = self.QW, self.Hkv, self.hkv, self.rep
         ok, ov = H, H + Hkv                     # column offsets of k and v in the [M, QW] qkv buffers (LLaMA / OPT)
         qkv = B("qkv", (M, QW))
         W = ws["W"]
         if self.family in ("llama", "falcon"):
-            ops.linear_fwd(a1q, W["qkv"], qkv, bias=ws["bqkv"])
+            self._linear(a1q, a1q8, ws, "qkv", qkv, bias=ws["bqkv"])
         else:
-            sc = d ** -0.5
-            ops.gemm(a1q, W["qkv"], qkv, M=M, N=H, K=H, lda=H, ldb=H, ldc=QW, bias=ws["bq_scaled"], alpha=sc)
-            ops.gemm(a1q, W["qkv"][H:], qkv[:, H:], M=M, N=2 * H, K=H, lda=H, ldb=H, ldc=QW,
-                     bias=None if ws["bqkv"] is None else ws["bqkv"][H:])
+            self._linear(a1q, a1q8, ws, "qkv", qkv[:, :H], bias=ws["bq_scaled"], rows=(0, H), alpha=d ** -0.5)
+            self._linear(a1q, a1q8, ws, "qkv", qkv[:, H:], bias=None if ws["bqkv"] is None else ws["bqkv"][H:], rows=(H, 3 * H))
         # ---- Q/K/V operands of QuantMatMul
         abits = self.q.abits if self._act_quant else 16
         parts = ((0, H, h), (ok, ov, hkv), (ov, QW, hkv))     # (column range, heads) of q, k, v
@@ -443,21 +482,22 @@ class BlockEngine:
                 for h0, nh, cq, ck, cv, sb in groups:
                     ops.gemm(P[s, h0:], qkvq[r, cv:], O[r, h0 * d:], M=T, N=d, K=T, lda=T, ldb=QW, b_mn=True, ldc=H, batch=nh,
                              strideA=T * T, strideB=sb, strideC=d, causal=2 * cz)
-        Oq = self._aq(O, "Oq")
+        Oq, Oq8 = self._aq(O, "Oq")
         h1 = B("h1", (M, H))
         self._join()                # o / fc1 / fc2 operands of this step come from the side stream
-        ops.linear_fwd(Oq, W["o"], h1, bias=ws["bo"], residual=x)
+        self._linear(Oq, Oq8, ws, "o", h1, bias=ws["bo"], residual=x)
         a2 = B("a2", (M, H))
         self.st2 = (B("mean2", (M,), F32), B("rstd2", (M,), F32))
         # Falcon: ln_mlp acts on the block input, attention and MLP run in parallel (int_falcon_layer.py:272-301)
-        a2q = self._norm_aq(x if falcon else h1, ws["ln2w"], ws["ln2b"], a2, "a2q", self.st2)
+        a2q, a2q8 = self._norm_aq(x if falcon else h1, ws["ln2w"], ws["ln2b"], a2, "a2q", self.st2)
         f1 = B("f1", (M, W["fc1"].shape[0]))
-        ops.linear_fwd(a2q, W["fc1"], f1, bias=ws["bfc1"])
+        self._linear(a2q, a2q8, ws, "fc1", f1, bias=ws["bfc1"])
         if self.glu and self._act_quant:
             # SwiGLU and down_proj's input quantiser in one pass; m itself is re-derived in the backward
             m = None
             mq = B("mq", (M, F_))
-            ops.swiglu_act_quant_fwd(f1, mq, n_bits=self.q.abits, recip_div=self.q.recip_div)
+            mq8 = self._s8buf("mq", (M, F_))
+            ops.swiglu_act_quant_fwd(f1, mq, n_bits=self.q.abits, recip_div=self.q.recip_div, s8=mq8)
         else:
             m = B("m", (M, F_))
             if self.glu:
@@ -466,10 +506,10 @@ class BlockEngine:
                 ops.gelu_fwd(f1, m)
             else:
                 ops.relu_fwd(f1, m)
-            mq = self._aq(m, "mq")
+            mq, mq8 = self._aq(m, "mq")
         if out is None:
             out = B("out", (M, H))
-        ops.linear_fwd(mq, W["fc2"], out, bias=ws["bfc2"], residual=h1)
+        self._linear(mq, mq8, ws, "fc2", out, bias=ws["bfc2"], residual=h1)
         self.saved = dict(a1=a1, a1q=a1q, O=O, Oq=Oq, h1=h1, a2=a2, a2q=a2q, f1=f1, m=m, mq=mq, P=P, ws=ws)
         return out
 

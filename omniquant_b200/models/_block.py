@@ -299,8 +299,9 @@ class QuantDecoderLayerBase(nn.Module):
                     nm.register_buffer("bias", t[b].clone())
             nm.use_temporary_parameter = False
         # operands of the post-calibration forward (raw-weight branch of QuantLinear.forward, int_linear.py:56-58)
-        self._final_ws = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in t.items() if k != "W"}
+        self._final_ws = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in t.items() if k not in ("W", "W8")}
         self._final_ws["W"] = {g: w.clone() for g, w in eng.Wq.items()}
+        self._final_ws["W8"] = None if eng.W8 is None else {g: o.clone() for g, o in eng.W8.items()}
 
     def _named_omni(self, use_shift=True):
         template = "smooth" if use_shift else "smooth_scale"

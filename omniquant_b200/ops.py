@@ -40,9 +40,51 @@ def _rowmajor(t: torch.Tensor, name: str):
 
 
 # ------------------------------------------------------------------ weight path
+class S8Operand:
+    """Exact-integer operand of gemm_s8 as emitted by a quantiser kernel: signed codes [rows, C] int8 (code - z0) and the
+    per-row vectors scale, t = scale * sum_k (code - z0), beta = (z0 - zero_point) * scale (views of one [3, rows] buffer)."""
+
+    def __init__(self, rows, C, device):
+        self.codes = torch.empty(rows, C, device=device, dtype=torch.int8)
+        self.meta = torch.empty(3, rows, device=device, dtype=F32)
+
+    @property
+    def scale(self):
+        return self.meta[0]
+
+    @property
+    def t(self):
+        return self.meta[1]
+
+    @property
+    def beta(self):
+        return self.meta[2]
+
+    def rows(self, r0, r1):
+        """The operand restricted to rows [r0, r1) (shares storage)."""
+        v = object.__new__(S8Operand)
+        v.codes, v.meta = self.codes[r0:r1], self.meta[:, r0:r1]
+        return v
+
+    def clone(self):
+        v = object.__new__(S8Operand)
+        v.codes, v.meta = self.codes.clone(), self.meta.clone()
+        return v
+
+
+def _s8_args(s8, rows, C):
+    if s8 is None:
+        return None, 0, None
+    _chk(s8.codes, torch.int8, "s8.codes")
+    _chk(s8.meta, F32, "s8.meta")
+    if tuple(s8.codes.shape) != (rows, C) or s8.codes.stride(1) != 1 or tuple(s8.meta.shape) != (3, rows) or not s8.meta.is_contiguous():
+        raise OqError(f"s8 operand must hold codes [{rows}, {C}] and a contiguous meta [3, {rows}]")
+    return s8.codes.data_ptr(), s8.codes.stride(0), s8.meta.data_ptr()
+
+
 def weight_quant_fwd(W, *, n_bits, symmetric=False, group_size=0, up=None, low=None, col_scale=None, row_scale=None,
                      row_op=0, shift=None, matvec_out=None, recip_div=True, wq_bf16=None, wq_f32=None, codes=None,
-                     scale_out=None, zp_out=None, xmin_out=None, xmax_out=None):
+                     scale_out=None, zp_out=None, xmin_out=None, xmax_out=None, s8=None):
     _chk(W, F32, "W")
     for n, t in (("up", up), ("low", low), ("col_scale", col_scale), ("row_scale", row_scale), ("shift", shift),
                  ("matvec_out", matvec_out), ("wq_f32", wq_f32), ("scale_out", scale_out), ("zp_out", zp_out),
@@ -54,9 +96,16 @@ def weight_quant_fwd(W, *, n_bits, symmetric=False, group_size=0, up=None, low=N
         raise OqError("W must be contiguous [N, K]")
     N, K = W.shape
     ld = _rowmajor(wq_bf16, "wq_bf16") if wq_bf16 is not None else 0
+    c8 = t8 = b8 = None
+    if s8 is not None:      # the weight's scale goes to s8.meta[0] (== scale_out when the caller did not ask for its own)
+        if tuple(s8.codes.shape) != (N, K) or not s8.codes.is_contiguous():
+            raise OqError("weight_quant_fwd: s8 operand must hold contiguous codes [N, K]")
+        if scale_out is not None and scale_out.data_ptr() != s8.scale.data_ptr():
+            raise OqError("weight_quant_fwd: with an s8 operand scale_out must be s8.scale (or None)")
+        scale_out, c8, t8, b8 = s8.scale, s8.codes.data_ptr(), s8.t.data_ptr(), s8.beta.data_ptr()
     lib().call("oq_weight_quant_fwd", _p(W), N, K, _p(col_scale), _p(row_scale), row_op, _p(shift), _p(matvec_out),
                n_bits, int(symmetric), int(group_size or 0), _p(up), _p(low), int(recip_div), _p(wq_bf16), ld,
-               _p(wq_f32), _p(codes), _p(scale_out), _p(zp_out), _p(xmin_out), _p(xmax_out), _stream())
+               _p(wq_f32), _p(codes), _p(scale_out), _p(zp_out), _p(xmin_out), _p(xmax_out), c8, t8, b8, _stream())
 
 
 def weight_quant_bwd(W, grad_wq, xmin, xmax, *, n_bits, symmetric=False, group_size=0, up=None, low=None,
@@ -87,13 +136,14 @@ def _rows2(x: torch.Tensor, name: str):
 
 
 def act_quant_fwd(x, y, *, n_bits, symmetric=False, recip_div=True, cos=None, sin=None, seq_len=0, rope_inner=0,
-                  scale_out=None, zp_out=None):
+                  scale_out=None, zp_out=None, s8=None):
     rows, C, ri, lo, li = _rows2(x, "x")
     rows2, C2, ri2, lo2, li2 = _rows2(y, "y")
     if (rows, C, ri) != (rows2, C2, ri2):
         raise OqError("act_quant_fwd: x / y shape mismatch")
+    c8, ld8, m8 = _s8_args(s8, rows, C)
     lib().call("oq_act_quant_fwd", _p(x), rows, C, ri, lo, li, n_bits, int(symmetric), int(recip_div), _p(cos), _p(sin),
-               seq_len, rope_inner, _p(y), lo2, li2, _p(scale_out), _p(zp_out), _stream())
+               seq_len, rope_inner, _p(y), lo2, li2, _p(scale_out), _p(zp_out), c8, ld8, m8, _stream())
 
 
 def act_quant_bwd(x, gy, gx, *, n_bits, symmetric=False, recip_div=True, cos=None, sin=None, seq_len=0, rope_inner=0):
@@ -106,14 +156,15 @@ def act_quant_bwd(x, gy, gx, *, n_bits, symmetric=False, recip_div=True, cos=Non
                seq_len, rope_inner, _p(gy), glo, gli, _p(gx), xlo, xli, _stream())
 
 
-def swiglu_act_quant_fwd(gu, mq, *, n_bits, symmetric=False, recip_div=True):
+def swiglu_act_quant_fwd(gu, mq, *, n_bits, symmetric=False, recip_div=True, s8=None):
     """mq = fake_quant(silu(gate) * up) for gu = [gate | up]; the product itself is not stored."""
     _chk(gu, BF16, "gu"); _chk(mq, BF16, "mq")
     rows, F = mq.shape
     if gu.shape != (rows, 2 * F):
         raise OqError("swiglu_act_quant_fwd: gu must be [rows, 2F]")
+    c8, ld8, m8 = _s8_args(s8, rows, F)
     lib().call("oq_swiglu_act_quant_fwd", _p(gu), _rowmajor(gu, "gu"), rows, F, n_bits, int(symmetric), int(recip_div),
-               _p(mq), _rowmajor(mq, "mq"), _stream())
+               _p(mq), _rowmajor(mq, "mq"), c8, ld8, m8, _stream())
 
 
 def swiglu_act_quant_bwd(gu, gy, dgu, *, n_bits, symmetric=False, recip_div=True):
@@ -132,12 +183,13 @@ def norm_fwd(x, w, b, eps, kind, y, mean_out=None, rstd_out=None):
                _rowmajor(y, "y"), _p(mean_out), _p(rstd_out), _stream())
 
 
-def norm_act_quant_fwd(x, w, b, eps, kind, y, yq, *, n_bits, symmetric=False, recip_div=True, mean_out=None, rstd_out=None):
+def norm_act_quant_fwd(x, w, b, eps, kind, y, yq, *, n_bits, symmetric=False, recip_div=True, mean_out=None, rstd_out=None,
+                       s8=None):
     """y = norm(x) (optional) and yq = fake_quant(y) per token, one pass."""
     _chk(x, BF16, "x"); _chk(y, BF16, "y"); _chk(yq, BF16, "yq"); _chk(w, F32, "w"); _chk(b, F32, "b")
     lib().call("oq_norm_act_quant_fwd", _p(x), x.shape[0], x.shape[1], _rowmajor(x, "x"), _p(w), _p(b), float(eps), kind,
                _p(y), _rowmajor(y, "y") if y is not None else 0, _p(mean_out), _p(rstd_out), n_bits, int(symmetric),
-               int(recip_div), _p(yq), _rowmajor(yq, "yq"), _stream())
+               int(recip_div), _p(yq), _rowmajor(yq, "yq"), *_s8_args(s8, x.shape[0], x.shape[1]), _stream())
 
 
 def norm_bwd(x, w, kind, mean, rstd, dy, dx=None, dx_add=None, dw_acc=None, db_acc=None):
@@ -149,12 +201,13 @@ def norm_bwd(x, w, kind, mean, rstd, dy, dx=None, dx_add=None, dw_acc=None, db_a
 
 # ------------------------------------------------------------------ GEMM
 _CDT = {BF16: 0, F32: 1, torch.float16: 2}
-GEMM_TIMER = None   # bench.py sets this to a list to collect (event0, event1, flops, tile) per GEMM launch
+GEMM_TIMER = None   # bench.py sets this to a list to collect (event0, event1, flops, kind: lin | attn | s8) per GEMM launch
 
 
-def gemm_s8(A, B, C, row_scale, col_scale, *, corr=None, bias=None, residual=None):
-    """EXPERIMENTAL: C = row_scale[:, None] * col_scale[None, :] * (A.int() @ B.int().T) for int8 code matrices A [M, K],
-    B [N, K] (exact integer sum on the tensor cores); corr = (row_t, row_beta, col_t, col_beta) or None."""
+def gemm_s8(A, B, C, row_scale, col_scale, *, corr=None, alpha=1.0, bias=None, residual=None):
+    """C = alpha * row_scale[:, None] * col_scale[None, :] * (A.int() @ B.int().T) (+ zero-point corrections) (+ bias)
+    (+ residual) for int8 code matrices A [M, K], B [N, K] (exact integer sum on the tensor cores);
+    corr = (row_t, row_beta, col_t, col_beta) or None."""
     if A.dtype != torch.int8 or B.dtype != torch.int8 or A.dim() != 2 or B.dim() != 2 or A.shape[1] != B.shape[1]:
         raise OqError("gemm_s8: A [M, K] and B [N, K] must be int8")
     if A.stride(1) != 1 or B.stride(1) != 1 or C.stride(1) != 1:
@@ -162,9 +215,22 @@ def gemm_s8(A, B, C, row_scale, col_scale, *, corr=None, bias=None, residual=Non
     M, K = A.shape
     N = B.shape[0]
     rt, rb, ct, cb = corr if corr is not None else (None, None, None, None)
+    if GEMM_TIMER is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     lib().call("oq_gemm_s8", _p(A), A.stride(0), _p(B), B.stride(0), _p(C), _CDT[C.dtype], C.stride(0), M, N, K,
-               _p(row_scale), _p(col_scale), _p(rt), _p(rb), _p(ct), _p(cb), _p(bias), _p(residual),
+               _p(row_scale), _p(col_scale), _p(rt), _p(rb), _p(ct), _p(cb), float(alpha), _p(bias), _p(residual),
                residual.stride(0) if residual is not None else 0, _stream())
+    if GEMM_TIMER is not None:
+        e1.record()
+        GEMM_TIMER.append((e0, e1, 2.0 * M * N * K, "s8"))
+
+
+def linear_s8_fwd(xs: "S8Operand", ws: "S8Operand", out, bias=None, residual=None, alpha=1.0):
+    """out[M,N] = alpha * x_q[M,K] @ w_q[N,K]^T + bias + residual from the integer codes of both fake-quantised operands
+    (QuantLinear.forward with use_act_quant and a quantised weight, quantize/int_linear.py:48-65)."""
+    gemm_s8(xs.codes, ws.codes, out, xs.scale, ws.scale, corr=(xs.t, xs.beta, ws.t, ws.beta), alpha=alpha, bias=bias,
+            residual=residual)
 
 
 def launch_count() -> int:
@@ -186,7 +252,7 @@ def gemm(A, B, C, *, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=No
                causal, int(accumulate), tile_n, max_ctas, _stream())
     if GEMM_TIMER is not None:
         e1.record()
-        GEMM_TIMER.append((e0, e1, 2.0 * M * N * K * batch * (0.5 if causal else 1.0), batch > 1))
+        GEMM_TIMER.append((e0, e1, 2.0 * M * N * K * batch * (0.5 if causal else 1.0), "attn" if batch > 1 else "lin"))
 
 
 def linear_fwd(x, wq, out, bias=None, residual=None):

@@ -247,7 +247,7 @@ class QCfg:
     """The six quantiser-parameter dicts main.py:268-303 builds, flattened."""
 
     def __init__(self, wbits=4, abits=4, group_size=None, symmetric=False, lwc=True, let=True,
-                 recip_div=False, emu16=None):
+                 recip_div=False, emu16=None, exact_int=None):
         self.wbits, self.abits, self.group_size = wbits, abits, group_size
         self.symmetric, self.lwc, self.let = symmetric, lwc, let
         self.recip_div = recip_div
@@ -255,6 +255,10 @@ class QCfg:
         # GEMM operands) at the same points, with identity gradient -- SURVEY.md §7 hard part 2b.  None = the
         # reference's fp32 (--deactive_amp) arithmetic.
         self.emu16 = emu16
+        # exact_int: with 16-bit storage emulation, a linear whose activation AND (per-channel) weight are quantised to
+        # <= 8 bits is contracted from the un-rounded dequantised operands -- the engine multiplies the integer codes
+        # exactly (oq_gemm_s8) instead of rounding (code - zp) * scale to bf16 first.  Default: on whenever emu16 is on.
+        self.exact_int = (emu16 is not None) if exact_int is None else exact_int
 
 
 def st(t, cfg):
@@ -262,6 +266,13 @@ def st(t, cfg):
     if t is None or cfg.emu16 is None:
         return t
     return t + (t.to(cfg.emu16).to(t.dtype) - t).detach()
+
+
+def lin_operand_st(cfg, act_quant):
+    """storage rounding applied to the two operands of a QuantLinear GEMM (see QCfg.exact_int)."""
+    if cfg.emu16 is not None and cfg.exact_int and act_quant and cfg.abits <= 8 and cfg.wbits <= 8 and not cfg.group_size:
+        return lambda t: t
+    return lambda t: st(t, cfg)
 
 
 def st_scores(t, cfg):
@@ -353,8 +364,9 @@ def llama_forward(x, T, n_heads, cos, sin, mask, cfg: QCfg, act_quant=True, eps=
     d = H // n_heads
     n_kv = n_kv_heads or n_heads
     S = lambda t: st(t, cfg)
-    lin = lambda t, n, res=None: S((F.linear(S(aq(t, cfg, act_quant)), S(T[f"{n}.w"]), T[f"{n}.b"])) if res is None else
-                                   (res + F.linear(S(aq(t, cfg, act_quant)), S(T[f"{n}.w"]), T[f"{n}.b"])))
+    So = lin_operand_st(cfg, act_quant)
+    lin = lambda t, n, res=None: S((F.linear(So(aq(t, cfg, act_quant)), So(T[f"{n}.w"]), T[f"{n}.b"])) if res is None else
+                                   (res + F.linear(So(aq(t, cfg, act_quant)), So(T[f"{n}.w"]), T[f"{n}.b"])))
     a1 = S(rms_norm(x, T["ln1w"], T["ln1b"], eps))
     q = lin(a1, "q").view(b, L, n_heads, d).transpose(1, 2)
     k = lin(a1, "k").view(b, L, n_kv, d).transpose(1, 2)
@@ -421,8 +433,9 @@ def opt_forward(x, T, n_heads, mask, cfg: QCfg, act_quant=True, eps=1e-5):
     b, L, H = x.shape
     d = H // n_heads
     S = lambda t: st(t, cfg)
-    lin = lambda t, n, res=None, sc=1.0: S((F.linear(S(aq(t, cfg, act_quant)), S(T[f"{n}.w"]), T[f"{n}.b"]) * sc) if res is None
-                                           else (res + F.linear(S(aq(t, cfg, act_quant)), S(T[f"{n}.w"]), T[f"{n}.b"])))
+    So = lin_operand_st(cfg, act_quant)
+    lin = lambda t, n, res=None, sc=1.0: S((F.linear(So(aq(t, cfg, act_quant)), So(T[f"{n}.w"]), T[f"{n}.b"]) * sc) if res is None
+                                           else (res + F.linear(So(aq(t, cfg, act_quant)), So(T[f"{n}.w"]), T[f"{n}.b"])))
     sh = lambda t: t.view(b, L, n_heads, d).transpose(1, 2).contiguous().view(b * n_heads, L, d)
     a1 = S(layer_norm(x, T["ln1w"], T["ln1b"], eps))
     q = S(aq(lin(a1, "q", sc=d ** -0.5), cfg, act_quant))
@@ -466,8 +479,9 @@ def falcon_forward(x, T, n_heads, n_kv, cos, sin, cfg: QCfg, act_quant=True, eps
     d = H // n_heads
     rep = n_heads // n_kv
     S = lambda t: st(t, cfg)
-    lin = lambda t, n, res=None: S(F.linear(S(aq(t, cfg, act_quant)), S(T[f"{n}.w"]), T[f"{n}.b"]) if res is None else
-                                   res + F.linear(S(aq(t, cfg, act_quant)), S(T[f"{n}.w"]), T[f"{n}.b"]))
+    So = lin_operand_st(cfg, act_quant)
+    lin = lambda t, n, res=None: S(F.linear(So(aq(t, cfg, act_quant)), So(T[f"{n}.w"]), T[f"{n}.b"]) if res is None else
+                                   res + F.linear(So(aq(t, cfg, act_quant)), So(T[f"{n}.w"]), T[f"{n}.b"]))
     a1 = S(layer_norm(x, T["ln1w"], T["ln1b"], eps))
     a2 = S(layer_norm(x, T["ln2w"], T["ln2b"], eps))
     qkv = lin(a1, "qkv").view(b, L, n_kv, rep + 2, d)

@@ -706,3 +706,135 @@ def test_gemm_s8_exact(ops):
         torch.cuda.synchronize()
         full = ref + rt[:, None] * cb[None, :] + rb[:, None] * ct[None, :] + K * rb[:, None] * cb[None, :] + bias + res.float()
         torch.testing.assert_close(Cb.float(), full, rtol=1e-2, atol=1e-2 * float(full.abs().max()))
+
+
+# ---------------------------------------------------------------- exact-integer operands (s8 side outputs)
+def _s8_reconstruct(o):
+    """(code - z0) * scale + beta == (code - zp) * scale: the dequantised row the integer operand stands for."""
+    return o.codes.float() * o.scale[:, None] + o.beta[:, None]
+
+
+@pytest.mark.parametrize("n_bits", [4, 6, 8])
+def test_s8_side_output_of_the_activation_quantisers(ops, n_bits):
+    """oq_act_quant_fwd / oq_norm_act_quant_fwd / oq_swiglu_act_quant_fwd with an s8 operand: the bf16 fake-quant output is
+    unchanged (bit for bit equal to the call without the side output), the integer operand reconstructs the same
+    dequantised values, t is the scaled code sum, and rows whose zero point leaves the int8-representable range (all-positive
+    / all-negative rows) carry the remainder in beta."""
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    rows, C = 96, 512
+    x = torch.randn(rows, C, device="cuda", generator=gen)
+    x[3] = x[3].abs() + 2.0          # zero point far below 0
+    x[7] = -x[7].abs() - 1.0         # zero point above qmax
+    xb = x.to(torch.bfloat16)
+    y0, y1 = torch.empty_like(xb), torch.empty_like(xb)
+    o = ops.S8Operand(rows, C, "cuda")
+    ops.act_quant_fwd(xb, y0, n_bits=n_bits)
+    ops.act_quant_fwd(xb, y1, n_bits=n_bits, s8=o)
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1)
+    deq = orc.fake_quant(xb.float(), n_bits, recip_div=True)     # fp32 dequantised values (before the bf16 store)
+    torch.testing.assert_close(_s8_reconstruct(o), deq, rtol=2e-6, atol=1e-6)
+    torch.testing.assert_close(o.t, o.scale * o.codes.float().sum(1), rtol=1e-6, atol=1e-6)
+    assert float(o.beta[3].abs()) > 0 and float(o.beta[7].abs()) > 0
+    if n_bits < 8:
+        assert int((o.beta == 0).sum()) >= rows - 2            # rows that straddle zero need no correction
+    assert int(o.codes.int().abs().max()) <= 128
+    # norm + quantiser
+    w = torch.rand(C, device="cuda", generator=gen) + 0.5
+    yn, q0, q1 = torch.empty_like(xb), torch.empty_like(xb), torch.empty_like(xb)
+    o2 = ops.S8Operand(rows, C, "cuda")
+    ops.norm_act_quant_fwd(xb, w, None, 1e-6, 0, yn, q0, n_bits=n_bits)
+    ops.norm_act_quant_fwd(xb, w, None, 1e-6, 0, yn, q1, n_bits=n_bits, s8=o2)
+    torch.cuda.synchronize()
+    assert torch.equal(q0, q1)
+    torch.testing.assert_close(_s8_reconstruct(o2), orc.fake_quant(yn.float(), n_bits, recip_div=True), rtol=2e-6, atol=1e-6)
+    torch.testing.assert_close(o2.t, o2.scale * o2.codes.float().sum(1), rtol=1e-6, atol=1e-6)
+    # SwiGLU + quantiser
+    F_ = 768
+    gu = torch.randn(rows, 2 * F_, device="cuda", generator=gen).to(torch.bfloat16)
+    m0, m1 = torch.empty(rows, F_, device="cuda", dtype=torch.bfloat16), torch.empty(rows, F_, device="cuda", dtype=torch.bfloat16)
+    o3 = ops.S8Operand(rows, F_, "cuda")
+    ops.swiglu_act_quant_fwd(gu, m0, n_bits=n_bits)
+    ops.swiglu_act_quant_fwd(gu, m1, n_bits=n_bits, s8=o3)
+    torch.cuda.synchronize()
+    assert torch.equal(m0, m1)
+    torch.testing.assert_close(_s8_reconstruct(o3).to(torch.bfloat16).float(), m1.float(), rtol=1e-2, atol=1e-6)
+    torch.testing.assert_close(o3.t, o3.scale * o3.codes.float().sum(1), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("n_bits,let", [(4, True), (6, False), (8, True)])
+def test_s8_side_output_of_the_weight_quantiser(ops, n_bits, let):
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    N, K = 320, 1024
+    W = (torch.randn(N, K, device="cuda", generator=gen) * 0.05).half().float()
+    W[5] = W[5].abs() + 0.01          # a channel that does not straddle zero
+    up = torch.full((N,), 3.0, device="cuda")
+    kw = dict(col_scale=torch.rand(K, device="cuda", generator=gen) + 0.5,
+              row_scale=torch.rand(N, device="cuda", generator=gen) + 0.5, row_op=2) if let else {}
+    ref = run_wq(ops, W, n_bits, False, 0, up, up, True, **kw)
+    o = ops.S8Operand(N, K, "cuda")
+    out = dict(wq_f32=torch.empty(N, K, device="cuda"), zp_out=torch.empty(N, device="cuda"))
+    ops.weight_quant_fwd(W, n_bits=n_bits, up=up, low=up, recip_div=True, s8=o, **out, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(out["wq_f32"], ref["wq_f32"]) and torch.equal(o.scale, ref["scale_out"]) and torch.equal(out["zp_out"], ref["zp_out"])
+    torch.testing.assert_close(_s8_reconstruct(o), ref["wq_f32"], rtol=2e-6, atol=1e-7)
+    torch.testing.assert_close(o.t, o.scale * o.codes.float().sum(1), rtol=1e-6, atol=1e-7)
+    assert float(o.beta[5].abs()) > 0
+    z0 = ref["zp_out"].clamp(max(0, 2 ** n_bits - 1 - 127), min(2 ** n_bits - 1, 128))
+    assert torch.equal(o.codes.float(), ref["codes"].float() - z0[:, None])
+
+
+def test_linear_s8_equals_the_linear_of_the_fake_quantised_operands(ops):
+    """QuantLinear forward from the integer operands (quantiser side outputs -> oq_gemm_s8) against F.linear of the fp32
+    dequantised operands, LLaMA-7B down_proj-like K, including rows / channels with out-of-range zero points."""
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    M, N, K = 384, 512, 11008
+    x = torch.randn(M, K, device="cuda", generator=gen)
+    x[1] = x[1].abs() + 0.5
+    W = (torch.randn(N, K, device="cuda", generator=gen) * 0.02).half().float()
+    W[2] = -W[2].abs() - 0.001
+    xb = x.to(torch.bfloat16)
+    for bits in (4, 6):
+        xq, wq = torch.empty_like(xb), torch.empty(N, K, device="cuda")
+        xo, wo = ops.S8Operand(M, K, "cuda"), ops.S8Operand(N, K, "cuda")
+        ops.act_quant_fwd(xb, xq, n_bits=bits, s8=xo)
+        ops.weight_quant_fwd(W, n_bits=bits, recip_div=True, wq_f32=wq, s8=wo)
+        bias = torch.randn(N, device="cuda", generator=gen)
+        res = torch.randn(M, N, device="cuda", generator=gen).to(torch.bfloat16)
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ops.linear_s8_fwd(xo, wo, out, bias=bias, residual=res, alpha=0.5)
+        torch.cuda.synchronize()
+        xdeq = orc.fake_quant(xb.float(), bits, recip_div=True)
+        want = 0.5 * (xdeq.double() @ wq.double().t()).float() + bias + res.float()
+        torch.testing.assert_close(out.float(), want, rtol=8e-3, atol=8e-3 * float(want.abs().mean()))
+        # tighter: fp32 output, no bf16 rounding of the result
+        out32 = torch.empty(M, N, device="cuda")
+        ops.linear_s8_fwd(xo, wo, out32)
+        torch.cuda.synchronize()
+        want32 = (xdeq.double() @ wq.double().t()).float()
+        torch.testing.assert_close(out32, want32, rtol=1e-4, atol=1e-4 * float(want32.abs().mean()))
+
+
+def test_engine_s8_forward_agrees_with_the_bf16_forward(monkeypatch):
+    """The same W4A4 block stepped with the exact-integer forward linears and with the bf16 ones: first-step loss within
+    the bf16 operand-rounding band, gradients aligned."""
+    from omniquant_b200.engine import BlockEngine, QuantConfig
+    g = torch.Generator().manual_seed(0)
+    H, F_, heads, T = 512, 1024, 4, 128
+    r = lambda *s, sc=0.03: (torch.randn(*s, generator=g) * sc).half().float()
+    W = {"q": r(H, H), "k": r(H, H), "v": r(H, H), "o": r(H, H), "gate": r(F_, H), "up": r(F_, H), "down": r(H, F_),
+         "ln1": 1 + r(H, sc=0.1), "ln2": 1 + r(H, sc=0.1)}
+    x = torch.randn(T, H, generator=g).cuda().to(torch.bfloat16)
+    tgt = torch.roll(x, 1, 0)
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("OQ_S8", flag)
+        eng = BlockEngine("llama", W, n_heads=heads, seq_len=T, eps=1e-6,
+                          qcfg=QuantConfig(wbits=4, abits=4, group_size=0, lwc=True, let=True, recip_div=True))
+        assert eng.s8 == (flag == "1")
+        loss = float(eng.train_step(x, tgt).clone())
+        torch.cuda.synchronize()
+        res.append((loss, eng.grads.clone()))
+    assert abs(res[0][0] - res[1][0]) / res[1][0] < 5e-3, (res[0][0], res[1][0])
+    a, b = res[0][1].double(), res[1][1].double()
+    assert float((a @ b) / (a.norm() * b.norm())) > 0.98

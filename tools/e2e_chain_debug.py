@@ -33,3 +33,19 @@ try:
     omniquant(lm, args, None, act, None, logging.getLogger("oq"), inps=x)
 except FloatingPointError as e:
     print("FAILED:", e)
+    from omniquant_b200.models import _block
+    torch.cuda.synchronize()
+    for eng in _block._ENGINES.values():
+        fin = lambda t: bool(torch.isfinite(t.float()).all())
+        st = lambda t: f"min {float(t.float().min()):.4g} max {float(t.float().max()):.4g} finite {fin(t)}"
+        for k in eng.layout:
+            print("  param", k, st(eng.p[k]), "| grad", st(eng.g[k]))
+        for g, w in eng.Wq.items():
+            print("  Wq", g, st(w), "| W", st(eng.W[g]))
+        for k, st_ in eng.qstat.items():
+            print("  qstat", k, "scale", st(st_["scale"]), "zp", st(st_["zp"]))
+        for k, b in eng.bufs.items():
+            if not fin(b):
+                print("  non-finite buffer", k, tuple(b.shape), b.dtype, "nan frac", float(torch.isnan(b.float()).float().mean()),
+                      "inf frac", float(torch.isinf(b.float()).float().mean()))
+        print("  step", int(eng.step_dev))
