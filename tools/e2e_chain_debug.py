@@ -27,6 +27,52 @@ args = SimpleNamespace(net=c.net, nsamples=ns, batch_size=1, epochs=c.epochs, le
                        output_dir=None, cuda_graph=os.environ.get("OQ_NO_GRAPH") != "1", deactive_amp=True)
 quant_param_dicts(args)
 model, act, layers = bench._host_model(c, W, blocks)
+
+# ---- per-step finiteness watch (OQ_NO_GRAPH=1): at the first non-finite loss dump the forward buffers of that step
+from omniquant_b200 import engine as E  # noqa: E402
+_orig_step = E.BlockEngine.train_step
+_state = {"n": 0}
+
+
+def _fin(t):
+    t = t.codes if hasattr(t, "codes") else t
+    return bool(torch.isfinite(t.float()).all())
+
+
+def _watched(self, x, target, target2=None, allreduce=None):
+    out = _orig_step(self, x, target, target2, allreduce)
+    _state["n"] += 1
+    if os.environ.get("OQ_NO_GRAPH") == "1" and not bool(torch.isfinite(out).all()):
+        print(f"first non-finite loss at engine step {_state['n']} (AdamW step {int(self.step_dev)})")
+        print("  input x finite", _fin(x), "target finite", _fin(target))
+        st = lambda t: f"min {float(t.float().min()):.4g} max {float(t.float().max()):.4g} finite {_fin(t)}"
+        for k in self.layout:
+            print("  param", k, st(self.p[k]), "| grad", st(self.g[k]))
+        for k, v in self.tmp.items():
+            if isinstance(v, torch.Tensor):
+                print("  tmp", k, st(v))
+        for g, w in self.Wq.items():
+            print("  Wq", g, st(w))
+        for k, q in self.qstat.items():
+            print("  qstat", k, "scale", st(q["scale"]), "zp", st(q["zp"]), "xmin", st(q["xmin"]), "xmax", st(q["xmax"]))
+        order = ["a1", "a1q", "qkv", "qkvq", "S", "P", "O", "Oq", "h1", "a2", "a2q", "f1", "mq", "out", "dout"]
+        for k in order + [k for k in self.bufs if k not in order]:
+            b = self.bufs.get(k)
+            if b is None:
+                continue
+            t = b.codes if hasattr(b, "codes") else b
+            if not _fin(t):
+                tf = t.float()
+                bad = ~torch.isfinite(tf)
+                rows = bad.reshape(-1, tf.shape[-1]).any(1).nonzero().flatten()[:5].tolist()
+                print(f"  NON-FINITE {k} {tuple(t.shape)} nan {float(torch.isnan(tf).float().mean()):.4f} inf {float(torch.isinf(tf).float().mean()):.4f} first bad rows {rows}")
+            else:
+                print(f"  ok         {k} {tuple(t.shape)} absmax {float(t.float().abs().max()):.4g}")
+        raise FloatingPointError("stopped at the first non-finite step")
+    return out
+
+
+E.BlockEngine.train_step = _watched
 logging.basicConfig(level=logging.INFO, stream=sys.stdout, format="%(message)s")
 lm = SimpleNamespace(model=model, device=dev, _device=dev, seqlen=bench.T)
 try:
@@ -35,8 +81,8 @@ except FloatingPointError as e:
     print("FAILED:", e)
     from omniquant_b200.models import _block
     torch.cuda.synchronize()
-    for eng in _block._ENGINES.values():
-        fin = lambda t: bool(torch.isfinite(t.float()).all())
+    for eng in ([] if os.environ.get("OQ_NO_GRAPH") == "1" else _block._ENGINES.values()):
+        fin = lambda t: bool(torch.isfinite((t.codes if hasattr(t, "codes") else t).float()).all())
         st = lambda t: f"min {float(t.float().min()):.4g} max {float(t.float().max()):.4g} finite {fin(t)}"
         for k in eng.layout:
             print("  param", k, st(eng.p[k]), "| grad", st(eng.g[k]))
