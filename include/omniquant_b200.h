@@ -145,6 +145,25 @@ int oq_gemm_bf16(const void* A, int a_mn, long lda, long strideA, const void* B,
                  const void* residual, long ldr, long strideR, float alpha, int causal, int accumulate, int tile_n,
                  int max_ctas, oq_stream_t stream);
 
+/* ---- K5/K6: fused causal attention of QuantMatMul (QK^T -> softmax -> PV in one kernel; recompute backward) --------
+ * Replaces qkt_matmul / softmax / pv_matmul of QuantLlamaAttention.forward (models/int_llama_layer.py:141-163; OPT
+ * models/int_opt_layer.py:124-197, Falcon models/int_falcon_layer.py:148-176) and their autograd on the already rotated +
+ * fake-quantised operands.  qkv: [batch*T, ld] bf16 holding every head's q / k / v rows (`width` valid columns);
+ * q of head h at column cq + (h / rep)*gq + (h % rep)*head_dim, k / v of K/V head g at ck / cv + g*gk (rep = heads /
+ * kv_heads; LLaMA / OPT [q | k | v]: cq 0, gq rep*d, ck H, cv H+Hkv, gk d; Falcon per group [rep q | k | v]: gq = gk =
+ * (rep+2)*d, ck rep*d, cv (rep+1)*d).  Scores are alpha*(q.k) rounded to fp16, softmax in fp32 with the causal mask,
+ * P rounded to bf16 after normalisation.  O: [batch*T, heads*head_dim] bf16.  row_max / row_invl: [batch, heads, T] fp32
+ * softmax statistics saved for the backward (nothing of size T x T is written).  Needs head_dim 128 and T %% 128 == 0
+ * (oq_attn_supported); other shapes use oq_gemm_bf16 + oq_softmax_fwd/bwd.
+ * Backward: dqkv (same column layout as qkv, row stride ldg) receives dq, dk, dv of every head (each element written
+ * once; K/V heads shared by several query heads are summed inside the kernel); delta_ws: [batch, heads, T] fp32 scratch. */
+int oq_attn_supported(int T, int head_dim);
+int oq_attn_fwd(const void* qkv, long ld, long width, int batch, int T, int heads, int kv_heads, int head_dim, int cq, int gq,
+                int ck, int cv, int gk, float alpha, void* O, long ldo, float* row_max, float* row_invl, oq_stream_t stream);
+int oq_attn_bwd(const void* qkv, long ld, long width, int batch, int T, int heads, int kv_heads, int head_dim, int cq, int gq,
+                int ck, int cv, int gk, float alpha, const void* O, long ldo, const void* dO, long lddo, const float* row_max,
+                const float* row_invl, float* delta_ws, void* dqkv, long ldg, oq_stream_t stream);
+
 /* ---- elementwise / reductions ----------------------------------------------
  * SwiGLU of QuantLlamaMLP.forward (models/int_llama_layer.py:44-45): gu = [gate | up] [rows, 2F]. */
 int oq_swiglu_fwd(const void* gu, long ldgu, void* m, long ldm, long rows, int F, oq_stream_t stream);

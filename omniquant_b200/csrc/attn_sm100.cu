@@ -1,0 +1,823 @@
+// K5 / K6: fused causal attention of QuantMatMul -- QK^T, softmax and PV in one kernel, and a recompute backward -- on the
+// 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA with 128-byte swizzle), sm_100a only.
+//
+// Reference: QuantLlamaAttention.forward, models/int_llama_layer.py:141-163 (qkt_matmul -> / sqrt(d) -> + mask ->
+// fp32 softmax -> cast -> pv_matmul) and its autograd; OPT / Falcon call sites models/int_opt_layer.py:124-197,
+// models/int_falcon_layer.py:148-176.  The operands are the already rotated + fake-quantised Q / K / V rows of the fused
+// [tokens, q | k | v] matrix (csrc/act_quant.cu: aq_warp), so quantisation stays exactly where the reference has it.
+//
+// Why: the unfused chain (batched GEMM -> softmax kernel -> batched GEMM, and five launches in the backward) moves the
+// [heads, T, T] scores / probabilities / their gradients through HBM: ~1.5 GB per optimiser step at LLaMA-7B shapes for
+// ~0.2 GB of algorithmic Q / K / V / O traffic (profiles/r1_gemm_ncu_full_summary.csv).  Here nothing of size T x T
+// leaves the SM: the forward keeps only two fp32 row statistics, the backward recomputes the probabilities tile by tile.
+//
+// Numerics follow the unfused path: scores are alpha * (q . k) rounded to fp16 (the reference's autocast dtype), the
+// softmax is evaluated in fp32 with the FINAL row maximum and sum (two passes over the key tiles: P is normalised before
+// it is rounded to bf16, like softmax-then-cast), P and dS are bf16 MMA operands, O / dQ / dK / dV are bf16.
+//
+//   forward   CTA = (sample, head, 128-query tile); key tiles j <= i.  pass 1: S_j -> m, l.  pass 2: S_j -> P_j -> O += P_j V_j.
+//   dK / dV   CTA = (sample, K/V head, 128-key tile); loops over the group's query heads and the 64-query half tiles at or
+//             below the diagonal; transposed formulation (S^T = K Q^T, dP^T = V dO^T) so that P^T and dS^T come out of TMEM
+//             with one key row per thread and feed dV += P^T dO, dK += dS^T Q as K-major A operands.
+//   dQ        CTA = (sample, head, 128-query tile); loops over 64-key half tiles; dQ += dS K.
+// No atomics: every output element has one writer (dK / dV of a grouped-query K/V head are summed in TMEM).
+//
+// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM allocator, warps 4-7 softmax /
+// epilogue (one accumulator row per thread: TMEM lane = row).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "mbar.cuh"
+
+namespace {
+
+constexpr int D = 128;                 // head dimension
+constexpr int NUM_THREADS = 256;
+constexpr int ROW_B = 128;             // bytes per shared-memory row of a 64-column bf16 block (one swizzle row)
+constexpr int BLK128 = 128 * ROW_B;    // 64-column block of a 128-row tile: 16 KB
+constexpr int BLK64 = 64 * ROW_B;      // 64-column block of a  64-row tile:  8 KB
+constexpr int TILE128 = 2 * BLK128;    // [128 x 128] bf16
+constexpr int TILE64 = 2 * BLK64;      // [ 64 x 128] bf16
+
+struct AttnParams {
+  int T, heads, kv_heads, rep, batch;
+  int cq, gq, ck, cv, gk;   // column of q head h: cq + (h / rep) * gq + (h % rep) * D;  k / v of K/V head g: ck / cv + g * gk
+  float alpha;
+  bf16* O; long ldo;                      // forward output [batch*T, heads*D]
+  float* row_max; float* row_invl;        // [batch, heads, T]: max of the fp16 scores, 1 / sum exp(s - max)
+  const float* delta;                     // [batch, heads, T]: rowsum(dO * O)
+  bf16* dqkv; long ldg;                   // backward output, same column layout as the operand matrix
+};
+
+__device__ __forceinline__ int col_q(const AttnParams& p, int head) { return p.cq + (head / p.rep) * p.gq + (head % p.rep) * D; }
+__device__ __forceinline__ int col_k(const AttnParams& p, int g) { return p.ck + g * p.gk; }
+__device__ __forceinline__ int col_v(const AttnParams& p, int g) { return p.cv + g * p.gk; }
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// 64-bit shared-memory matrix descriptor, SWIZZLE_128B (same encoding as gemm_sm100.cu)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;      // SBO: 8-row groups 1024 B apart
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// K-major operand: rows of 128 B, a 64-column block per `blk` bytes; k-step s (16 elements) of a K = 16*nsteps operand
+__device__ __forceinline__ uint64_t desc_k(uint32_t base, int s, uint32_t blk) { return make_desc(base + (s >> 2) * blk + (s & 3) * 32, 16); }
+// MN-major operand (the row-major tile read with the row index as K): 64-column blocks `blk` bytes apart (LBO), 16 rows per k-step
+__device__ __forceinline__ uint64_t desc_mn(uint32_t base, int s, uint32_t blk) { return make_desc(base + s * (16 * ROW_B), blk); }
+// instruction descriptor: D = f32, A = B = bf16, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc(int n, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(b_mn ? 1 : 0) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// alpha * acc rounded to fp16 (the dtype the reference's autocast keeps the scores in), as fp32
+__device__ __forceinline__ float score16(uint32_t bits, float alpha) {
+  return __half2float(__float2half_rn(__uint_as_float(bits) * alpha));
+}
+// 8 values -> one 16-byte chunk of a swizzled 128-byte row (row r of a 1024-byte aligned block, logical chunk c)
+__device__ __forceinline__ void st_chunk(uint8_t* blk, int r, int c, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf2(v[0], v[1]); u.y = pack_bf2(v[2], v[3]); u.z = pack_bf2(v[4], v[5]); u.w = pack_bf2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(blk + r * ROW_B + ((c ^ (r & 7)) << 4)) = u;
+}
+
+// ================================================================== forward
+constexpr int FWD_SMEM = TILE128 /*Q*/ + 2 * 2 * TILE128 /*K,V x 2 stages*/ + TILE128 /*P*/ + 1024 + 256;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + TILE128;                 // stage s: K at sKV + s * 2 * TILE128, V right behind it
+  uint8_t* sP = sKV + 4 * TILE128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + TILE128);
+  uint64_t* q_full = bars;          // [1]
+  uint64_t* kv_full = bars + 1;     // [2]
+  uint64_t* kv_empty = bars + 3;    // [2]
+  uint64_t* s_full = bars + 5;      // [2] MMA -> softmax
+  uint64_t* s_empty = bars + 7;     // [2] softmax -> MMA (one arrive per softmax warp)
+  uint64_t* p_full = bars + 9;      // [1] softmax -> MMA
+  uint64_t* p_empty = bars + 10;    // [1] MMA -> softmax
+  uint64_t* o_full = bars + 11;     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = p.T / 128, per = p.heads * p.batch;
+  const int qt = nt - 1 - (int)blockIdx.x / per;          // heavy (late) query tiles first
+  const int rem = (int)blockIdx.x % per;
+  const int head = rem % p.heads, b = rem / p.heads;
+  const int g = head / p.rep;
+  const int row0 = b * p.T;
+  const int nj = qt + 1, nit = 2 * nj;
+  const int qc = col_q(p, head), kc = col_k(p, g), vc = col_v(p, g);
+
+  if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm128) : "memory");
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(p_empty, 1);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;      // S0 [0,128)  S1 [128,256)  O [256,384)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TILE128);
+      tma_load_2d(sQ, &tm128, q_full, qc, row0 + qt * 128);
+      tma_load_2d(sQ + BLK128, &tm128, q_full, qc + 64, row0 + qt * 128);
+      for (int t = 0; t < nit; ++t) {
+        const int st = t & 1, pass = t >= nj, j = pass ? t - nj : t;
+        mbar_wait(&kv_empty[st], ((t >> 1) & 1) ^ 1);
+        uint8_t* sK = sKV + st * 2 * TILE128;
+        mbar_expect_tx(&kv_full[st], pass ? 2 * TILE128 : TILE128);
+        tma_load_2d(sK, &tm128, &kv_full[st], kc, row0 + j * 128);
+        tma_load_2d(sK + BLK128, &tm128, &kv_full[st], kc + 64, row0 + j * 128);
+        if (pass) {
+          tma_load_2d(sK + TILE128, &tm128, &kv_full[st], vc, row0 + j * 128);
+          tma_load_2d(sK + TILE128 + BLK128, &tm128, &kv_full[st], vc + 64, row0 + j * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_s = make_idesc(128, 0), id_o = make_idesc(128, 1);
+      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+      uint32_t p_phase = 0;
+      auto pv = [&](int u) {        // O += P(u) V(u)
+        const uint32_t aV = smem_u32(sKV + (u & 1) * 2 * TILE128 + TILE128);
+        mbar_wait(p_full, p_phase);
+        p_phase ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 8; ++s) tc_mma(tmem + 256, desc_k(aP, s, BLK128), desc_mn(aV, s, BLK128), id_o, (u > nj || s > 0) ? 1u : 0u);
+        tc_commit(p_empty);
+        tc_commit(&kv_empty[u & 1]);
+      };
+      mbar_wait(q_full, 0);
+      for (int t = 0; t < nit; ++t) {
+        const int st = t & 1;
+        const uint32_t ph = (t >> 1) & 1;
+        mbar_wait(&kv_full[st], ph);
+        mbar_wait(&s_empty[st], ph ^ 1);
+        tc_fence_after();
+        const uint32_t aK = smem_u32(sKV + st * 2 * TILE128);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) tc_mma(tmem + st * 128, desc_k(aQ, s, BLK128), desc_k(aK, s, BLK128), id_s, s > 0 ? 1u : 0u);
+        if (t < nj) tc_commit(&kv_empty[st]);
+        tc_commit(&s_full[st]);
+        if (t > nj) pv(t - 1);
+      }
+      pv(nit - 1);
+      tc_commit(o_full);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3, r = q * 32 + lane;
+    const int qrow = qt * 128 + r;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    float m = -INFINITY, l = 0.f;
+    // ---- pass 1: row maximum and sum
+    for (int t = 0; t < nj; ++t) {
+      const int sb = t & 1;
+      mbar_wait(&s_full[sb], (t >> 1) & 1);
+      tc_fence_after();
+      const int lim = (t == qt) ? r + 1 : 128;        // causal: keys c <= r on the diagonal tile
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(lane_base + sb * 128 + c0, v);
+        tc_wait_ld();
+        float s[32], mx = m;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          s[i] = (c0 + i < lim) ? score16(v[i], p.alpha) : -INFINITY;
+          mx = fmaxf(mx, s[i]);
+        }
+        float add = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) add += __expf(s[i] - mx);
+        l = l * __expf(m - mx) + add;      // first chunk: m = -inf, l = 0 -> 0 * exp(-inf) = 0 (key 0 is always visible: mx finite)
+        m = mx;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);
+    }
+    const float inv = 1.0f / l;
+    const long srow = ((long)b * p.heads + head) * p.T + qrow;
+    p.row_max[srow] = m;
+    p.row_invl[srow] = inv;
+    // ---- pass 2: probabilities with the final statistics -> shared memory (A operand of P V)
+    for (int t = nj; t < nit; ++t) {
+      const int sb = t & 1, j = t - nj;
+      mbar_wait(&s_full[sb], (t >> 1) & 1);
+      tc_fence_after();
+      if (j > 0) mbar_wait(p_empty, (j - 1) & 1);      // P V of the previous tile has finished reading sP
+      const int lim = (j == qt) ? r + 1 : 128;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(lane_base + sb * 128 + c0, v);
+        tc_wait_ld();
+        uint8_t* blk = sP + (c0 >> 6) * BLK128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float pr[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = c0 + ch * 8 + e;
+            pr[e] = (c < lim) ? __expf(score16(v[ch * 8 + e], p.alpha) - m) * inv : 0.f;
+          }
+          st_chunk(blk, r, ((c0 & 63) >> 3) + ch, pr);
+        }
+      }
+      fence_proxy_async();      // generic-proxy writes of sP -> visible to the tensor core's async proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(p_full);
+        mbar_arrive(&s_empty[sb]);
+      }
+    }
+    // ---- epilogue
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    bf16* orow = p.O + (long)(row0 + qrow) * p.ldo + head * D;
+#pragma unroll 1
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t v[32];
+      tc_ld32(lane_base + 256 + c0, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        float t8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t8[e] = __uint_as_float(v[i + e]);
+        store_bf8(orow + c0 + i, t8);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// ================================================================== backward: delta = rowsum(dO * O)
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* O, long ldo, const bf16* dO, long lddo, float* delta, int batch,
+                                                         int T, int heads) {
+  const long w = (long)blockIdx.x * 8 + (threadIdx.x >> 5);      // one warp per (token row, head)
+  const int lane = threadIdx.x & 31;
+  const long total = (long)batch * T * heads;
+  if (w >= total) return;
+  const long row = w / heads;
+  const int head = (int)(w % heads);
+  float a[4], c[4];
+  load_bf4(O + row * ldo + head * D + lane * 4, a);
+  load_bf4(dO + row * lddo + head * D + lane * 4, c);
+  float s = a[0] * c[0] + a[1] * c[1] + a[2] * c[2] + a[3] * c[3];
+  s = warp_reduce(s, OpSum());
+  if (lane == 0) {
+    const long bi = row / T, t = row % T;
+    delta[(bi * heads + head) * T + t] = s;
+  }
+}
+
+// ================================================================== backward: dK, dV
+constexpr int DKV_SMEM = 2 * TILE128 /*K,V*/ + 2 * 2 * TILE64 /*Q,dO x 2*/ + 2 * 2 * BLK128 /*P^T,dS^T x 2*/ + 2 * 64 * 16 /*stats*/ + 1024 + 256;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64,
+                const __grid_constant__ CUtensorMap tmdo64, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + TILE128;
+  uint8_t* sQdO = sV + TILE128;               // stage s: Q at + s * 2 * TILE64, dO right behind it
+  uint8_t* sPS = sQdO + 4 * TILE64;           // buffer s: P^T at + s * 2 * BLK128, dS^T right behind it
+  float4* sstat = reinterpret_cast<float4*>(sPS + 4 * BLK128);   // [2][64]: (max, 1/l, delta, -) of the stage's queries
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sstat) + 2 * 64 * 16);
+  uint64_t* kv_full = bars;          // [1]
+  uint64_t* qdo_full = bars + 1;     // [2]
+  uint64_t* qdo_empty = bars + 3;    // [2]
+  uint64_t* s_full = bars + 5;       // [2]
+  uint64_t* s_empty = bars + 7;      // [2]
+  uint64_t* p_full = bars + 9;       // [2]
+  uint64_t* p_empty = bars + 11;     // [2]
+  uint64_t* acc_full = bars + 13;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = p.T / 128, per = p.kv_heads * p.batch;
+  const int j = (int)blockIdx.x / per;                      // key tile; early tiles see the most queries: heavy first
+  const int rem = (int)blockIdx.x % per;
+  const int g = rem % p.kv_heads, b = rem / p.kv_heads;
+  const int row0 = b * p.T;
+  const int nh = 2 * nt - 2 * j;                            // 64-query half tiles at or below the diagonal
+  const int nit = p.rep * nh;
+  const int kc = col_k(p, g), vc = col_v(p, g);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm128) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm64) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmdo64) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;   // buffer s: S^T [s*128, +64)  dP^T [s*128+64, +64);  dK [256,384)  dV [384,512)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * TILE128);
+      tma_load_2d(sK, &tm128, kv_full, kc, row0 + j * 128);
+      tma_load_2d(sK + BLK128, &tm128, kv_full, kc + 64, row0 + j * 128);
+      tma_load_2d(sV, &tm128, kv_full, vc, row0 + j * 128);
+      tma_load_2d(sV + BLK128, &tm128, kv_full, vc + 64, row0 + j * 128);
+      for (int it = 0; it < nit; ++it) {
+        const int st = it & 1, head = g * p.rep + it / nh, i64 = 2 * j + it % nh;
+        mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
+        uint8_t* sQ = sQdO + st * 2 * TILE64;
+        mbar_expect_tx(&qdo_full[st], 2 * TILE64);
+        const int qc = col_q(p, head), r = row0 + i64 * 64;
+        tma_load_2d(sQ, &tm64, &qdo_full[st], qc, r);
+        tma_load_2d(sQ + BLK64, &tm64, &qdo_full[st], qc + 64, r);
+        tma_load_2d(sQ + TILE64, &tmdo64, &qdo_full[st], head * D, r);
+        tma_load_2d(sQ + TILE64 + BLK64, &tmdo64, &qdo_full[st], head * D + 64, r);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_s = make_idesc(64, 0), id_a = make_idesc(128, 1);
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+      auto accumulate = [&](int u) {     // dV += P^T dO,  dK += dS^T Q   (K = the 64 queries of stage u)
+        const int sb = u & 1;
+        const uint32_t aQ = smem_u32(sQdO + sb * 2 * TILE64), adO = aQ + TILE64;
+        const uint32_t aPT = smem_u32(sPS + sb * 2 * BLK128), adST = aPT + BLK128;
+        mbar_wait(&p_full[sb], (u >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 4; ++s) tc_mma(tmem + 384, desc_k(aPT, s, BLK128), desc_mn(adO, s, BLK64), id_a, (u > 0 || s > 0) ? 1u : 0u);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) tc_mma(tmem + 256, desc_k(adST, s, BLK128), desc_mn(aQ, s, BLK64), id_a, (u > 0 || s > 0) ? 1u : 0u);
+        tc_commit(&p_empty[sb]);
+        tc_commit(&qdo_empty[sb]);
+      };
+      mbar_wait(kv_full, 0);
+      for (int it = 0; it < nit; ++it) {
+        const int st = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&qdo_full[st], ph);
+        mbar_wait(&s_empty[st], ph ^ 1);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQdO + st * 2 * TILE64), adO = aQ + TILE64;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) tc_mma(tmem + st * 128, desc_k(aK, s, BLK128), desc_k(aQ, s, BLK64), id_s, s > 0 ? 1u : 0u);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) tc_mma(tmem + st * 128 + 64, desc_k(aV, s, BLK128), desc_k(adO, s, BLK64), id_s, s > 0 ? 1u : 0u);
+        tc_commit(&s_full[st]);
+        if (it > 0) accumulate(it - 1);
+      }
+      accumulate(nit - 1);
+      tc_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3, kr = q * 32 + lane;           // key row of this thread
+    const int kg = j * 128 + kr;
+    const int tid = threadIdx.x - 128;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    for (int it = 0; it < nit; ++it) {
+      const int sb = it & 1, head = g * p.rep + it / nh, i64 = 2 * j + it % nh;
+      const uint32_t ph = (it >> 1) & 1;
+      if (tid < 64) {
+        const long sr = ((long)b * p.heads + head) * p.T + i64 * 64 + tid;
+        sstat[sb * 64 + tid] = make_float4(p.row_max[sr], p.row_invl[sr], p.delta[sr], 0.f);
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(&s_full[sb], ph);
+      tc_fence_after();
+      mbar_wait(&p_empty[sb], ph ^ 1);        // the accumulate MMAs that read this P^T / dS^T buffer two steps ago are done
+      uint8_t* bPT = sPS + sb * 2 * BLK128;
+      uint8_t* bdST = bPT + BLK128;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t sv[32], dv[32];
+        tc_ld32(lane_base + sb * 128 + c0, sv);
+        tc_ld32(lane_base + sb * 128 + 64 + c0, dv);
+        tc_wait_ld();
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float pr[8], ds[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = c0 + ch * 8 + e;
+            const float4 stt = sstat[sb * 64 + c];
+            const bool vis = kg <= i64 * 64 + c;             // causal: key position <= query position
+            const float pe = vis ? __expf(score16(sv[ch * 8 + e], p.alpha) - stt.x) * stt.y : 0.f;
+            pr[e] = pe;
+            ds[e] = pe * (__uint_as_float(dv[ch * 8 + e]) - stt.z);
+          }
+          st_chunk(bPT, kr, (c0 >> 3) + ch, pr);
+          st_chunk(bdST, kr, (c0 >> 3) + ch, ds);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&p_full[sb]);
+        mbar_arrive(&s_empty[sb]);
+      }
+    }
+    // ---- epilogue: dK (x alpha: s = alpha q.k), dV
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    bf16* grow = p.dqkv + (long)(row0 + kg) * p.ldg;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 2 * D; c0 += 32) {
+      uint32_t v[32];
+      tc_ld32(lane_base + 256 + c0, v);
+      tc_wait_ld();
+      const bool is_k = c0 < D;
+      bf16* dst = grow + (is_k ? kc + c0 : vc + c0 - D);
+      const float sc = is_k ? p.alpha : 1.0f;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        float t8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t8[e] = __uint_as_float(v[i + e]) * sc;
+        store_bf8(dst + i, t8);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// ================================================================== backward: dQ
+constexpr int DQ_SMEM = 2 * TILE128 /*Q,dO*/ + 2 * 2 * TILE64 /*K,V x 2*/ + 2 * BLK128 /*dS x 2*/ + 1024 + 256;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64,
+               const __grid_constant__ CUtensorMap tmdo128, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + TILE128;
+  uint8_t* sKV = sdO + TILE128;                // stage s: K at + s * 2 * TILE64, V right behind it
+  uint8_t* sdS = sKV + 4 * TILE64;             // buffer s at + s * BLK128
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * BLK128);
+  uint64_t* qdo_full = bars;         // [1]
+  uint64_t* kv_full = bars + 1;      // [2]
+  uint64_t* kv_empty = bars + 3;     // [2]
+  uint64_t* s_full = bars + 5;       // [2]
+  uint64_t* s_empty = bars + 7;      // [2]
+  uint64_t* p_full = bars + 9;       // [2]
+  uint64_t* p_empty = bars + 11;     // [2]
+  uint64_t* acc_full = bars + 13;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = p.T / 128, per = p.heads * p.batch;
+  const int i = nt - 1 - (int)blockIdx.x / per;            // heavy (late) query tiles first
+  const int rem = (int)blockIdx.x % per;
+  const int head = rem % p.heads, b = rem / p.heads;
+  const int g = head / p.rep;
+  const int row0 = b * p.T;
+  const int nit = 2 * i + 2;                               // 64-key half tiles up to the diagonal
+  const int qc = col_q(p, head), kc = col_k(p, g), vc = col_v(p, g);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm128) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm64) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmdo128) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(qdo_full, 1);
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&kv_full[k], 1);
+      mbar_init(&kv_empty[k], 1);
+      mbar_init(&s_full[k], 1);
+      mbar_init(&s_empty[k], 4);
+      mbar_init(&p_full[k], 4);
+      mbar_init(&p_empty[k], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;   // buffer s: S [s*128, +64)  dP [s*128+64, +64);  dQ [256,384)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(qdo_full, 2 * TILE128);
+      tma_load_2d(sQ, &tm128, qdo_full, qc, row0 + i * 128);
+      tma_load_2d(sQ + BLK128, &tm128, qdo_full, qc + 64, row0 + i * 128);
+      tma_load_2d(sdO, &tmdo128, qdo_full, head * D, row0 + i * 128);
+      tma_load_2d(sdO + BLK128, &tmdo128, qdo_full, head * D + 64, row0 + i * 128);
+      for (int it = 0; it < nit; ++it) {
+        const int st = it & 1;
+        mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
+        uint8_t* sK = sKV + st * 2 * TILE64;
+        mbar_expect_tx(&kv_full[st], 2 * TILE64);
+        const int r = row0 + it * 64;
+        tma_load_2d(sK, &tm64, &kv_full[st], kc, r);
+        tma_load_2d(sK + BLK64, &tm64, &kv_full[st], kc + 64, r);
+        tma_load_2d(sK + TILE64, &tm64, &kv_full[st], vc, r);
+        tma_load_2d(sK + TILE64 + BLK64, &tm64, &kv_full[st], vc + 64, r);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_s = make_idesc(64, 0), id_a = make_idesc(128, 1);
+      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO);
+      auto accumulate = [&](int u) {     // dQ += dS K   (K = the 64 keys of stage u)
+        const int sb = u & 1;
+        const uint32_t aK = smem_u32(sKV + sb * 2 * TILE64), adS = smem_u32(sdS + sb * BLK128);
+        mbar_wait(&p_full[sb], (u >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 4; ++s) tc_mma(tmem + 256, desc_k(adS, s, BLK128), desc_mn(aK, s, BLK64), id_a, (u > 0 || s > 0) ? 1u : 0u);
+        tc_commit(&p_empty[sb]);
+        tc_commit(&kv_empty[sb]);
+      };
+      mbar_wait(qdo_full, 0);
+      for (int it = 0; it < nit; ++it) {
+        const int st = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&kv_full[st], ph);
+        mbar_wait(&s_empty[st], ph ^ 1);
+        tc_fence_after();
+        const uint32_t aK = smem_u32(sKV + st * 2 * TILE64), aV = aK + TILE64;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) tc_mma(tmem + st * 128, desc_k(aQ, s, BLK128), desc_k(aK, s, BLK64), id_s, s > 0 ? 1u : 0u);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) tc_mma(tmem + st * 128 + 64, desc_k(adO, s, BLK128), desc_k(aV, s, BLK64), id_s, s > 0 ? 1u : 0u);
+        tc_commit(&s_full[st]);
+        if (it > 0) accumulate(it - 1);
+      }
+      accumulate(nit - 1);
+      tc_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3, r = q * 32 + lane;
+    const int qg = i * 128 + r;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    const long sr = ((long)b * p.heads + head) * p.T + qg;
+    const float m = p.row_max[sr], inv = p.row_invl[sr], dl = p.delta[sr];
+    for (int it = 0; it < nit; ++it) {
+      const int sb = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&s_full[sb], ph);
+      tc_fence_after();
+      mbar_wait(&p_empty[sb], ph ^ 1);
+      uint8_t* bdS = sdS + sb * BLK128;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t sv[32], dv[32];
+        tc_ld32(lane_base + sb * 128 + c0, sv);
+        tc_ld32(lane_base + sb * 128 + 64 + c0, dv);
+        tc_wait_ld();
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float ds[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = c0 + ch * 8 + e;
+            const bool vis = it * 64 + c <= qg;
+            const float pe = vis ? __expf(score16(sv[ch * 8 + e], p.alpha) - m) * inv : 0.f;
+            ds[e] = pe * (__uint_as_float(dv[ch * 8 + e]) - dl);
+          }
+          st_chunk(bdS, r, (c0 >> 3) + ch, ds);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&p_full[sb]);
+        mbar_arrive(&s_empty[sb]);
+      }
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    bf16* dst = p.dqkv + (long)(row0 + qg) * p.ldg + qc;
+#pragma unroll 1
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t v[32];
+      tc_ld32(lane_base + 256 + c0, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int k = 0; k < 32; k += 8) {
+        float t8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t8[e] = __uint_as_float(v[k + e]) * p.alpha;
+        store_bf8(dst + c0 + k, t8);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+// 2-D bf16 map over a [rows, cols] row-major matrix (row stride ld elements); box 64 columns x box_rows rows
+int make_map(CUtensorMap* map, const void* base, long cols, long rows, long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  OQ_REQUIRE(enc, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  OQ_REQUIRE(r == CUDA_SUCCESS, "attention: cuTensorMapEncodeTiled failed (%d): base=%p cols=%ld rows=%ld ld=%ld", (int)r, base, cols, rows, ld);
+  return 0;
+}
+template <typename K>
+int set_smem(K kernel, int bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    oq_set_error("%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+int check_common(const char* fn, const void* qkv, long ld, int batch, int T, int heads, int kv_heads, int head_dim, int cq, int gq,
+                 int ck, int cv, int gk, long width) {
+  OQ_REQUIRE(qkv && batch > 0 && heads > 0 && kv_heads > 0 && heads % kv_heads == 0, "%s: null pointer or bad head counts", fn);
+  OQ_REQUIRE(head_dim == D && T >= 128 && T % 128 == 0, "%s: needs head_dim 128 and a sequence length that is a multiple of 128 "
+             "(got d=%d T=%d); use the unfused GEMM + softmax path otherwise", fn, head_dim, T);
+  OQ_REQUIRE(ld % 8 == 0 && (uintptr_t)qkv % 16 == 0 && cq % 8 == 0 && gq % 8 == 0 && ck % 8 == 0 && cv % 8 == 0 && gk % 8 == 0,
+             "%s: operand matrix must be 16-byte aligned with column offsets / strides that are multiples of 8", fn);
+  const int rep = heads / kv_heads;
+  const long last_q = cq + (long)(kv_heads - 1) * gq + (long)(rep - 1) * D + D;
+  const long last_k = ck + (long)(kv_heads - 1) * gk + D, last_v = cv + (long)(kv_heads - 1) * gk + D;
+  OQ_REQUIRE(last_q <= width && last_k <= width && last_v <= width && width <= ld, "%s: head columns exceed the matrix width", fn);
+  return 0;
+}
+AttnParams base_params(int batch, int T, int heads, int kv_heads, int cq, int gq, int ck, int cv, int gk, float alpha) {
+  AttnParams p = {};
+  p.T = T; p.heads = heads; p.kv_heads = kv_heads; p.rep = heads / kv_heads; p.batch = batch;
+  p.cq = cq; p.gq = gq; p.ck = ck; p.cv = cv; p.gk = gk; p.alpha = alpha;
+  return p;
+}
+
+}  // namespace
+
+extern "C" int oq_attn_supported(int T, int head_dim) { return (head_dim == D && T >= 128 && T % 128 == 0) ? 1 : 0; }
+
+extern "C" int oq_attn_fwd(const void* qkv, long ld, long width, int batch, int T, int heads, int kv_heads, int head_dim, int cq,
+                           int gq, int ck, int cv, int gk, float alpha, void* O, long ldo, float* row_max, float* row_invl,
+                           cudaStream_t stream) {
+  if (check_common("oq_attn_fwd", qkv, ld, batch, T, heads, kv_heads, head_dim, cq, gq, ck, cv, gk, width)) return -1;
+  OQ_REQUIRE(O && row_max && row_invl && ldo % 8 == 0 && (uintptr_t)O % 16 == 0 && ldo >= (long)heads * D,
+             "oq_attn_fwd: output / statistics pointers missing or misaligned");
+  static bool attr = false;
+  if (!attr) {
+    if (int e = set_smem(attn_fwd_kernel, FWD_SMEM, "oq_attn_fwd")) return e;
+    attr = true;
+  }
+  CUtensorMap tm128;
+  if (make_map(&tm128, qkv, width, (long)batch * T, ld, 128)) return -1;
+  AttnParams p = base_params(batch, T, heads, kv_heads, cq, gq, ck, cv, gk, alpha);
+  p.O = (bf16*)O; p.ldo = ldo; p.row_max = row_max; p.row_invl = row_invl;
+  const int grid = batch * heads * (T / 128);
+  attn_fwd_kernel<<<grid, NUM_THREADS, FWD_SMEM, stream>>>(tm128, p);
+  return oq_check_launch("oq_attn_fwd");
+}
+
+extern "C" int oq_attn_bwd(const void* qkv, long ld, long width, int batch, int T, int heads, int kv_heads, int head_dim, int cq,
+                           int gq, int ck, int cv, int gk, float alpha, const void* O, long ldo, const void* dO, long lddo,
+                           const float* row_max, const float* row_invl, float* delta_ws, void* dqkv, long ldg,
+                           cudaStream_t stream) {
+  if (check_common("oq_attn_bwd", qkv, ld, batch, T, heads, kv_heads, head_dim, cq, gq, ck, cv, gk, width)) return -1;
+  OQ_REQUIRE(O && dO && row_max && row_invl && delta_ws && dqkv, "oq_attn_bwd: null pointer");
+  OQ_REQUIRE(ldo % 8 == 0 && lddo % 8 == 0 && ldg % 8 == 0 && (uintptr_t)O % 16 == 0 && (uintptr_t)dO % 16 == 0 &&
+                 (uintptr_t)dqkv % 16 == 0 && ldg >= width && lddo >= (long)heads * D && ldo >= (long)heads * D,
+             "oq_attn_bwd: O / dO / dqkv must be 16-byte aligned with leading dimensions that are multiples of 8");
+  static bool attr = false;
+  if (!attr) {
+    if (int e = set_smem(attn_dkv_kernel, DKV_SMEM, "oq_attn_bwd")) return e;
+    if (int e = set_smem(attn_dq_kernel, DQ_SMEM, "oq_attn_bwd")) return e;
+    attr = true;
+  }
+  const long rows = (long)batch * T;
+  CUtensorMap tm128, tm64, tmdo128, tmdo64;
+  if (make_map(&tm128, qkv, width, rows, ld, 128) || make_map(&tm64, qkv, width, rows, ld, 64) ||
+      make_map(&tmdo128, dO, (long)heads * D, rows, lddo, 128) || make_map(&tmdo64, dO, (long)heads * D, rows, lddo, 64))
+    return -1;
+  AttnParams p = base_params(batch, T, heads, kv_heads, cq, gq, ck, cv, gk, alpha);
+  p.row_max = const_cast<float*>(row_max); p.row_invl = const_cast<float*>(row_invl); p.delta = delta_ws;
+  p.dqkv = (bf16*)dqkv; p.ldg = ldg;
+  const long nw = rows * heads;
+  attn_delta_kernel<<<(unsigned)((nw + 7) / 8), 256, 0, stream>>>((const bf16*)O, ldo, (const bf16*)dO, lddo, delta_ws, batch, T, heads);
+  if (int e = oq_check_launch("oq_attn_bwd (delta)")) return e;
+  attn_dkv_kernel<<<batch * kv_heads * (T / 128), NUM_THREADS, DKV_SMEM, stream>>>(tm128, tm64, tmdo64, p);
+  if (int e = oq_check_launch("oq_attn_bwd (dK, dV)")) return e;
+  attn_dq_kernel<<<batch * heads * (T / 128), NUM_THREADS, DQ_SMEM, stream>>>(tm128, tm64, tmdo128, p);
+  return oq_check_launch("oq_attn_bwd (dQ)");
+}

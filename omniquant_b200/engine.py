@@ -200,6 +200,10 @@ class BlockEngine:
         self._qstat_home = {n: (st["scale"], st["zp"]) for n, st in self.qstat.items()}
         self._let_init_names = tuple(let_init) if let_init else ()
         self._graph_state = None      # captured optimiser step, kept across reload(): see train()
+        # QK^T -> softmax -> PV (and the recompute backward) in one tcgen05 kernel each when the shape allows it
+        # (csrc/attn_sm100.cu: causal, head_dim 128, T %% 128 == 0); otherwise batched GEMMs + softmax kernels
+        self.fused_attn = (self.causal and self.dev.type == "cuda" and os.environ.get("OQ_FUSED_ATTN", "1") != "0"
+                           and ops.attn_supported(seq_len, self.d))
 
     def reload(self, weights: Dict[str, torch.Tensor], let_init: Optional[Dict[str, torch.Tensor]] = None):
         """Next decoder block of the same shape into the SAME device buffers: raw weights / norms / biases are copied in
@@ -466,13 +470,19 @@ class BlockEngine:
                 qkvq = qkv
             alpha = 1.0
         self.qkv, self.qkvq, self.att_alpha = qkv, qkvq, alpha
-        P = B("P", (nb, h, T, T))
-        passes = self._att_passes()
-        hmax = max(c1 - c0 for c0, c1, _ in passes)
-        S = B("S", (hmax, T, T), torch.float16)     # scores in fp16 like the reference's autocast (int_llama_layer.py:143)
         O = B("O", (M, H))
+        if self.fused_attn:
+            P = None
+            self.att_stats = (B("att_max", (nb, h, T), F32), B("att_invl", (nb, h, T), F32))
+            ops.attn_fwd(qkvq, O, *self.att_stats, batch=nb, T=T, heads=h, kv_heads=hkv, head_dim=d, layout=self._att_cols(),
+                         alpha=alpha)
+        else:
+            P = B("P", (nb, h, T, T))
+            passes = self._att_passes()
+            hmax = max(c1 - c0 for c0, c1, _ in passes)
+            S = B("S", (hmax, T, T), torch.float16)     # scores in fp16 like the reference's autocast (int_llama_layer.py:143)
         cz = 1 if self.causal else 0
-        for s in range(nb):
+        for s in range(0 if self.fused_attn else nb):
             r = slice(s * T, (s + 1) * T)
             for c0, c1, groups in passes:       # a few heads at a time: scores + probabilities of a pass stay in L2
                 for h0, nh, cq, ck, cv, sb in groups:
@@ -512,6 +522,15 @@ class BlockEngine:
         self._linear(mq, mq8, ws, "fc2", out, bias=ws["bfc2"], residual=h1)
         self.saved = dict(a1=a1, a1q=a1q, O=O, Oq=Oq, h1=h1, a2=a2, a2q=a2q, f1=f1, m=m, mq=mq, P=P, ws=ws)
         return out
+
+    def _att_cols(self):
+        """Column layout of the heads inside the [M, QW] qkv buffers for the fused attention kernels
+        (include/omniquant_b200.h, oq_attn_fwd): LLaMA / OPT store [q | k | v], Falcon per K/V group [rep q heads | k | v]."""
+        d, rep = self.d, self.rep
+        if self.family == "falcon":
+            gw = (rep + 2) * d
+            return dict(cq=0, gq=gw, ck=rep * d, cv=(rep + 1) * d, gk=gw)
+        return dict(cq=0, gq=rep * d, ck=self.H, cv=self.H + self.Hkv, gk=d)
 
     def _att_layout(self):
         """Launch groups of the attention GEMMs: (first head, heads in the launch, q / k / v column offsets in the
@@ -622,13 +641,17 @@ class BlockEngine:
         QW, Hkv, hkv, rep = self.QW, self.Hkv, self.hkv, self.rep
         ok, ov = H, H + Hkv
         dqkvq = B("dqkvq", (M, QW))
-        passes = self._att_passes()
-        hmax = max(c1 - c0 for c0, c1, _ in passes)
-        dP = B("S", (hmax, T, T), torch.float16).view(BF16)   # same scratch storage as the scores
         cz = 1 if self.causal else 0
         shared = rep > 1
-        dkv32 = B("dkv32", (T, 2 * Hkv), F32) if shared else None     # K/V gradients summed over the group's Q heads
-        for s in range(nb):
+        if self.fused_attn:
+            ops.attn_bwd(qkvq, sv["O"], dO, *self.att_stats, B("att_delta", (nb, h, T), F32), dqkvq, batch=nb, T=T, heads=h,
+                         kv_heads=hkv, head_dim=d, layout=self._att_cols(), alpha=alpha)
+        else:
+            passes = self._att_passes()
+            hmax = max(c1 - c0 for c0, c1, _ in passes)
+            dP = B("S", (hmax, T, T), torch.float16).view(BF16)   # same scratch storage as the scores
+            dkv32 = B("dkv32", (T, 2 * Hkv), F32) if shared else None     # K/V gradients summed over the group's Q heads
+        for s in range(0 if self.fused_attn else nb):
             r = slice(s * T, (s + 1) * T)
             P = sv["P"][s]
             for c0, c1, groups in passes:

@@ -279,6 +279,38 @@ def linear_wgrad(dy, x, dw):
          ldc=_rowmajor(dw, "dw"))
 
 
+# ------------------------------------------------------------------ fused attention
+def attn_supported(T: int, head_dim: int) -> bool:
+    return bool(lib().fns["oq_attn_supported"](int(T), int(head_dim)))
+
+
+def _attn_common(qkv, layout):
+    _chk(qkv, BF16, "qkv")
+    if qkv.dim() != 2 or qkv.stride(1) != 1:
+        raise OqError("attention: qkv must be a 2-D [batch*T, width] view with contiguous columns")
+    return tuple(int(layout[k]) for k in ("cq", "gq", "ck", "cv", "gk"))
+
+
+def attn_fwd(qkv, O, row_max, row_invl, *, batch, T, heads, kv_heads, head_dim, layout, alpha):
+    """O = softmax_causal(alpha * q k^T) v for every (sample, head) of the fused operand matrix, one launch."""
+    cq, gq, ck, cv, gk = _attn_common(qkv, layout)
+    _chk(O, BF16, "O"); _chk(row_max, F32, "row_max"); _chk(row_invl, F32, "row_invl")
+    lib().call("oq_attn_fwd", _p(qkv), qkv.stride(0), qkv.shape[1], batch, T, heads, kv_heads, head_dim, cq, gq, ck, cv, gk,
+               float(alpha), _p(O), _rowmajor(O, "O"), _p(row_max), _p(row_invl), _stream())
+
+
+def attn_bwd(qkv, O, dO, row_max, row_invl, delta_ws, dqkv, *, batch, T, heads, kv_heads, head_dim, layout, alpha):
+    """dq | dk | dv into dqkv (same column layout as qkv); recomputes the probabilities from the saved row statistics."""
+    cq, gq, ck, cv, gk = _attn_common(qkv, layout)
+    for n, t in (("O", O), ("dO", dO), ("dqkv", dqkv)):
+        _chk(t, BF16, n)
+    for n, t in (("row_max", row_max), ("row_invl", row_invl), ("delta_ws", delta_ws)):
+        _chk(t, F32, n)
+    lib().call("oq_attn_bwd", _p(qkv), qkv.stride(0), qkv.shape[1], batch, T, heads, kv_heads, head_dim, cq, gq, ck, cv, gk,
+               float(alpha), _p(O), _rowmajor(O, "O"), _p(dO), _rowmajor(dO, "dO"), _p(row_max), _p(row_invl), _p(delta_ws),
+               _p(dqkv), _rowmajor(dqkv, "dqkv"), _stream())
+
+
 # ------------------------------------------------------------------ elementwise
 def swiglu_fwd(gu, m):
     lib().call("oq_swiglu_fwd", _p(gu), _rowmajor(gu, "gu"), _p(m), _rowmajor(m, "m"), m.shape[0], m.shape[1], _stream())

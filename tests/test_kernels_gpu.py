@@ -838,3 +838,99 @@ def test_engine_s8_forward_agrees_with_the_bf16_forward(monkeypatch):
     assert abs(res[0][0] - res[1][0]) / res[1][0] < 5e-3, (res[0][0], res[1][0])
     a, b = res[0][1].double(), res[1][1].double()
     assert float((a @ b) / (a.norm() * b.norm())) > 0.9      # 4-bit codes downstream flip on 2^-9 operand differences (0.968 measured)
+
+
+# ---------------------------------------------------------------- fused attention (QK^T -> softmax -> PV, recompute backward)
+def _attn_reference(q, k, v, alpha):
+    """fp32 torch evaluation of QuantMatMul attention on [heads, T, d] operands with the engine's rounding points
+    (scores to fp16, probabilities to bf16, straight-through gradients), causal."""
+    T = q.shape[1]
+    s = torch.matmul(q, k.transpose(1, 2)) * alpha
+    s = s + (s.half().float() - s).detach()
+    mask = torch.triu(torch.ones(T, T, dtype=torch.bool, device=q.device), diagonal=1)
+    s = s.masked_fill(mask, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    p = p + (p.to(torch.bfloat16).float() - p).detach()
+    return torch.matmul(p, v)
+
+
+@pytest.mark.parametrize("layout,heads,kv,T,batch", [("llama", 4, 4, 256, 1), ("llama", 8, 2, 384, 2), ("falcon", 6, 2, 256, 1),
+                                                     ("llama", 2, 2, 2048, 1)])
+def test_fused_attention_fwd_bwd(ops, layout, heads, kv, T, batch):
+    """oq_attn_fwd / oq_attn_bwd against the fp32 torch evaluation of the same expression (MHA, grouped-query heads in
+    the LLaMA [q | k | v] and the Falcon per-group layouts, several samples) and against the unfused kernel chain."""
+    d, rep = 128, heads // kv
+    gen = torch.Generator(device="cuda").manual_seed(heads * 131 + T)
+    H, Hkv = heads * d, kv * d
+    QW = H + 2 * Hkv
+    M = batch * T
+    qkv = (torch.randn(M, QW, device="cuda", generator=gen) * 1.5).to(torch.bfloat16)
+    dO = torch.randn(M, H, device="cuda", generator=gen).to(torch.bfloat16)
+    if layout == "falcon":
+        gw = (rep + 2) * d
+        cols = dict(cq=0, gq=gw, ck=rep * d, cv=(rep + 1) * d, gk=gw)
+        view = qkv.view(M, kv, rep + 2, d)
+        qf, kf, vf = view[:, :, :rep].reshape(M, heads, d), view[:, :, rep], view[:, :, rep + 1]
+    else:
+        cols = dict(cq=0, gq=rep * d, ck=H, cv=H + Hkv, gk=d)
+        qf, kf, vf = qkv[:, :H].view(M, heads, d), qkv[:, H:H + Hkv].view(M, kv, d), qkv[:, H + Hkv:].view(M, kv, d)
+    alpha = d ** -0.5
+    O = torch.empty(M, H, device="cuda", dtype=torch.bfloat16)
+    rmax, rinv = torch.empty(batch, heads, T, device="cuda"), torch.empty(batch, heads, T, device="cuda")
+    kw = dict(batch=batch, T=T, heads=heads, kv_heads=kv, head_dim=d, layout=cols, alpha=alpha)
+    ops.attn_fwd(qkv, O, rmax, rinv, **kw)
+    dqkv = torch.full_like(qkv, float("nan"))
+    ops.attn_bwd(qkv, O, dO, rmax, rinv, torch.empty(batch, heads, T, device="cuda"), dqkv, **kw)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(O.float()).all()) and bool(torch.isfinite(dqkv.float()).all())   # every element written
+    # fp32 reference with autograd, sample by sample
+    want_O = torch.empty(M, H, device="cuda")
+    want_g = torch.zeros(M, QW, device="cuda")
+    for s in range(batch):
+        r = slice(s * T, (s + 1) * T)
+        q = qf[r].float().transpose(0, 1).contiguous().requires_grad_(True)           # [heads, T, d]
+        k = kf[r].float().transpose(0, 1).contiguous().requires_grad_(True)           # [kv, T, d]
+        v = vf[r].float().transpose(0, 1).contiguous().requires_grad_(True)
+        o = _attn_reference(q, k.repeat_interleave(rep, 0), v.repeat_interleave(rep, 0), alpha)
+        want_O[r] = o.transpose(0, 1).reshape(T, H)
+        o.backward(dO[r].float().view(T, heads, d).transpose(0, 1))
+        gq, gk, gv = (t.grad.transpose(0, 1) for t in (q, k, v))
+        if layout == "falcon":
+            gview = want_g[r].view(T, kv, rep + 2, d)
+            gview[:, :, :rep] = gq.reshape(T, kv, rep, d)
+            gview[:, :, rep], gview[:, :, rep + 1] = gk, gv
+        else:
+            want_g[r, :H], want_g[r, H:H + Hkv], want_g[r, H + Hkv:] = gq.reshape(T, H), gk.reshape(T, Hkv), gv.reshape(T, Hkv)
+    rel = lambda a, b: float((a.float() - b).norm() / b.norm())
+    print(f"fused attention {layout} h{heads}/{kv} T{T} b{batch}: O rel {rel(O, want_O):.2e}  grad rel {rel(dqkv, want_g):.2e}")
+    assert rel(O, want_O) < 4e-3
+    assert rel(dqkv, want_g) < 1.2e-2
+    # softmax statistics
+    s0 = (torch.matmul(qf[:T].float().transpose(0, 1), kf[:T].float().transpose(0, 1).repeat_interleave(rep, 0).transpose(1, 2)) * alpha).half().float()
+    s0 = s0.masked_fill(torch.triu(torch.ones(T, T, dtype=torch.bool, device="cuda"), diagonal=1), float("-inf"))
+    torch.testing.assert_close(rmax[0], s0.amax(-1), rtol=0, atol=2e-2)
+
+
+def test_engine_fused_attention_agrees_with_the_unfused_chain(monkeypatch):
+    """One optimiser step of the same W4A4 block with the fused attention kernels and with batched GEMMs + softmax kernels."""
+    from omniquant_b200.engine import BlockEngine, QuantConfig
+    g = torch.Generator().manual_seed(0)
+    H, F_, heads, T = 512, 1024, 4, 256
+    r = lambda *s, sc=0.03: (torch.randn(*s, generator=g) * sc).half().float()
+    W = {"q": r(H, H), "k": r(H, H), "v": r(H, H), "o": r(H, H), "gate": r(F_, H), "up": r(F_, H), "down": r(H, F_),
+         "ln1": 1 + r(H, sc=0.1), "ln2": 1 + r(H, sc=0.1)}
+    x = torch.randn(T, H, generator=g).cuda().to(torch.bfloat16)
+    tgt = torch.roll(x, 1, 0)
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("OQ_FUSED_ATTN", flag)
+        eng = BlockEngine("llama", W, n_heads=heads, seq_len=T, eps=1e-6,
+                          qcfg=QuantConfig(wbits=4, abits=16, group_size=0, lwc=True, let=True, recip_div=True))
+        assert eng.fused_attn == (flag == "1")
+        loss = float(eng.train_step(x, tgt).clone())
+        torch.cuda.synchronize()
+        res.append((loss, eng.grads.clone(), eng.bufs["O"].clone()))
+    assert float((res[0][2].float() - res[1][2].float()).norm() / res[1][2].float().norm()) < 2e-3
+    assert abs(res[0][0] - res[1][0]) / res[1][0] < 2e-3, (res[0][0], res[1][0])
+    a, b = res[0][1].double(), res[1][1].double()
+    assert float((a - b).norm() / b.norm()) < 3e-2

@@ -68,6 +68,18 @@ def _watched(self, x, target, target2=None, allreduce=None):
                 print(f"  NON-FINITE {k} {tuple(t.shape)} nan {float(torch.isnan(tf).float().mean()):.4f} inf {float(torch.isinf(tf).float().mean()):.4f} first bad rows {rows}")
             else:
                 print(f"  ok         {k} {tuple(t.shape)} absmax {float(t.float().abs().max()):.4g}")
+        qv, qq = self.bufs.get("qkv"), self.bufs.get("qkvq")
+        if qv is not None and qq is not None:
+            d = self.d
+            bad = (~torch.isfinite(qq.float())).view(qq.shape[0], -1, d).any(-1)       # [rows, heads3]
+            idx = bad.nonzero()[:12].tolist()
+            print("  NaN (row, head-slot) pairs:", idx, " per segment q/k/v:",
+                  [int(bad[:, a:b].sum()) for a, b in ((0, self.h), (self.h, self.h + self.hkv), (self.h + self.hkv, self.h + 2 * self.hkv))])
+            for r, h in idx[:6]:
+                row = qv[r, h * d:(h + 1) * d].float()
+                print(f"    row {r} slot {h}: raw qkv min {float(row.min()):.6g} max {float(row.max()):.6g} unique {int(row.unique().numel())} "
+                      f"| a1q row absmax {float(self.bufs['a1q'][r].float().abs().max()):.4g} nonzero {int((self.bufs['a1q'][r] != 0).sum())} "
+                      f"| a1 row absmax {float(self.bufs['a1'][r].float().abs().max()):.4g}")
         raise FloatingPointError("stopped at the first non-finite step")
     return out
 
