@@ -510,7 +510,10 @@ def run_e2e(a, c, W, x_host, dev, world, rank):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        omniquant(lm, args, None, act if c.let else None, None, None, inps=inps_view)
+        # LET initialisation from activation statistics collected in each block's FP pass (generate_act_scale_shift.py
+        # semantics, omniquant(act_scales=None)): in a CHAINED model random statistics do not match the real outlier channels
+        # and a W4A4 block can then quantise whole token rows to zero, which is NaN in the reference's arithmetic as well
+        omniquant(lm, args, None, None, None, None, inps=inps_view)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         w0 = next(iter(layers[0].parameters()), None)
@@ -528,7 +531,8 @@ def run_e2e(a, c, W, x_host, dev, world, rank):
     return {"value": round(float(t), 4), "unit": "s/block", "h2d_bytes_per_step": int(wbytes + x_host.numel() * 2 // n_blocks),
             "d2h_bytes_per_step": int(wbytes), "steps": n_calls * n_blocks, "blocks_per_call": n_blocks,
             "api": f"omniquant_b200.quantize.omniquant.omniquant() on a {n_blocks}-block model (weights pinned on the host, next block "
-                   "prefetched on a copy stream, quantised blocks written back asynchronously); wall clock / blocks, max over ranks"}
+                   "prefetched on a copy stream, quantised blocks written back asynchronously, LET statistics collected online in "
+                   "the FP pass); wall clock / blocks, max over ranks"}
 
 
 # ---------------------------------------------------------------------------------------------- baselines (oracle port)
