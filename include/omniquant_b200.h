@@ -47,12 +47,17 @@ int oq_sm_count(void);
  * semantics (multiply by the fp32 reciprocal).  Any of the outputs may be NULL.  n_bits >= 16: fold only (the quantiser
  * is the identity, quantize/quantizer.py:109) -- this mode also implements smooth_*_{temporary,inplace} on their own.
  * codes_s8 / s8_t / s8_beta (all or none; per-channel, needs scale_out): the exact-integer operand of oq_gemm_s8, see there.
+ * Row segments (n_seg in 1..3, HOST arrays; row_scale must be NULL): one launch over several weights stacked along N that
+ * share col_scale / shift but differ in the row fold -- rows [seg_end[s-1], seg_end[s]) use the DEVICE vector seg_row[s]
+ * (indexed from the segment's first row; NULL = no row fold) with operation seg_op[s].  This is q | k | v of one block:
+ * smooth_ln_fcs on all three, then smooth_q_k on q (/) and k (*), smooth_fc_fc on v (/) (models/int_llama_layer.py:285-292).
  * Replaces models/int_llama_layer.py:285-304 (smooth_and_quant_temporary) per weight. */
 int oq_weight_quant_fwd(const float* W, int N, int K, const float* col_scale, const float* row_scale, int row_op,
                         const float* shift, float* matvec_out, int n_bits, int symmetric, int group_size,
                         const float* up, const float* low, int recip_div, void* wq_bf16, long ld_bf16, float* wq_f32,
                         uint8_t* codes, float* scale_out, float* zp_out, float* xmin_out, float* xmax_out,
-                        int8_t* codes_s8, float* s8_t, float* s8_beta, oq_stream_t stream);
+                        int8_t* codes_s8, float* s8_t, float* s8_beta, int n_seg, const int* seg_end_host,
+                        const float* const* seg_row_host, const int* seg_op_host, oq_stream_t stream);
 
 /* Backward of the above (autograd of quantizer.py:84-147 + transformation.py folds).
  * grad_wq: dL/dW_q [N,K] (bf16, or fp32 when grad_is_f32).  xmin/xmax: raw group extrema saved by the
@@ -65,7 +70,8 @@ int oq_weight_quant_bwd(const float* W, int N, int K, const float* col_scale, co
                         const float* xmin, const float* xmax, const float* scale_saved, const float* zp_saved,
                         const void* grad_wq, int grad_is_f32, long ld_grad,
                         const float* e_row, float* d_up, float* d_low, float* dcol_acc, float* drow, float* dshift_acc,
-                        float* dW_full, oq_stream_t stream);
+                        float* dW_full, int n_seg, const int* seg_end_host, const float* const* seg_row_host,
+                        const int* seg_op_host, oq_stream_t stream);
 
 /* ---- K4: per-token dynamic activation fake-quant ---------------------------
  * UniformAffineQuantizer(dynamic_method="per_token") forward, quantizer.py:108-147,:84-105, as called by

@@ -28,6 +28,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "mbar.cuh"
@@ -115,6 +116,19 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int b_mn) {
 __device__ __forceinline__ float score16(uint32_t bits, float alpha) {
   return __half2float(__float2half_rn(__uint_as_float(bits) * alpha));
 }
+// exp2 on the SFU without the denormal-range fix-up of exp2f / __expf (arguments are <= 0 here: results below 2^-126 flush to 0)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float LOG2E = 1.4426950408889634f;
+// The element loops below are written branch-free on purpose: `visible ? exp(..) : 0` compiles to a divergent branch with
+// a reconvergence barrier PER ELEMENT (measured: 10x slower kernels); masking the SCORE with -inf (one select) and letting
+// ex2(-inf) = 0 do the rest keeps one straight instruction stream, and tiles off the diagonal skip the select altogether.
+template <bool MASK>
+__device__ __forceinline__ float masked(float s, bool visible) { return (MASK && !visible) ? -INFINITY : s; }
+
 // 8 values -> one 16-byte chunk of a swizzled 128-byte row (row r of a 1024-byte aligned block, logical chunk c)
 __device__ __forceinline__ void st_chunk(uint8_t* blk, int r, int c, const float (&v)[8]) {
   uint4 u;
@@ -230,30 +244,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
     const int q = warp & 3, r = q * 32 + lane;
     const int qrow = qt * 128 + r;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f;      // row maximum of the fp16 scores and sum exp(s - m)
     // ---- pass 1: row maximum and sum
-    for (int t = 0; t < nj; ++t) {
-      const int sb = t & 1;
-      mbar_wait(&s_full[sb], (t >> 1) & 1);
-      tc_fence_after();
-      const int lim = (t == qt) ? r + 1 : 128;        // causal: keys c <= r on the diagonal tile
+    auto stats_tile = [&](int sb, auto mask_tag) {
+      constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t v[32];
         tc_ld32(lane_base + sb * 128 + c0, v);
         tc_wait_ld();
-        float s[32], mx = m;
+        float sc[32], mx = m;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          s[i] = (c0 + i < lim) ? score16(v[i], p.alpha) : -INFINITY;
-          mx = fmaxf(mx, s[i]);
+          sc[i] = masked<MASK>(score16(v[i], p.alpha), c0 + i <= r);     // causal: keys c <= r on the diagonal tile
+          mx = fmaxf(mx, sc[i]);
         }
-        float add = 0.f;
+        const float mx2 = mx * LOG2E;
+        float add0 = 0.f, add1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) add += __expf(s[i] - mx);
-        l = l * __expf(m - mx) + add;      // first chunk: m = -inf, l = 0 -> 0 * exp(-inf) = 0 (key 0 is always visible: mx finite)
+        for (int i = 0; i < 32; i += 2) {
+          add0 += ex2_ftz(fmaf(sc[i], LOG2E, -mx2));
+          add1 += ex2_ftz(fmaf(sc[i + 1], LOG2E, -mx2));
+        }
+        l = l * ex2_ftz((m - mx) * LOG2E) + (add0 + add1);   // first chunk: m = -inf, l = 0 (key 0 is always visible: mx finite)
         m = mx;
       }
+    };
+    for (int t = 0; t < nj; ++t) {
+      const int sb = t & 1;
+      mbar_wait(&s_full[sb], (t >> 1) & 1);
+      tc_fence_after();
+      if (t == qt) stats_tile(sb, std::true_type{});
+      else stats_tile(sb, std::false_type{});
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
@@ -262,13 +284,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
     const long srow = ((long)b * p.heads + head) * p.T + qrow;
     p.row_max[srow] = m;
     p.row_invl[srow] = inv;
+    const float m2 = m * LOG2E;
     // ---- pass 2: probabilities with the final statistics -> shared memory (A operand of P V)
-    for (int t = nj; t < nit; ++t) {
-      const int sb = t & 1, j = t - nj;
-      mbar_wait(&s_full[sb], (t >> 1) & 1);
-      tc_fence_after();
-      if (j > 0) mbar_wait(p_empty, (j - 1) & 1);      // P V of the previous tile has finished reading sP
-      const int lim = (j == qt) ? r + 1 : 128;
+    auto prob_tile = [&](int sb, auto mask_tag) {
+      constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t v[32];
@@ -281,11 +300,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int c = c0 + ch * 8 + e;
-            pr[e] = (c < lim) ? __expf(score16(v[ch * 8 + e], p.alpha) - m) * inv : 0.f;
+            pr[e] = ex2_ftz(fmaf(masked<MASK>(score16(v[ch * 8 + e], p.alpha), c <= r), LOG2E, -m2)) * inv;
           }
           st_chunk(blk, r, ((c0 & 63) >> 3) + ch, pr);
         }
       }
+    };
+    for (int t = nj; t < nit; ++t) {
+      const int sb = t & 1, j = t - nj;
+      mbar_wait(&s_full[sb], (t >> 1) & 1);
+      tc_fence_after();
+      if (j > 0) mbar_wait(p_empty, (j - 1) & 1);      // P V of the previous tile has finished reading sP
+      if (j == qt) prob_tile(sb, std::true_type{});
+      else prob_tile(sb, std::false_type{});
       fence_proxy_async();      // generic-proxy writes of sP -> visible to the tensor core's async proxy
       tc_fence_before();
       __syncwarp();
@@ -465,7 +492,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
       const uint32_t ph = (it >> 1) & 1;
       if (tid < 64) {
         const long sr = ((long)b * p.heads + head) * p.T + i64 * 64 + tid;
-        sstat[sb * 64 + tid] = make_float4(p.row_max[sr], p.row_invl[sr], p.delta[sr], 0.f);
+        sstat[sb * 64 + tid] = make_float4(p.row_max[sr] * LOG2E, p.row_invl[sr], p.delta[sr], 0.f);
       }
       named_bar_sync(1, 128);
       mbar_wait(&s_full[sb], ph);
@@ -473,28 +500,33 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
       mbar_wait(&p_empty[sb], ph ^ 1);        // the accumulate MMAs that read this P^T / dS^T buffer two steps ago are done
       uint8_t* bPT = sPS + sb * 2 * BLK128;
       uint8_t* bdST = bPT + BLK128;
+      const int lo = kg - i64 * 64;            // causal: query column c is visible to this key row iff c >= lo
+      auto tile = [&](auto mask_tag) {
+        constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t sv[32], dv[32];
-        tc_ld32(lane_base + sb * 128 + c0, sv);
-        tc_ld32(lane_base + sb * 128 + 64 + c0, dv);
-        tc_wait_ld();
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t sv[32], dv[32];
+          tc_ld32(lane_base + sb * 128 + c0, sv);
+          tc_ld32(lane_base + sb * 128 + 64 + c0, dv);
+          tc_wait_ld();
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          float pr[8], ds[8];
+          for (int ch = 0; ch < 4; ++ch) {
+            float pr[8], ds[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = c0 + ch * 8 + e;
-            const float4 stt = sstat[sb * 64 + c];
-            const bool vis = kg <= i64 * 64 + c;             // causal: key position <= query position
-            const float pe = vis ? __expf(score16(sv[ch * 8 + e], p.alpha) - stt.x) * stt.y : 0.f;
-            pr[e] = pe;
-            ds[e] = pe * (__uint_as_float(dv[ch * 8 + e]) - stt.z);
+            for (int e = 0; e < 8; ++e) {
+              const int c = c0 + ch * 8 + e;
+              const float4 stt = sstat[sb * 64 + c];          // (max * log2e, 1/l, delta, -) of query column c
+              const float pe = ex2_ftz(fmaf(masked<MASK>(score16(sv[ch * 8 + e], p.alpha), c >= lo), LOG2E, -stt.x)) * stt.y;
+              pr[e] = pe;
+              ds[e] = pe * (__uint_as_float(dv[ch * 8 + e]) - stt.z);
+            }
+            st_chunk(bPT, kr, (c0 >> 3) + ch, pr);
+            st_chunk(bdST, kr, (c0 >> 3) + ch, ds);
           }
-          st_chunk(bPT, kr, (c0 >> 3) + ch, pr);
-          st_chunk(bdST, kr, (c0 >> 3) + ch, ds);
         }
-      }
+      };
+      if (i64 < 2 * j + 2) tile(std::true_type{});      // the two half tiles that touch the diagonal
+      else tile(std::false_type{});
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -648,7 +680,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
     const int qg = i * 128 + r;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const long sr = ((long)b * p.heads + head) * p.T + qg;
-    const float m = p.row_max[sr], inv = p.row_invl[sr], dl = p.delta[sr];
+    const float m2 = p.row_max[sr] * LOG2E, inv = p.row_invl[sr], dl = p.delta[sr];
     for (int it = 0; it < nit; ++it) {
       const int sb = it & 1;
       const uint32_t ph = (it >> 1) & 1;
@@ -656,25 +688,30 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
       tc_fence_after();
       mbar_wait(&p_empty[sb], ph ^ 1);
       uint8_t* bdS = sdS + sb * BLK128;
+      const int hi = qg - it * 64;             // causal: key column c is visible to this query row iff c <= hi
+      auto tile = [&](auto mask_tag) {
+        constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t sv[32], dv[32];
-        tc_ld32(lane_base + sb * 128 + c0, sv);
-        tc_ld32(lane_base + sb * 128 + 64 + c0, dv);
-        tc_wait_ld();
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t sv[32], dv[32];
+          tc_ld32(lane_base + sb * 128 + c0, sv);
+          tc_ld32(lane_base + sb * 128 + 64 + c0, dv);
+          tc_wait_ld();
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          float ds[8];
+          for (int ch = 0; ch < 4; ++ch) {
+            float ds[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = c0 + ch * 8 + e;
-            const bool vis = it * 64 + c <= qg;
-            const float pe = vis ? __expf(score16(sv[ch * 8 + e], p.alpha) - m) * inv : 0.f;
-            ds[e] = pe * (__uint_as_float(dv[ch * 8 + e]) - dl);
+            for (int e = 0; e < 8; ++e) {
+              const int c = c0 + ch * 8 + e;
+              const float pe = ex2_ftz(fmaf(masked<MASK>(score16(sv[ch * 8 + e], p.alpha), c <= hi), LOG2E, -m2)) * inv;
+              ds[e] = pe * (__uint_as_float(dv[ch * 8 + e]) - dl);
+            }
+            st_chunk(bdS, r, (c0 >> 3) + ch, ds);
           }
-          st_chunk(bdS, r, (c0 >> 3) + ch, ds);
         }
-      }
+      };
+      if (it >= 2 * i) tile(std::true_type{});           // the two half tiles that touch the diagonal
+      else tile(std::false_type{});
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();

@@ -26,6 +26,9 @@ struct WqArgs {
   const float* col;  // [K] or null
   const float* row;  // [N] or null
   int row_op;        // 0 none 1 mul 2 div
+  // optional row segments (one launch over several stacked weights, e.g. q | k | v): rows [seg_end[s-1], seg_end[s]) use
+  // seg_row[s] (indexed from the segment's first row) with seg_op[s]; nseg == 0: `row` / `row_op` apply to every row
+  int nseg; int seg_end[3]; const float* seg_row[3]; int seg_op[3];
   const float* shift;  // [K] or null
   float* mv;           // [N] W@shift
   int n_bits, symmetric, group, recip_div;
@@ -64,6 +67,20 @@ struct Team {
     }
   }
 };
+
+// row scale and fold operation of row n (segment table or the launch-wide vector); op 0: rs = 1
+__device__ __forceinline__ void wq_row_fold(const WqArgs& a, long n, float& rs, int& op) {
+  if (a.nseg == 0) {
+    op = a.row ? a.row_op : 0;
+    rs = op ? a.row[n] : 1.0f;
+    return;
+  }
+  int s = 0;
+  while (s + 1 < a.nseg && n >= a.seg_end[s]) ++s;
+  const long first = s ? a.seg_end[s - 1] : 0;
+  op = a.seg_row[s] ? a.seg_op[s] : 0;
+  rs = op ? a.seg_row[s][n - first] : 1.0f;
+}
 
 __device__ __forceinline__ float load_g(const WqArgs& a, long idx) {
   return a.g_is_f32 ? reinterpret_cast<const float*>(a.g)[idx] : bf2f(reinterpret_cast<const bf16*>(a.g)[idx]);
@@ -298,7 +315,8 @@ extern "C" int oq_weight_quant_fwd(const float* W, int N, int K, const float* co
                                    int group_size, const float* up, const float* low, int recip_div, void* wq_bf16,
                                    long ld_bf16, float* wq_f32, uint8_t* codes, float* scale_out, float* zp_out,
                                    float* xmin_out, float* xmax_out, int8_t* codes_s8, float* s8_t, float* s8_beta,
-                                   cudaStream_t stream) {
+                                   int n_seg, const int* seg_end_host, const float* const* seg_row_host,
+                                   const int* seg_op_host, cudaStream_t stream) {
   OQ_REQUIRE((codes_s8 == nullptr) == (s8_t == nullptr) && (codes_s8 == nullptr) == (s8_beta == nullptr),
              "oq_weight_quant_fwd: codes_s8, s8_t and s8_beta go together");
   OQ_REQUIRE(!codes_s8 || (group_size == 0 && n_bits <= 8 && scale_out && (uintptr_t)codes_s8 % 4 == 0),
@@ -317,6 +335,15 @@ extern "C" int oq_weight_quant_fwd(const float* W, int N, int K, const float* co
   a.q_bf = (bf16*)wq_bf16; a.ld_bf = ld_bf16 ? ld_bf16 : K; a.q_f32 = wq_f32; a.codes = codes;
   a.scale_out = scale_out; a.zp_out = zp_out; a.xmin_out = xmin_out; a.xmax_out = xmax_out;
   a.codes8 = codes_s8; a.s8_t = s8_t; a.s8_beta = s8_beta;
+  OQ_REQUIRE(n_seg >= 0 && n_seg <= 3 && (n_seg == 0 || (seg_end_host && seg_row_host && seg_op_host && !row_scale)),
+             "oq_weight_quant_fwd: bad row segment table (at most 3 segments; row_scale must be NULL with segments)");
+  a.nseg = n_seg;
+  for (int i = 0; i < n_seg; ++i) {
+    a.seg_end[i] = seg_end_host[i]; a.seg_row[i] = seg_row_host[i]; a.seg_op[i] = seg_op_host[i];
+    OQ_REQUIRE(a.seg_op[i] >= 0 && a.seg_op[i] <= 2 && a.seg_end[i] > (i ? a.seg_end[i - 1] : 0), "oq_weight_quant_fwd: bad segment %d", i);
+  }
+  OQ_REQUIRE(n_seg == 0 || (a.seg_end[n_seg - 1] == N && group_size == 0 && n_bits <= 8),
+             "oq_weight_quant_fwd: segments must cover the N rows; per-channel quantisation only");
   const bool team_warp = group_size > 0;
   const long G = group_size ? (K + group_size - 1) / group_size : 1;
   const bool vec = (K % 4 == 0) && (group_size % 4 == 0) && (a.ld_bf % 4 == 0) && ((uintptr_t)W % 16 == 0) &&
@@ -326,7 +353,7 @@ extern "C" int oq_weight_quant_fwd(const float* W, int N, int K, const float* co
     if (e != cudaSuccess) return (int)e;
   }
   // fast register-resident paths (weight_quant_fast.cuh); the generic kernels below cover everything else
-  const bool let = col_scale || row_scale || shift;
+  const bool let = col_scale || row_scale || shift || n_seg;
   const bool fast_al = vec && al(col_scale, 16) && al(shift, 16);
   if (!ident && fast_al && !team_warp && K <= 16384) {
     const size_t smem = let ? sizeof(float) * 2 * K : 0;
@@ -340,6 +367,7 @@ extern "C" int oq_weight_quant_fwd(const float* W, int N, int K, const float* co
     if (let ? launch_grp<true, false>(a, g, 0, stream) : launch_grp<false, false>(a, g, 0, stream))
       return oq_check_launch("oq_weight_quant_fwd");
   }
+  OQ_REQUIRE(!n_seg, "oq_weight_quant_fwd: row segments need the per-channel fast path (K %% 4 == 0, K <= 16384, aligned pointers)");
   OQ_REQUIRE(!codes_s8, "oq_weight_quant_fwd: the s8 side output needs the per-channel fast path (K %% 4 == 0, K <= 16384, "
                         "16-byte aligned W / col_scale / shift)");
   const int grid = pick_grid((long)N * G, team_warp, 8);
@@ -358,7 +386,8 @@ extern "C" int oq_weight_quant_bwd(const float* W, int N, int K, const float* co
                                    const float* low, int recip_div, const float* xmin, const float* xmax,
                                    const float* scale_saved, const float* zp_saved, const void* grad_wq, int grad_is_f32, long ld_grad, const float* e_row,
                                    float* d_up, float* d_low, float* dcol_acc, float* drow, float* dshift_acc,
-                                   float* dW_full, cudaStream_t stream) {
+                                   float* dW_full, int n_seg, const int* seg_end_host, const float* const* seg_row_host,
+                                   const int* seg_op_host, cudaStream_t stream) {
   OQ_REQUIRE(W && grad_wq && xmin && xmax && N > 0 && K > 0, "oq_weight_quant_bwd: null input or bad shape");
   OQ_REQUIRE((n_bits >= 2 && n_bits <= 8) || n_bits >= 16, "oq_weight_quant_bwd: n_bits %d not in [2,8] or >= 16 (fold only)", n_bits);
   const bool ident = n_bits >= 16;
@@ -371,6 +400,15 @@ extern "C" int oq_weight_quant_bwd(const float* W, int N, int K, const float* co
   a.scale_in = scale_saved; a.zp_in = zp_saved;
   a.g = grad_wq; a.g_is_f32 = grad_is_f32; a.ld_g = ld_grad ? ld_grad : K; a.xmin_in = xmin; a.xmax_in = xmax;
   a.e_row = e_row; a.d_up = d_up; a.d_low = d_low; a.dcol = dcol_acc; a.drow = drow; a.dshift = dshift_acc; a.dW = dW_full;
+  OQ_REQUIRE(n_seg >= 0 && n_seg <= 3 && (n_seg == 0 || (seg_end_host && seg_row_host && seg_op_host && !row_scale)),
+             "oq_weight_quant_bwd: bad row segment table (at most 3 segments; row_scale must be NULL with segments)");
+  a.nseg = n_seg;
+  for (int i = 0; i < n_seg; ++i) {
+    a.seg_end[i] = seg_end_host[i]; a.seg_row[i] = seg_row_host[i]; a.seg_op[i] = seg_op_host[i];
+    OQ_REQUIRE(a.seg_op[i] >= 0 && a.seg_op[i] <= 2 && a.seg_end[i] > (i ? a.seg_end[i - 1] : 0), "oq_weight_quant_bwd: bad segment %d", i);
+  }
+  OQ_REQUIRE(n_seg == 0 || (a.seg_end[n_seg - 1] == N && group_size == 0 && n_bits <= 8),
+             "oq_weight_quant_bwd: segments must cover the N rows; per-channel quantisation only");
   const bool team_warp = group_size > 0;
   const long G = group_size ? (K + group_size - 1) / group_size : 1;
   const size_t smem = sizeof(float) * K * ((dcol_acc ? 1 : 0) + (dshift_acc ? 1 : 0));
@@ -379,7 +417,7 @@ extern "C" int oq_weight_quant_bwd(const float* W, int N, int K, const float* co
     cudaError_t e = cudaMemsetAsync(drow, 0, sizeof(float) * N, stream);
     if (e != cudaSuccess) return (int)e;
   }
-  const bool let = col_scale || row_scale || e_row || dcol_acc || dshift_acc;
+  const bool let = col_scale || row_scale || e_row || dcol_acc || dshift_acc || n_seg;
   const bool fast_al = !ident && (K % 4 == 0) && (group_size % 4 == 0) && (a.ld_g % 4 == 0) && al(W, 16) && al(grad_wq, 16) &&
                        al(col_scale, 16) && al(dW_full, 16);
   if (fast_al && !team_warp && !let && !dW_full) {       // LWC only: R per row, one warp per row
@@ -390,6 +428,7 @@ extern "C" int oq_weight_quant_bwd(const float* W, int N, int K, const float* co
   if (fast_al && !team_warp && let && !dW_full && K % 8 == 0 && a.ld_g % 8 == 0) {   // bulk copies: 16-byte rows
     if (launch_pc_bwd_ws(a, stream)) return oq_check_launch("oq_weight_quant_bwd");
   }
+  OQ_REQUIRE(!n_seg, "oq_weight_quant_bwd: row segments need the streaming per-channel path (K %% 8 == 0, K <= 8192, aligned pointers)");
   if (fast_al && !team_warp && K <= 16384) {
     const size_t sm2 = let ? sizeof(float) * 3 * K : 0;
     if (sm2 <= 200 * 1024) {

@@ -59,7 +59,8 @@ __device__ __forceinline__ float warp_max_f32(float v) {
 // all rows a block visits are evaluated once up front (one row per thread), the block-wide min / max is two CREDUX
 // + one barrier, and the bit-exact rounding guard of oq_rint_div is evaluated branch-free with one fallback branch
 // per float4 (the exact IEEE-division path re-does those four elements; probability ~1e-5).
-template <int NV, bool LET, bool ROWDIV>
+// ROWMODE: 0 the row fold multiplies (or is absent), 1 it divides, 2 per-row segment table (q | k | v in one launch)
+template <int NV, bool LET, int ROWMODE>
 __global__ void __launch_bounds__(256) wq_pc_fwd(WqArgs a) {
   extern __shared__ float4 dsm4[];
   __shared__ float red[2][4][8];
@@ -107,7 +108,17 @@ __global__ void __launch_bounds__(256) wq_pc_fwd(WqArgs a) {
         if (idx < K4) wn[i] = ld4(a.W + (long)nn * a.K + 4 * idx);
       }
     }
-    const float rs = (LET && a.row && a.row_op != 0) ? a.row[n] : 1.0f;
+    float rs = 1.0f;
+    bool rdiv = ROWMODE == 1;
+    if (LET) {
+      if (ROWMODE == 2) {
+        int op;
+        wq_row_fold(a, n, rs, op);
+        rdiv = op == 2;
+      } else {
+        rs = (a.row && a.row_op != 0) ? a.row[n] : 1.0f;
+      }
+    }
     float sm = 0.f, mlo = -INFINITY, mhi = -INFINITY;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -119,7 +130,7 @@ __global__ void __launch_bounds__(256) wq_pc_fwd(WqArgs a) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float f1 = OQ_MUL(f4(w[i], j), f4(const_cast<float4&>(c4), j));
-            f4(w[i], j) = ROWDIV ? OQ_DIV(f1, rs) : OQ_MUL(f1, rs);  // (W * col) {*,/} row; a factor 1 is exact
+            f4(w[i], j) = rdiv ? OQ_DIV(f1, rs) : OQ_MUL(f1, rs);  // (W * col) {*,/} row; a factor 1 is exact
           }
         }
         mlo = fmaxf(mlo, fmaxf(fmaxf(-w[i].x, -w[i].y), fmaxf(-w[i].z, -w[i].w)));
@@ -614,7 +625,7 @@ __global__ void __launch_bounds__(256) wq_grp_bwd(WqArgs a) {
 }
 
 // ------------------------------------------------------------------ dispatch helpers
-template <bool LET, bool ROWDIV>
+template <bool LET, int ROWDIV>
 static bool launch_pc_fwd2(const WqArgs& a, int grid, size_t smem, cudaStream_t s) {
   const int nv = (a.K / 4 + 255) / 256;
 #define OQ_PC_FWD(NVV)                                                                                          \
@@ -634,8 +645,9 @@ static bool launch_pc_fwd2(const WqArgs& a, int grid, size_t smem, cudaStream_t 
 }
 template <bool LET>
 static bool launch_pc_fwd(const WqArgs& a, int grid, size_t smem, cudaStream_t s) {
-  if (LET && a.row && a.row_op == 2) return launch_pc_fwd2<LET, true>(a, grid, smem, s);
-  return launch_pc_fwd2<LET, false>(a, grid, smem, s);
+  if (LET && a.nseg) return launch_pc_fwd2<LET, 2>(a, grid, smem, s);
+  if (LET && a.row && a.row_op == 2) return launch_pc_fwd2<LET, 1>(a, grid, smem, s);
+  return launch_pc_fwd2<LET, 0>(a, grid, smem, s);
 }
 template <bool LET>
 static bool launch_pc_bwd(const WqArgs& a, int grid, size_t smem, cudaStream_t s) {

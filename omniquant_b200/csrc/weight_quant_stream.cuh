@@ -85,8 +85,10 @@ struct WsRowHdr {
   float rmul, en, xmin, xmax, zp, inv, qmax, su, sl, tolmax, tolmin, pad;
 };
 
-template <int NV, int STAGES, bool ROWDIV>
+// ROWMODE: 0 the row fold multiplies (or is absent), 1 it divides, 2 per-row segment table (q | k | v in one launch)
+template <int NV, int STAGES, int ROWMODE>
 __global__ void __launch_bounds__(288, NV <= 4 ? 2 : 1) wq_pc_bwd_ws(WqArgs a) {
+  constexpr bool ROWDIV = ROWMODE != 0;      // consumers: recognise the extrema within the row's tolerance (0 when it multiplies)
   extern __shared__ __align__(128) unsigned char psm[];
   __shared__ uint64_t full[STAGES], empty[STAGES];
   __shared__ WsRowHdr hdr[STAGES];
@@ -112,10 +114,17 @@ __global__ void __launch_bounds__(288, NV <= 4 ? 2 : 1) wq_pc_bwd_ws(WqArgs a) {
 
   if (warp == 8) {
     // ---------------------------------------------------------------- control warp
-    struct Raw { float rs, en, xmin, xmax, scale, zp, up, low; };
+    struct Raw { float rs, en, xmin, xmax, scale, zp, up, low; int div; };
     auto load_raw = [&](long row) {
       Raw r;
-      r.rs = (a.row && a.row_op != 0) ? a.row[row] : 1.0f;
+      if (ROWMODE == 2) {
+        int op;
+        wq_row_fold(a, row, r.rs, op);
+        r.div = op == 2;
+      } else {
+        r.rs = (a.row && a.row_op != 0) ? a.row[row] : 1.0f;
+        r.div = ROWMODE == 1;
+      }
       r.en = a.e_row ? a.e_row[row] : 0.0f;
       r.xmin = a.xmin_in[row];
       r.xmax = a.xmax_in[row];
@@ -137,11 +146,11 @@ __global__ void __launch_bounds__(288, NV <= 4 ? 2 : 1) wq_pc_bwd_ws(WqArgs a) {
       } else {
         q = oq_qparams(r.xmin, r.xmax, h.su, h.sl, lwc, a.n_bits, a.symmetric, a.recip_div);
       }
-      h.rmul = ROWDIV ? 1.0f / r.rs : r.rs;
+      h.rmul = r.div ? 1.0f / r.rs : r.rs;
       h.en = r.en; h.xmin = r.xmin; h.xmax = r.xmax; h.zp = q.zp; h.qmax = q.qmax;
       h.inv = OQ_DIV(1.0f, q.scale);
-      h.tolmax = ROWDIV ? 2.4e-7f * fabsf(r.xmax) : 0.0f;
-      h.tolmin = ROWDIV ? 2.4e-7f * fabsf(r.xmin) : 0.0f;
+      h.tolmax = r.div ? 2.4e-7f * fabsf(r.xmax) : 0.0f;
+      h.tolmin = r.div ? 2.4e-7f * fabsf(r.xmin) : 0.0f;
       h.pad = 0.f;
       hdr[st] = h;
       fence_proxy_async();
@@ -320,7 +329,7 @@ __global__ void __launch_bounds__(288, NV <= 4 ? 2 : 1) wq_pc_bwd_ws(WqArgs a) {
   }
 }
 
-template <bool ROWDIV>
+template <int ROWDIV>
 static bool launch_pc_bwd_ws2(const WqArgs& a, cudaStream_t s) {
   constexpr int STAGES = 3;
   const int nv = (a.K / 4 + 255) / 256;
@@ -342,5 +351,6 @@ static bool launch_pc_bwd_ws2(const WqArgs& a, cudaStream_t s) {
   return false;
 }
 static bool launch_pc_bwd_ws(const WqArgs& a, cudaStream_t s) {
-  return (a.row && a.row_op == 2) ? launch_pc_bwd_ws2<true>(a, s) : launch_pc_bwd_ws2<false>(a, s);
+  if (a.nseg) return launch_pc_bwd_ws2<2>(a, s);
+  return (a.row && a.row_op == 2) ? launch_pc_bwd_ws2<1>(a, s) : launch_pc_bwd_ws2<0>(a, s);
 }

@@ -142,12 +142,19 @@ class BlockEngine:
                 layout[n] = (off, H)
                 off += H
         self.n_let = off
+        self.group_units = {g: [u for u in U if u.group == g] for g in dict.fromkeys(u.group for u in U)}
+        self.glayout = {}          # weight group -> (offset of its ups, offset of its lows, items): one launch can serve a group
         if qcfg.lwc:
-            for u in U:
-                n = u.N * G(u.K)
-                layout[f"{u.name}.up"] = (off, n)
-                layout[f"{u.name}.low"] = (off + n, n)
-                off += 2 * n
+            for g, us in self.group_units.items():
+                tot = sum(u.N * G(u.K) for u in us)
+                self.glayout[g] = (off, off + tot, tot)
+                o2 = off
+                for u in us:
+                    n = u.N * G(u.K)
+                    layout[f"{u.name}.up"] = (o2, n)
+                    layout[f"{u.name}.low"] = (o2 + tot, n)
+                    o2 += n
+                off += 2 * tot
         self.n_params = off
         self.layout = layout
         z = lambda n, dt=F32: torch.zeros(n, device=self.dev, dtype=dt)
@@ -158,6 +165,9 @@ class BlockEngine:
         self.step_dev = torch.zeros(1, device=self.dev, dtype=torch.int32)
         self.p = {n: self.params[o:o + c] for n, (o, c) in layout.items()}
         self.g = {n: self.grads[o:o + c] for n, (o, c) in layout.items()}
+        # group-level views of the LWC factors / their gradients: (up, low) over all units of a weight group
+        self.pg = {g: (self.params[a:a + n], self.params[b:b + n]) for g, (a, b, n) in self.glayout.items()}
+        self.gg = {g: (self.grads[a:a + n], self.grads[b:b + n]) for g, (a, b, n) in self.glayout.items()}
         if qcfg.lwc:
             for u in U:
                 self.p[f"{u.name}.up"].fill_(4.0)     # quantizer.py:62
@@ -182,8 +192,17 @@ class BlockEngine:
         self._mvbuf = z(4 * H + F1)         # packed W@shift outputs (layout: include/omniquant_b200.h, oq_let_fold_vec)
         mvv = {"q": self._mvbuf[:H], "k": self._mvbuf[H:2 * H], "v": self._mvbuf[2 * H:3 * H], "o": self._mvbuf[3 * H:4 * H],
                "fc1": self._mvbuf[4 * H:], "fc2": z(H)}
-        self.qstat = {u.name: dict(xmin=z(u.N * G(u.K)), xmax=z(u.N * G(u.K)), zp=z(u.N * G(u.K)), mv=mvv.get(u.name),
-                                    scale=self.W8[u.group].scale[u.r0:u.r1] if self.s8 else z(u.N * G(u.K))) for u in U}
+        self.qstat, self.gstat = {}, {}
+        for g, us in self.group_units.items():
+            tot = sum(u.N * G(u.K) for u in us)
+            gs = dict(xmin=z(tot), xmax=z(tot), zp=z(tot), scale=self.W8[g].scale if (self.s8 and tot == self.W[g].shape[0]) else z(tot))
+            self.gstat[g] = gs
+            o2 = 0
+            for u in us:
+                n = u.N * G(u.K)
+                self.qstat[u.name] = dict(xmin=gs["xmin"][o2:o2 + n], xmax=gs["xmax"][o2:o2 + n], zp=gs["zp"][o2:o2 + n],
+                                          scale=gs["scale"][o2:o2 + n], mv=mvv.get(u.name))
+                o2 += n
         self._tmpv = z(9 * H + F1)
         self.tmp = {}     # folded vectors of the current step
         self.bufs = {}
@@ -338,8 +357,20 @@ class BlockEngine:
                                              tv, part)
         first = [u for u in self.units if u.group == "qkv"]
         later = [u for u in self.units if u.group != "qkv"]
-        for u in first:                 # what the first GEMM of the forward needs, on the main stream
-            quant_unit(u)
+        if self._merged(first, final):      # q | k | v in ONE launch (row segments carry the per-weight row folds)
+            g0 = first[0].group
+            gs = self.gstat[g0]
+            kw = dict(s8=self.W8[g0]) if (self.s8 and q.wbits < 16) else {}
+            up, low = self.pg[g0] if q.lwc else (None, None)
+            u0 = first[0]
+            ops.weight_quant_fwd(self.W[g0], n_bits=q.wbits, symmetric=q.symmetric, group_size=q.group_size, up=up, low=low,
+                                 col_scale=p.get(u0.col) if u0.col else None, shift=p.get(u0.shift) if u0.shift else None,
+                                 matvec_out=self._mvbuf[:self.QW] if u0.shift else None, recip_div=q.recip_div,
+                                 wq_bf16=self.Wq[g0], xmin_out=gs["xmin"], xmax_out=gs["xmax"], scale_out=gs["scale"],
+                                 zp_out=gs["zp"], segments=self._segments(first), **kw)
+        else:
+            for u in first:             # what the first GEMM of the forward needs, on the main stream
+                quant_unit(u)
         if q.let:
             fold(1)
         self._fork()
@@ -364,6 +395,22 @@ class BlockEngine:
         t["W"] = self.Wq
         t["W8"] = self.W8
         return extra
+
+    def _merged(self, us, final=False):
+        """One weight-quantiser launch for all units of a weight group (q | k | v): always possible without LET (no
+        fold: the units differ in nothing); with LET when the per-channel streaming kernels apply (row segment table)."""
+        q = self.q
+        if final or len(us) < 2 or q.wbits >= 16 or os.environ.get("OQ_WQ_MERGE", "1") == "0":
+            return False
+        if not q.let:
+            return True
+        u0 = us[0]
+        return (not q.group_size and u0.K % 8 == 0 and u0.K <= 8192 and all(u.col == u0.col and u.shift == u0.shift for u in us))
+
+    def _segments(self, us):
+        if not self.q.let:
+            return None
+        return [(u.r1, self.p.get(u.row) if u.row else None, u.row_op if u.row else 0) for u in us]
 
     def fp_weights(self):
         """bf16 copies of the raw weights for the full-precision pass (quantize/omniquant.py:165-172)."""
@@ -773,8 +820,22 @@ class BlockEngine:
             ev = self.buf("e_qkv", (3 * H,), F32)
             ops.let_prep_bwd(H, self.params[:7 * H], dbqkv, self._qscale, ev)
             e = {"q": ev[:H], "k": ev[H:2 * H], "v": ev[2 * H:]}
-        for u in self.units:
-            if u.group == "qkv":
+        first = [u for u in self.units if u.group == "qkv"]
+        if self._merged(first):
+            g0, u0 = first[0].group, first[0]
+            gs, acc = self.gstat[g0], self._acc
+            colacc = {"qkv_s": acc["dcol_qkv"], "out_s": acc["dcol_out"], "fc1_s": acc["dcol_fc1"]}
+            shacc = {"qkv_d": acc["dsh_qkv"], "out_d": acc["dsh_out"], "fc1_d": acc["dsh_fc1"]}
+            up, low = self.pg[g0] if q.lwc else (None, None)
+            d_up, d_low = self.gg[g0] if q.lwc else (None, None)
+            ops.weight_quant_bwd(self.W[g0], dW[g0], gs["xmin"], gs["xmax"], n_bits=q.wbits, symmetric=q.symmetric,
+                                 group_size=q.group_size, up=up, low=low, col_scale=self.p.get(u0.col) if u0.col else None,
+                                 recip_div=q.recip_div, e_row=ev if (let and u0.shift) else None, d_up=d_up, d_low=d_low,
+                                 dcol_acc=colacc[u0.col] if u0.col else None, drow=self._drowbuf if let else None,
+                                 dshift_acc=shacc[u0.shift] if u0.shift else None, scale=gs["scale"], zp=gs["zp"],
+                                 segments=self._segments(first))
+        else:
+            for u in first:
                 self._unit_bwd(u, dW, e.get(u.name))
         self._join()
         if let:

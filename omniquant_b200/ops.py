@@ -82,9 +82,24 @@ def _s8_args(s8, rows, C):
     return s8.codes.data_ptr(), s8.codes.stride(0), s8.meta.data_ptr()
 
 
+def _segments(segments, N):
+    """(n_seg, seg_end, seg_row, seg_op) ctypes arguments of a row segment table [(end_row, row_scale | None, op), ...]."""
+    import ctypes
+    if not segments:
+        return 0, None, None, None
+    if len(segments) > 3 or segments[-1][0] != N:
+        raise OqError("row segments: at most 3, the last one must end at N")
+    for _, t, _ in segments:
+        _chk(t, F32, "segment row scale")
+    ends = (ctypes.c_int * len(segments))(*[int(e) for e, _, _ in segments])
+    rows = (ctypes.c_void_p * len(segments))(*[(t.data_ptr() if t is not None else None) for _, t, _ in segments])
+    opsv = (ctypes.c_int * len(segments))(*[int(o) for _, _, o in segments])
+    return len(segments), ends, rows, opsv
+
+
 def weight_quant_fwd(W, *, n_bits, symmetric=False, group_size=0, up=None, low=None, col_scale=None, row_scale=None,
                      row_op=0, shift=None, matvec_out=None, recip_div=True, wq_bf16=None, wq_f32=None, codes=None,
-                     scale_out=None, zp_out=None, xmin_out=None, xmax_out=None, s8=None):
+                     scale_out=None, zp_out=None, xmin_out=None, xmax_out=None, s8=None, segments=None):
     _chk(W, F32, "W")
     for n, t in (("up", up), ("low", low), ("col_scale", col_scale), ("row_scale", row_scale), ("shift", shift),
                  ("matvec_out", matvec_out), ("wq_f32", wq_f32), ("scale_out", scale_out), ("zp_out", zp_out),
@@ -105,12 +120,13 @@ def weight_quant_fwd(W, *, n_bits, symmetric=False, group_size=0, up=None, low=N
         scale_out, c8, t8, b8 = s8.scale, s8.codes.data_ptr(), s8.t.data_ptr(), s8.beta.data_ptr()
     lib().call("oq_weight_quant_fwd", _p(W), N, K, _p(col_scale), _p(row_scale), row_op, _p(shift), _p(matvec_out),
                n_bits, int(symmetric), int(group_size or 0), _p(up), _p(low), int(recip_div), _p(wq_bf16), ld,
-               _p(wq_f32), _p(codes), _p(scale_out), _p(zp_out), _p(xmin_out), _p(xmax_out), c8, t8, b8, _stream())
+               _p(wq_f32), _p(codes), _p(scale_out), _p(zp_out), _p(xmin_out), _p(xmax_out), c8, t8, b8,
+               *_segments(segments, N), _stream())
 
 
 def weight_quant_bwd(W, grad_wq, xmin, xmax, *, n_bits, symmetric=False, group_size=0, up=None, low=None,
                      col_scale=None, row_scale=None, row_op=0, recip_div=True, e_row=None, d_up=None, d_low=None,
-                     dcol_acc=None, drow=None, dshift_acc=None, dW_full=None, scale=None, zp=None):
+                     dcol_acc=None, drow=None, dshift_acc=None, dW_full=None, scale=None, zp=None, segments=None):
     _chk(W, F32, "W")
     if grad_wq.dtype not in (BF16, F32):
         raise OqError("grad_wq must be bf16 or fp32")
@@ -119,7 +135,7 @@ def weight_quant_bwd(W, grad_wq, xmin, xmax, *, n_bits, symmetric=False, group_s
     lib().call("oq_weight_quant_bwd", _p(W), N, K, _p(col_scale), _p(row_scale), row_op, n_bits, int(symmetric),
                int(group_size or 0), _p(up), _p(low), int(recip_div), _p(xmin), _p(xmax), _p(scale), _p(zp), _p(grad_wq),
                int(grad_wq.dtype == F32), ldg, _p(e_row), _p(d_up), _p(d_low), _p(dcol_acc), _p(drow), _p(dshift_acc),
-               _p(dW_full), _stream())
+               _p(dW_full), *_segments(segments, N), _stream())
 
 
 # ------------------------------------------------------------------ activations

@@ -33,7 +33,7 @@ def test_bad_arguments_fail_loudly_without_gpu():
     l = _lib.lib()
     with pytest.raises(_lib.OqError, match="n_bits"):
         l.call("oq_weight_quant_fwd", 16, 4, 4, None, None, 0, None, None, 1, 0, 0, None, None, 0, None, 0, None, None,
-               None, None, None, None, None, None, None, None)
+               None, None, None, None, None, None, None, 0, None, None, None, None)
     with pytest.raises(_lib.OqError, match="multiples of 8"):
         l.call("oq_gemm_bf16", 16, 0, 7, 0, 16, 0, 8, 0, 16, 0, 8, 0, 8, 8, 8, 1, None, None, 0, 0, 1.0, 0, 0, 0, 0, None)
 

@@ -934,3 +934,51 @@ def test_engine_fused_attention_agrees_with_the_unfused_chain(monkeypatch):
     assert abs(res[0][0] - res[1][0]) / res[1][0] < 2e-3, (res[0][0], res[1][0])
     a, b = res[0][1].double(), res[1][1].double()
     assert float((a - b).norm() / b.norm()) < 3e-2
+
+
+def test_weight_quant_row_segments_equal_separate_launches(ops):
+    """q | k | v in ONE launch (row segment table: shared column scale / shift, per-weight row vector and operation) against
+    three separate launches: forward outputs bit for bit, backward reductions to atomic-order round-off."""
+    gen = torch.Generator(device="cuda").manual_seed(13)
+    H, K = 384, 512
+    W = (torch.randn(3 * H, K, device="cuda", generator=gen) * 0.05).half().float()
+    col = torch.rand(K, device="cuda", generator=gen) + 0.5
+    shift = torch.randn(K, device="cuda", generator=gen) * 0.1
+    rq, rv = torch.rand(H, device="cuda", generator=gen) + 0.5, torch.rand(H, device="cuda", generator=gen) + 0.5
+    up = torch.randn(3 * H, device="cuda", generator=gen) + 3
+    low = torch.randn(3 * H, device="cuda", generator=gen) + 3
+    g = (torch.randn(3 * H, K, device="cuda", generator=gen) * 0.01).to(torch.bfloat16)
+    e = torch.randn(3 * H, device="cuda", generator=gen)
+    segs = [(H, rq, 2), (2 * H, rq, 1), (3 * H, rv, 2)]
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, device="cuda", dtype=dt)
+
+    def fwd(Wp, upp, lowp, **kw):
+        n = Wp.shape[0]
+        out = dict(wq_f32=z(n, K), wq_bf16=z(n, K, dt=torch.bfloat16), scale_out=z(n), zp_out=z(n), xmin_out=z(n), xmax_out=z(n),
+                   matvec_out=z(n))
+        ops.weight_quant_fwd(Wp, n_bits=4, up=upp, low=lowp, col_scale=col, shift=shift, recip_div=True, **out, **kw)
+        return out
+
+    def bwd(Wp, gp, upp, lowp, st, ep, **kw):
+        n = Wp.shape[0]
+        out = dict(d_up=z(n), d_low=z(n), dcol_acc=z(K), drow=z(n), dshift_acc=z(K))
+        ops.weight_quant_bwd(Wp, gp, st["xmin_out"], st["xmax_out"], n_bits=4, up=upp, low=lowp, col_scale=col, recip_div=True,
+                             e_row=ep, scale=st["scale_out"], zp=st["zp_out"], **out, **kw)
+        return out
+
+    one = fwd(W, up, low, segments=segs)
+    oneb = bwd(W, g, up, low, one, e, segments=segs)
+    parts, partsb = [], []
+    for i, (row, op) in enumerate(((rq, 2), (rq, 1), (rv, 2))):
+        r = slice(i * H, (i + 1) * H)
+        parts.append(fwd(W[r].contiguous(), up[r].contiguous(), low[r].contiguous(), row_scale=row, row_op=op))
+        partsb.append(bwd(W[r].contiguous(), g[r].contiguous(), up[r].contiguous(), low[r].contiguous(), parts[-1], e[r].contiguous(),
+                          row_scale=row, row_op=op))
+    torch.cuda.synchronize()
+    for k in ("wq_f32", "wq_bf16", "scale_out", "zp_out", "xmin_out", "xmax_out"):
+        assert torch.equal(one[k], torch.cat([p_[k] for p_ in parts], 0)), k
+    torch.testing.assert_close(one["matvec_out"], torch.cat([p_["matvec_out"] for p_ in parts]), rtol=1e-5, atol=1e-6)
+    for k in ("d_up", "d_low", "drow"):
+        torch.testing.assert_close(oneb[k], torch.cat([p_[k] for p_ in partsb]), rtol=2e-4, atol=1e-6)
+    for k in ("dcol_acc", "dshift_acc"):
+        torch.testing.assert_close(oneb[k], sum(p_[k] for p_ in partsb), rtol=2e-4, atol=1e-5)
