@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) aq_fwd_block_reg(AqArgs a) {
     return;
   }
   const float z0 = oq_s8_z0(q.zp, q.qmax);
-  float csum = 0.f;
+  int isum = 0;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (threadIdx.x + i * 256) * 8;
@@ -255,10 +255,10 @@ __global__ void __launch_bounds__(256) aq_fwd_block_reg(AqArgs a) {
       float cd[8];
       aq_quant_codes<8>(v[i], cd, q, inv, inv_ok);
       store_bf8(yr + c, v[i]);
-      s8_store8(a.s8.codes + r * a.s8.ld + c, cd, z0, csum);
+      s8_store8(a.s8.codes + r * a.s8.ld + c, cd, z0, isum);
     }
   }
-  csum = warp_reduce(csum, OpSum());
+  const float csum = (float)__reduce_add_sync(0xffffffffu, isum);
   if (lane == 0) scratch[16 + warp] = csum;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(512, 2) swiglu_aq_fwd_kernel(GluArgs a) {
     return;
   }
   const float z0 = oq_s8_z0(q.zp, q.qmax);
-  float csum = 0.f;
+  int isum = 0;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (threadIdx.x + i * 512) * 8;
@@ -416,10 +416,10 @@ __global__ void __launch_bounds__(512, 2) swiglu_aq_fwd_kernel(GluArgs a) {
       float cd[8];
       aq_quant_codes<8>(v[i], cd, q, inv, inv_ok);
       store_bf8(yr + c, v[i]);
-      s8_store8(a.s8.codes + r * a.s8.ld + c, cd, z0, csum);
+      s8_store8(a.s8.codes + r * a.s8.ld + c, cd, z0, isum);
     }
   }
-  csum = warp_reduce(csum, OpSum());
+  const float csum = (float)__reduce_add_sync(0xffffffffu, isum);
   if ((threadIdx.x & 31) == 0) scratch[32 + (threadIdx.x >> 5)] = csum;
   __syncthreads();
   if (threadIdx.x == 0) {

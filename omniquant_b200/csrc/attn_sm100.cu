@@ -137,25 +137,31 @@ __device__ __forceinline__ void st_chunk(uint8_t* blk, int r, int c, const float
 }
 
 // ================================================================== forward
-constexpr int FWD_SMEM = TILE128 /*Q*/ + 2 * 2 * TILE128 /*K,V x 2 stages*/ + TILE128 /*P*/ + 1024 + 256;
+constexpr int FWD_SMEM = TILE128 /*Q*/ + 2 * TILE128 /*K ring*/ + 2 * TILE128 /*V ring*/ + TILE128 /*P*/ + 1024 + 256;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // K and V travel through SEPARATE two-slot rings: a K tile is released as soon as its S MMAs retire, a V tile only after
+  // its P V MMAs -- one shared ring would hold K hostage until the softmax of its tile is done and expose the whole
+  // TMA round trip in every iteration (measured: 7.2k cycles per tile pair instead of ~2.5k)
   uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + TILE128;                 // stage s: K at sKV + s * 2 * TILE128, V right behind it
-  uint8_t* sP = sKV + 4 * TILE128;
+  uint8_t* sKr = sQ + TILE128;                 // K ring: slot s at sKr + s * TILE128
+  uint8_t* sVr = sKr + 2 * TILE128;            // V ring
+  uint8_t* sP = sVr + 2 * TILE128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + TILE128);
   uint64_t* q_full = bars;          // [1]
-  uint64_t* kv_full = bars + 1;     // [2]
-  uint64_t* kv_empty = bars + 3;    // [2]
+  uint64_t* k_full = bars + 1;      // [2]
+  uint64_t* k_empty = bars + 3;     // [2]
   uint64_t* s_full = bars + 5;      // [2] MMA -> softmax
   uint64_t* s_empty = bars + 7;     // [2] softmax -> MMA (one arrive per softmax warp)
   uint64_t* p_full = bars + 9;      // [1] softmax -> MMA
   uint64_t* p_empty = bars + 10;    // [1] MMA -> softmax
   uint64_t* o_full = bars + 11;     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* v_full = bars + 12;     // [2]
+  uint64_t* v_empty = bars + 14;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = p.T / 128, per = p.heads * p.batch;
@@ -171,8 +177,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 4);
     }
@@ -197,14 +205,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
       tma_load_2d(sQ + BLK128, &tm128, q_full, qc + 64, row0 + qt * 128);
       for (int t = 0; t < nit; ++t) {
         const int st = t & 1, pass = t >= nj, j = pass ? t - nj : t;
-        mbar_wait(&kv_empty[st], ((t >> 1) & 1) ^ 1);
-        uint8_t* sK = sKV + st * 2 * TILE128;
-        mbar_expect_tx(&kv_full[st], pass ? 2 * TILE128 : TILE128);
-        tma_load_2d(sK, &tm128, &kv_full[st], kc, row0 + j * 128);
-        tma_load_2d(sK + BLK128, &tm128, &kv_full[st], kc + 64, row0 + j * 128);
+        mbar_wait(&k_empty[st], ((t >> 1) & 1) ^ 1);
+        uint8_t* sK = sKr + st * TILE128;
+        mbar_expect_tx(&k_full[st], TILE128);
+        tma_load_2d(sK, &tm128, &k_full[st], kc, row0 + j * 128);
+        tma_load_2d(sK + BLK128, &tm128, &k_full[st], kc + 64, row0 + j * 128);
         if (pass) {
-          tma_load_2d(sK + TILE128, &tm128, &kv_full[st], vc, row0 + j * 128);
-          tma_load_2d(sK + TILE128 + BLK128, &tm128, &kv_full[st], vc + 64, row0 + j * 128);
+          const int vs = j & 1;
+          mbar_wait(&v_empty[vs], ((j >> 1) & 1) ^ 1);
+          uint8_t* sV = sVr + vs * TILE128;
+          mbar_expect_tx(&v_full[vs], TILE128);
+          tma_load_2d(sV, &tm128, &v_full[vs], vc, row0 + j * 128);
+          tma_load_2d(sV + BLK128, &tm128, &v_full[vs], vc + 64, row0 + j * 128);
         }
       }
     }
@@ -213,27 +225,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
       const uint32_t id_s = make_idesc(128, 0), id_o = make_idesc(128, 1);
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
       uint32_t p_phase = 0;
-      auto pv = [&](int u) {        // O += P(u) V(u)
-        const uint32_t aV = smem_u32(sKV + (u & 1) * 2 * TILE128 + TILE128);
+      auto pv = [&](int u) {        // O += P(u) V(u);  u counts from nj (pass 2), key tile j = u - nj
+        const int j = u - nj, vs = j & 1;
+        const uint32_t aV = smem_u32(sVr + vs * TILE128);
+        mbar_wait(&v_full[vs], (j >> 1) & 1);
         mbar_wait(p_full, p_phase);
         p_phase ^= 1;
         tc_fence_after();
 #pragma unroll
         for (int s = 0; s < 8; ++s) tc_mma(tmem + 256, desc_k(aP, s, BLK128), desc_mn(aV, s, BLK128), id_o, (u > nj || s > 0) ? 1u : 0u);
         tc_commit(p_empty);
-        tc_commit(&kv_empty[u & 1]);
+        tc_commit(&v_empty[vs]);
       };
       mbar_wait(q_full, 0);
       for (int t = 0; t < nit; ++t) {
         const int st = t & 1;
         const uint32_t ph = (t >> 1) & 1;
-        mbar_wait(&kv_full[st], ph);
+        mbar_wait(&k_full[st], ph);
         mbar_wait(&s_empty[st], ph ^ 1);
         tc_fence_after();
-        const uint32_t aK = smem_u32(sKV + st * 2 * TILE128);
+        const uint32_t aK = smem_u32(sKr + st * TILE128);
 #pragma unroll
         for (int s = 0; s < 8; ++s) tc_mma(tmem + st * 128, desc_k(aQ, s, BLK128), desc_k(aK, s, BLK128), id_s, s > 0 ? 1u : 0u);
-        if (t < nj) tc_commit(&kv_empty[st]);
+        tc_commit(&k_empty[st]);
         tc_commit(&s_full[st]);
         if (t > nj) pv(t - 1);
       }
@@ -368,7 +382,9 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* O, long ldo
 }
 
 // ================================================================== backward: dK, dV
-constexpr int DKV_SMEM = 2 * TILE128 /*K,V*/ + 2 * 2 * TILE64 /*Q,dO x 2*/ + 2 * 2 * BLK128 /*P^T,dS^T x 2*/ + 2 * 64 * 16 /*stats*/ + 1024 + 256;
+constexpr int DKV_ST = 3;      // Q / dO stages: a stage is needed twice (S^T / dP^T early, the accumulate MMAs after the softmax),
+                               // so it is held for a whole iteration; three stages keep the TMA round trip off the critical path
+constexpr int DKV_SMEM = 2 * TILE128 /*K,V*/ + DKV_ST * 2 * TILE64 /*Q,dO*/ + 2 * BLK128 /*P^T,dS^T*/ + DKV_ST * 64 * 16 /*stats*/ + 1024 + 256;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64,
@@ -378,16 +394,16 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
   uint8_t* sK = smem;
   uint8_t* sV = sK + TILE128;
   uint8_t* sQdO = sV + TILE128;               // stage s: Q at + s * 2 * TILE64, dO right behind it
-  uint8_t* sPS = sQdO + 4 * TILE64;           // buffer s: P^T at + s * 2 * BLK128, dS^T right behind it
-  float4* sstat = reinterpret_cast<float4*>(sPS + 4 * BLK128);   // [2][64]: (max, 1/l, delta, -) of the stage's queries
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sstat) + 2 * 64 * 16);
+  uint8_t* sPS = sQdO + DKV_ST * 2 * TILE64;  // P^T, dS^T right behind it (one buffer: the accumulate MMAs read it for ~500 cycles)
+  float4* sstat = reinterpret_cast<float4*>(sPS + 2 * BLK128);   // [DKV_ST][64]: (max*log2e, 1/l, delta, -) of the stage's queries
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sstat) + DKV_ST * 64 * 16);
   uint64_t* kv_full = bars;          // [1]
-  uint64_t* qdo_full = bars + 1;     // [2]
-  uint64_t* qdo_empty = bars + 3;    // [2]
-  uint64_t* s_full = bars + 5;       // [2]
-  uint64_t* s_empty = bars + 7;      // [2]
-  uint64_t* p_full = bars + 9;       // [2]
-  uint64_t* p_empty = bars + 11;     // [2]
+  uint64_t* qdo_full = bars + 1;     // [DKV_ST]
+  uint64_t* qdo_empty = bars + 4;    // [DKV_ST]
+  uint64_t* s_full = bars + 7;       // [2]
+  uint64_t* s_empty = bars + 9;      // [2]
+  uint64_t* p_full = bars + 11;      // [1]
+  uint64_t* p_empty = bars + 12;     // [1]
   uint64_t* acc_full = bars + 13;    // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
@@ -408,14 +424,16 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < DKV_ST; ++i) {
       mbar_init(&qdo_full[i], 1);
       mbar_init(&qdo_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 4);
-      mbar_init(&p_full[i], 4);
-      mbar_init(&p_empty[i], 1);
     }
+    mbar_init(p_full, 4);
+    mbar_init(p_empty, 1);
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -436,8 +454,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
       tma_load_2d(sV, &tm128, kv_full, vc, row0 + j * 128);
       tma_load_2d(sV + BLK128, &tm128, kv_full, vc + 64, row0 + j * 128);
       for (int it = 0; it < nit; ++it) {
-        const int st = it & 1, head = g * p.rep + it / nh, i64 = 2 * j + it % nh;
-        mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
+        const int st = it % DKV_ST, head = g * p.rep + it / nh, i64 = 2 * j + it % nh;
+        mbar_wait(&qdo_empty[st], ((it / DKV_ST) & 1) ^ 1);
         uint8_t* sQ = sQdO + st * 2 * TILE64;
         mbar_expect_tx(&qdo_full[st], 2 * TILE64);
         const int qc = col_q(p, head), r = row0 + i64 * 64;
@@ -452,31 +470,30 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
       const uint32_t id_s = make_idesc(64, 0), id_a = make_idesc(128, 1);
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
       auto accumulate = [&](int u) {     // dV += P^T dO,  dK += dS^T Q   (K = the 64 queries of stage u)
-        const int sb = u & 1;
-        const uint32_t aQ = smem_u32(sQdO + sb * 2 * TILE64), adO = aQ + TILE64;
-        const uint32_t aPT = smem_u32(sPS + sb * 2 * BLK128), adST = aPT + BLK128;
-        mbar_wait(&p_full[sb], (u >> 1) & 1);
+        const int st = u % DKV_ST;
+        const uint32_t aQ = smem_u32(sQdO + st * 2 * TILE64), adO = aQ + TILE64;
+        const uint32_t aPT = smem_u32(sPS), adST = aPT + BLK128;
+        mbar_wait(p_full, u & 1);
         tc_fence_after();
 #pragma unroll
         for (int s = 0; s < 4; ++s) tc_mma(tmem + 384, desc_k(aPT, s, BLK128), desc_mn(adO, s, BLK64), id_a, (u > 0 || s > 0) ? 1u : 0u);
 #pragma unroll
         for (int s = 0; s < 4; ++s) tc_mma(tmem + 256, desc_k(adST, s, BLK128), desc_mn(aQ, s, BLK64), id_a, (u > 0 || s > 0) ? 1u : 0u);
-        tc_commit(&p_empty[sb]);
-        tc_commit(&qdo_empty[sb]);
+        tc_commit(p_empty);
+        tc_commit(&qdo_empty[st]);
       };
       mbar_wait(kv_full, 0);
       for (int it = 0; it < nit; ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(&qdo_full[st], ph);
-        mbar_wait(&s_empty[st], ph ^ 1);
+        const int st = it % DKV_ST, sb = it & 1;
+        mbar_wait(&qdo_full[st], (it / DKV_ST) & 1);
+        mbar_wait(&s_empty[sb], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t aQ = smem_u32(sQdO + st * 2 * TILE64), adO = aQ + TILE64;
 #pragma unroll
-        for (int s = 0; s < 8; ++s) tc_mma(tmem + st * 128, desc_k(aK, s, BLK128), desc_k(aQ, s, BLK64), id_s, s > 0 ? 1u : 0u);
+        for (int s = 0; s < 8; ++s) tc_mma(tmem + sb * 128, desc_k(aK, s, BLK128), desc_k(aQ, s, BLK64), id_s, s > 0 ? 1u : 0u);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) tc_mma(tmem + st * 128 + 64, desc_k(aV, s, BLK128), desc_k(adO, s, BLK64), id_s, s > 0 ? 1u : 0u);
-        tc_commit(&s_full[st]);
+        for (int s = 0; s < 8; ++s) tc_mma(tmem + sb * 128 + 64, desc_k(aV, s, BLK128), desc_k(adO, s, BLK64), id_s, s > 0 ? 1u : 0u);
+        tc_commit(&s_full[sb]);
         if (it > 0) accumulate(it - 1);
       }
       accumulate(nit - 1);
@@ -488,17 +505,17 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
     const int tid = threadIdx.x - 128;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     for (int it = 0; it < nit; ++it) {
-      const int sb = it & 1, head = g * p.rep + it / nh, i64 = 2 * j + it % nh;
+      const int sb = it & 1, ss = it % DKV_ST, head = g * p.rep + it / nh, i64 = 2 * j + it % nh;
       const uint32_t ph = (it >> 1) & 1;
-      if (tid < 64) {
+      if (tid < 64) {      // (slot ss was last read in iteration it - 3; every thread has passed two named barriers since)
         const long sr = ((long)b * p.heads + head) * p.T + i64 * 64 + tid;
-        sstat[sb * 64 + tid] = make_float4(p.row_max[sr] * LOG2E, p.row_invl[sr], p.delta[sr], 0.f);
+        sstat[ss * 64 + tid] = make_float4(p.row_max[sr] * LOG2E, p.row_invl[sr], p.delta[sr], 0.f);
       }
       named_bar_sync(1, 128);
       mbar_wait(&s_full[sb], ph);
       tc_fence_after();
-      mbar_wait(&p_empty[sb], ph ^ 1);        // the accumulate MMAs that read this P^T / dS^T buffer two steps ago are done
-      uint8_t* bPT = sPS + sb * 2 * BLK128;
+      if (it > 0) mbar_wait(p_empty, (it - 1) & 1);     // the accumulate MMAs of the previous step have finished reading P^T / dS^T
+      uint8_t* bPT = sPS;
       uint8_t* bdST = bPT + BLK128;
       const int lo = kg - i64 * 64;            // causal: query column c is visible to this key row iff c >= lo
       auto tile = [&](auto mask_tag) {
@@ -515,7 +532,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int c = c0 + ch * 8 + e;
-              const float4 stt = sstat[sb * 64 + c];          // (max * log2e, 1/l, delta, -) of query column c
+              const float4 stt = sstat[ss * 64 + c];          // (max * log2e, 1/l, delta, -) of query column c
               const float pe = ex2_ftz(fmaf(masked<MASK>(score16(sv[ch * 8 + e], p.alpha), c >= lo), LOG2E, -stt.x)) * stt.y;
               pr[e] = pe;
               ds[e] = pe * (__uint_as_float(dv[ch * 8 + e]) - stt.z);
@@ -531,7 +548,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&p_full[sb]);
+        mbar_arrive(p_full);
         mbar_arrive(&s_empty[sb]);
       }
     }
@@ -565,7 +582,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
 }
 
 // ================================================================== backward: dQ
-constexpr int DQ_SMEM = 2 * TILE128 /*Q,dO*/ + 2 * 2 * TILE64 /*K,V x 2*/ + 2 * BLK128 /*dS x 2*/ + 1024 + 256;
+constexpr int DQ_KST = 4;      // K ring: a K half tile serves S early and dQ += dS K after the softmax (held for a whole iteration)
+constexpr int DQ_SMEM = 2 * TILE128 /*Q,dO*/ + DQ_KST * TILE64 /*K ring*/ + 2 * TILE64 /*V ring*/ + 2 * BLK128 /*dS x 2*/ + 1024 + 256;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64,
@@ -574,18 +592,21 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + TILE128;
-  uint8_t* sKV = sdO + TILE128;                // stage s: K at + s * 2 * TILE64, V right behind it
-  uint8_t* sdS = sKV + 4 * TILE64;             // buffer s at + s * BLK128
+  uint8_t* sKr = sdO + TILE128;                // K ring: slot s at + s * TILE64
+  uint8_t* sVr = sKr + DQ_KST * TILE64;        // V ring (2 slots): V only feeds dP and is released with the S / dP MMAs
+  uint8_t* sdS = sVr + 2 * TILE64;             // buffer s at + s * BLK128
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * BLK128);
   uint64_t* qdo_full = bars;         // [1]
-  uint64_t* kv_full = bars + 1;      // [2]
-  uint64_t* kv_empty = bars + 3;     // [2]
-  uint64_t* s_full = bars + 5;       // [2]
-  uint64_t* s_empty = bars + 7;      // [2]
-  uint64_t* p_full = bars + 9;       // [2]
-  uint64_t* p_empty = bars + 11;     // [2]
-  uint64_t* acc_full = bars + 13;    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* k_full = bars + 1;       // [DQ_KST]
+  uint64_t* k_empty = bars + 5;      // [DQ_KST]
+  uint64_t* v_full = bars + 9;       // [2]
+  uint64_t* v_empty = bars + 11;     // [2]
+  uint64_t* s_full = bars + 13;      // [2]
+  uint64_t* s_empty = bars + 15;     // [2]
+  uint64_t* p_full = bars + 17;      // [2]
+  uint64_t* p_empty = bars + 19;     // [2]
+  uint64_t* acc_full = bars + 21;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = p.T / 128, per = p.heads * p.batch;
@@ -604,9 +625,13 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     mbar_init(qdo_full, 1);
+    for (int k = 0; k < DQ_KST; ++k) {
+      mbar_init(&k_full[k], 1);
+      mbar_init(&k_empty[k], 1);
+    }
     for (int k = 0; k < 2; ++k) {
-      mbar_init(&kv_full[k], 1);
-      mbar_init(&kv_empty[k], 1);
+      mbar_init(&v_full[k], 1);
+      mbar_init(&v_empty[k], 1);
       mbar_init(&s_full[k], 1);
       mbar_init(&s_empty[k], 4);
       mbar_init(&p_full[k], 4);
@@ -632,43 +657,48 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
       tma_load_2d(sdO, &tmdo128, qdo_full, head * D, row0 + i * 128);
       tma_load_2d(sdO + BLK128, &tmdo128, qdo_full, head * D + 64, row0 + i * 128);
       for (int it = 0; it < nit; ++it) {
-        const int st = it & 1;
-        mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
-        uint8_t* sK = sKV + st * 2 * TILE64;
-        mbar_expect_tx(&kv_full[st], 2 * TILE64);
+        const int ks = it % DQ_KST, vs = it & 1;
         const int r = row0 + it * 64;
-        tma_load_2d(sK, &tm64, &kv_full[st], kc, r);
-        tma_load_2d(sK + BLK64, &tm64, &kv_full[st], kc + 64, r);
-        tma_load_2d(sK + TILE64, &tm64, &kv_full[st], vc, r);
-        tma_load_2d(sK + TILE64 + BLK64, &tm64, &kv_full[st], vc + 64, r);
+        mbar_wait(&k_empty[ks], ((it / DQ_KST) & 1) ^ 1);
+        uint8_t* sK = sKr + ks * TILE64;
+        mbar_expect_tx(&k_full[ks], TILE64);
+        tma_load_2d(sK, &tm64, &k_full[ks], kc, r);
+        tma_load_2d(sK + BLK64, &tm64, &k_full[ks], kc + 64, r);
+        mbar_wait(&v_empty[vs], ((it >> 1) & 1) ^ 1);
+        uint8_t* sV = sVr + vs * TILE64;
+        mbar_expect_tx(&v_full[vs], TILE64);
+        tma_load_2d(sV, &tm64, &v_full[vs], vc, r);
+        tma_load_2d(sV + BLK64, &tm64, &v_full[vs], vc + 64, r);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t id_s = make_idesc(64, 0), id_a = make_idesc(128, 1);
       const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO);
-      auto accumulate = [&](int u) {     // dQ += dS K   (K = the 64 keys of stage u)
-        const int sb = u & 1;
-        const uint32_t aK = smem_u32(sKV + sb * 2 * TILE64), adS = smem_u32(sdS + sb * BLK128);
+      auto accumulate = [&](int u) {     // dQ += dS K   (K = the 64 keys of step u)
+        const int sb = u & 1, ks = u % DQ_KST;
+        const uint32_t aK = smem_u32(sKr + ks * TILE64), adS = smem_u32(sdS + sb * BLK128);
         mbar_wait(&p_full[sb], (u >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int s = 0; s < 4; ++s) tc_mma(tmem + 256, desc_k(adS, s, BLK128), desc_mn(aK, s, BLK64), id_a, (u > 0 || s > 0) ? 1u : 0u);
         tc_commit(&p_empty[sb]);
-        tc_commit(&kv_empty[sb]);
+        tc_commit(&k_empty[ks]);
       };
       mbar_wait(qdo_full, 0);
       for (int it = 0; it < nit; ++it) {
-        const int st = it & 1;
+        const int st = it & 1, ks = it % DQ_KST;
         const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(&kv_full[st], ph);
+        mbar_wait(&k_full[ks], (it / DQ_KST) & 1);
+        mbar_wait(&v_full[st], ph);
         mbar_wait(&s_empty[st], ph ^ 1);
         tc_fence_after();
-        const uint32_t aK = smem_u32(sKV + st * 2 * TILE64), aV = aK + TILE64;
+        const uint32_t aK = smem_u32(sKr + ks * TILE64), aV = smem_u32(sVr + st * TILE64);
 #pragma unroll
         for (int s = 0; s < 8; ++s) tc_mma(tmem + st * 128, desc_k(aQ, s, BLK128), desc_k(aK, s, BLK64), id_s, s > 0 ? 1u : 0u);
 #pragma unroll
         for (int s = 0; s < 8; ++s) tc_mma(tmem + st * 128 + 64, desc_k(adO, s, BLK128), desc_k(aV, s, BLK64), id_s, s > 0 ? 1u : 0u);
+        tc_commit(&v_empty[st]);
         tc_commit(&s_full[st]);
         if (it > 0) accumulate(it - 1);
       }

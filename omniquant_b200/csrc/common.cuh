@@ -117,25 +117,26 @@ struct S8Side {
   float* meta;              // [3, rows]: scale | t = scale * sum_k (code - z0) | beta = (z0 - zp) * scale
   long rows;
 };
-// 8 consecutive codes -> 8 bytes (one 8-byte store); adds sum (code - z0) to `sum`
-__device__ __forceinline__ void s8_store8(int8_t* p, const float (&c)[8], float z0, float& sum) {
-  uint32_t w[2] = {0u, 0u};
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float d = c[j] - z0;          // integer valued, |d| <= 128
-    sum += d;
-    w[j >> 2] |= ((uint32_t)(__float2int_rn(d)) & 0xffu) << (8 * (j & 3));
-  }
-  *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
+// (code - z0) is an integer-valued float with |.| <= 255: adding 1.5 * 2^23 leaves the two's-complement integer in the low
+// mantissa bits, so the int8 is the low byte of the float's bit pattern (1 FADD instead of a convert + mask + shift);
+// four such bytes are gathered with two PRMT + one PRMT, and their sum is ONE dp4a against 0x01010101.
+__device__ __forceinline__ uint32_t s8_pack4(float d0, float d1, float d2, float d3) {
+  const float magic = 12582912.0f;
+  const uint32_t b0 = __float_as_uint(d0 + magic), b1 = __float_as_uint(d1 + magic);
+  const uint32_t b2 = __float_as_uint(d2 + magic), b3 = __float_as_uint(d3 + magic);
+  return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
 }
-__device__ __forceinline__ void s8_store4(int8_t* p, const float (&c)[4], float z0, float& sum) {
-  uint32_t w = 0u;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float d = c[j] - z0;
-    sum += d;
-    w |= ((uint32_t)(__float2int_rn(d)) & 0xffu) << (8 * j);
-  }
+// 8 consecutive codes -> 8 bytes (one 8-byte store); adds sum (code - z0) to the integer accumulator `isum`
+__device__ __forceinline__ void s8_store8(int8_t* p, const float (&c)[8], float z0, int& isum) {
+  const uint32_t w0 = s8_pack4(c[0] - z0, c[1] - z0, c[2] - z0, c[3] - z0);
+  const uint32_t w1 = s8_pack4(c[4] - z0, c[5] - z0, c[6] - z0, c[7] - z0);
+  isum = __dp4a((int)w0, 0x01010101, isum);
+  isum = __dp4a((int)w1, 0x01010101, isum);
+  *reinterpret_cast<uint2*>(p) = make_uint2(w0, w1);
+}
+__device__ __forceinline__ void s8_store4(int8_t* p, const float (&c)[4], float z0, int& isum) {
+  const uint32_t w = s8_pack4(c[0] - z0, c[1] - z0, c[2] - z0, c[3] - z0);
+  isum = __dp4a((int)w, 0x01010101, isum);
   *reinterpret_cast<uint32_t*>(p) = w;
 }
 // a degenerate row (constant: scale 0 / zero point NaN) dequantises to NaN in the fake-quant path; the integer path

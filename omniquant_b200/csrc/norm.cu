@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(TPB) norm_fwd_reg(NormArgs a) {
   const float inv = OQ_DIV(1.0f, q.scale);
   const bool fast = oq_inv_ok(inv);
   const float z0 = oq_s8_z0(q.zp, q.qmax);
-  float csum[1] = {0.f};
+  int isum = 0;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (threadIdx.x + i * TPB) * 8;
@@ -179,10 +179,11 @@ __global__ void __launch_bounds__(TPB) norm_fwd_reg(NormArgs a) {
         }
       }
       store_bf8(a.yq + r * a.ldyq + c, v[i]);
-      if (a.s8.codes) s8_store8(a.s8.codes + r * a.s8.ld + c, cd, z0, csum[0]);
+      if (a.s8.codes) s8_store8(a.s8.codes + r * a.s8.ld + c, cd, z0, isum);
     }
   }
   if (a.s8.codes) {
+    float csum[1] = {(float)isum};        // exact: |sum| <= 128 * C < 2^24
     block_reduce<1>(csum, scratch, OpSum(), 0.0f);
     if (threadIdx.x == 0) s8_write_meta(a.s8, r, q, z0, csum[0]);
   }
