@@ -170,6 +170,20 @@ int oq_attn_bwd(const void* qkv, long ld, long width, int batch, int T, int head
                 int ck, int cv, int gk, float alpha, const void* O, long ldo, const void* dO, long lddo, const float* row_max,
                 const float* row_invl, float* delta_ws, void* dqkv, long ldg, oq_stream_t stream);
 
+/* ---- K1 as the north star words it: LWC fake-quant fused INTO the GEMM ------------------------------------------
+ * oq_gemm_fq: C[M,N] (bf16) = A[M,K] (bf16) . fq(W)[N,K]^T (+ bias) (+ residual), where the fp32 master weight tile is
+ * loaded by TMA, quantised / rounded / dequantised by transform warps in shared memory with the per-row (group_size 0) or
+ * per-group scale / zero point [N, K/group_size], and consumed by tcgen05 from there (QuantLinear.forward with
+ * use_weight_quant, quantize/int_linear.py:48-65 + quantize/quantizer.py:84-105).  The operand is bit-identical to
+ * oq_weight_quant_fwd's bf16 output.  oq_lwc_qparams evaluates scale / zero point (quantizer.py:131-147) from the saved
+ * group extrema and the LWC factors.  The engine uses the pre-pass + GEMM form instead; this entry point carries the
+ * measured comparison (profiles/r2_k1_ab.txt).  K %% 64 == 0; group_size 0 or a multiple of 64. */
+int oq_lwc_qparams(const float* xmin, const float* xmax, const float* up, const float* low, long n, int n_bits, int symmetric,
+                   int recip_div, float* scale_out, float* zp_out, oq_stream_t stream);
+int oq_gemm_fq(const void* A, long lda, const float* W, long ldw, int M, int N, int K, const float* scale, const float* zp,
+               int group_size, int n_bits, void* C, long ldc, const float* bias, const void* residual, long ldr, int max_ctas,
+               oq_stream_t stream);
+
 /* ---- elementwise / reductions ----------------------------------------------
  * SwiGLU of QuantLlamaMLP.forward (models/int_llama_layer.py:44-45): gu = [gate | up] [rows, 2F]. */
 int oq_swiglu_fwd(const void* gu, long ldgu, void* m, long ldm, long rows, int F, oq_stream_t stream);

@@ -22,8 +22,10 @@
 //   dQ        CTA = (sample, head, 128-query tile); loops over 64-key half tiles; dQ += dS K.
 // No atomics: every output element has one writer (dK / dV of a grouped-query K/V head are summed in TMEM).
 //
-// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM allocator, warps 4-7 softmax /
-// epilogue (one accumulator row per thread: TMEM lane = row).
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM allocator, warps 4-11 softmax /
+// epilogue: TMEM lane = accumulator row = thread lane; the two warps of a lane quadrant (w and w + 4) split the columns.
+// (One softmax warp per scheduler issued at IPC 0.38 -- fixed-latency and TMEM-load stalls with nothing to switch to,
+// ncu profiles/r2_attn_ncu_summary.txt; two per scheduler hide most of it.)
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -36,7 +38,9 @@
 namespace {
 
 constexpr int D = 128;                 // head dimension
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;       // 4 control warps + 8 softmax warps
+constexpr int SM_WARPS = 8;            // softmax / epilogue warps: two per TMEM lane quadrant, each takes half of the columns
+constexpr int SM_THREADS = SM_WARPS * 32;
 constexpr int ROW_B = 128;             // bytes per shared-memory row of a 64-column bf16 block (one swizzle row)
 constexpr int BLK128 = 128 * ROW_B;    // 64-column block of a 128-row tile: 16 KB
 constexpr int BLK64 = 64 * ROW_B;      // 64-column block of a  64-row tile:  8 KB
@@ -182,9 +186,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&s_empty[i], SM_WARPS);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full, SM_WARPS);
     mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     fence_mbar_init();
@@ -255,15 +259,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
       tc_commit(o_full);
     }
   } else if (warp >= 4) {
-    const int q = warp & 3, r = q * 32 + lane;
+    const int q = warp & 3, r = q * 32 + lane, half = (warp - 4) >> 2;     // this warp's columns: [64 half, 64 half + 64)
     const int qrow = qt * 128 + r;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    float m = -INFINITY, l = 0.f;      // row maximum of the fp16 scores and sum exp(s - m)
+    float m = -INFINITY, l = 0.f;      // row maximum of the fp16 scores and sum exp(s - m) over this warp's columns
     // ---- pass 1: row maximum and sum
     auto stats_tile = [&](int sb, auto mask_tag) {
       constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 32) {
         uint32_t v[32];
         tc_ld32(lane_base + sb * 128 + c0, v);
         tc_wait_ld();
@@ -273,14 +277,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
           sc[i] = masked<MASK>(score16(v[i], p.alpha), c0 + i <= r);     // causal: keys c <= r on the diagonal tile
           mx = fmaxf(mx, sc[i]);
         }
-        const float mx2 = mx * LOG2E;
+        // a warp whose columns are all masked so far (second column half, first rows of the first query tile) keeps
+        // mx = -inf: use 0 as the reference then (every term is exp2(-inf) = 0) instead of forming inf - inf
+        const float mx2 = (mx == -INFINITY) ? 0.f : mx * LOG2E;
         float add0 = 0.f, add1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           add0 += ex2_ftz(fmaf(sc[i], LOG2E, -mx2));
           add1 += ex2_ftz(fmaf(sc[i + 1], LOG2E, -mx2));
         }
-        l = l * ex2_ftz((m - mx) * LOG2E) + (add0 + add1);   // first chunk: m = -inf, l = 0 (key 0 is always visible: mx finite)
+        l = l * ((m == mx) ? 1.0f : ex2_ftz((m - mx) * LOG2E)) + (add0 + add1);   // m = -inf < mx: l = 0 * 0
         m = mx;
       }
     };
@@ -294,16 +300,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
     }
+    {   // merge the two column halves of every row: (m, l) pairs meet through shared memory (sP is still unused)
+      float2* xch = reinterpret_cast<float2*>(sP);
+      xch[half * 128 + r] = make_float2(m, l);
+      named_bar_sync(1, SM_THREADS);
+      const float2 o = xch[(half ^ 1) * 128 + r];
+      const float mf = fmaxf(m, o.x);       // finite: key 0 is visible to every row and lies in half 0
+      l = l * ex2_ftz((m - mf) * LOG2E) + o.y * ex2_ftz((o.x - mf) * LOG2E);
+      m = mf;
+      named_bar_sync(1, SM_THREADS);        // everybody has read the exchange area before pass 2 writes P over it
+    }
     const float inv = 1.0f / l;
     const long srow = ((long)b * p.heads + head) * p.T + qrow;
-    p.row_max[srow] = m;
-    p.row_invl[srow] = inv;
+    if (half == 0) {
+      p.row_max[srow] = m;
+      p.row_invl[srow] = inv;
+    }
     const float m2 = m * LOG2E;
     // ---- pass 2: probabilities with the final statistics -> shared memory (A operand of P V)
     auto prob_tile = [&](int sb, auto mask_tag) {
       constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 32) {
         uint32_t v[32];
         tc_ld32(lane_base + sb * 128 + c0, v);
         tc_wait_ld();
@@ -340,7 +358,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
     tc_fence_after();
     bf16* orow = p.O + (long)(row0 + qrow) * p.ldo + head * D;
 #pragma unroll 1
-    for (int c0 = 0; c0 < D; c0 += 32) {
+    for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 32) {
       uint32_t v[32];
       tc_ld32(lane_base + 256 + c0, v);
       tc_wait_ld();
@@ -430,9 +448,9 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&s_empty[i], SM_WARPS);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full, SM_WARPS);
     mbar_init(p_empty, 1);
     mbar_init(acc_full, 1);
     fence_mbar_init();
@@ -500,7 +518,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
       tc_commit(acc_full);
     }
   } else if (warp >= 4) {
-    const int q = warp & 3, kr = q * 32 + lane;           // key row of this thread
+    const int q = warp & 3, kr = q * 32 + lane, half = (warp - 4) >> 2;   // key row of this thread; query columns [32 half, +32)
     const int kg = j * 128 + kr;
     const int tid = threadIdx.x - 128;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
@@ -511,7 +529,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
         const long sr = ((long)b * p.heads + head) * p.T + i64 * 64 + tid;
         sstat[ss * 64 + tid] = make_float4(p.row_max[sr] * LOG2E, p.row_invl[sr], p.delta[sr], 0.f);
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, SM_THREADS);
       mbar_wait(&s_full[sb], ph);
       tc_fence_after();
       if (it > 0) mbar_wait(p_empty, (it - 1) & 1);     // the accumulate MMAs of the previous step have finished reading P^T / dS^T
@@ -520,8 +538,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
       const int lo = kg - i64 * 64;            // causal: query column c is visible to this key row iff c >= lo
       auto tile = [&](auto mask_tag) {
         constexpr bool MASK = decltype(mask_tag)::value;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 32) {
+        {
+          const int c0 = 32 * half;
           uint32_t sv[32], dv[32];
           tc_ld32(lane_base + sb * 128 + c0, sv);
           tc_ld32(lane_base + sb * 128 + 64 + c0, dv);
@@ -557,7 +575,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
     tc_fence_after();
     bf16* grow = p.dqkv + (long)(row0 + kg) * p.ldg;
 #pragma unroll 1
-    for (int c0 = 0; c0 < 2 * D; c0 += 32) {
+    for (int c0 = D * half; c0 < D * half + D; c0 += 32) {      // half 0 stores dK, half 1 stores dV
       uint32_t v[32];
       tc_ld32(lane_base + 256 + c0, v);
       tc_wait_ld();
@@ -633,8 +651,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
       mbar_init(&v_full[k], 1);
       mbar_init(&v_empty[k], 1);
       mbar_init(&s_full[k], 1);
-      mbar_init(&s_empty[k], 4);
-      mbar_init(&p_full[k], 4);
+      mbar_init(&s_empty[k], SM_WARPS);
+      mbar_init(&p_full[k], SM_WARPS);
       mbar_init(&p_empty[k], 1);
     }
     mbar_init(acc_full, 1);
@@ -706,7 +724,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
       tc_commit(acc_full);
     }
   } else if (warp >= 4) {
-    const int q = warp & 3, r = q * 32 + lane;
+    const int q = warp & 3, r = q * 32 + lane, half = (warp - 4) >> 2;     // key columns [32 half, +32) of every half tile
     const int qg = i * 128 + r;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const long sr = ((long)b * p.heads + head) * p.T + qg;
@@ -721,8 +739,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
       const int hi = qg - it * 64;             // causal: key column c is visible to this query row iff c <= hi
       auto tile = [&](auto mask_tag) {
         constexpr bool MASK = decltype(mask_tag)::value;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 32) {
+        {
+          const int c0 = 32 * half;
           uint32_t sv[32], dv[32];
           tc_ld32(lane_base + sb * 128 + c0, sv);
           tc_ld32(lane_base + sb * 128 + 64 + c0, dv);
@@ -754,7 +772,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
     tc_fence_after();
     bf16* dst = p.dqkv + (long)(row0 + qg) * p.ldg + qc;
 #pragma unroll 1
-    for (int c0 = 0; c0 < D; c0 += 32) {
+    for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 32) {
       uint32_t v[32];
       tc_ld32(lane_base + 256 + c0, v);
       tc_wait_ld();

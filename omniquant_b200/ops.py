@@ -295,6 +295,28 @@ def linear_wgrad(dy, x, dw):
          ldc=_rowmajor(dw, "dw"))
 
 
+def lwc_qparams(xmin, xmax, up, low, *, n_bits, symmetric=False, recip_div=True, scale_out=None, zp_out=None):
+    """scale / zero point of every (row, group) from the saved extrema and the LWC factors (quantizer.py:131-147)."""
+    for n, t in (("xmin", xmin), ("xmax", xmax), ("up", up), ("low", low)):
+        _chk(t, F32, n)
+    scale_out = torch.empty_like(xmin) if scale_out is None else scale_out
+    zp_out = torch.empty_like(xmin) if zp_out is None else zp_out
+    lib().call("oq_lwc_qparams", _p(xmin), _p(xmax), _p(up), _p(low), xmin.numel(), n_bits, int(symmetric), int(recip_div),
+               _p(scale_out), _p(zp_out), _stream())
+    return scale_out, zp_out
+
+
+def gemm_fq(x, W, scale, zp, out, *, n_bits, group_size=0, bias=None, residual=None, max_ctas=0):
+    """out[M,N] = x[M,K] @ fake_quant(W)[N,K]^T with the weight quantiser fused into the GEMM's operand path (K1)."""
+    _chk(x, BF16, "x"); _chk(W, F32, "W"); _chk(out, BF16, "out"); _chk(scale, F32, "scale"); _chk(zp, F32, "zp")
+    _chk(bias, F32, "bias"); _chk(residual, BF16, "residual")
+    M, K = x.shape
+    N = W.shape[0]
+    lib().call("oq_gemm_fq", _p(x), _rowmajor(x, "x"), _p(W), _rowmajor(W, "W"), M, N, K, _p(scale), _p(zp), int(group_size or 0),
+               n_bits, _p(out), _rowmajor(out, "out"), _p(bias), _p(residual),
+               _rowmajor(residual, "residual") if residual is not None else 0, max_ctas, _stream())
+
+
 # ------------------------------------------------------------------ fused attention
 def attn_supported(T: int, head_dim: int) -> bool:
     return bool(lib().fns["oq_attn_supported"](int(T), int(head_dim)))

@@ -982,3 +982,42 @@ def test_weight_quant_row_segments_equal_separate_launches(ops):
         torch.testing.assert_close(oneb[k], torch.cat([p_[k] for p_ in partsb]), rtol=2e-4, atol=1e-6)
     for k in ("dcol_acc", "dshift_acc"):
         torch.testing.assert_close(oneb[k], sum(p_[k] for p_ in partsb), rtol=2e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------- K1: weight fake-quant fused into the GEMM
+@pytest.mark.parametrize("N,K,grp,bits", [(256, 512, 0, 4), (384, 1024, 128, 3), (200, 256, 64, 2), (4096, 4096, 0, 4)])
+def test_gemm_fq_operand_is_bit_exact(ops, N, K, grp, bits):
+    """oq_gemm_fq with A = identity returns the operand the tensor cores consumed: it must equal the bf16 output of the
+    stand-alone weight quantiser bit for bit (same scale / zero point, same exact-rounding guard)."""
+    gen = torch.Generator(device="cuda").manual_seed(N + K)
+    W = (torch.randn(N, K, device="cuda", generator=gen) * 0.03).half().float()
+    G = K // grp if grp else 1
+    up = torch.randn(N * G, device="cuda", generator=gen) + 3
+    low = torch.randn(N * G, device="cuda", generator=gen) + 3
+    ref = run_wq(ops, W, bits, False, grp, up, low, True)
+    scale, zp = ops.lwc_qparams(ref["xmin_out"], ref["xmax_out"], up, low, n_bits=bits)
+    assert torch.equal(scale, ref["scale_out"]) and torch.equal(zp, ref["zp_out"])
+    eye = torch.eye(K, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(K, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_fq(eye, W, scale, zp, out, n_bits=bits, group_size=grp)
+    torch.cuda.synchronize()
+    assert torch.equal(out.t().contiguous(), ref["wq_bf16"]), float((out.t().float() - ref["wq_bf16"].float()).abs().max())
+
+
+def test_gemm_fq_matches_prepass_plus_gemm(ops):
+    """The fused kernel against the path the engine uses (oq_weight_quant_fwd -> oq_gemm_bf16), ragged M, bias + residual."""
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    M, N, K = 700, 640, 1024
+    x = torch.randn(M, K, device="cuda", generator=gen).to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda", generator=gen) * 0.03).half().float()
+    up = torch.randn(N, device="cuda", generator=gen) + 3
+    ref = run_wq(ops, W, 4, False, 0, up, up, True)
+    bias = torch.randn(N, device="cuda", generator=gen)
+    res = torch.randn(M, N, device="cuda", generator=gen).to(torch.bfloat16)
+    want = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.linear_fwd(x, ref["wq_bf16"], want, bias=bias, residual=res)
+    got = torch.empty_like(want)
+    ops.gemm_fq(x, W, ref["scale_out"], ref["zp_out"], got, n_bits=4, bias=bias, residual=res)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(got.float(), want.float(), rtol=1e-2, atol=1e-2)
+    assert float((got.float() - want.float()).abs().max()) <= 2.0 ** -6 * float(want.float().abs().max())
