@@ -74,14 +74,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -97,20 +89,30 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// 64-bit shared-memory matrix descriptor, SWIZZLE_128B (same encoding as gemm_sm100.cu)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;      // SBO: 8-row groups 1024 B apart
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
+// 64-bit shared-memory matrix descriptor, SWIZZLE_128B (same encoding as gemm_sm100.cu), kept as two 32-bit halves: the high
+// word (SBO = 1024 B, version 1, 128-byte swizzle) is a constant, and every k-step / ring slot only ADDS a multiple of 16 bytes to
+// the start-address field of the low word.  The MMA-issuing thread is the critical resource of these kernels (one thread issues
+// 20-48 small MMAs per tile pair; with descriptors rebuilt by shift / mask / or chains and the TMEM address broadcast from a
+// vector register every instruction cost ~150-200 cycles to issue -- profiles/r2_attn_ncu_summary.csv), so everything that
+// is not `base + immediate` is hoisted out of the issue loops.
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+// low word of a K-major operand (rows of 128 B; LBO unused = 16 B)
+__device__ __forceinline__ uint32_t klo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+// low word of an MN-major operand whose 64-column blocks are `blk` bytes apart (LBO)
+__device__ __forceinline__ uint32_t mnlo(uint32_t saddr, uint32_t blk) { return ((saddr & 0x3FFFFu) >> 4) | ((blk >> 4) << 16); }
+// address-field increment of k-step s (16 elements): K-major operand made of 64-column blocks `blk` bytes apart / MN-major (16 rows)
+__device__ __forceinline__ constexpr uint32_t kstep(int s, uint32_t blk) { return ((uint32_t)(s >> 2) * blk + (uint32_t)(s & 3) * 32u) >> 4; }
+__device__ __forceinline__ constexpr uint32_t mnstep(int s) { return (uint32_t)s * (16u * ROW_B >> 4); }
+__device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
-// K-major operand: rows of 128 B, a 64-column block per `blk` bytes; k-step s (16 elements) of a K = 16*nsteps operand
-__device__ __forceinline__ uint64_t desc_k(uint32_t base, int s, uint32_t blk) { return make_desc(base + (s >> 2) * blk + (s & 3) * 32, 16); }
-// MN-major operand (the row-major tile read with the row index as K): 64-column blocks `blk` bytes apart (LBO), 16 rows per k-step
-__device__ __forceinline__ uint64_t desc_mn(uint32_t base, int s, uint32_t blk) { return make_desc(base + s * (16 * ROW_B), blk); }
 // instruction descriptor: D = f32, A = B = bf16, M = 128, N = n
 __device__ __forceinline__ uint32_t make_idesc(int n, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(b_mn ? 1 : 0) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -176,6 +178,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
   const int row0 = b * p.T;
   const int nj = qt + 1, nit = 2 * nj;
   const int qc = col_q(p, head), kc = col_k(p, g), vc = col_v(p, g);
+  // shared-memory base as a value the compiler KNOWS to be warp-uniform (lane-0 broadcast): the descriptors derived from it
+  // stay in uniform registers and the MMA issue loop needs no per-instruction register -> uniform-register transfer
+  const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
 
   if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm128) : "memory");
   if (warp == 1 && lane == 0) {
@@ -200,7 +205,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;      // S0 [0,128)  S1 [128,256)  O [256,384)
+  // The CTA owns all 512 TMEM columns, so the allocation starts at column 0 / lane 0: TMEM addresses are literals below
+  // (a register-held base would have to be broadcast into a uniform register before every MMA).
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem = 0;           // S0 [0,128)  S1 [128,256)  O [256,384)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -227,17 +235,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t id_s = make_idesc(128, 0), id_o = make_idesc(128, 1);
-      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+      const uint32_t qlo = klo(sbase), plo = klo(sbase + 5 * TILE128);
+      const uint32_t klo0 = klo(sbase + TILE128), vlo0 = mnlo(sbase + 3 * TILE128, BLK128);
       uint32_t p_phase = 0;
       auto pv = [&](int u) {        // O += P(u) V(u);  u counts from nj (pass 2), key tile j = u - nj
         const int j = u - nj, vs = j & 1;
-        const uint32_t aV = smem_u32(sVr + vs * TILE128);
+        const uint32_t vlo = vlo0 + vs * (TILE128 >> 4);
         mbar_wait(&v_full[vs], (j >> 1) & 1);
         mbar_wait(p_full, p_phase);
         p_phase ^= 1;
         tc_fence_after();
+        tc_mma2(256, plo, vlo, id_o, u > nj ? 1u : 0u);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) tc_mma(tmem + 256, desc_k(aP, s, BLK128), desc_mn(aV, s, BLK128), id_o, (u > nj || s > 0) ? 1u : 0u);
+        for (int s = 1; s < 8; ++s) tc_mma2(256, plo + kstep(s, BLK128), vlo + mnstep(s), id_o, 1u);
         tc_commit(p_empty);
         tc_commit(&v_empty[vs]);
       };
@@ -248,9 +258,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
         mbar_wait(&k_full[st], ph);
         mbar_wait(&s_empty[st], ph ^ 1);
         tc_fence_after();
-        const uint32_t aK = smem_u32(sKr + st * TILE128);
+        const uint32_t kl = klo0 + st * (TILE128 >> 4);
+        tc_mma2(st * 128, qlo, kl, id_s, 0u);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) tc_mma(tmem + st * 128, desc_k(aQ, s, BLK128), desc_k(aK, s, BLK128), id_s, s > 0 ? 1u : 0u);
+        for (int s = 1; s < 8; ++s) tc_mma2(st * 128, qlo + kstep(s, BLK128), kl + kstep(s, BLK128), id_s, 1u);
         tc_commit(&k_empty[st]);
         tc_commit(&s_full[st]);
         if (t > nj) pv(t - 1);
@@ -434,6 +445,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
   const int nh = 2 * nt - 2 * j;                            // 64-query half tiles at or below the diagonal
   const int nit = p.rep * nh;
   const int kc = col_k(p, g), vc = col_v(p, g);
+  const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);     // warp-uniform by construction (see attn_fwd_kernel)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm128) : "memory");
@@ -462,7 +474,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;   // buffer s: S^T [s*128, +64)  dP^T [s*128+64, +64);  dK [256,384)  dV [384,512)
+  if (*tmem_slot != 0u) __trap();      // whole TMEM allocated: base 0 (see attn_fwd_kernel)
+  constexpr uint32_t tmem = 0;         // buffer s: S^T [s*128, +64)  dP^T [s*128+64, +64);  dK [256,384)  dV [384,512)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -486,17 +499,21 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t id_s = make_idesc(64, 0), id_a = make_idesc(128, 1);
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+      const uint32_t kl = klo(sbase), vl = klo(sbase + TILE128);
+      const uint32_t q_k0 = klo(sbase + 2 * TILE128), q_mn0 = mnlo(sbase + 2 * TILE128, BLK64);     // stage 0: Q, then dO at + TILE64
+      const uint32_t ptlo = klo(sbase + 2 * TILE128 + DKV_ST * 2 * TILE64), dstlo = ptlo + (BLK128 >> 4);
       auto accumulate = [&](int u) {     // dV += P^T dO,  dK += dS^T Q   (K = the 64 queries of stage u)
         const int st = u % DKV_ST;
-        const uint32_t aQ = smem_u32(sQdO + st * 2 * TILE64), adO = aQ + TILE64;
-        const uint32_t aPT = smem_u32(sPS), adST = aPT + BLK128;
+        const uint32_t qmn = q_mn0 + st * (2 * TILE64 >> 4), domn = qmn + (TILE64 >> 4);
+        const uint32_t first = u > 0 ? 1u : 0u;
         mbar_wait(p_full, u & 1);
         tc_fence_after();
+        tc_mma2(384, ptlo, domn, id_a, first);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) tc_mma(tmem + 384, desc_k(aPT, s, BLK128), desc_mn(adO, s, BLK64), id_a, (u > 0 || s > 0) ? 1u : 0u);
+        for (int s = 1; s < 4; ++s) tc_mma2(384, ptlo + kstep(s, BLK128), domn + mnstep(s), id_a, 1u);
+        tc_mma2(256, dstlo, qmn, id_a, first);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) tc_mma(tmem + 256, desc_k(adST, s, BLK128), desc_mn(aQ, s, BLK64), id_a, (u > 0 || s > 0) ? 1u : 0u);
+        for (int s = 1; s < 4; ++s) tc_mma2(256, dstlo + kstep(s, BLK128), qmn + mnstep(s), id_a, 1u);
         tc_commit(p_empty);
         tc_commit(&qdo_empty[st]);
       };
@@ -506,11 +523,13 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
         mbar_wait(&qdo_full[st], (it / DKV_ST) & 1);
         mbar_wait(&s_empty[sb], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t aQ = smem_u32(sQdO + st * 2 * TILE64), adO = aQ + TILE64;
+        const uint32_t qk = q_k0 + st * (2 * TILE64 >> 4), dok = qk + (TILE64 >> 4);
+        tc_mma2(sb * 128, kl, qk, id_s, 0u);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) tc_mma(tmem + sb * 128, desc_k(aK, s, BLK128), desc_k(aQ, s, BLK64), id_s, s > 0 ? 1u : 0u);
+        for (int s = 1; s < 8; ++s) tc_mma2(sb * 128, kl + kstep(s, BLK128), qk + kstep(s, BLK64), id_s, 1u);
+        tc_mma2(sb * 128 + 64, vl, dok, id_s, 0u);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) tc_mma(tmem + sb * 128 + 64, desc_k(aV, s, BLK128), desc_k(adO, s, BLK64), id_s, s > 0 ? 1u : 0u);
+        for (int s = 1; s < 8; ++s) tc_mma2(sb * 128 + 64, vl + kstep(s, BLK128), dok + kstep(s, BLK64), id_s, 1u);
         tc_commit(&s_full[sb]);
         if (it > 0) accumulate(it - 1);
       }
@@ -635,6 +654,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
   const int row0 = b * p.T;
   const int nit = 2 * i + 2;                               // 64-key half tiles up to the diagonal
   const int qc = col_q(p, head), kc = col_k(p, g), vc = col_v(p, g);
+  const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);     // warp-uniform by construction (see attn_fwd_kernel)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm128) : "memory");
@@ -665,7 +685,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;   // buffer s: S [s*128, +64)  dP [s*128+64, +64);  dQ [256,384)
+  if (*tmem_slot != 0u) __trap();      // whole TMEM allocated: base 0 (see attn_fwd_kernel)
+  constexpr uint32_t tmem = 0;         // buffer s: S [s*128, +64)  dP [s*128+64, +64);  dQ [256,384)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -692,14 +713,17 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t id_s = make_idesc(64, 0), id_a = make_idesc(128, 1);
-      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO);
+      const uint32_t ql = klo(sbase), dol = klo(sbase + TILE128);
+      const uint32_t k_k0 = klo(sbase + 2 * TILE128), k_mn0 = mnlo(sbase + 2 * TILE128, BLK64);
+      const uint32_t v_k0 = klo(sbase + 2 * TILE128 + DQ_KST * TILE64), ds0 = klo(sbase + 2 * TILE128 + (DQ_KST + 2) * TILE64);
       auto accumulate = [&](int u) {     // dQ += dS K   (K = the 64 keys of step u)
         const int sb = u & 1, ks = u % DQ_KST;
-        const uint32_t aK = smem_u32(sKr + ks * TILE64), adS = smem_u32(sdS + sb * BLK128);
+        const uint32_t kmn = k_mn0 + ks * (TILE64 >> 4), dsl = ds0 + sb * (BLK128 >> 4);
         mbar_wait(&p_full[sb], (u >> 1) & 1);
         tc_fence_after();
+        tc_mma2(256, dsl, kmn, id_a, u > 0 ? 1u : 0u);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) tc_mma(tmem + 256, desc_k(adS, s, BLK128), desc_mn(aK, s, BLK64), id_a, (u > 0 || s > 0) ? 1u : 0u);
+        for (int s = 1; s < 4; ++s) tc_mma2(256, dsl + kstep(s, BLK128), kmn + mnstep(s), id_a, 1u);
         tc_commit(&p_empty[sb]);
         tc_commit(&k_empty[ks]);
       };
@@ -711,11 +735,13 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
         mbar_wait(&v_full[st], ph);
         mbar_wait(&s_empty[st], ph ^ 1);
         tc_fence_after();
-        const uint32_t aK = smem_u32(sKr + ks * TILE64), aV = smem_u32(sVr + st * TILE64);
+        const uint32_t kk = k_k0 + ks * (TILE64 >> 4), vk = v_k0 + st * (TILE64 >> 4);
+        tc_mma2(st * 128, ql, kk, id_s, 0u);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) tc_mma(tmem + st * 128, desc_k(aQ, s, BLK128), desc_k(aK, s, BLK64), id_s, s > 0 ? 1u : 0u);
+        for (int s = 1; s < 8; ++s) tc_mma2(st * 128, ql + kstep(s, BLK128), kk + kstep(s, BLK64), id_s, 1u);
+        tc_mma2(st * 128 + 64, dol, vk, id_s, 0u);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) tc_mma(tmem + st * 128 + 64, desc_k(adO, s, BLK128), desc_k(aV, s, BLK64), id_s, s > 0 ? 1u : 0u);
+        for (int s = 1; s < 8; ++s) tc_mma2(st * 128 + 64, dol + kstep(s, BLK128), vk + kstep(s, BLK64), id_s, 1u);
         tc_commit(&v_empty[st]);
         tc_commit(&s_full[st]);
         if (it > 0) accumulate(it - 1);
