@@ -143,7 +143,7 @@ __device__ __forceinline__ void st_chunk(uint8_t* blk, int r, int c, const float
 }
 
 // ================================================================== forward
-constexpr int FWD_SMEM = TILE128 /*Q*/ + 2 * TILE128 /*K ring*/ + 2 * TILE128 /*V ring*/ + TILE128 /*P*/ + 1024 + 256;
+constexpr int FWD_SMEM = TILE128 /*Q*/ + 2 * TILE128 /*K ring*/ + 2 * TILE128 /*V ring*/ + 2 * TILE128 /*P x 2*/ + 1024 + 256;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
@@ -155,19 +155,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
   uint8_t* sQ = smem;
   uint8_t* sKr = sQ + TILE128;                 // K ring: slot s at sKr + s * TILE128
   uint8_t* sVr = sKr + 2 * TILE128;            // V ring
-  uint8_t* sP = sVr + 2 * TILE128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + TILE128);
+  uint8_t* sP = sVr + 2 * TILE128;             // two P buffers: the softmax of tile j + 1 writes while P V of tile j reads
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TILE128);
   uint64_t* q_full = bars;          // [1]
   uint64_t* k_full = bars + 1;      // [2]
   uint64_t* k_empty = bars + 3;     // [2]
   uint64_t* s_full = bars + 5;      // [2] MMA -> softmax
   uint64_t* s_empty = bars + 7;     // [2] softmax -> MMA (one arrive per softmax warp)
-  uint64_t* p_full = bars + 9;      // [1] softmax -> MMA
-  uint64_t* p_empty = bars + 10;    // [1] MMA -> softmax
-  uint64_t* o_full = bars + 11;     // [1]
-  uint64_t* v_full = bars + 12;     // [2]
-  uint64_t* v_empty = bars + 14;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* p_full = bars + 9;      // [2] softmax -> MMA
+  uint64_t* p_empty = bars + 11;    // [2] MMA -> softmax
+  uint64_t* o_full = bars + 13;     // [1]
+  uint64_t* v_full = bars + 14;     // [2]
+  uint64_t* v_empty = bars + 16;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = p.T / 128, per = p.heads * p.batch;
@@ -192,9 +192,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], SM_WARPS);
+      mbar_init(&p_full[i], SM_WARPS);
+      mbar_init(&p_empty[i], 1);
     }
-    mbar_init(p_full, SM_WARPS);
-    mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
@@ -237,18 +237,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
       const uint32_t id_s = make_idesc(128, 0), id_o = make_idesc(128, 1);
       const uint32_t qlo = klo(sbase), plo = klo(sbase + 5 * TILE128);
       const uint32_t klo0 = klo(sbase + TILE128), vlo0 = mnlo(sbase + 3 * TILE128, BLK128);
-      uint32_t p_phase = 0;
       auto pv = [&](int u) {        // O += P(u) V(u);  u counts from nj (pass 2), key tile j = u - nj
         const int j = u - nj, vs = j & 1;
-        const uint32_t vlo = vlo0 + vs * (TILE128 >> 4);
+        const uint32_t vlo = vlo0 + vs * (TILE128 >> 4), pl = plo + vs * (TILE128 >> 4);
         mbar_wait(&v_full[vs], (j >> 1) & 1);
-        mbar_wait(p_full, p_phase);
-        p_phase ^= 1;
+        mbar_wait(&p_full[vs], (j >> 1) & 1);
         tc_fence_after();
-        tc_mma2(256, plo, vlo, id_o, u > nj ? 1u : 0u);
+        tc_mma2(256, pl, vlo, id_o, u > nj ? 1u : 0u);
 #pragma unroll
-        for (int s = 1; s < 8; ++s) tc_mma2(256, plo + kstep(s, BLK128), vlo + mnstep(s), id_o, 1u);
-        tc_commit(p_empty);
+        for (int s = 1; s < 8; ++s) tc_mma2(256, pl + kstep(s, BLK128), vlo + mnstep(s), id_o, 1u);
+        tc_commit(&p_empty[vs]);
         tc_commit(&v_empty[vs]);
       };
       mbar_wait(q_full, 0);
@@ -329,14 +327,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
     }
     const float m2 = m * LOG2E;
     // ---- pass 2: probabilities with the final statistics -> shared memory (A operand of P V)
-    auto prob_tile = [&](int sb, auto mask_tag) {
+    auto prob_tile = [&](int sb, uint8_t* pbuf, auto mask_tag) {
       constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll 1
       for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 32) {
         uint32_t v[32];
         tc_ld32(lane_base + sb * 128 + c0, v);
         tc_wait_ld();
-        uint8_t* blk = sP + (c0 >> 6) * BLK128;
+        uint8_t* blk = pbuf + (c0 >> 6) * BLK128;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           float pr[8];
@@ -353,14 +351,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
       const int sb = t & 1, j = t - nj;
       mbar_wait(&s_full[sb], (t >> 1) & 1);
       tc_fence_after();
-      if (j > 0) mbar_wait(p_empty, (j - 1) & 1);      // P V of the previous tile has finished reading sP
-      if (j == qt) prob_tile(sb, std::true_type{});
-      else prob_tile(sb, std::false_type{});
+      const int pb = j & 1;
+      mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);      // P V of tile j - 2 has finished reading this P buffer
+      if (j == qt) prob_tile(sb, sP + pb * TILE128, std::true_type{});
+      else prob_tile(sb, sP + pb * TILE128, std::false_type{});
       fence_proxy_async();      // generic-proxy writes of sP -> visible to the tensor core's async proxy
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(p_full);
+        mbar_arrive(&p_full[pb]);
         mbar_arrive(&s_empty[sb]);
       }
     }
@@ -551,32 +550,37 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
       named_bar_sync(1, SM_THREADS);
       mbar_wait(&s_full[sb], ph);
       tc_fence_after();
-      if (it > 0) mbar_wait(p_empty, (it - 1) & 1);     // the accumulate MMAs of the previous step have finished reading P^T / dS^T
       uint8_t* bPT = sPS;
       uint8_t* bdST = bPT + BLK128;
       const int lo = kg - i64 * 64;            // causal: query column c is visible to this key row iff c >= lo
       auto tile = [&](auto mask_tag) {
         constexpr bool MASK = decltype(mask_tag)::value;
-        {
-          const int c0 = 32 * half;
-          uint32_t sv[32], dv[32];
-          tc_ld32(lane_base + sb * 128 + c0, sv);
-          tc_ld32(lane_base + sb * 128 + 64 + c0, dv);
-          tc_wait_ld();
+        const int c0 = 32 * half;
+        uint32_t sv[32], dv[32];
+        tc_ld32(lane_base + sb * 128 + c0, sv);
+        tc_ld32(lane_base + sb * 128 + 64 + c0, dv);
+        tc_wait_ld();
+        uint4 pk[4], dk[4];       // packed bf16 results: computed while the previous step's accumulate MMAs still read the buffer
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            float pr[8], ds[8];
+        for (int ch = 0; ch < 4; ++ch) {
+          float pr[8], ds[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int c = c0 + ch * 8 + e;
-              const float4 stt = sstat[ss * 64 + c];          // (max * log2e, 1/l, delta, -) of query column c
-              const float pe = ex2_ftz(fmaf(masked<MASK>(score16(sv[ch * 8 + e], p.alpha), c >= lo), LOG2E, -stt.x)) * stt.y;
-              pr[e] = pe;
-              ds[e] = pe * (__uint_as_float(dv[ch * 8 + e]) - stt.z);
-            }
-            st_chunk(bPT, kr, (c0 >> 3) + ch, pr);
-            st_chunk(bdST, kr, (c0 >> 3) + ch, ds);
+          for (int e = 0; e < 8; ++e) {
+            const int c = c0 + ch * 8 + e;
+            const float4 stt = sstat[ss * 64 + c];          // (max * log2e, 1/l, delta, -) of query column c
+            const float pe = ex2_ftz(fmaf(masked<MASK>(score16(sv[ch * 8 + e], p.alpha), c >= lo), LOG2E, -stt.x)) * stt.y;
+            pr[e] = pe;
+            ds[e] = pe * (__uint_as_float(dv[ch * 8 + e]) - stt.z);
           }
+          pk[ch] = make_uint4(pack_bf2(pr[0], pr[1]), pack_bf2(pr[2], pr[3]), pack_bf2(pr[4], pr[5]), pack_bf2(pr[6], pr[7]));
+          dk[ch] = make_uint4(pack_bf2(ds[0], ds[1]), pack_bf2(ds[2], ds[3]), pack_bf2(ds[4], ds[5]), pack_bf2(ds[6], ds[7]));
+        }
+        if (it > 0) mbar_wait(p_empty, (it - 1) & 1);     // the accumulate MMAs of the previous step have finished reading P^T / dS^T
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int off = kr * ROW_B + ((((c0 >> 3) + ch) ^ (kr & 7)) << 4);
+          *reinterpret_cast<uint4*>(bPT + off) = pk[ch];
+          *reinterpret_cast<uint4*>(bdST + off) = dk[ch];
         }
       };
       if (i64 < 2 * j + 2) tile(std::true_type{});      // the two half tiles that touch the diagonal
