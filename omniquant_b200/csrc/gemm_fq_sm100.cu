@@ -36,7 +36,7 @@ constexpr int A_HALF = 128 * BK * 2;        // one 128-row K-major bf16 block: 1
 constexpr int A_BYTES = 2 * A_HALF;         // 32 KB
 constexpr int W_BYTES = BN * BK * 4;        // fp32 stage: 32 KB
 constexpr int B_BYTES = BN * BK * 2;        // bf16 operand: 16 KB
-constexpr int SMEM_BYTES = SA * A_BYTES + SW * W_BYTES + SB * B_BYTES + 1024 + 256;
+constexpr int SMEM_BYTES = SA * A_BYTES + SW * W_BYTES + SB * B_BYTES + BN * 16 /*row parameters*/ + 1024 + 256;
 
 struct FqParams {
   int M, N, K;
@@ -106,7 +106,8 @@ gemm_fq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sA = smem;                        // [SA][2 halves][128 rows x 128 B]
   uint8_t* sW = sA + SA * A_BYTES;           // [SW][128 rows x 256 B] fp32, not swizzled
   uint8_t* sB = sW + SW * W_BYTES;           // [SB][128 rows x 128 B] bf16, SWIZZLE_128B (written by the transform warps)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SB * B_BYTES);
+  float4* sPar = reinterpret_cast<float4*>(sB + SB * B_BYTES);     // [BN] (scale, zero point, 1/scale, flag) of the tile's rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPar) + BN * 16);
   uint64_t* a_full = bars;             // [SA]
   uint64_t* a_empty = a_full + SA;     // [SA]
   uint64_t* w_full = a_empty + SA;     // [SW]
@@ -195,20 +196,28 @@ gemm_fq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== transform warps: fp32 stage -> fake-quantised bf16 operand =====================
     const int tw = warp - 8;                 // rows [16 tw, 16 tw + 16) of the tile
     const float qmax = (float)((1 << p.n_bits) - 1);
+    float4* par = sPar + tw * 16;            // this warp's 16 rows: (scale, zero point, 1/scale, reciprocal usable)
     Ring rw, rb;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n0 = (tile / p.num_m) * BN;
       const int myrow = n0 + tw * 16 + (lane & 15);
       for (int kb = 0; kb < num_kb; ++kb) {
-        // scale / zero point of this lane's row for the group this k-block lies in (lanes 16-31 mirror lanes 0-15)
-        const int gi = p.group ? (kb * BK) / p.group : 0;
-        float sc = 1.0f, zp = 0.0f;
-        if (myrow < p.N) {
-          sc = __ldg(p.scale + (long)myrow * p.G + gi);
-          zp = __ldg(p.zp + (long)myrow * p.G + gi);
+        // scale / zero point of the warp's rows for the group this k-block lies in: refreshed when the group changes
+        // (per-channel: once per tile), kept in shared memory so that a row's parameters are ONE broadcast load
+        if (kb == 0 || (p.group && (kb * BK) % p.group == 0)) {
+          __syncwarp();
+          if (lane < 16) {
+            const int gi = p.group ? (kb * BK) / p.group : 0;
+            float sc = 1.0f, zp = 0.0f;
+            if (myrow < p.N) {
+              sc = __ldg(p.scale + (long)myrow * p.G + gi);
+              zp = __ldg(p.zp + (long)myrow * p.G + gi);
+            }
+            const float inv = OQ_DIV(1.0f, sc);
+            par[lane] = make_float4(sc, zp, inv, oq_inv_ok(inv) ? 1.0f : 0.0f);
+          }
+          __syncwarp();
         }
-        const float inv = OQ_DIV(1.0f, sc);
-        const int ok = oq_inv_ok(inv);
         mbar_wait(&w_full[rw.idx], rw.phase);
         mbar_wait(&b_empty[rb.idx], rb.phase ^ 1);
         const uint8_t* src = sW + rw.idx * W_BYTES;
@@ -216,14 +225,23 @@ gemm_fq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 4
         for (int i = 0; i < 16; ++i) {
           const int r = tw * 16 + i;
-          const float s_i = __shfl_sync(0xffffffffu, sc, i), z_i = __shfl_sync(0xffffffffu, zp, i);
-          const float inv_i = __shfl_sync(0xffffffffu, inv, i);
-          const int ok_i = __shfl_sync(0xffffffffu, ok, i);
+          const float4 pr = par[i];
           const float2 w = *reinterpret_cast<const float2*>(src + r * (BK * 4) + lane * 8);
           OqQParams q;
-          q.scale = s_i; q.zp = z_i; q.qmax = qmax;
-          const float c0 = oq_clampf(OQ_ADD(oq_rint_div(w.x, s_i, inv_i, ok_i), z_i), 0.0f, qmax);
-          const float c1 = oq_clampf(OQ_ADD(oq_rint_div(w.y, s_i, inv_i, ok_i), z_i), 0.0f, qmax);
+          q.scale = pr.x; q.zp = pr.y; q.qmax = qmax;
+          // branch-free fast path of oq_rint_div (same guard: the reciprocal product decides unless it sits within 2.4e-7
+          // relative of a half-integer); ONE rarely taken fallback for the pair -- a branch per element costs a
+          // reconvergence barrier each and made the first version of this kernel 6x slower than the pre-pass + GEMM
+          const float qa0 = OQ_MUL(w.x, pr.z), qa1 = OQ_MUL(w.y, pr.z);
+          const float r0 = rintf(qa0), r1 = rintf(qa1);
+          bool redo = pr.w == 0.0f;
+          redo |= !(fabsf(fabsf(qa0 - r0) - 0.5f) > fabsf(qa0) * 2.4e-7f + 1e-30f);
+          redo |= !(fabsf(fabsf(qa1 - r1) - 0.5f) > fabsf(qa1) * 2.4e-7f + 1e-30f);
+          float c0 = fminf(fmaxf(OQ_ADD(r0, pr.y), 0.0f), qmax), c1 = fminf(fmaxf(OQ_ADD(r1, pr.y), 0.0f), qmax);
+          if (redo) {      // exact IEEE division (and the NaN-preserving clamp)
+            c0 = oq_code(w.x, q);
+            c1 = oq_code(w.y, q);
+          }
           const uint32_t packed = pack_bf2(oq_dequant(c0, q), oq_dequant(c1, q));
           *reinterpret_cast<uint32_t*>(dst + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4) = packed;
         }

@@ -58,12 +58,14 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_s8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_s8_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -79,17 +81,6 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// 64-bit shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart (SBO)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;               // LBO (unused for K-major swizzled) = 16 B
-  d |= (uint64_t)(1024 >> 4) << 32;     // SBO
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 
 template <int BN>
 struct Cfg {
@@ -163,6 +154,12 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // instruction descriptor: D = s32 (2), A = B = int8 (1), both K-major, N>>3, M>>4
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // descriptor words hoisted out of the issue loop: the high word is a constant, a stage / k-step only adds to the
+      // start-address field of the low word.  An int8 MMA of this shape occupies the tensor pipe for 64 cycles only, so
+      // the issuing thread has to stay well below that per instruction.
+      const uint32_t sa0 = __shfl_sync(0x1u, smem_u32(smem), 0);
+      const uint32_t alo0 = ((sa0 & 0x3FFFF) >> 4) | (1u << 16), blo0 = (((sa0 + C::A_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -174,11 +171,10 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t sb = sa + C::A_BYTES;
+          const uint32_t alo = alo0 + (uint32_t)stage * (C::STAGE_BYTES >> 4), blo = blo0 + (uint32_t)stage * (C::STAGE_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < BKB / UMMA_KB; ++k)
-            tc_mma_s8(d_tmem, make_desc(sa + k * UMMA_KB), make_desc(sb + k * UMMA_KB), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_mma_s8_lo(d_tmem, alo + k * (UMMA_KB >> 4), blo + k * (UMMA_KB >> 4), DESC_HI, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           tc_commit(&empty[stage]);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }

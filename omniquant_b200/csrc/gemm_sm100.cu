@@ -61,12 +61,15 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// same instruction with the descriptors given as (low word, shared high word)
+__device__ __forceinline__ void tc_mma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -82,17 +85,6 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// 64-bit shared-memory matrix descriptor (SWIZZLE_128B, sm_100 "version 1")
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 
 template <int BN>
 struct Cfg {
@@ -203,7 +195,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (=16 B).
       // MN-major: 64-element (128 B) MN blocks 64*BK*2 B apart (LBO), 8-k-row groups 1024 B apart (SBO).
       const uint32_t a_lbo = p.a_mn ? 64 * BK * 2 : 16, b_lbo = p.b_mn ? 64 * BK * 2 : 16;
-      const uint32_t a_kstep = p.a_mn ? UMMA_K * 128 : UMMA_K * 2, b_kstep = p.b_mn ? UMMA_K * 128 : UMMA_K * 2;
+      // The descriptor's high word is a constant and a k-step / ring stage only adds a multiple of 16 bytes to the start-address
+      // field of the low word: everything else is hoisted out of the issue loop (the issuing thread is a serial resource:
+      // one MMA must be issued every 128 cycles to keep the tensor pipe busy).
+      const uint32_t a_k16 = (p.a_mn ? UMMA_K * 128 : UMMA_K * 2) >> 4, b_k16 = (p.b_mn ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+      const uint32_t sa0 = __shfl_sync(0x1u, smem_u32(smem), 0);
+      const uint32_t alo0 = ((sa0 & 0x3FFFF) >> 4) | (((a_lbo >> 4) & 0x3FFF) << 16);
+      const uint32_t blo0 = (((sa0 + C::A_BYTES) & 0x3FFFF) >> 4) | (((b_lbo >> 4) & 0x3FFF) << 16);
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -220,14 +219,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t sb = sa + C::A_BYTES;
+          const uint32_t alo = alo0 + (uint32_t)stage * (C::STAGE_BYTES >> 4), blo = blo0 + (uint32_t)stage * (C::STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t ad = make_desc(sa + k * a_kstep, a_lbo, 1024);
-            const uint64_t bd = make_desc(sb + k * b_kstep, b_lbo, 1024);
-            tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            tc_mma_bf16_lo(d_tmem, alo + k * a_k16, blo + k * b_k16, DESC_HI, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           tc_commit(&empty[stage]);  // frees the smem stage when these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
