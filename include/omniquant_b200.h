@@ -159,7 +159,7 @@ int oq_gemm_bf16(const void* A, int a_mn, long lda, long strideA, const void* B,
  * kv_heads; LLaMA / OPT [q | k | v]: cq 0, gq rep*d, ck H, cv H+Hkv, gk d; Falcon per group [rep q | k | v]: gq = gk =
  * (rep+2)*d, ck rep*d, cv (rep+1)*d).  Scores are alpha*(q.k) rounded to fp16, softmax in fp32 with the causal mask,
  * P rounded to bf16 after normalisation.  O: [batch*T, heads*head_dim] bf16.  row_max / row_invl: [batch, heads, T] fp32
- * softmax statistics saved for the backward (nothing of size T x T is written).  Needs head_dim 128 and T %% 128 == 0
+ * softmax statistics saved for the backward (nothing of size T x T is written).  Needs head_dim 64 or 128 and T %% 128 == 0
  * (oq_attn_supported); other shapes use oq_gemm_bf16 + oq_softmax_fwd/bwd.
  * Backward: dqkv (same column layout as qkv, row stride ldg) receives dq, dk, dv of every head (each element written
  * once; K/V heads shared by several query heads are summed inside the kernel); delta_ws: [batch, heads, T] fp32 scratch. */

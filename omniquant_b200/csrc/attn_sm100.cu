@@ -37,19 +37,22 @@
 
 namespace {
 
-constexpr int D = 128;                 // head dimension
 constexpr int NUM_THREADS = 384;       // 4 control warps + 8 softmax warps
 constexpr int SM_WARPS = 8;            // softmax / epilogue warps: two per TMEM lane quadrant, each takes half of the columns
 constexpr int SM_THREADS = SM_WARPS * 32;
 constexpr int ROW_B = 128;             // bytes per shared-memory row of a 64-column bf16 block (one swizzle row)
 constexpr int BLK128 = 128 * ROW_B;    // 64-column block of a 128-row tile: 16 KB
 constexpr int BLK64 = 64 * ROW_B;      // 64-column block of a  64-row tile:  8 KB
-constexpr int TILE128 = 2 * BLK128;    // [128 x 128] bf16
-constexpr int TILE64 = 2 * BLK64;      // [ 64 x 128] bf16
+constexpr int PTILE = 2 * BLK128;      // a [128 x 128] bf16 probability tile (two 64-key blocks), whatever the head dimension
+// Kernels are templates on the head dimension DH (64 or 128); inside them: NB = DH / 64 blocks per operand tile,
+// KS = DH / 16 k-steps of a contraction over d, TILE128 / TILE64 = bytes of a [128 x DH] / [64 x DH] bf16 tile.
+#define OQ_HEAD_DIM_CONSTS                                                                         \
+  constexpr int D = DH, NB = DH / 64, KS = DH / 16, TILE128 = NB * BLK128, TILE64 = NB * BLK64;      \
+  (void)NB; (void)KS; (void)TILE64; (void)TILE128
 
 struct AttnParams {
-  int T, heads, kv_heads, rep, batch;
-  int cq, gq, ck, cv, gk;   // column of q head h: cq + (h / rep) * gq + (h % rep) * D;  k / v of K/V head g: ck / cv + g * gk
+  int T, heads, kv_heads, rep, batch, d;
+  int cq, gq, ck, cv, gk;   // column of q head h: cq + (h / rep) * gq + (h % rep) * d;  k / v of K/V head g: ck / cv + g * gk
   float alpha;
   bf16* O; long ldo;                      // forward output [batch*T, heads*D]
   float* row_max; float* row_invl;        // [batch, heads, T]: max of the fp16 scores, 1 / sum exp(s - max)
@@ -57,7 +60,7 @@ struct AttnParams {
   bf16* dqkv; long ldg;                   // backward output, same column layout as the operand matrix
 };
 
-__device__ __forceinline__ int col_q(const AttnParams& p, int head) { return p.cq + (head / p.rep) * p.gq + (head % p.rep) * D; }
+__device__ __forceinline__ int col_q(const AttnParams& p, int head) { return p.cq + (head / p.rep) * p.gq + (head % p.rep) * p.d; }
 __device__ __forceinline__ int col_k(const AttnParams& p, int g) { return p.ck + g * p.gk; }
 __device__ __forceinline__ int col_v(const AttnParams& p, int g) { return p.cv + g * p.gk; }
 
@@ -68,6 +71,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
           smem_u32(smem_dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// a [rows x DH] tile = NB blocks of 64 columns: one TMA box each
+template <int NB>
+__device__ __forceinline__ void load_tile(uint8_t* dst, int blk_bytes, const CUtensorMap* map, uint64_t* bar, int col, int row) {
+#pragma unroll
+  for (int b = 0; b < NB; ++b) tma_load_2d(dst + b * blk_bytes, map, bar, col + 64 * b, row);
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -143,10 +152,13 @@ __device__ __forceinline__ void st_chunk(uint8_t* blk, int r, int c, const float
 }
 
 // ================================================================== forward
-constexpr int FWD_SMEM = TILE128 /*Q*/ + 2 * TILE128 /*K ring*/ + 2 * TILE128 /*V ring*/ + 2 * TILE128 /*P x 2*/ + 1024 + 256;
+template <int DH>
+constexpr int fwd_smem() { return 5 * (DH / 64) * BLK128 /*Q, K ring, V ring*/ + 2 * PTILE /*P x 2*/ + 1024 + 256; }
 
+template <int DH>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
+  OQ_HEAD_DIM_CONSTS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // K and V travel through SEPARATE two-slot rings: a K tile is released as soon as its S MMAs retire, a V tile only after
@@ -156,7 +168,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
   uint8_t* sKr = sQ + TILE128;                 // K ring: slot s at sKr + s * TILE128
   uint8_t* sVr = sKr + 2 * TILE128;            // V ring
   uint8_t* sP = sVr + 2 * TILE128;             // two P buffers: the softmax of tile j + 1 writes while P V of tile j reads
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TILE128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * PTILE);
   uint64_t* q_full = bars;          // [1]
   uint64_t* k_full = bars + 1;      // [2]
   uint64_t* k_empty = bars + 3;     // [2]
@@ -213,33 +225,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(q_full, TILE128);
-      tma_load_2d(sQ, &tm128, q_full, qc, row0 + qt * 128);
-      tma_load_2d(sQ + BLK128, &tm128, q_full, qc + 64, row0 + qt * 128);
+      load_tile<NB>(sQ, BLK128, &tm128, q_full, qc, row0 + qt * 128);
       for (int t = 0; t < nit; ++t) {
         const int st = t & 1, pass = t >= nj, j = pass ? t - nj : t;
         mbar_wait(&k_empty[st], ((t >> 1) & 1) ^ 1);
         uint8_t* sK = sKr + st * TILE128;
         mbar_expect_tx(&k_full[st], TILE128);
-        tma_load_2d(sK, &tm128, &k_full[st], kc, row0 + j * 128);
-        tma_load_2d(sK + BLK128, &tm128, &k_full[st], kc + 64, row0 + j * 128);
+        load_tile<NB>(sK, BLK128, &tm128, &k_full[st], kc, row0 + j * 128);
         if (pass) {
           const int vs = j & 1;
           mbar_wait(&v_empty[vs], ((j >> 1) & 1) ^ 1);
           uint8_t* sV = sVr + vs * TILE128;
           mbar_expect_tx(&v_full[vs], TILE128);
-          tma_load_2d(sV, &tm128, &v_full[vs], vc, row0 + j * 128);
-          tma_load_2d(sV + BLK128, &tm128, &v_full[vs], vc + 64, row0 + j * 128);
+          load_tile<NB>(sV, BLK128, &tm128, &v_full[vs], vc, row0 + j * 128);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t id_s = make_idesc(128, 0), id_o = make_idesc(128, 1);
+      const uint32_t id_s = make_idesc(128, 0), id_o = make_idesc(D, 1);
       const uint32_t qlo = klo(sbase), plo = klo(sbase + 5 * TILE128);
       const uint32_t klo0 = klo(sbase + TILE128), vlo0 = mnlo(sbase + 3 * TILE128, BLK128);
       auto pv = [&](int u) {        // O += P(u) V(u);  u counts from nj (pass 2), key tile j = u - nj
         const int j = u - nj, vs = j & 1;
-        const uint32_t vlo = vlo0 + vs * (TILE128 >> 4), pl = plo + vs * (TILE128 >> 4);
+        const uint32_t vlo = vlo0 + vs * (TILE128 >> 4), pl = plo + vs * (PTILE >> 4);
         mbar_wait(&v_full[vs], (j >> 1) & 1);
         mbar_wait(&p_full[vs], (j >> 1) & 1);
         tc_fence_after();
@@ -259,7 +268,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
         const uint32_t kl = klo0 + st * (TILE128 >> 4);
         tc_mma2(st * 128, qlo, kl, id_s, 0u);
 #pragma unroll
-        for (int s = 1; s < 8; ++s) tc_mma2(st * 128, qlo + kstep(s, BLK128), kl + kstep(s, BLK128), id_s, 1u);
+        for (int s = 1; s < KS; ++s) tc_mma2(st * 128, qlo + kstep(s, BLK128), kl + kstep(s, BLK128), id_s, 1u);
         tc_commit(&k_empty[st]);
         tc_commit(&s_full[st]);
         if (t > nj) pv(t - 1);
@@ -353,8 +362,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
       tc_fence_after();
       const int pb = j & 1;
       mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);      // P V of tile j - 2 has finished reading this P buffer
-      if (j == qt) prob_tile(sb, sP + pb * TILE128, std::true_type{});
-      else prob_tile(sb, sP + pb * TILE128, std::false_type{});
+      if (j == qt) prob_tile(sb, sP + pb * PTILE, std::true_type{});
+      else prob_tile(sb, sP + pb * PTILE, std::false_type{});
       fence_proxy_async();      // generic-proxy writes of sP -> visible to the tensor core's async proxy
       tc_fence_before();
       __syncwarp();
@@ -368,7 +377,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
     tc_fence_after();
     bf16* orow = p.O + (long)(row0 + qrow) * p.ldo + head * D;
 #pragma unroll 1
-    for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 32) {
+    for (int c0 = (D / 2) * half; c0 < (D / 2) * half + D / 2; c0 += 32) {
       uint32_t v[32];
       tc_ld32(lane_base + 256 + c0, v);
       tc_wait_ld();
@@ -390,18 +399,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
 }
 
 // ================================================================== backward: delta = rowsum(dO * O)
+template <int DH>
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* O, long ldo, const bf16* dO, long lddo, float* delta, int batch,
                                                          int T, int heads) {
+  constexpr int D = DH;
   const long w = (long)blockIdx.x * 8 + (threadIdx.x >> 5);      // one warp per (token row, head)
   const int lane = threadIdx.x & 31;
   const long total = (long)batch * T * heads;
   if (w >= total) return;
   const long row = w / heads;
   const int head = (int)(w % heads);
-  float a[4], c[4];
-  load_bf4(O + row * ldo + head * D + lane * 4, a);
-  load_bf4(dO + row * lddo + head * D + lane * 4, c);
-  float s = a[0] * c[0] + a[1] * c[1] + a[2] * c[2] + a[3] * c[3];
+  float s;
+  if constexpr (D == 128) {
+    float a[4], c[4];
+    load_bf4(O + row * ldo + head * D + lane * 4, a);
+    load_bf4(dO + row * lddo + head * D + lane * 4, c);
+    s = a[0] * c[0] + a[1] * c[1] + a[2] * c[2] + a[3] * c[3];
+  } else {
+    float a0, a1, c0, c1;
+    unpack_bf2(*reinterpret_cast<const uint32_t*>(O + row * ldo + head * D + lane * 2), a0, a1);
+    unpack_bf2(*reinterpret_cast<const uint32_t*>(dO + row * lddo + head * D + lane * 2), c0, c1);
+    s = a0 * c0 + a1 * c1;
+  }
   s = warp_reduce(s, OpSum());
   if (lane == 0) {
     const long bi = row / T, t = row % T;
@@ -412,11 +431,16 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* O, long ldo
 // ================================================================== backward: dK, dV
 constexpr int DKV_ST = 3;      // Q / dO stages: a stage is needed twice (S^T / dP^T early, the accumulate MMAs after the softmax),
                                // so it is held for a whole iteration; three stages keep the TMA round trip off the critical path
-constexpr int DKV_SMEM = 2 * TILE128 /*K,V*/ + DKV_ST * 2 * TILE64 /*Q,dO*/ + 2 * BLK128 /*P^T,dS^T*/ + DKV_ST * 64 * 16 /*stats*/ + 1024 + 256;
+template <int DH>
+constexpr int dkv_smem() {
+  return 2 * (DH / 64) * BLK128 /*K,V*/ + DKV_ST * 2 * (DH / 64) * BLK64 /*Q,dO*/ + 2 * BLK128 /*P^T,dS^T*/ + DKV_ST * 64 * 16 /*stats*/ + 1024 + 256;
+}
 
+template <int DH>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64,
                 const __grid_constant__ CUtensorMap tmdo64, const AttnParams p) {
+  OQ_HEAD_DIM_CONSTS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sK = smem;
@@ -479,25 +503,21 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(kv_full, 2 * TILE128);
-      tma_load_2d(sK, &tm128, kv_full, kc, row0 + j * 128);
-      tma_load_2d(sK + BLK128, &tm128, kv_full, kc + 64, row0 + j * 128);
-      tma_load_2d(sV, &tm128, kv_full, vc, row0 + j * 128);
-      tma_load_2d(sV + BLK128, &tm128, kv_full, vc + 64, row0 + j * 128);
+      load_tile<NB>(sK, BLK128, &tm128, kv_full, kc, row0 + j * 128);
+      load_tile<NB>(sV, BLK128, &tm128, kv_full, vc, row0 + j * 128);
       for (int it = 0; it < nit; ++it) {
         const int st = it % DKV_ST, head = g * p.rep + it / nh, i64 = 2 * j + it % nh;
         mbar_wait(&qdo_empty[st], ((it / DKV_ST) & 1) ^ 1);
         uint8_t* sQ = sQdO + st * 2 * TILE64;
         mbar_expect_tx(&qdo_full[st], 2 * TILE64);
         const int qc = col_q(p, head), r = row0 + i64 * 64;
-        tma_load_2d(sQ, &tm64, &qdo_full[st], qc, r);
-        tma_load_2d(sQ + BLK64, &tm64, &qdo_full[st], qc + 64, r);
-        tma_load_2d(sQ + TILE64, &tmdo64, &qdo_full[st], head * D, r);
-        tma_load_2d(sQ + TILE64 + BLK64, &tmdo64, &qdo_full[st], head * D + 64, r);
+        load_tile<NB>(sQ, BLK64, &tm64, &qdo_full[st], qc, r);
+        load_tile<NB>(sQ + TILE64, BLK64, &tmdo64, &qdo_full[st], head * D, r);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t id_s = make_idesc(64, 0), id_a = make_idesc(128, 1);
+      const uint32_t id_s = make_idesc(64, 0), id_a = make_idesc(D, 1);
       const uint32_t kl = klo(sbase), vl = klo(sbase + TILE128);
       const uint32_t q_k0 = klo(sbase + 2 * TILE128), q_mn0 = mnlo(sbase + 2 * TILE128, BLK64);     // stage 0: Q, then dO at + TILE64
       const uint32_t ptlo = klo(sbase + 2 * TILE128 + DKV_ST * 2 * TILE64), dstlo = ptlo + (BLK128 >> 4);
@@ -507,9 +527,9 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
         const uint32_t first = u > 0 ? 1u : 0u;
         mbar_wait(p_full, u & 1);
         tc_fence_after();
-        tc_mma2(384, ptlo, domn, id_a, first);
+        tc_mma2(256 + D, ptlo, domn, id_a, first);
 #pragma unroll
-        for (int s = 1; s < 4; ++s) tc_mma2(384, ptlo + kstep(s, BLK128), domn + mnstep(s), id_a, 1u);
+        for (int s = 1; s < 4; ++s) tc_mma2(256 + D, ptlo + kstep(s, BLK128), domn + mnstep(s), id_a, 1u);
         tc_mma2(256, dstlo, qmn, id_a, first);
 #pragma unroll
         for (int s = 1; s < 4; ++s) tc_mma2(256, dstlo + kstep(s, BLK128), qmn + mnstep(s), id_a, 1u);
@@ -525,10 +545,10 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
         const uint32_t qk = q_k0 + st * (2 * TILE64 >> 4), dok = qk + (TILE64 >> 4);
         tc_mma2(sb * 128, kl, qk, id_s, 0u);
 #pragma unroll
-        for (int s = 1; s < 8; ++s) tc_mma2(sb * 128, kl + kstep(s, BLK128), qk + kstep(s, BLK64), id_s, 1u);
+        for (int s = 1; s < KS; ++s) tc_mma2(sb * 128, kl + kstep(s, BLK128), qk + kstep(s, BLK64), id_s, 1u);
         tc_mma2(sb * 128 + 64, vl, dok, id_s, 0u);
 #pragma unroll
-        for (int s = 1; s < 8; ++s) tc_mma2(sb * 128 + 64, vl + kstep(s, BLK128), dok + kstep(s, BLK64), id_s, 1u);
+        for (int s = 1; s < KS; ++s) tc_mma2(sb * 128 + 64, vl + kstep(s, BLK128), dok + kstep(s, BLK64), id_s, 1u);
         tc_commit(&s_full[sb]);
         if (it > 0) accumulate(it - 1);
       }
@@ -624,11 +644,16 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
 
 // ================================================================== backward: dQ
 constexpr int DQ_KST = 4;      // K ring: a K half tile serves S early and dQ += dS K after the softmax (held for a whole iteration)
-constexpr int DQ_SMEM = 2 * TILE128 /*Q,dO*/ + DQ_KST * TILE64 /*K ring*/ + 2 * TILE64 /*V ring*/ + 2 * BLK128 /*dS x 2*/ + 1024 + 256;
+template <int DH>
+constexpr int dq_smem() {
+  return 2 * (DH / 64) * BLK128 /*Q,dO*/ + (DQ_KST + 2) * (DH / 64) * BLK64 /*K ring, V ring*/ + 2 * BLK128 /*dS x 2*/ + 1024 + 256;
+}
 
+template <int DH>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64,
                const __grid_constant__ CUtensorMap tmdo128, const AttnParams p) {
+  OQ_HEAD_DIM_CONSTS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
@@ -695,28 +720,24 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(qdo_full, 2 * TILE128);
-      tma_load_2d(sQ, &tm128, qdo_full, qc, row0 + i * 128);
-      tma_load_2d(sQ + BLK128, &tm128, qdo_full, qc + 64, row0 + i * 128);
-      tma_load_2d(sdO, &tmdo128, qdo_full, head * D, row0 + i * 128);
-      tma_load_2d(sdO + BLK128, &tmdo128, qdo_full, head * D + 64, row0 + i * 128);
+      load_tile<NB>(sQ, BLK128, &tm128, qdo_full, qc, row0 + i * 128);
+      load_tile<NB>(sdO, BLK128, &tmdo128, qdo_full, head * D, row0 + i * 128);
       for (int it = 0; it < nit; ++it) {
         const int ks = it % DQ_KST, vs = it & 1;
         const int r = row0 + it * 64;
         mbar_wait(&k_empty[ks], ((it / DQ_KST) & 1) ^ 1);
         uint8_t* sK = sKr + ks * TILE64;
         mbar_expect_tx(&k_full[ks], TILE64);
-        tma_load_2d(sK, &tm64, &k_full[ks], kc, r);
-        tma_load_2d(sK + BLK64, &tm64, &k_full[ks], kc + 64, r);
+        load_tile<NB>(sK, BLK64, &tm64, &k_full[ks], kc, r);
         mbar_wait(&v_empty[vs], ((it >> 1) & 1) ^ 1);
         uint8_t* sV = sVr + vs * TILE64;
         mbar_expect_tx(&v_full[vs], TILE64);
-        tma_load_2d(sV, &tm64, &v_full[vs], vc, r);
-        tma_load_2d(sV + BLK64, &tm64, &v_full[vs], vc + 64, r);
+        load_tile<NB>(sV, BLK64, &tm64, &v_full[vs], vc, r);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t id_s = make_idesc(64, 0), id_a = make_idesc(128, 1);
+      const uint32_t id_s = make_idesc(64, 0), id_a = make_idesc(D, 1);
       const uint32_t ql = klo(sbase), dol = klo(sbase + TILE128);
       const uint32_t k_k0 = klo(sbase + 2 * TILE128), k_mn0 = mnlo(sbase + 2 * TILE128, BLK64);
       const uint32_t v_k0 = klo(sbase + 2 * TILE128 + DQ_KST * TILE64), ds0 = klo(sbase + 2 * TILE128 + (DQ_KST + 2) * TILE64);
@@ -742,10 +763,10 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
         const uint32_t kk = k_k0 + ks * (TILE64 >> 4), vk = v_k0 + st * (TILE64 >> 4);
         tc_mma2(st * 128, ql, kk, id_s, 0u);
 #pragma unroll
-        for (int s = 1; s < 8; ++s) tc_mma2(st * 128, ql + kstep(s, BLK128), kk + kstep(s, BLK64), id_s, 1u);
+        for (int s = 1; s < KS; ++s) tc_mma2(st * 128, ql + kstep(s, BLK128), kk + kstep(s, BLK64), id_s, 1u);
         tc_mma2(st * 128 + 64, dol, vk, id_s, 0u);
 #pragma unroll
-        for (int s = 1; s < 8; ++s) tc_mma2(st * 128 + 64, dol + kstep(s, BLK128), vk + kstep(s, BLK64), id_s, 1u);
+        for (int s = 1; s < KS; ++s) tc_mma2(st * 128 + 64, dol + kstep(s, BLK128), vk + kstep(s, BLK64), id_s, 1u);
         tc_commit(&v_empty[st]);
         tc_commit(&s_full[st]);
         if (it > 0) accumulate(it - 1);
@@ -802,7 +823,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
     tc_fence_after();
     bf16* dst = p.dqkv + (long)(row0 + qg) * p.ldg + qc;
 #pragma unroll 1
-    for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 32) {
+    for (int c0 = (D / 2) * half; c0 < (D / 2) * half + D / 2; c0 += 32) {
       uint32_t v[32];
       tc_ld32(lane_base + 256 + c0, v);
       tc_wait_ld();
@@ -864,8 +885,9 @@ int set_smem(K kernel, int bytes, const char* what) {
 int check_common(const char* fn, const void* qkv, long ld, int batch, int T, int heads, int kv_heads, int head_dim, int cq, int gq,
                  int ck, int cv, int gk, long width) {
   OQ_REQUIRE(qkv && batch > 0 && heads > 0 && kv_heads > 0 && heads % kv_heads == 0, "%s: null pointer or bad head counts", fn);
-  OQ_REQUIRE(head_dim == D && T >= 128 && T % 128 == 0, "%s: needs head_dim 128 and a sequence length that is a multiple of 128 "
-             "(got d=%d T=%d); use the unfused GEMM + softmax path otherwise", fn, head_dim, T);
+  OQ_REQUIRE((head_dim == 64 || head_dim == 128) && T >= 128 && T % 128 == 0, "%s: needs head_dim 64 or 128 and a sequence length that "
+             "is a multiple of 128 (got d=%d T=%d); use the unfused GEMM + softmax path otherwise", fn, head_dim, T);
+  const int D = head_dim;
   OQ_REQUIRE(ld % 8 == 0 && (uintptr_t)qkv % 16 == 0 && cq % 8 == 0 && gq % 8 == 0 && ck % 8 == 0 && cv % 8 == 0 && gk % 8 == 0,
              "%s: operand matrix must be 16-byte aligned with column offsets / strides that are multiples of 8", fn);
   const int rep = heads / kv_heads;
@@ -874,34 +896,37 @@ int check_common(const char* fn, const void* qkv, long ld, int batch, int T, int
   OQ_REQUIRE(last_q <= width && last_k <= width && last_v <= width && width <= ld, "%s: head columns exceed the matrix width", fn);
   return 0;
 }
-AttnParams base_params(int batch, int T, int heads, int kv_heads, int cq, int gq, int ck, int cv, int gk, float alpha) {
+AttnParams base_params(int batch, int T, int heads, int kv_heads, int d, int cq, int gq, int ck, int cv, int gk, float alpha) {
   AttnParams p = {};
-  p.T = T; p.heads = heads; p.kv_heads = kv_heads; p.rep = heads / kv_heads; p.batch = batch;
+  p.T = T; p.heads = heads; p.kv_heads = kv_heads; p.rep = heads / kv_heads; p.batch = batch; p.d = d;
   p.cq = cq; p.gq = gq; p.ck = ck; p.cv = cv; p.gk = gk; p.alpha = alpha;
   return p;
 }
 
 }  // namespace
 
-extern "C" int oq_attn_supported(int T, int head_dim) { return (head_dim == D && T >= 128 && T % 128 == 0) ? 1 : 0; }
+extern "C" int oq_attn_supported(int T, int head_dim) { return ((head_dim == 64 || head_dim == 128) && T >= 128 && T % 128 == 0) ? 1 : 0; }
 
 extern "C" int oq_attn_fwd(const void* qkv, long ld, long width, int batch, int T, int heads, int kv_heads, int head_dim, int cq,
                            int gq, int ck, int cv, int gk, float alpha, void* O, long ldo, float* row_max, float* row_invl,
                            cudaStream_t stream) {
   if (check_common("oq_attn_fwd", qkv, ld, batch, T, heads, kv_heads, head_dim, cq, gq, ck, cv, gk, width)) return -1;
+  const int D = head_dim;
   OQ_REQUIRE(O && row_max && row_invl && ldo % 8 == 0 && (uintptr_t)O % 16 == 0 && ldo >= (long)heads * D,
              "oq_attn_fwd: output / statistics pointers missing or misaligned");
   static bool attr = false;
   if (!attr) {
-    if (int e = set_smem(attn_fwd_kernel, FWD_SMEM, "oq_attn_fwd")) return e;
+    if (int e = set_smem(attn_fwd_kernel<64>, fwd_smem<64>(), "oq_attn_fwd")) return e;
+    if (int e = set_smem(attn_fwd_kernel<128>, fwd_smem<128>(), "oq_attn_fwd")) return e;
     attr = true;
   }
   CUtensorMap tm128;
   if (make_map(&tm128, qkv, width, (long)batch * T, ld, 128)) return -1;
-  AttnParams p = base_params(batch, T, heads, kv_heads, cq, gq, ck, cv, gk, alpha);
+  AttnParams p = base_params(batch, T, heads, kv_heads, D, cq, gq, ck, cv, gk, alpha);
   p.O = (bf16*)O; p.ldo = ldo; p.row_max = row_max; p.row_invl = row_invl;
   const int grid = batch * heads * (T / 128);
-  attn_fwd_kernel<<<grid, NUM_THREADS, FWD_SMEM, stream>>>(tm128, p);
+  if (D == 128) attn_fwd_kernel<128><<<grid, NUM_THREADS, fwd_smem<128>(), stream>>>(tm128, p);
+  else attn_fwd_kernel<64><<<grid, NUM_THREADS, fwd_smem<64>(), stream>>>(tm128, p);
   return oq_check_launch("oq_attn_fwd");
 }
 
@@ -911,13 +936,16 @@ extern "C" int oq_attn_bwd(const void* qkv, long ld, long width, int batch, int 
                            cudaStream_t stream) {
   if (check_common("oq_attn_bwd", qkv, ld, batch, T, heads, kv_heads, head_dim, cq, gq, ck, cv, gk, width)) return -1;
   OQ_REQUIRE(O && dO && row_max && row_invl && delta_ws && dqkv, "oq_attn_bwd: null pointer");
+  const int D = head_dim;
   OQ_REQUIRE(ldo % 8 == 0 && lddo % 8 == 0 && ldg % 8 == 0 && (uintptr_t)O % 16 == 0 && (uintptr_t)dO % 16 == 0 &&
                  (uintptr_t)dqkv % 16 == 0 && ldg >= width && lddo >= (long)heads * D && ldo >= (long)heads * D,
              "oq_attn_bwd: O / dO / dqkv must be 16-byte aligned with leading dimensions that are multiples of 8");
   static bool attr = false;
   if (!attr) {
-    if (int e = set_smem(attn_dkv_kernel, DKV_SMEM, "oq_attn_bwd")) return e;
-    if (int e = set_smem(attn_dq_kernel, DQ_SMEM, "oq_attn_bwd")) return e;
+    if (int e = set_smem(attn_dkv_kernel<64>, dkv_smem<64>(), "oq_attn_bwd")) return e;
+    if (int e = set_smem(attn_dq_kernel<64>, dq_smem<64>(), "oq_attn_bwd")) return e;
+    if (int e = set_smem(attn_dkv_kernel<128>, dkv_smem<128>(), "oq_attn_bwd")) return e;
+    if (int e = set_smem(attn_dq_kernel<128>, dq_smem<128>(), "oq_attn_bwd")) return e;
     attr = true;
   }
   const long rows = (long)batch * T;
@@ -925,14 +953,19 @@ extern "C" int oq_attn_bwd(const void* qkv, long ld, long width, int batch, int 
   if (make_map(&tm128, qkv, width, rows, ld, 128) || make_map(&tm64, qkv, width, rows, ld, 64) ||
       make_map(&tmdo128, dO, (long)heads * D, rows, lddo, 128) || make_map(&tmdo64, dO, (long)heads * D, rows, lddo, 64))
     return -1;
-  AttnParams p = base_params(batch, T, heads, kv_heads, cq, gq, ck, cv, gk, alpha);
+  AttnParams p = base_params(batch, T, heads, kv_heads, D, cq, gq, ck, cv, gk, alpha);
   p.row_max = const_cast<float*>(row_max); p.row_invl = const_cast<float*>(row_invl); p.delta = delta_ws;
   p.dqkv = (bf16*)dqkv; p.ldg = ldg;
   const long nw = rows * heads;
-  attn_delta_kernel<<<(unsigned)((nw + 7) / 8), 256, 0, stream>>>((const bf16*)O, ldo, (const bf16*)dO, lddo, delta_ws, batch, T, heads);
+  const unsigned gd = (unsigned)((nw + 7) / 8);
+  const int gkv = batch * kv_heads * (T / 128), gq_ = batch * heads * (T / 128);
+  if (D == 128) attn_delta_kernel<128><<<gd, 256, 0, stream>>>((const bf16*)O, ldo, (const bf16*)dO, lddo, delta_ws, batch, T, heads);
+  else attn_delta_kernel<64><<<gd, 256, 0, stream>>>((const bf16*)O, ldo, (const bf16*)dO, lddo, delta_ws, batch, T, heads);
   if (int e = oq_check_launch("oq_attn_bwd (delta)")) return e;
-  attn_dkv_kernel<<<batch * kv_heads * (T / 128), NUM_THREADS, DKV_SMEM, stream>>>(tm128, tm64, tmdo64, p);
+  if (D == 128) attn_dkv_kernel<128><<<gkv, NUM_THREADS, dkv_smem<128>(), stream>>>(tm128, tm64, tmdo64, p);
+  else attn_dkv_kernel<64><<<gkv, NUM_THREADS, dkv_smem<64>(), stream>>>(tm128, tm64, tmdo64, p);
   if (int e = oq_check_launch("oq_attn_bwd (dK, dV)")) return e;
-  attn_dq_kernel<<<batch * heads * (T / 128), NUM_THREADS, DQ_SMEM, stream>>>(tm128, tm64, tmdo128, p);
+  if (D == 128) attn_dq_kernel<128><<<gq_, NUM_THREADS, dq_smem<128>(), stream>>>(tm128, tm64, tmdo128, p);
+  else attn_dq_kernel<64><<<gq_, NUM_THREADS, dq_smem<64>(), stream>>>(tm128, tm64, tmdo128, p);
   return oq_check_launch("oq_attn_bwd (dQ)");
 }

@@ -220,7 +220,7 @@ class BlockEngine:
         self._let_init_names = tuple(let_init) if let_init else ()
         self._graph_state = None      # captured optimiser step, kept across reload(): see train()
         # QK^T -> softmax -> PV (and the recompute backward) in one tcgen05 kernel each when the shape allows it
-        # (csrc/attn_sm100.cu: causal, head_dim 128, T %% 128 == 0); otherwise batched GEMMs + softmax kernels
+        # (csrc/attn_sm100.cu: causal, head_dim 64 or 128, T %% 128 == 0); otherwise batched GEMMs + softmax kernels
         self.fused_attn = (self.causal and self.dev.type == "cuda" and os.environ.get("OQ_FUSED_ATTN", "1") != "0"
                            and ops.attn_supported(seq_len, self.d))
 

@@ -854,13 +854,16 @@ def _attn_reference(q, k, v, alpha):
     return torch.matmul(p, v)
 
 
-@pytest.mark.parametrize("layout,heads,kv,T,batch", [("llama", 4, 4, 256, 1), ("llama", 8, 2, 384, 2), ("falcon", 6, 2, 256, 1),
-                                                     ("llama", 2, 2, 2048, 1)])
-def test_fused_attention_fwd_bwd(ops, layout, heads, kv, T, batch):
+@pytest.mark.parametrize("layout,heads,kv,T,batch,d", [("llama", 4, 4, 256, 1, 128), ("llama", 8, 2, 384, 2, 128),
+                                                       ("falcon", 6, 2, 256, 1, 128), ("llama", 2, 2, 2048, 1, 128),
+                                                       ("llama", 4, 4, 384, 2, 64), ("falcon", 8, 2, 256, 1, 64),
+                                                       ("llama", 3, 3, 2048, 1, 64)])
+def test_fused_attention_fwd_bwd(ops, layout, heads, kv, T, batch, d):
     """oq_attn_fwd / oq_attn_bwd against the fp32 torch evaluation of the same expression (MHA, grouped-query heads in
-    the LLaMA [q | k | v] and the Falcon per-group layouts, several samples) and against the unfused kernel chain."""
-    d, rep = 128, heads // kv
-    gen = torch.Generator(device="cuda").manual_seed(heads * 131 + T)
+    the LLaMA [q | k | v] and the Falcon per-group layouts, several samples, head dimensions 128 and 64 -- OPT-125m and
+    Falcon-180B have 64)."""
+    rep = heads // kv
+    gen = torch.Generator(device="cuda").manual_seed(heads * 131 + T + d)
     H, Hkv = heads * d, kv * d
     QW = H + 2 * Hkv
     M = batch * T
