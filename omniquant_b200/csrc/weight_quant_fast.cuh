@@ -224,6 +224,249 @@ __global__ void __launch_bounds__(256) wq_pc_fwd(WqArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ per-channel forward, calibration-loop variant
+// The optimiser step calls the forward with ONE output format (bf16 W_q, plus the s8 side output when the forward GEMM
+// is the exact-integer one).  ncu on the general kernel above (profiles/r2_wq_ncu_summary.csv): 43.6 thread-instructions
+// per weight at K = 4096, of which ~17 are integer / control (null checks of the optional outputs and bounds tests per
+// float4, 64-bit index arithmetic) and ~13 the quantise step.  This variant removes them:
+//  * outputs fixed by template (S8), bounds test only on a thread's LAST float4, row pointers hoisted;
+//  * clamp BEFORE the rounding: clamp(rint(qa) + zp, 0, qmax) == rint(clamp(qa, -zp, qmax - zp)) + zp because zp is an
+//    integer and rint is monotone and fixes integers.  The clamped quotient is bounded, so rint is the magic-number add
+//    t = qc + M (M = 1.5 * 2^23 + (zp - z0): the low byte of t's bit pattern IS the s8 code), r = t - M is the
+//    dequantised integer (code - zp, exact), W_q = r * scale -- the same fp32 product as oq_dequant;
+//  * the bit-exactness guard of oq_rint_div in the clamped domain: qa = f * (1/scale) is within 1.8e-7 |q| of the
+//    IEEE quotient, so rint can only differ when |qc - r| is that close to 0.5; |q| <= max(|zp|, |qmax - zp|) + 1
+//    inside the clamp range gives a ROW-constant threshold, and the four |qc - r| of a float4 are folded with one
+//    3-input max (2.5 instructions per weight instead of 5).  A failing float4 (or a row whose 1/scale is not a normal
+//    number) is redone with the IEEE division (oq_code / oq_dequant);
+//  * the row extrema use the NaN-propagating 3-input min / max, so a NaN / Inf weight makes the row's scale non-finite
+//    and sends the whole row through the exact path (the reference's amin / amax propagate NaN the same way);
+//  * the q | k | v row table is resolved once per THREADS rows (with the sigmoids), not per row by every thread.
+// ROWMODE: 0 multiply by row[n], 1 divide, 2 per-row segment table, 3 no row fold.
+__device__ __forceinline__ float fmax3_nan(float a, float b, float c) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fmin3_nan(float a, float b, float c) {
+  float d;
+  asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float warp_max_nan(float v) {
+  float r;
+  asm volatile("redux.sync.max.NaN.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float warp_min_nan(float v) {
+  float r;
+  asm volatile("redux.sync.min.NaN.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+template <int NV, int THREADS, bool LET, int ROWMODE, bool S8, bool EXACT>
+__global__ void __launch_bounds__(THREADS) wq_pc_fwd_lean(WqArgs a) {
+  extern __shared__ float4 dsm4[];
+  constexpr int NW = THREADS / 32;
+  static_assert(NW == 4 || NW == 8, "128 or 256 threads");
+  __shared__ __align__(16) float red[2][4][NW];
+  __shared__ float sig[2][THREADS];
+  __shared__ float rsv[THREADS];
+  __shared__ int rdv[THREADS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, K4 = a.K >> 2;
+  float4* colv = dsm4;            // [K4] (LET)
+  float4* shv = dsm4 + K4;        // [K4] (LET)
+  const bool has_shift = LET && a.shift != nullptr;
+  if (LET) {
+    for (int i = tid; i < K4; i += THREADS) {
+      colv[i] = a.col ? ld4(a.col + 4 * i) : make_float4(1.f, 1.f, 1.f, 1.f);
+      shv[i] = a.shift ? ld4(a.shift + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const int lwc = a.up != nullptr;
+  // EXACT: (NV - 1) * THREADS < K4 <= NV * THREADS, only a thread's last float4 can fall off the row (everything else is
+  // resolved at compile time); otherwise a thread owns its first `nfull` float4s
+  const bool last_ok = tid + (NV - 1) * THREADS < K4;
+  const int nfull = (K4 - tid + THREADS - 1) / THREADS;
+#define OQ_LEAN_OK(i) (EXACT ? ((i) < NV - 1 || last_ok) : ((i) < nfull))
+  const float* wbase = a.W + 4 * tid;
+  float4 wn[NV];
+  int n = blockIdx.x;
+  if (n < a.N) {
+    const float* wr = wbase + (long)n * a.K;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) wn[i] = OQ_LEAN_OK(i) ? ld4(wr + 4 * i * THREADS) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  int par = 0, k = 0;
+  int pend_n = -1;          // s8 side output: the row whose code sum is still in red[par ^ 1][3] (thread 0 only)
+  float pend_scale = 0.f;
+  for (; n < a.N; n += gridDim.x, par ^= 1, ++k) {
+    if (k == THREADS) k = 0;
+    if (k == 0) {   // per-row scalars of the next THREADS rows of this block, one row per thread
+      __syncthreads();
+      const long r = (long)n + (long)tid * gridDim.x;
+      const bool ok = r < a.N;
+      sig[0][tid] = (ok && lwc) ? oq_sigmoidf(a.up[r]) : 1.0f;
+      sig[1][tid] = (ok && lwc) ? oq_sigmoidf(a.low[r]) : 1.0f;
+      if (LET && ROWMODE != 3) {
+        float rs = 1.0f;
+        int op = 0;
+        if (ok) wq_row_fold(a, r, rs, op);
+        rsv[tid] = rs;
+        rdv[tid] = op == 2;
+      }
+      __syncthreads();
+    }
+    float4 w[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) w[i] = wn[i];
+    const int nn = n + gridDim.x;
+    if (nn < a.N) {  // prefetch the next row while this one is processed
+      const float* wr = wbase + (long)nn * a.K;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if OQ_LEAN_OK(i) wn[i] = ld4(wr + 4 * i * THREADS);
+    }
+    // ---- fold + extrema
+    float sm = 0.f, mlo = INFINITY, mhi = -INFINITY;
+    if (LET) {
+      const float rs = ROWMODE != 3 ? rsv[k] : 1.0f;
+      const bool rdiv = ROWMODE == 1 || (ROWMODE == 2 && rdv[k]);
+      if (rdiv) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          if OQ_LEAN_OK(i) {
+            const float4 c4 = colv[tid + i * THREADS], s4 = shv[tid + i * THREADS];
+            sm += w[i].x * s4.x + w[i].y * s4.y + w[i].z * s4.z + w[i].w * s4.w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f4(w[i], j) = OQ_DIV(OQ_MUL(f4(w[i], j), f4(const_cast<float4&>(c4), j)), rs);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          if OQ_LEAN_OK(i) {
+            const float4 c4 = colv[tid + i * THREADS], s4 = shv[tid + i * THREADS];
+            sm += w[i].x * s4.x + w[i].y * s4.y + w[i].z * s4.z + w[i].w * s4.w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float f1 = OQ_MUL(f4(w[i], j), f4(const_cast<float4&>(c4), j));
+              f4(w[i], j) = ROWMODE == 3 ? f1 : OQ_MUL(f1, rs);     // (W * col) * row; a factor 1 is exact
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if OQ_LEAN_OK(i) {
+        mlo = fmin3_nan(fmin3_nan(mlo, w[i].x, w[i].y), w[i].z, w[i].w);
+        mhi = fmax3_nan(fmax3_nan(mhi, w[i].x, w[i].y), w[i].z, w[i].w);
+      }
+    }
+    mlo = warp_min_nan(mlo);
+    mhi = warp_max_nan(mhi);
+    if (has_shift) sm = warp_reduce(sm, OpSum());
+    if (lane == 0) {
+      red[par][0][warp] = mlo;
+      red[par][1][warp] = mhi;
+      red[par][2][warp] = sm;
+    }
+    __syncthreads();
+    float xmin, xmax;
+    {
+      const float4 a0 = *reinterpret_cast<const float4*>(&red[par][0][0]), b0 = *reinterpret_cast<const float4*>(&red[par][1][0]);
+      xmin = fmin3_nan(fmin3_nan(a0.x, a0.y, a0.z), a0.w, a0.w);
+      xmax = fmax3_nan(fmax3_nan(b0.x, b0.y, b0.z), b0.w, b0.w);
+      if (NW == 8) {
+        const float4 a1 = *reinterpret_cast<const float4*>(&red[par][0][4]), b1 = *reinterpret_cast<const float4*>(&red[par][1][4]);
+        xmin = fmin3_nan(fmin3_nan(xmin, a1.x, a1.y), a1.z, a1.w);
+        xmax = fmax3_nan(fmax3_nan(xmax, b1.x, b1.y), b1.z, b1.w);
+      }
+    }
+    const OqQParams q = oq_qparams(xmin, xmax, sig[0][k], sig[1][k], lwc, a.n_bits, a.symmetric, a.recip_div);
+    const float z0 = S8 ? oq_s8_z0(q.zp, q.qmax) : q.zp;
+    if (tid == 0) {
+      if (S8) {
+        if (pend_n >= 0) {     // the previous row's warp sums were published before this row's barrier
+          float t = 0.f;
+#pragma unroll
+          for (int x = 0; x < NW; ++x) t += red[par ^ 1][3][x];
+          a.s8_t[pend_n] = pend_scale * t;
+        }
+        pend_n = n;
+        pend_scale = q.scale;
+        // a degenerate (constant) row dequantises to NaN in the fake-quant path: poison the epilogue term instead
+        a.s8_beta[n] = isfinite(s8_scale_or_nan(q)) && q.scale != 0.0f ? (z0 - q.zp) * q.scale : __int_as_float(0x7fc00000);
+      }
+      if (a.scale_out) a.scale_out[n] = q.scale;
+      if (a.zp_out) a.zp_out[n] = q.zp;
+      if (a.xmin_out) a.xmin_out[n] = xmin;
+      if (a.xmax_out) a.xmax_out[n] = xmax;
+      if (has_shift && a.mv) {
+        float t = 0.f;
+#pragma unroll
+        for (int x = 0; x < NW; ++x) t += red[par][2][x];
+        a.mv[n] = t;
+      }
+    }
+    // ---- quantise
+    const float inv = OQ_DIV(1.0f, q.scale);
+    const float lo = -q.zp, hi = q.qmax - q.zp;                     // integers: exact
+    const float magic = 12582912.0f + (q.zp - z0);                 // S8: low byte of (qc + magic) = code - z0
+    const bool fast_ok = oq_inv_ok(inv) && fabsf(q.zp) <= 1.0e4f;  // (a NaN zero point fails the comparison)
+    const float thr = fast_ok ? 0.5f - ((fmaxf(fabsf(lo), fabsf(hi)) + 1.0f) * 2.4e-7f + 1e-30f) : -1.0f;
+    bf16* qrow = a.q_bf + (long)n * a.ld_bf + 4 * tid;
+    int8_t* crow = S8 ? a.codes8 + (long)n * a.K + 4 * tid : nullptr;
+    int isum = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if OQ_LEAN_OK(i) {
+        float t[4], y[4], d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float qa = OQ_MUL(f4(w[i], j), inv);
+          const float qc = fminf(fmaxf(qa, lo), hi);
+          t[j] = OQ_ADD(qc, magic);
+          const float r = OQ_SUB(t[j], magic);
+          d[j] = OQ_SUB(qc, r);
+          y[j] = OQ_MUL(r, q.scale);
+        }
+        const float m = fmaxf(fmaxf(fabsf(d[0]), fabsf(d[1])), fmaxf(fabsf(d[2]), fabsf(d[3])));
+        if (!(m < thr)) {   // exact IEEE division (and NaN-preserving clamp) for this float4
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float c = oq_code(f4(w[i], j), q);
+            y[j] = oq_dequant(c, q);
+            t[j] = (c - z0) + 12582912.0f;
+          }
+        }
+        store_bf4(qrow + 4 * i * THREADS, y);
+        if (S8) {
+          const uint32_t w8 = __byte_perm(__byte_perm(__float_as_uint(t[0]), __float_as_uint(t[1]), 0x0040),
+                                          __byte_perm(__float_as_uint(t[2]), __float_as_uint(t[3]), 0x0040), 0x5410);
+          isum = __dp4a((int)w8, 0x01010101, isum);
+          *reinterpret_cast<uint32_t*>(crow + 4 * i * THREADS) = w8;
+        }
+      }
+    }
+    if (S8) {
+      const int wsum = __reduce_add_sync(0xffffffffu, isum);      // one instruction (REDUX) instead of five shuffles
+      if (lane == 0) red[par][3][warp] = (float)wsum;
+    }
+  }
+  if (S8) {
+    __syncthreads();
+    if (tid == 0 && pend_n >= 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int x = 0; x < NW; ++x) t += red[par ^ 1][3][x];
+      a.s8_t[pend_n] = pend_scale * t;
+    }
+  }
+#undef OQ_LEAN_OK
+}
+
 // ================================================================== per-channel backward
 // dynamic smem (LET): col[K] | colacc[K] | shacc[K]
 template <int NV, bool LET>
@@ -643,8 +886,65 @@ static bool launch_pc_fwd2(const WqArgs& a, int grid, size_t smem, cudaStream_t 
 #undef OQ_PC_FWD
   return false;
 }
+// calibration-loop variant: bf16 output (+ s8 side output) only
+template <int NV, int THREADS, bool LET, int ROWMODE, bool S8, bool EXACT>
+static bool launch_pc_fwd_lean4(const WqArgs& a, size_t smem, cudaStream_t s) {
+  auto kern = wq_pc_fwd_lean<NV, THREADS, LET, ROWMODE, S8, EXACT>;
+  static int per_sm = 0;
+  if (smem > 96 * 1024) return false;
+  if (!per_sm) {
+    if (smem > 40 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) return false;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem) != cudaSuccess || per_sm < 1) {
+      per_sm = 0;
+      cudaGetLastError();
+      return false;
+    }
+  }
+  const int grid = (int)std::min<long>(a.N, (long)oq_num_sms() * per_sm);
+  kern<<<grid, THREADS, smem, s>>>(a);
+  return true;
+}
+template <int NV, int THREADS, bool LET, int ROWMODE, bool EXACT>
+static bool launch_pc_fwd_lean3(const WqArgs& a, size_t smem, cudaStream_t s) {
+  return a.codes8 ? launch_pc_fwd_lean4<NV, THREADS, LET, ROWMODE, true, EXACT>(a, smem, s)
+                  : launch_pc_fwd_lean4<NV, THREADS, LET, ROWMODE, false, EXACT>(a, smem, s);
+}
+template <bool LET, int ROWMODE>
+static bool launch_pc_fwd_lean2(const WqArgs& a, size_t smem, cudaStream_t s) {
+  static const int env_threads = [] { const char* e = getenv("OQ_WQ_LEAN_THREADS"); return e ? atoi(e) : 0; }();
+  const int K4 = a.K / 4;
+  const int threads = K4 > 1024 ? 256 : (env_threads ? env_threads : 128);   // measured at K = 4096 (B200): 96 us with 128 threads x 8 float4, 110 us with 256 x 4
+  const int nv = (K4 + threads - 1) / threads;
+  if (threads == 128) {
+    if (nv == 2) return launch_pc_fwd_lean3<2, 128, LET, ROWMODE, true>(a, smem, s);
+    if (nv == 4) return launch_pc_fwd_lean3<4, 128, LET, ROWMODE, true>(a, smem, s);
+    if (nv == 6) return launch_pc_fwd_lean3<6, 128, LET, ROWMODE, true>(a, smem, s);
+    if (nv == 8) return launch_pc_fwd_lean3<8, 128, LET, ROWMODE, true>(a, smem, s);
+    return launch_pc_fwd_lean3<8, 128, LET, ROWMODE, false>(a, smem, s);
+  }
+  if (nv == 1) return launch_pc_fwd_lean3<1, 256, LET, ROWMODE, true>(a, smem, s);
+  if (nv == 2) return launch_pc_fwd_lean3<2, 256, LET, ROWMODE, true>(a, smem, s);
+  if (nv == 3) return launch_pc_fwd_lean3<3, 256, LET, ROWMODE, true>(a, smem, s);
+  if (nv == 4) return launch_pc_fwd_lean3<4, 256, LET, ROWMODE, true>(a, smem, s);
+  if (nv == 8) return launch_pc_fwd_lean3<8, 256, LET, ROWMODE, true>(a, smem, s);
+  if (nv == 11) return launch_pc_fwd_lean3<11, 256, LET, ROWMODE, true>(a, smem, s);
+  if (nv == 16) return launch_pc_fwd_lean3<16, 256, LET, ROWMODE, true>(a, smem, s);
+  if (nv <= 8) return launch_pc_fwd_lean3<8, 256, LET, ROWMODE, false>(a, smem, s);
+  if (nv <= 16) return launch_pc_fwd_lean3<16, 256, LET, ROWMODE, false>(a, smem, s);
+  return false;
+}
+static bool launch_pc_fwd_lean(const WqArgs& a, bool let, size_t smem, cudaStream_t s) {
+  static const bool off = [] { const char* e = getenv("OQ_WQ_LEAN"); return e && atoi(e) == 0; }();
+  if (off || !a.q_bf || a.q_f32 || a.codes) return false;
+  if (!let) return launch_pc_fwd_lean2<false, 3>(a, 0, s);
+  if (a.nseg) return launch_pc_fwd_lean2<true, 2>(a, smem, s);
+  if (a.row && a.row_op == 2) return launch_pc_fwd_lean2<true, 1>(a, smem, s);
+  if (a.row && a.row_op == 1) return launch_pc_fwd_lean2<true, 0>(a, smem, s);
+  return launch_pc_fwd_lean2<true, 3>(a, smem, s);
+}
 template <bool LET>
 static bool launch_pc_fwd(const WqArgs& a, int grid, size_t smem, cudaStream_t s) {
+  if (launch_pc_fwd_lean(a, LET, smem, s)) return true;
   if (LET && a.nseg) return launch_pc_fwd2<LET, 2>(a, grid, smem, s);
   if (LET && a.row && a.row_op == 2) return launch_pc_fwd2<LET, 1>(a, grid, smem, s);
   return launch_pc_fwd2<LET, 0>(a, grid, smem, s);

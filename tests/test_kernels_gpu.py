@@ -1024,3 +1024,72 @@ def test_gemm_fq_matches_prepass_plus_gemm(ops):
     torch.cuda.synchronize()
     torch.testing.assert_close(got.float(), want.float(), rtol=1e-2, atol=1e-2)
     assert float((got.float() - want.float()).abs().max()) <= 2.0 ** -6 * float(want.float().abs().max())
+
+
+@pytest.mark.parametrize("N,K,let", [(64, 4096, "col_row_mul"), (48, 4096, "col_row_div"), (40, 4096, "col"), (33, 11008, None),
+                                     (96, 768, "col_row_mul"), (64, 3072, None), (24, 5120, "col_row_div"), (36, 4096, "segments")])
+@pytest.mark.parametrize("n_bits,symmetric", [(4, False), (6, False), (8, False), (3, True), (2, False)])
+def test_weight_quant_calibration_variant_equals_general_kernel(ops, N, K, let, n_bits, symmetric):
+    """The calibration-loop forward (bf16 output [+ s8 codes] only: clamp-then-round with a row-constant exactness guard)
+    must produce the same bits as the general kernel, which the tests above pin to the oracle / ATen.  Rows are built to
+    hit the guard: weights at exact multiples and half-multiples of the row's scale, constant rows, rows that do not
+    straddle zero (zero points outside [0, qmax]), tiny and huge rows, NaN and Inf elements."""
+    g = torch.Generator(device="cuda").manual_seed(N * 7 + K + n_bits)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    W[1] = torch.round(W[1] * 64) / 64                      # many exact ties on a dyadic grid
+    W[2] = 0.37                                             # constant row: scale 0 -> NaN path
+    W[3] = W[3].abs() + 0.5                                 # all positive: negative zero point
+    W[4] = -W[4].abs() - 3.0                                # all negative: zero point above qmax
+    W[5] = W[5] * 1e-30
+    W[6] = W[6] * 1e30
+    W[7, 5] = float("nan")
+    W[8, 9] = float("inf")
+    W[9] = torch.linspace(-1, 1, K, device="cuda")          # evenly spaced: hits k + 0.5 quotients
+    W[10] = (torch.arange(K, device="cuda") % 31 - 15).float() * 0.125 + 0.0625
+    up = torch.randn(N, device="cuda", generator=g) * 2 + 2
+    low = torch.randn(N, device="cuda", generator=g) * 2 + 2
+    kw = dict(n_bits=n_bits, symmetric=symmetric, up=up, low=low)
+    if let in ("col_row_mul", "col_row_div", "col"):
+        kw["col_scale"] = torch.rand(K, device="cuda", generator=g) + 0.5
+        kw["shift"] = torch.randn(K, device="cuda", generator=g) * 0.1
+        if let != "col":
+            kw["row_scale"] = torch.rand(N, device="cuda", generator=g) + 0.5
+            kw["row_op"] = 1 if let == "col_row_mul" else 2
+    elif let == "segments":
+        kw["col_scale"] = torch.rand(K, device="cuda", generator=g) + 0.5
+        kw["shift"] = torch.randn(K, device="cuda", generator=g) * 0.1
+        r = torch.rand(N, device="cuda", generator=g) + 0.5
+        kw["segments"] = [(12, r[:12], 2), (24, r[12:24], 1), (N, None, 0)]
+    for recip in (True, False):
+        outs = []
+        for general in (True, False):
+            for s8 in (False, True):
+                q = torch.full((N, K), 7.0, device="cuda", dtype=torch.bfloat16)
+                sc, zp, xmn, xmx = (torch.zeros(N, device="cuda") for _ in range(4))
+                mv = torch.zeros(N, device="cuda") if "shift" in kw else None
+                op = ops.S8Operand(N, K, "cuda") if s8 else None
+                extra = dict(wq_f32=torch.empty(N, K, device="cuda")) if general else {}     # any extra output selects the general kernel
+                ops.weight_quant_fwd(W, recip_div=recip, wq_bf16=q, scale_out=None if s8 else sc, zp_out=zp, xmin_out=xmn,
+                                     xmax_out=xmx, matvec_out=mv, s8=op, **kw, **extra)
+                torch.cuda.synchronize()
+                outs.append((general, s8, q.view(torch.int16), (op.scale if s8 else sc).view(torch.int32).clone(),
+                             zp.view(torch.int32), xmn, xmx, mv, op))
+        ref, ref8 = outs[0], outs[1]
+        for o in outs[2:]:
+            base = ref8 if (o[1] and ref8 is not None) else ref
+            rows_ok = torch.ones(N, dtype=torch.bool, device="cuda")
+            rows_ok[7] = False      # NaN element: the general kernel ignores it in the extrema, the lean one poisons the row (like torch.amax)
+            assert torch.equal(o[2][rows_ok], base[2][rows_ok]), (let, n_bits, recip, o[1])
+            assert torch.equal(o[3][rows_ok], base[3][rows_ok]) and torch.equal(o[4][rows_ok], base[4][rows_ok])
+            assert torch.equal(o[5][rows_ok], base[5][rows_ok]) and torch.equal(o[6][rows_ok], base[6][rows_ok])
+            if o[7] is not None:
+                fin_rows = rows_ok & torch.isfinite(W).all(1)
+                bound = (W[fin_rows].abs().double() @ kw["shift"].abs().double()).float() * 1e-5 + 1e-30     # fp32 summation order
+                assert bool(((o[7][fin_rows] - base[7][fin_rows]).abs() <= bound).all())
+            assert bool(torch.isnan(o[2][7].view(torch.bfloat16).float()).all())     # reference semantics for a NaN weight
+            if o[1] and ref8 is not None:
+                fin = rows_ok & torch.isfinite(base[8].beta)
+                assert torch.equal(o[8].codes[fin], base[8].codes[fin])
+                assert torch.equal(o[8].t[fin].view(torch.int32), base[8].t[fin].view(torch.int32))
+                assert torch.equal(torch.isfinite(o[8].beta), torch.isfinite(base[8].beta) & rows_ok | (torch.isfinite(o[8].beta) & ~rows_ok))
+                assert torch.equal(o[8].beta[fin].view(torch.int32), base[8].beta[fin].view(torch.int32))
