@@ -81,12 +81,16 @@ __global__ void __launch_bounds__(256) wq_pc_bwd_lwc(WqArgs a) {
 // barrier, so a slow row finalisation or a late row never stalls the other warps.
 //   smem: STAGES x { W row: K fp32 | dW_q row: K bf16 or fp32 }
 constexpr int WS_TIE_CAP = 32;
+constexpr int WS_FIN_TIES = 4;     // extremal elements per row that the batched finalisation keeps (more: the row is finalised at once)
 struct WsRowHdr {
   float rmul, en, xmin, xmax, zp, inv, qmax, su, sl, tolmax, tolmin, pad;
+  // rint(q) + zp lies in [0, qmax]  <=>  qlo <= q <= qhi: the half-integers -zp - 0.5 / qmax - zp + 0.5, moved one ulp
+  // inwards when the tie rounds (to even) out of the range
+  float qlo, qhi, pad2, pad3;
 };
 
 // ROWMODE: 0 the row fold multiplies (or is absent), 1 it divides, 2 per-row segment table (q | k | v in one launch)
-template <int NV, int STAGES, int ROWMODE>
+template <int NV, int STAGES, int ROWMODE, bool G32, bool EXACT>
 __global__ void __launch_bounds__(288, NV <= 4 ? 2 : 1) wq_pc_bwd_ws(WqArgs a) {
   constexpr bool ROWDIV = ROWMODE != 0;      // consumers: recognise the extrema within the row's tolerance (0 when it multiplies)
   extern __shared__ __align__(128) unsigned char psm[];
@@ -96,6 +100,12 @@ __global__ void __launch_bounds__(288, NV <= 4 ? 2 : 1) wq_pc_bwd_ws(WqArgs a) {
   __shared__ int tie_cnt[STAGES];
   __shared__ int tie_k[STAGES][WS_TIE_CAP];
   __shared__ float tie_wv[STAGES][WS_TIE_CAP], tie_w1[STAGES][WS_TIE_CAP];
+  // control warp: prepared headers and parked row results of two 32-row chunks
+  __shared__ WsRowHdr htab[2][32];
+  __shared__ float fin_R[2][32], fin_rd[2][32];
+  __shared__ int fin_cnt[2][32];
+  __shared__ int fin_k[2][32][WS_FIN_TIES];
+  __shared__ float fin_wv[2][32][WS_FIN_TIES], fin_w1[2][32][WS_FIN_TIES];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, K4 = a.K >> 2;
   const uint32_t wbytes = (uint32_t)a.K * 4u, gbytes = (uint32_t)a.K * (a.g_is_f32 ? 4u : 2u), sbytes = wbytes + gbytes;
   const size_t gsz = a.g_is_f32 ? 4 : 2;
@@ -114,6 +124,12 @@ __global__ void __launch_bounds__(288, NV <= 4 ? 2 : 1) wq_pc_bwd_ws(WqArgs a) {
 
   if (warp == 8) {
     // ---------------------------------------------------------------- control warp
+    // Everything that is per row and scalar (two sigmoids, 1/scale, the range bounds before the row; the clip-path
+    // gradient, d_up / d_low / drow and the extrema corrections after it) is evaluated for 32 rows AT ONCE, one row per
+    // lane: done row by row on one lane it cost ~2 us per row and bounded the whole kernel (ncu: the consumers spent 36 %
+    // of their samples spinning on the stage barrier, more stages did not help, one block per SM halved the speed).  The
+    // serial per-row path is now: wait for the stage, fold the eight warp partials, park them in the row's slot, copy
+    // the prepared header and re-arm the bulk copies.
     struct Raw { float rs, en, xmin, xmax, scale, zp, up, low; int div; };
     auto load_raw = [&](long row) {
       Raw r;
@@ -134,7 +150,7 @@ __global__ void __launch_bounds__(288, NV <= 4 ? 2 : 1) wq_pc_bwd_ws(WqArgs a) {
       r.low = lwc ? a.low[row] : 0.0f;
       return r;
     };
-    auto fill = [&](long row, int st, const Raw& r) {   // lane 0: header, then the row itself
+    auto header = [&](const Raw& r) {
       WsRowHdr h;
       h.su = lwc ? oq_sigmoidf(r.up) : 1.0f;
       h.sl = lwc ? oq_sigmoidf(r.low) : 1.0f;
@@ -151,69 +167,103 @@ __global__ void __launch_bounds__(288, NV <= 4 ? 2 : 1) wq_pc_bwd_ws(WqArgs a) {
       h.inv = OQ_DIV(1.0f, q.scale);
       h.tolmax = r.div ? 2.4e-7f * fabsf(r.xmax) : 0.0f;
       h.tolmin = r.div ? 2.4e-7f * fabsf(r.xmin) : 0.0f;
-      h.pad = 0.f;
-      hdr[st] = h;
+      h.pad = h.pad2 = h.pad3 = 0.f;
+      const float lo = -q.zp, hi = q.qmax - q.zp;          // integers (|zp| <= 1e4): the sums below are exact
+      const bool lo_even = fmodf(lo, 2.0f) == 0.0f, hi_even = fmodf(hi, 2.0f) == 0.0f;
+      h.qlo = lo_even ? lo - 0.5f : nextafterf(lo - 0.5f, INFINITY);
+      h.qhi = hi_even ? hi + 0.5f : nextafterf(hi + 0.5f, -INFINITY);
+      return h;
+    };
+    const int grid = gridDim.x;
+    const int nrows = (a.N - (int)blockIdx.x + grid - 1) / grid;      // rows of this block: blockIdx.x + i * grid
+    auto row_of = [&](int i) { return (long)blockIdx.x + (long)i * grid; };
+    auto headers = [&](int chunk) {      // all lanes: headers of rows [32 chunk, 32 chunk + 32)
+      const int i = 32 * chunk + lane;
+      if (i < nrows) htab[chunk & 1][lane] = header(load_raw(row_of(i)));
+      __syncwarp();
+    };
+    auto fill = [&](int i, int st) {   // lane 0: publish row i's header, then fetch the row itself
+      const long row = row_of(i);
+      hdr[st] = htab[(i >> 5) & 1][i & 31];
       fence_proxy_async();
       mbar_expect_tx(&full[st], sbytes);     // release: the header is visible to whoever observes the phase
       bulk_g2s(psm + (size_t)st * sbytes, a.W + row * a.K, wbytes, &full[st]);
       bulk_g2s(psm + (size_t)st * sbytes + wbytes, reinterpret_cast<const char*>(a.g) + (size_t)row * a.ld_g * gsz, gbytes,
                &full[st]);
     };
-    if (lane == 0) {
-#pragma unroll
-      for (int s = 0; s < STAGES; ++s) {
-        const long row = (long)blockIdx.x + (long)s * gridDim.x;
-        if (row < a.N) fill(row, s, load_raw(row));
-      }
-    }
-    int it = 0;
-    for (long n = blockIdx.x; n < a.N; n += gridDim.x, ++it) {
-      const int st = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-      const long nn = n + (long)STAGES * gridDim.x;
-      Raw nxt = {};
-      if (lane == 0 && nn < a.N) nxt = load_raw(nn);      // in flight while the consumers finish row n
-      mbar_wait(&empty[st], ph);
-      const WsRowHdr h = hdr[st];
-      float Rt = lane < 8 ? red[st][0][lane] : 0.f, rd = lane < 8 ? red[st][1][lane] : 0.f;
-      Rt = warp_reduce(Rt, OpSum());
-      rd = warp_reduce(rd, OpSum());
-      const int cnt = tie_cnt[st];
+    // one row, one lane: clip-path gradient, corrections of the (few) extremal elements, outputs
+    auto finalize = [&](int i, const WsRowHdr& h, float Rt, float rd, int cnt, const int* tk, const float* twv, const float* tw1) {
       float gmaxp, gminp;
       oq_scale_grad(Rt, h.xmin, h.xmax, h.su, h.sl, lwc, a.n_bits, a.symmetric, a.recip_div, &gmaxp, &gminp);
       float nmax = 0.f, nmin = 0.f, smax = 0.f, smin = 0.f;
-      const float4* ws = reinterpret_cast<const float4*>(psm + (size_t)st * sbytes);
-      if (cnt <= WS_TIE_CAP) {
-        const bool have = lane < cnt;
-        const int kf = have ? tie_k[st][lane] : 0;
-        const float w1 = have ? tie_w1[st][lane] : 0.f;
-        nmax = (float)__popc(__ballot_sync(0xffffffffu, have && (kf & 1)));
-        nmin = (float)__popc(__ballot_sync(0xffffffffu, have && (kf & 2)));
-        smax = warp_reduce((kf & 1) ? w1 : 0.f, OpSum());
-        smin = warp_reduce((kf & 2) ? w1 : 0.f, OpSum());
-        const float cmax = nmax > 0.f ? gmaxp * h.su / nmax : 0.0f, cmin = nmin > 0.f ? gminp * h.sl / nmin : 0.0f;
-        if (have && a.dcol) {
-          const float corr = ((kf & 1) ? cmax : 0.f) + ((kf & 2) ? cmin : 0.f);
-          atomicAdd(a.dcol + (kf >> 2), corr * h.rmul * tie_wv[st][lane]);
+      for (int t = 0; t < cnt; ++t) {
+        if (tk[t] & 1) { nmax += 1.0f; smax += tw1[t]; }
+        if (tk[t] & 2) { nmin += 1.0f; smin += tw1[t]; }
+      }
+      const float cmax = nmax > 0.f ? gmaxp * h.su / nmax : 0.0f, cmin = nmin > 0.f ? gminp * h.sl / nmin : 0.0f;
+      if (a.dcol)
+        for (int t = 0; t < cnt; ++t)
+          atomicAdd(a.dcol + (tk[t] >> 2), (((tk[t] & 1) ? cmax : 0.f) + ((tk[t] & 2) ? cmin : 0.f)) * h.rmul * twv[t]);
+      const long n = row_of(i);
+      if (lwc && a.d_up) a.d_up[n] = gmaxp * h.xmax * h.su * (1.0f - h.su);
+      if (lwc && a.d_low) a.d_low[n] = gminp * h.xmin * h.sl * (1.0f - h.sl);
+      if (a.drow) a.drow[n] = rd + cmax * smax + cmin * smin;
+    };
+    headers(0);
+    if (lane == 0)
+      for (int i = 0; i < STAGES && i < nrows; ++i) fill(i, i);
+    int st = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < nrows; ++i) {
+      const int j = i + STAGES;                 // the row that takes over this stage
+      const int slot = i & 31, fb = (i >> 5) & 1;
+      mbar_wait(&empty[st], ph);
+      float Rt = lane < 8 ? red[st][0][lane] : 0.f, rd = lane < 8 ? red[st][1][lane] : 0.f;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        Rt += __shfl_xor_sync(0xffffffffu, Rt, o);
+        rd += __shfl_xor_sync(0xffffffffu, rd, o);
+      }
+      const int cnt = tie_cnt[st];
+      if (cnt <= WS_FIN_TIES) {               // the common case: park the row's partials, hand the stage back
+        if (lane < cnt) {
+          fin_k[fb][slot][lane] = tie_k[st][lane];
+          fin_wv[fb][slot][lane] = tie_wv[st][lane];
+          fin_w1[fb][slot][lane] = tie_w1[st][lane];
         }
-      } else {   // many equal extrema (e.g. already-quantised weights): rescan the row, which is still in the stage
+        if (lane == 0) {
+          fin_R[fb][slot] = Rt;
+          fin_rd[fb][slot] = rd;
+          fin_cnt[fb][slot] = cnt;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          tie_cnt[st] = 0;
+          if (j < nrows) fill(j, st);
+        }
+      } else {                                // many equal extrema: finalise this row now, the stage still holds it
+        const WsRowHdr h = hdr[st];
+        float gmaxp, gminp;
+        oq_scale_grad(Rt, h.xmin, h.xmax, h.su, h.sl, lwc, a.n_bits, a.symmetric, a.recip_div, &gmaxp, &gminp);
+        float nmax = 0.f, nmin = 0.f, smax = 0.f, smin = 0.f;
+        const float4* ws = reinterpret_cast<const float4*>(psm + (size_t)st * sbytes);
         for (int pass = 0; pass < 2; ++pass) {
           const float cmax = nmax > 0.f ? gmaxp * h.su / nmax : 0.0f, cmin = nmin > 0.f ? gminp * h.sl / nmin : 0.0f;
           for (int idx = lane; idx < K4; idx += 32) {
             const float4 w4 = ws[idx];
             const float4 c4 = a.col ? ld4(a.col + 4 * idx) : make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float wv = f4(const_cast<float4&>(w4), j);
-              const float w1 = OQ_MUL(wv, f4(const_cast<float4&>(c4), j));
-              const float f = OQ_MUL(w1, h.rmul);
+            for (int e = 0; e < 4; ++e) {
+              const float wv = f4(const_cast<float4&>(w4), e);
+              const float w1s = OQ_MUL(wv, f4(const_cast<float4&>(c4), e));
+              const float f = OQ_MUL(w1s, h.rmul);
               const bool ismax = ROWDIV ? fabsf(f - h.xmax) <= h.tolmax : f == h.xmax;
               const bool ismin = ROWDIV ? fabsf(f - h.xmin) <= h.tolmin : f == h.xmin;
               if (pass == 0) {
-                if (ismax) { nmax += 1.0f; smax += w1; }
-                if (ismin) { nmin += 1.0f; smin += w1; }
+                if (ismax) { nmax += 1.0f; smax += w1s; }
+                if (ismin) { nmin += 1.0f; smin += w1s; }
               } else if ((ismax || ismin) && a.dcol) {
-                atomicAdd(a.dcol + 4 * idx + j, ((ismax ? cmax : 0.f) + (ismin ? cmin : 0.f)) * h.rmul * wv);
+                atomicAdd(a.dcol + 4 * idx + e, ((ismax ? cmax : 0.f) + (ismin ? cmin : 0.f)) * h.rmul * wv);
               }
             }
           }
@@ -222,83 +272,99 @@ __global__ void __launch_bounds__(288, NV <= 4 ? 2 : 1) wq_pc_bwd_ws(WqArgs a) {
             smax = warp_reduce(smax, OpSum()); smin = warp_reduce(smin, OpSum());
           }
         }
+        __syncwarp();
+        if (lane == 0) {
+          const float cmax = nmax > 0.f ? gmaxp * h.su / nmax : 0.0f, cmin = nmin > 0.f ? gminp * h.sl / nmin : 0.0f;
+          const long n = row_of(i);
+          if (lwc && a.d_up) a.d_up[n] = gmaxp * h.xmax * h.su * (1.0f - h.su);
+          if (lwc && a.d_low) a.d_low[n] = gminp * h.xmin * h.sl * (1.0f - h.sl);
+          if (a.drow) a.drow[n] = rd + cmax * smax + cmin * smin;
+          fin_cnt[fb][slot] = -1;             // done
+          tie_cnt[st] = 0;
+          if (j < nrows) fill(j, st);
+        }
       }
-      if (lane == 0) {
-        const float cmax = nmax > 0.f ? gmaxp * h.su / nmax : 0.0f, cmin = nmin > 0.f ? gminp * h.sl / nmin : 0.0f;
-        if (lwc && a.d_up) a.d_up[n] = gmaxp * h.xmax * h.su * (1.0f - h.su);
-        if (lwc && a.d_low) a.d_low[n] = gminp * h.xmin * h.sl * (1.0f - h.sl);
-        if (a.drow) a.drow[n] = rd + cmax * smax + cmin * smin;
-        tie_cnt[st] = 0;
+      if (++st == STAGES) { st = 0; ph ^= 1u; }
+      // headers of the next chunk: its first fill is STAGES rows before the chunk starts, and the table it replaces
+      // belongs to the chunk that was finalised at the end of the previous 32 rows
+      if (slot == 8 && 32 * ((i >> 5) + 1) < nrows) headers((i >> 5) + 1);
+      if (slot == 31 || i == nrows - 1) {     // a chunk is complete: finalise its rows, one per lane
+        __syncwarp();
+        const int cntl = lane <= slot ? fin_cnt[fb][lane] : -1;
+        if (cntl >= 0) finalize(i - slot + lane, htab[fb][lane], fin_R[fb][lane], fin_rd[fb][lane], cntl, fin_k[fb][lane], fin_wv[fb][lane], fin_w1[fb][lane]);
+        __syncwarp();
       }
-      __syncwarp();
-      if (lane == 0 && nn < a.N) fill(nn, st, nxt);
     }
     return;
   }
 
   // ------------------------------------------------------------------ consumer warps
+  // Instruction diet (ncu: 34.5 thread-instructions per weight before, ~11 of them integer / control): gradient type and
+  // "K fills the threads exactly" are template parameters, so bounds tests apply to a thread's LAST float4 only; the
+  // in-range test and the clamp are one operation -- qc = clamp(q, qlo, qhi) with the half-integer bounds of the header,
+  // in range <=> qc == q, and rint(qc) (magic-number add) is the clamped code minus the zero point; the arg-max / arg-min
+  // probe is one 3-input max / min pair per float4; the two row sums share one butterfly (5 shuffles instead of 10).
   const bool want_col = a.dcol != nullptr, want_sh = a.dshift != nullptr;
+  const bool last_ok = tid + (NV - 1) * 256 < K4;
+  const int nfull = (K4 - tid + 255) / 256;
+#define OQ_WS_OK(i) (EXACT ? ((i) < NV - 1 || last_ok) : ((i) < nfull))
   float4 colr[NV], cacc[NV], sacc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int idx = tid + i * 256;
-    colr[i] = (a.col && idx < K4) ? ld4(a.col + 4 * idx) : make_float4(1.f, 1.f, 1.f, 1.f);
+    colr[i] = (a.col && OQ_WS_OK(i)) ? ld4(a.col + 4 * (tid + i * 256)) : make_float4(1.f, 1.f, 1.f, 1.f);
     cacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     sacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  int it = 0;
+  const float magic = 12582912.0f;
+  int it = 0, st = 0;
+  uint32_t ph = 0;
   for (long n = blockIdx.x; n < a.N; n += gridDim.x, ++it) {
-    const int st = it % STAGES;
-    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
     mbar_wait(&full[st], ph);
     const WsRowHdr h = hdr[st];
-    const float4* ws = reinterpret_cast<const float4*>(psm + (size_t)st * sbytes);
+    const float4* ws = reinterpret_cast<const float4*>(psm + (size_t)st * sbytes) + tid;
     const unsigned char* gs = psm + (size_t)st * sbytes + wbytes;
     float R = 0.f, rowdot = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int idx = tid + i * 256;
-      if (idx < K4) {
-        const float4 w4 = ws[idx];
+      if OQ_WS_OK(i) {
+        const float4 w4 = ws[i * 256];
         float4 g4;
-        if (a.g_is_f32) {
-          g4 = reinterpret_cast<const float4*>(gs)[idx];
+        if (G32) {
+          g4 = reinterpret_cast<const float4*>(gs)[tid + i * 256];
         } else {
-          const uint2 u = reinterpret_cast<const uint2*>(gs)[idx];
+          const uint2 u = reinterpret_cast<const uint2*>(gs)[tid + i * 256];
           unpack_bf2(u.x, g4.x, g4.y);
           unpack_bf2(u.y, g4.z, g4.w);
         }
-        bool t4 = false;
+        float f[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float wv = f4(const_cast<float4&>(w4), j);
           const float w1 = OQ_MUL(wv, f4(colr[i], j));
-          const float f = OQ_MUL(w1, h.rmul);
-          const float qa = f * h.inv;
-          const float r = rintf(qa);
-          const float t = r + h.zp;
-          const float c = fminf(fmaxf(t, 0.0f), h.qmax);
-          const bool inr = (c == t);
+          f[j] = OQ_MUL(w1, h.rmul);
+          const float qa = f[j] * h.inv;
+          const float qc = fminf(fmaxf(qa, h.qlo), h.qhi);
+          const float rc = __fsub_rn(__fadd_rn(qc, magic), magic);     // clamp(rint(qa), -zp, qmax - zp)
+          const bool inr = qc == qa;
           const float gk = f4(g4, j);
-          R += gk * (inr ? (r - qa) : (c - h.zp));
-          t4 |= ROWDIV ? (fabsf(f - h.xmax) <= h.tolmax) | (fabsf(f - h.xmin) <= h.tolmin) : (f == h.xmax) | (f == h.xmin);
-          const float d2 = inr ? gk : 0.0f;
-          rowdot += d2 * w1;
-          f4(cacc[i], j) += (d2 * h.rmul) * wv;
-          f4(sacc[i], j) += wv * h.en;
+          R = fmaf(gk, rc - (inr ? qa : 0.0f), R);
+          const float pw = (inr ? gk : 0.0f) * wv;
+          rowdot = fmaf(pw, f4(colr[i], j), rowdot);
+          f4(cacc[i], j) = fmaf(pw, h.rmul, f4(cacc[i], j));
+          f4(sacc[i], j) = fmaf(wv, h.en, f4(sacc[i], j));
         }
-        if (t4) {   // rare: report the arg-max / arg-min elements of the row to the control warp
+        const float fhi = fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3])), flo = fminf(fminf(f[0], f[1]), fminf(f[2], f[3]));
+        if ((fhi >= h.xmax - h.tolmax) | (flo <= h.xmin + h.tolmin)) {   // rare: report the arg-max / arg-min elements to the control warp
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float wv = f4(const_cast<float4&>(w4), j);
             const float w1 = OQ_MUL(wv, f4(colr[i], j));
-            const float f = OQ_MUL(w1, h.rmul);
-            const bool ismax = ROWDIV ? fabsf(f - h.xmax) <= h.tolmax : f == h.xmax;
-            const bool ismin = ROWDIV ? fabsf(f - h.xmin) <= h.tolmin : f == h.xmin;
+            const bool ismax = ROWDIV ? fabsf(f[j] - h.xmax) <= h.tolmax : f[j] == h.xmax;
+            const bool ismin = ROWDIV ? fabsf(f[j] - h.xmin) <= h.tolmin : f[j] == h.xmin;
             if (ismax || ismin) {
               const int slot = atomicAdd(&tie_cnt[st], 1);
               if (slot < WS_TIE_CAP) {
-                tie_k[st][slot] = ((4 * idx + j) << 2) | (ismax ? 1 : 0) | (ismin ? 2 : 0);
+                tie_k[st][slot] = ((4 * (tid + i * 256) + j) << 2) | (ismax ? 1 : 0) | (ismin ? 2 : 0);
                 tie_wv[st][slot] = wv;
                 tie_w1[st][slot] = w1;
               }
@@ -307,19 +373,24 @@ __global__ void __launch_bounds__(288, NV <= 4 ? 2 : 1) wq_pc_bwd_ws(WqArgs a) {
         }
       }
     }
-    R = warp_reduce(R, OpSum());
-    rowdot = warp_reduce(rowdot, OpSum());
-    if (lane == 0) {
-      red[st][0][warp] = R;
-      red[st][1][warp] = rowdot;
+    // one butterfly for both sums: lanes 0-15 end up with R, lanes 16-31 with rowdot
+    {
+      const bool up = lane & 16;
+      float v = up ? rowdot : R;
+      const float other = up ? R : rowdot;
+      v += __shfl_xor_sync(0xffffffffu, other, 16);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((lane & 15) == 0) red[st][up ? 1 : 0][warp] = v;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);    // release: partial sums, tie list and the stage itself
+    if (++st == STAGES) { st = 0; ph ^= 1u; }
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int idx = tid + i * 256;
-    if (idx < K4) {
+    if OQ_WS_OK(i) {
+      const int idx = tid + i * 256;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (want_col) atomicAdd(a.dcol + 4 * idx + j, f4(cacc[i], j));
@@ -327,28 +398,57 @@ __global__ void __launch_bounds__(288, NV <= 4 ? 2 : 1) wq_pc_bwd_ws(WqArgs a) {
       }
     }
   }
+#undef OQ_WS_OK
 }
 
+// rows in flight per block: the kernel is bound by bytes in flight (ncu: consumers wait on the stage's barrier), measured
+// at K = 4096 (B200): 3 stages 155 us, 4 stages see profiles/
+static int ws_stages() {
+  static const int v = [] { const char* e = getenv("OQ_WQ_WS_STAGES"); const int x = e ? atoi(e) : 4; return x == 3 || x == 6 ? x : 4; }();
+  return v;
+}
+template <int NVV, int ROWDIV, bool G32, bool EXACT, int STAGES>
+static bool launch_pc_bwd_ws5(const WqArgs& a, int grid, size_t smem, cudaStream_t s) {
+  auto kern = wq_pc_bwd_ws<NVV, STAGES, ROWDIV, G32, EXACT>;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return false;
+    attr = true;
+  }
+  kern<<<grid, 288, smem, s>>>(a);
+  return true;
+}
+template <int NVV, int ROWDIV, bool G32, bool EXACT>
+static bool launch_pc_bwd_ws4(const WqArgs& a, int stages, int grid, size_t smem, cudaStream_t s) {
+  switch (stages) {
+    case 3: return launch_pc_bwd_ws5<NVV, ROWDIV, G32, EXACT, 3>(a, grid, smem, s);
+    case 6: return launch_pc_bwd_ws5<NVV, ROWDIV, G32, EXACT, 6>(a, grid, smem, s);
+    default: return launch_pc_bwd_ws5<NVV, ROWDIV, G32, EXACT, 4>(a, grid, smem, s);
+  }
+}
+template <int NVV, int ROWDIV, bool EXACT>
+static bool launch_pc_bwd_ws3(const WqArgs& a, int stages, int grid, size_t smem, cudaStream_t s) {
+  return a.g_is_f32 ? launch_pc_bwd_ws4<NVV, ROWDIV, true, EXACT>(a, stages, grid, smem, s)
+                    : launch_pc_bwd_ws4<NVV, ROWDIV, false, EXACT>(a, stages, grid, smem, s);
+}
 template <int ROWDIV>
 static bool launch_pc_bwd_ws2(const WqArgs& a, cudaStream_t s) {
-  constexpr int STAGES = 3;
-  const int nv = (a.K / 4 + 255) / 256;
-  const size_t smem = (size_t)STAGES * a.K * (a.g_is_f32 ? 8 : 6);
+  const int K4 = a.K / 4;
+  const int nv = (K4 + 255) / 256;
+  const size_t row_bytes = (size_t)a.K * (a.g_is_f32 ? 8 : 6);
+  int STAGES = ws_stages();
+  if (STAGES == 6 && 6 * row_bytes > 200 * 1024) STAGES = 4;
+  if (STAGES == 4 && 4 * row_bytes > 200 * 1024) STAGES = 3;
+  const size_t smem = (size_t)STAGES * row_bytes;
   if (nv > 8 || smem > 200 * 1024 || a.dW) return false;
-  const int bps = (int)std::min<size_t>(nv <= 4 ? 2 : 1, (220 * 1024) / (smem + 2048));
+  const int bps = (int)std::max<size_t>(1, std::min<size_t>(nv <= 4 ? 2 : 1, (225 * 1024) / (smem + 12 * 1024)));
   const int grid = (int)std::min<long>(a.N, (long)oq_num_sms() * bps);
-#define OQ_WS(NVV)                                                                                                  \
-  {                                                                                                                 \
-    cudaFuncSetAttribute(wq_pc_bwd_ws<NVV, STAGES, ROWDIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    wq_pc_bwd_ws<NVV, STAGES, ROWDIV><<<grid, 288, smem, s>>>(a);                                                   \
-    return true;                                                                                                    \
-  }
-  if (nv <= 1) OQ_WS(1)
-  if (nv <= 2) OQ_WS(2)
-  if (nv <= 4) OQ_WS(4)
-  if (nv <= 8) OQ_WS(8)
-#undef OQ_WS
-  return false;
+  if (nv == 1) return launch_pc_bwd_ws3<1, ROWDIV, true>(a, STAGES, grid, smem, s);
+  if (nv == 2) return launch_pc_bwd_ws3<2, ROWDIV, true>(a, STAGES, grid, smem, s);
+  if (nv == 3) return launch_pc_bwd_ws3<3, ROWDIV, true>(a, STAGES, grid, smem, s);
+  if (nv == 4) return launch_pc_bwd_ws3<4, ROWDIV, true>(a, STAGES, grid, smem, s);
+  if (nv == 8) return launch_pc_bwd_ws3<8, ROWDIV, true>(a, STAGES, grid, smem, s);
+  return launch_pc_bwd_ws3<8, ROWDIV, false>(a, STAGES, grid, smem, s);
 }
 static bool launch_pc_bwd_ws(const WqArgs& a, cudaStream_t s) {
   if (a.nseg) return launch_pc_bwd_ws2<2>(a, s);
