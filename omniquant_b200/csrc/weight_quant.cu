@@ -15,6 +15,7 @@
 // block per output channel (per-channel).  Grid = a multiple of the SM count,
 // teams stride over groups/rows.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -421,8 +422,10 @@ extern "C" int oq_weight_quant_bwd(const float* W, int N, int K, const float* co
   const bool fast_al = !ident && (K % 4 == 0) && (group_size % 4 == 0) && (a.ld_g % 4 == 0) && al(W, 16) && al(grad_wq, 16) &&
                        al(col_scale, 16) && al(dW_full, 16);
   if (fast_al && !team_warp && !let && !dW_full) {       // LWC only: R per row, one warp per row
-    const int g = (int)std::min<long>((N + 7) / 8, (long)oq_num_sms() * 8);
-    wq_pc_bwd_lwc<4><<<g, 256, 0, stream>>>(a);
+    // one warp per row, two rows per block: small blocks keep every SM busy to the end (N = 4096 rows are 27.7 per SM)
+    const int g = (int)std::min<long>((N + 1) / 2, (long)oq_num_sms() * 32);
+    if (a.g_is_f32) wq_pc_bwd_lwc<4, true><<<g, 64, 0, stream>>>(a);
+    else wq_pc_bwd_lwc<4, false><<<g, 64, 0, stream>>>(a);
     return oq_check_launch("oq_weight_quant_bwd");
   }
   if (fast_al && !team_warp && let && !dW_full && K % 8 == 0 && a.ld_g % 8 == 0) {   // bulk copies: 16-byte rows

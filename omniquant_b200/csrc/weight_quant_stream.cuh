@@ -13,13 +13,29 @@
 #pragma once
 #include "mbar.cuh"
 
-template <int U>
-__global__ void __launch_bounds__(256) wq_pc_bwd_lwc(WqArgs a) {
+template <int U, bool G32>
+__global__ void __launch_bounds__(64) wq_pc_bwd_lwc(WqArgs a) {
   const int lane = threadIdx.x & 31;
   const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
   const int K4 = a.K >> 2;
   const int lwc = a.up != nullptr;
+  const float magic = 12582912.0f;
+  using GV = typename std::conditional<G32, float4, uint2>::type;     // four gradients as loaded
   for (int n = wid; n < a.N; n += nw) {
+    const float* wr = a.W + (long)n * a.K;
+    const GV* gr = reinterpret_cast<const GV*>(reinterpret_cast<const char*>(a.g) + (size_t)n * a.ld_g * (G32 ? 4 : 2));
+    // the row's first chunk is in flight while the row scalars are evaluated; chunk c + 1 is in flight while chunk c is
+    // consumed (ncu on the unpipelined loop: 12 warp-cycles of long-scoreboard stall per issued instruction)
+    float4 w[U], wn[U];
+    GV g[U], gn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = lane + 32 * u;
+      if (idx < K4) {
+        wn[u] = ld4(wr + 4 * idx);
+        gn[u] = __ldg(gr + idx);
+      }
+    }
     const float xmin = a.xmin_in[n], xmax = a.xmax_in[n];
     const float su = lwc ? oq_sigmoidf(a.up[n]) : 1.0f, sl = lwc ? oq_sigmoidf(a.low[n]) : 1.0f;
     OqQParams q;
@@ -31,33 +47,42 @@ __global__ void __launch_bounds__(256) wq_pc_bwd_lwc(WqArgs a) {
       q = oq_qparams(xmin, xmax, su, sl, lwc, a.n_bits, a.symmetric, a.recip_div);
     }
     const float inv = OQ_DIV(1.0f, q.scale);
-    const float* wr = a.W + (long)n * a.K;
+    // in range (rint(qa) + zp in [0, qmax]) <=> qlo <= qa <= qhi, see WsRowHdr
+    const float lo = -q.zp, hi = q.qmax - q.zp;
+    const float qlo = fmodf(lo, 2.0f) == 0.0f ? lo - 0.5f : nextafterf(lo - 0.5f, INFINITY);
+    const float qhi = fmodf(hi, 2.0f) == 0.0f ? hi + 0.5f : nextafterf(hi + 0.5f, -INFINITY);
     float R = 0.f;
     for (int c0 = lane; c0 < K4; c0 += 32 * U) {
-      float4 w[U], g[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int idx = c0 + 32 * u;
+        w[u] = wn[u];
+        g[u] = gn[u];
+      }
+      const int c1 = c0 + 32 * U;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = c1 + 32 * u;
         if (idx < K4) {
-          w[u] = ld4(wr + 4 * idx);
-          if (a.g_is_f32) {
-            g[u] = ld4(reinterpret_cast<const float*>(a.g) + (long)n * a.ld_g + 4 * idx);
-          } else {
-            float t[4];
-            load_bf4(reinterpret_cast<const bf16*>(a.g) + (long)n * a.ld_g + 4 * idx, t);
-            g[u] = make_float4(t[0], t[1], t[2], t[3]);
-          }
+          wn[u] = ld4(wr + 4 * idx);
+          gn[u] = __ldg(gr + idx);
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (c0 + 32 * u < K4) {
+          float g4[4];
+          if constexpr (G32) {
+            g4[0] = g[u].x; g4[1] = g[u].y; g4[2] = g[u].z; g4[3] = g[u].w;
+          } else {
+            unpack_bf2(g[u].x, g4[0], g4[1]);
+            unpack_bf2(g[u].y, g4[2], g4[3]);
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float qa = f4(w[u], j) * inv;
-            const float t = rintf(qa) + q.zp;
-            const float c = fminf(fmaxf(t, 0.0f), q.qmax);
-            R += f4(g[u], j) * ((c - q.zp) - (c == t ? qa : 0.0f));
+            const float qc = fminf(fmaxf(qa, qlo), qhi);
+            const float rc = __fsub_rn(__fadd_rn(qc, magic), magic);     // clamp(rint(qa), -zp, qmax - zp)
+            R = fmaf(g4[j], rc - (qc == qa ? qa : 0.0f), R);
           }
         }
       }
