@@ -430,23 +430,32 @@ __global__ void __launch_bounds__(512, 2) swiglu_aq_fwd_kernel(GluArgs a) {
   }
 }
 
+// One 512-thread block per row, TWO blocks per SM: the row passes three phases separated by block reductions (extrema of
+// m, then R / tie counts), and with every operand in registers (128 per thread, one block per SM) nothing overlapped the
+// reductions or the loads (ncu: 93 us for 225 MB).  Each thread now parks its slice of m and of dL/dmq in shared memory
+// (the gradient arrives there straight from global memory with cp.async; a thread only ever reads back what it stored,
+// so no barrier guards the buffer) and keeps gate / up packed in registers: <= 64 registers, two rows in flight per SM.
 template <int NV>
-__global__ void __launch_bounds__(512, 1) swiglu_aq_bwd_kernel(GluArgs a) {
+__global__ void __launch_bounds__(512, 2) swiglu_aq_bwd_kernel(GluArgs a) {
+  extern __shared__ uint4 park[];            // [2][NV * 512]: m, dL/dmq
   __shared__ float scratch[5 * 16];
   const long r = blockIdx.x;
   const bf16* gr = a.gu + r * a.ldgu;
   const bf16* yr = a.gy + r * a.ldgy;
-  uint4 rg[NV], ru[NV], ry[NV], rm[NV];     // gate, up, dL/dmq, m -- all bf16-exact, kept packed
+  uint4* sm_m = park + threadIdx.x;
+  uint4* sm_y = park + NV * 512 + threadIdx.x;
+  uint4 rg[NV], ru[NV];                      // gate, up: bf16-exact, kept packed
   float mn = INFINITY, mx = -INFINITY;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (threadIdx.x + i * 512) * 8;
     if (c < a.F) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sm_y + i * 512)), "l"(yr + c) : "memory");
       rg[i] = *reinterpret_cast<const uint4*>(gr + c);
       ru[i] = *reinterpret_cast<const uint4*>(gr + a.F + c);
-      ry[i] = *reinterpret_cast<const uint4*>(yr + c);
     }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (threadIdx.x + i * 512) * 8;
@@ -455,11 +464,10 @@ __global__ void __launch_bounds__(512, 1) swiglu_aq_bwd_kernel(GluArgs a) {
       unpack_u4(rg[i], g);
       unpack_u4(ru[i], u);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        g[j] = swiglu_val(g[j], u[j]);
-      }
-      rm[i] = pack_u4(g);
-      unpack_u4(rm[i], g);
+      for (int j = 0; j < 8; ++j) g[j] = swiglu_val(g[j], u[j]);
+      const uint4 m = pack_u4(g);
+      sm_m[i * 512] = m;
+      unpack_u4(m, g);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { mn = fminf(mn, g[j]); mx = fmaxf(mx, g[j]); }
     }
@@ -469,15 +477,16 @@ __global__ void __launch_bounds__(512, 1) swiglu_aq_bwd_kernel(GluArgs a) {
   const float inv = OQ_DIV(1.0f, q.scale);
   const int inv_ok = oq_inv_ok(inv);
   float R = 0.f, nmax = 0.f, nmin = 0.f;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (threadIdx.x + i * 512) * 8;
     if (c < a.F) {
       float x[8], gy[8];
-      unpack_u4(rm[i], x);
-      unpack_u4(ry[i], gy);
+      unpack_u4(sm_m[i * 512], x);
+      unpack_u4(sm_y[i * 512], gy);
       aq_bwd_elems<8>(x, gy, q, inv, inv_ok, mn, mx, R, nmax, nmin);
-      ry[i] = pack_u4(gy);               // exact: entries are bf16 values or zero
+      sm_y[i * 512] = pack_u4(gy);       // exact: entries are bf16 values or zero
     }
   }
   {
@@ -498,8 +507,8 @@ __global__ void __launch_bounds__(512, 1) swiglu_aq_bwd_kernel(GluArgs a) {
     const int c = (threadIdx.x + i * 512) * 8;
     if (c < a.F) {
       float x[8], d[8], g[8], u[8];
-      unpack_u4(rm[i], x);
-      unpack_u4(ry[i], d);
+      unpack_u4(sm_m[i * 512], x);
+      unpack_u4(sm_y[i * 512], d);
       unpack_u4(rg[i], g);
       unpack_u4(ru[i], u);
 #pragma unroll
@@ -810,9 +819,16 @@ extern "C" int oq_swiglu_act_quant_bwd(const void* gu, long ldgu, long rows, int
   a.gu = (const bf16*)gu; a.ldgu = ldgu; a.gy = (const bf16*)gy; a.ldgy = ldgy; a.dgu = (bf16*)dgu; a.lddgu = lddgu;
   a.F = F; a.n_bits = n_bits; a.symmetric = symmetric; a.recip_div = recip_div;
   const unsigned g = (unsigned)rows;
-  if (F <= 4096) swiglu_aq_bwd_kernel<1><<<g, 512, 0, stream>>>(a);
-  else if (F <= 8192) swiglu_aq_bwd_kernel<2><<<g, 512, 0, stream>>>(a);
-  else if (F <= 12288) swiglu_aq_bwd_kernel<3><<<g, 512, 0, stream>>>(a);
-  else swiglu_aq_bwd_kernel<4><<<g, 512, 0, stream>>>(a);
+  static bool attr = false;
+  if (!attr) {      // the parked rows of the two largest variants exceed the 48 KB default
+    if (cudaFuncSetAttribute(swiglu_aq_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 3 * 512 * 16) != cudaSuccess ||
+        cudaFuncSetAttribute(swiglu_aq_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 512 * 16) != cudaSuccess)
+      return oq_check_launch("oq_swiglu_act_quant_bwd (shared memory attribute)");
+    attr = true;
+  }
+  if (F <= 4096) swiglu_aq_bwd_kernel<1><<<g, 512, 2 * 1 * 512 * 16, stream>>>(a);
+  else if (F <= 8192) swiglu_aq_bwd_kernel<2><<<g, 512, 2 * 2 * 512 * 16, stream>>>(a);
+  else if (F <= 12288) swiglu_aq_bwd_kernel<3><<<g, 512, 2 * 3 * 512 * 16, stream>>>(a);
+  else swiglu_aq_bwd_kernel<4><<<g, 512, 2 * 4 * 512 * 16, stream>>>(a);
   return oq_check_launch("oq_swiglu_act_quant_bwd");
 }

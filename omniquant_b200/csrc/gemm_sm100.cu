@@ -111,6 +111,85 @@ __device__ __forceinline__ void k_range(const GemmParams& p, int m0, int& kb0, i
   if (p.causal == 3) kb0 = min(m0 / BK, kb1);
 }
 
+// one 32-column chunk of an accumulator row: alpha, bias, residual, optional fp32 accumulate, store as bf16 / fp32 / fp16
+__device__ __forceinline__ void store_chunk(const GemmParams& p, const uint32_t (&r)[32], int row, int b, int nc, const bf16* resr,
+                                            bool vec_ok) {
+  {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+    const int valid = min(32, p.N - nc);
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < valid) v[j] += p.bias[nc + j];
+  }
+  if (resr) {
+    if (valid == 32 && p.ldr % 8 == 0 && p.strideR % 8 == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float t[8];
+        load_bf8(resr + nc + j, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j + e] += t[e];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < valid) v[j] += bf2f(resr[nc + j]);
+    }
+  }
+  if (p.c_dtype == 1) {
+    float* cr = reinterpret_cast<float*>(p.C) + (long)b * p.strideC + (long)row * p.ldc + nc;
+    if (p.accumulate) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < valid) v[j] += cr[j];
+    }
+    if (valid == 32 && vec_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < valid) cr[j] = v[j];
+    }
+  } else if (p.c_dtype == 2) {
+    __half* cr = reinterpret_cast<__half*>(p.C) + (long)b * p.strideC + (long)row * p.ldc + nc;
+    if (valid == 32 && vec_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 u;
+        __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+        __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(cr + j) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < valid) cr[j] = __float2half_rn(v[j]);
+    }
+  } else {
+    bf16* cr = reinterpret_cast<bf16*>(p.C) + (long)b * p.strideC + (long)row * p.ldc + nc;
+    if (valid == 32 && vec_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = v[j + e];
+        store_bf8(cr + j, t);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < valid) cr[j] = f2bf(v[j]);
+    }
+  }
+}
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -252,81 +331,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint32_t r[32];
         tc_ld32(taddr + c0, r);
         tc_wait_ld();
-        if (row < p.M) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-          const int nc = n0 + c0;
-          const int valid = min(32, p.N - nc);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < valid) v[j] += p.bias[nc + j];
-          }
-          if (resr) {
-            if (valid == 32 && p.ldr % 8 == 0 && p.strideR % 8 == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                float t[8];
-                load_bf8(resr + nc + j, t);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[j + e] += t[e];
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < valid) v[j] += bf2f(resr[nc + j]);
-            }
-          }
-          if (p.c_dtype == 1) {
-            float* cr = reinterpret_cast<float*>(p.C) + (long)b * p.strideC + (long)row * p.ldc + nc;
-            if (p.accumulate) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < valid) v[j] += cr[j];
-            }
-            if (valid == 32 && vec_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < valid) cr[j] = v[j];
-            }
-          } else if (p.c_dtype == 2) {
-            __half* cr = reinterpret_cast<__half*>(p.C) + (long)b * p.strideC + (long)row * p.ldc + nc;
-            if (valid == 32 && vec_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u;
-                __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-                __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
-                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(cr + j) = u;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < valid) cr[j] = __float2half_rn(v[j]);
-            }
-          } else {
-            bf16* cr = reinterpret_cast<bf16*>(p.C) + (long)b * p.strideC + (long)row * p.ldc + nc;
-            if (valid == 32 && vec_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                float t[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) t[e] = v[j + e];
-                store_bf8(cr + j, t);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < valid) cr[j] = f2bf(v[j]);
-            }
-          }
-        }
+        if (row < p.M) store_chunk(p, r, row, b, n0 + c0, resr, vec_ok);
       }
       tc_fence_before();
       __syncwarp();
@@ -340,6 +345,202 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ================================================================== CTA-pair variant (cta_group::2)
+// Two CTAs on the two SMs of a TPC (a 2-CTA cluster) compute one 256 x 256 output tile: CTA r of the pair owns rows
+// [128 r, 128 r + 128) of the tile (its A operand and its accumulator: 128 TMEM lanes x 256 columns) and stages HALF of the B
+// tile (N rows [128 r, 128 r + 128)); tcgen05.mma.cta_group::2 issued by the leader (rank 0) reads A from each CTA's own shared
+// memory and the two B halves from both.  Per CTA and k-block that is 16 KB of A + 16 KB of B for 2 x 128 x 256 x 64 flops --
+// two thirds of the L2 -> SM operand traffic of the single-CTA 128 x 256 tile (48 KB), which is what bounds that kernel
+// (its 96 B/clk/SM at the nominal MMA rate is more than the L2 delivers), and six stages fit instead of four.
+//   barriers: full[s] lives in the LEADER (count 1: the leader's arrive.expect_tx for both CTAs' bytes; the peer's TMA
+//   completes its bytes on the leader's barrier -- address through mapa); empty[s], tfull[a] in both CTAs, signalled
+//   by the leader's tcgen05.commit ... multicast::cluster; tempty[a] in the leader, count 8 (the four epilogue warps of each CTA).
+// Not batched, no causal modes (the linear layers of the block; attention has its own kernels).
+// shared::cluster address of the same object in the pair's leader CTA (rank 0)
+__device__ __forceinline__ uint32_t leader_addr(const void* ptr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(ptr)), "r"(0));
+  return r;
+}
+constexpr int STAGES2 = 6;
+constexpr int A2_BYTES = BM * BK * 2, B2_BYTES = 128 * BK * 2, STAGE2_BYTES = A2_BYTES + B2_BYTES;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(leader_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {     // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // release at cluster scope on the leader's copy
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
+  uint64_t* full = bars;                  // [STAGES2]  (used in the leader)
+  uint64_t* empty = bars + STAGES2;       // [STAGES2]
+  uint64_t* tfull = bars + 2 * STAGES2;   // [2]
+  uint64_t* tempty = tfull + 2;           // [2]        (used in the leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int total_tiles = p.num_m * p.num_n;      // num_m counts 256-row tiles here
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);  // one arrive per epilogue warp of either CTA
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();      // barriers initialised and TMEM allocated in both CTAs before anything crosses the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int kb1 = (p.K + BK - 1) / BK;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        const int m0 = (tile % p.num_m) * 256 + 128 * (int)rank;      // this CTA's 128 rows
+        const int n0 = (tile / p.num_m) * BN + 128 * (int)rank;       // this CTA's half of the B tile
+        for (int kb = 0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE2_BYTES;
+          uint8_t* sb = sa + A2_BYTES;
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * STAGE2_BYTES);
+          const int k0 = kb * BK;
+          if (!p.a_mn) {
+            tma_load_3d_2sm(sa, &tmA, &full[stage], k0, m0, 0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_3d_2sm(sa + j * (64 * BK * 2), &tmA, &full[stage], m0 + 64 * j, k0, 0);
+          }
+          if (!p.b_mn) {
+            tma_load_3d_2sm(sb, &tmB, &full[stage], k0, n0, 0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_3d_2sm(sb + j * (64 * BK * 2), &tmB, &full[stage], n0 + 64 * j, k0, 0);
+          }
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    if (lane == 0 && rank == 0) {
+      // M = 256 over the pair, N = 256 (each CTA contributes 128 rows of B)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
+                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t a_lbo = p.a_mn ? 64 * BK * 2 : 16, b_lbo = p.b_mn ? 64 * BK * 2 : 16;
+      const uint32_t a_k16 = (p.a_mn ? UMMA_K * 128 : UMMA_K * 2) >> 4, b_k16 = (p.b_mn ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+      const uint32_t sa0 = __shfl_sync(0x1u, smem_u32(smem), 0);
+      const uint32_t alo0 = ((sa0 & 0x3FFFF) >> 4) | (((a_lbo >> 4) & 0x3FFF) << 16);
+      const uint32_t blo0 = (((sa0 + A2_BYTES) & 0x3FFFF) >> 4) | (((b_lbo >> 4) & 0x3FFF) << 16);
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const int kb1 = (p.K + BK - 1) / BK;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t alo = alo0 + (uint32_t)stage * (STAGE2_BYTES >> 4), blo = blo0 + (uint32_t)stage * (STAGE2_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            tc_mma_bf16_2sm(d_tmem, alo + k * a_k16, blo + k * b_k16, DESC_HI, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit_2sm(&empty[stage]);  // frees the stage in both CTAs when these MMAs retire
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&tfull[acc]);  // accumulator complete: both CTAs' epilogues
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, each its own 128 rows) =====================
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = p.c_dtype == 1 ? (p.ldc % 4 == 0) : (p.ldc % 8 == 0);
+    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+      const int m0 = (tile % p.num_m) * 256 + 128 * (int)rank;
+      const int n0 = (tile / p.num_m) * BN;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const bf16* resr = p.res ? p.res + (long)row * p.ldr : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tc_ld32(taddr + c0, r);
+        tc_wait_ld();
+        if (row < p.M) store_chunk(p, r, row, 0, n0 + c0, resr, vec_ok);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();      // nobody frees TMEM or exits while the peer may still signal or read across the pair
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -398,6 +599,43 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int max_c
   return oq_check_launch("oq_gemm_bf16");
 }
 
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int max_ctas, cudaStream_t stream) {
+  static int max_pairs = 0;
+  if (!max_pairs) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (e != cudaSuccess) {
+      oq_set_error("oq_gemm_bf16: cudaFuncSetAttribute (CTA-pair kernel) failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * oq_num_sms());
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM2_BYTES;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, gemm2_kernel, &cfg);     // cluster size comes from __cluster_dims__
+    if (e != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = oq_num_sms() / 2;
+    }
+    max_pairs = std::min(n, oq_num_sms() / 2);
+  }
+  p.num_m = (p.M + 255) / 256;
+  p.num_n = (p.N + 255) / 256;
+  const long tiles = (long)p.num_m * p.num_n;
+  int pairs = (int)std::min<long>(tiles, max_pairs);
+  if (max_ctas > 1) pairs = std::min(pairs, max_ctas / 2);
+  gemm2_kernel<<<2 * pairs, NUM_THREADS, SMEM2_BYTES, stream>>>(ta, tb, p);
+  return oq_check_launch("oq_gemm_bf16 (CTA pair)");
+}
+
+// the CTA-pair kernel serves plain (unbatched, non-causal) products with at least one full pair tile per SM pair
+bool use_pair_kernel(int M, int N, int batch, int causal, int tile_n) {
+  static const int mode = [] { const char* e = getenv("OQ_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+  if (!mode || batch != 1 || causal || tile_n == 128) return false;
+  const long tiles = (long)((M + 255) / 256) * ((N + 255) / 256);
+  return M >= 256 && N >= 256 && tiles >= oq_num_sms() / 2;
+}
+
 }  // namespace
 
 extern "C" int oq_gemm_bf16(const void* A, int a_mn, long lda, long strideA, const void* B, int b_mn, long ldb,
@@ -413,6 +651,8 @@ extern "C" int oq_gemm_bf16(const void* A, int a_mn, long lda, long strideA, con
   OQ_REQUIRE(causal >= 0 && causal <= 3, "oq_gemm_bf16: bad causal mode %d", causal);
   OQ_REQUIRE(c_dtype >= 0 && c_dtype <= 2, "oq_gemm_bf16: c_dtype must be 0 (bf16), 1 (fp32) or 2 (fp16)");
   OQ_REQUIRE(tile_n == 0 || tile_n == 128 || tile_n == 256, "oq_gemm_bf16: tile_n must be 0, 128 or 256");
+  const bool pair = use_pair_kernel(M, N, batch, causal, tile_n);
+  if (pair) tile_n = 256;
   if (tile_n == 0) {
     // BN=256 halves the A re-reads; use BN=128 when N is small or the wider tile leaves SMs idle
     const long t256 = (long)((M + BM - 1) / BM) * ((N + 255) / 256) * batch;
@@ -431,7 +671,8 @@ extern "C" int oq_gemm_bf16(const void* A, int a_mn, long lda, long strideA, con
   // K-major: inner = K, rows = M|N, box rows = BM|BN.   MN-major: inner = M|N, rows = K, box = 64 x 64.
   if (!p.a_mn) { if (make_map(&ta, A, K, M, batchA, lda, strideA, BM)) return -1; }
   else         { if (make_map(&ta, A, M, K, batchA, lda, strideA, BK)) return -1; }
-  if (!p.b_mn) { if (make_map(&tb, B, K, N, batchB, ldb, strideB, tile_n)) return -1; }
+  if (!p.b_mn) { if (make_map(&tb, B, K, N, batchB, ldb, strideB, pair ? 128 : tile_n)) return -1; }
   else         { if (make_map(&tb, B, N, K, batchB, ldb, strideB, BK)) return -1; }
+  if (pair) return launch2(ta, tb, p, max_ctas, stream);
   return tile_n == 256 ? launch<256>(ta, tb, p, max_ctas, stream) : launch<128>(ta, tb, p, max_ctas, stream);
 }

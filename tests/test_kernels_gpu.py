@@ -438,6 +438,35 @@ def test_gemm_layouts(ops, a_mn, b_mn, M, N, K, tile_n):
         torch.testing.assert_close(C.float(), ref, **tol)
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(2000, 5000, 1000), (2048, 2560, 192), (1160, 4104, 4096)])
+def test_gemm_cta_pair_kernel(ops, a_mn, b_mn, M, N, K):
+    """Shapes with at least one 256 x 256 tile per SM pair go through the cta_group::2 kernel (two CTAs per tile, each
+    staging its own A rows and half of B): ragged M / N / K against the fp32 product, every operand layout and output type."""
+    gen = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=gen).to(torch.bfloat16)
+    B = torch.randn(N, K, device="cuda", generator=gen).to(torch.bfloat16)
+    As = A.t().contiguous() if a_mn else A
+    Bs = B.t().contiguous() if b_mn else B
+    bias = torch.randn(N, device="cuda", generator=gen)
+    res = torch.randn(M, N, device="cuda", generator=gen).to(torch.bfloat16)
+    ref = _gemm_ref(A, B, 0.25, bias, res)
+    for cdt in (torch.float32, torch.bfloat16):
+        C = torch.full((M, N), float("nan"), device="cuda", dtype=cdt)
+        ops.gemm(As, Bs, C, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, lda=As.stride(0), ldb=Bs.stride(0), ldc=N, bias=bias,
+                 residual=res, ldr=N, alpha=0.25)
+        torch.cuda.synchronize()
+        tol = dict(rtol=1e-3, atol=2e-2) if cdt == torch.float32 else dict(rtol=2e-2, atol=2e-1)
+        torch.testing.assert_close(C.float(), ref, **tol)
+    # and the same product through the single-CTA kernel (tile_n = 128 keeps it there): identical fp32 sums
+    C1 = torch.empty(M, N, device="cuda")
+    C2 = torch.empty(M, N, device="cuda")
+    ops.gemm(As, Bs, C1, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, lda=As.stride(0), ldb=Bs.stride(0), ldc=N)
+    ops.gemm(As, Bs, C2, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, lda=As.stride(0), ldb=Bs.stride(0), ldc=N, tile_n=128)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(C1, C2, rtol=1e-5, atol=1e-3)
+
+
 def test_gemm_llama_shapes_and_linear_helpers(ops):
     gen = torch.Generator(device="cuda").manual_seed(1)
     M, K, N = 2048, 4096, 4096
