@@ -68,6 +68,42 @@ __device__ __forceinline__ void tc_mma_s8_lo(uint32_t tmem_d, uint32_t a_lo, uin
       "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: see gemm_sm100.cu (gemm2_kernel) for the protocol
+__device__ __forceinline__ uint32_t leader_addr(const void* ptr) {      // same object in the pair's rank-0 CTA
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(ptr)), "r"(0));
+  return r;
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(leader_addr(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_s8_2sm(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -81,21 +117,28 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float f4c(const float4& v, int j) { return reinterpret_cast<const float*>(&v)[j]; }
 
-template <int BN>
+// PAIR: two CTAs (a 2-CTA cluster) per 256 x 256 tile; each stages its 128 rows of A and 128 of the 256 rows of B
+template <int BN, bool PAIR>
 struct Cfg {
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int STAGES = (PAIR || BN != 256) ? 6 : 4;
   static constexpr int A_BYTES = BM * BKB;
-  static constexpr int B_BYTES = BN * BKB;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BKB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int COLV_BYTES = 2 * 4 * BN * 4;   // per accumulator stage: column scale | beta | t | bias of the tile
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLV_BYTES;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const S8Params p) {
-  using C = Cfg<BN>;
+template <int BN, bool PAIR>
+__device__ __forceinline__ void gemm_s8_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const S8Params& p) {
+  using C = Cfg<BN, PAIR>;
+  constexpr int TM = PAIR ? 2 * BM : BM;        // rows of one scheduled tile
+  uint32_t rank = 0;
+  if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int row_off = PAIR ? BM * (int)rank : 0, bcol_off = PAIR ? (BN / 2) * (int)rank : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -104,6 +147,7 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * C::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* colv = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.num_m * p.num_n;
@@ -120,17 +164,24 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], PAIR ? 8 : 4);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -138,22 +189,28 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile % p.num_m) * BM, n0 = (tile / p.num_m) * BN;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int m0 = (tile % p.num_m) * TM + row_off, n0 = (tile / p.num_m) * BN + bcol_off;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
-          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full[stage], kb * BKB, m0);           // out-of-range rows / K tail are zero-filled
-          tma_load_2d(sa + C::A_BYTES, &tmB, &full[stage], kb * BKB, n0);
+          if (PAIR) {      // the leader's barrier collects the bytes of both CTAs
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+            tma_load_2d_2sm(sa, &tmA, &full[stage], kb * BKB, m0);
+            tma_load_2d_2sm(sa + C::A_BYTES, &tmB, &full[stage], kb * BKB, n0);
+          } else {
+            mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, &full[stage], kb * BKB, m0);           // out-of-range rows / K tail are zero-filled
+            tma_load_2d(sa + C::A_BYTES, &tmB, &full[stage], kb * BKB, n0);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // instruction descriptor: D = s32 (2), A = B = int8 (1), both K-major, N>>3, M>>4
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    if (lane == 0 && rank == 0) {
+      // instruction descriptor: D = s32 (2), A = B = int8 (1), both K-major, N>>3, M>>4 (M = 256 over a CTA pair)
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       // descriptor words hoisted out of the issue loop: the high word is a constant, a stage / k-step only adds to the
       // start-address field of the low word.  An int8 MMA of this shape occupies the tensor pipe for 64 cycles only, so
       // the issuing thread has to stay well below that per instruction.
@@ -164,7 +221,7 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -173,12 +230,16 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t alo = alo0 + (uint32_t)stage * (C::STAGE_BYTES >> 4), blo = blo0 + (uint32_t)stage * (C::STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BKB / UMMA_KB; ++k)
-            tc_mma_s8_lo(d_tmem, alo + k * (UMMA_KB >> 4), blo + k * (UMMA_KB >> 4), DESC_HI, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          tc_commit(&empty[stage]);
+          for (int k = 0; k < BKB / UMMA_KB; ++k) {
+            if (PAIR) tc_mma_s8_2sm(d_tmem, alo + k * (UMMA_KB >> 4), blo + k * (UMMA_KB >> 4), DESC_HI, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else tc_mma_s8_lo(d_tmem, alo + k * (UMMA_KB >> 4), blo + k * (UMMA_KB >> 4), DESC_HI, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          if (PAIR) tc_commit_2sm(&empty[stage]);
+          else tc_commit(&empty[stage]);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull[acc]);
+        if (PAIR) tc_commit_2sm(&tfull[acc]);
+        else tc_commit(&tfull[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -187,8 +248,22 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     const float fK = (float)p.K;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile % p.num_m) * BM, n0 = (tile / p.num_m) * BN;
+    // The per-column epilogue vectors (scale, beta, t, bias) are the same for every row: staged once per tile in shared
+    // memory by the 128 epilogue threads (before the accumulator is awaited, so it overlaps the main loop) and read back as
+    // broadcast 16-byte loads.  Reading them from global memory per element made the epilogue LSU-bound (4 loads per
+    // output: ~11k cycles per tile that the K = 4096 main loop of 16k cycles could not hide).
+    const int et = (warp - 4) * 32 + lane;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const int m0 = (tile % p.num_m) * TM + row_off, n0 = (tile / p.num_m) * BN;
+      float* cv = colv + acc * 4 * BN;
+      for (int x = et; x < BN; x += 128) {
+        const int c = min(n0 + x, p.N - 1);      // clamped column: loads stay in bounds, the value is not stored
+        cv[x] = p.cs[c];
+        cv[BN + x] = p.rt ? p.cbeta[c] : 0.f;
+        cv[2 * BN + x] = p.rt ? p.ct[c] : 0.f;
+        cv[3 * BN + x] = p.bias ? p.bias[c] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
@@ -207,16 +282,25 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int valid = min(32, p.N - nc);
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = nc + (j < valid ? j : 0);      // clamped column: loads stay in bounds, the value is not stored
-            float y = __fmul_rn(__fmul_rn(__int2float_rn((int)r[j]), rs), p.cs[c]);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 cs4 = *reinterpret_cast<const float4*>(cv + c0 + j);
+            float y[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) y[e] = __fmul_rn(__fmul_rn(__int2float_rn((int)r[j + e]), rs), f4c(cs4, e));
             if (p.rt) {
-              const float cb = p.cbeta[c];
-              y += rt * cb + rb * p.ct[c] + fK * rb * cb;
+              const float4 cb4 = *reinterpret_cast<const float4*>(cv + BN + c0 + j), ct4 = *reinterpret_cast<const float4*>(cv + 2 * BN + c0 + j);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) y[e] += rt * f4c(cb4, e) + rb * f4c(ct4, e) + fK * rb * f4c(cb4, e);
             }
-            y *= p.alpha;
-            if (p.bias) y += p.bias[c];
-            v[j] = y;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) y[e] *= p.alpha;
+            if (p.bias) {
+              const float4 b4 = *reinterpret_cast<const float4*>(cv + 3 * BN + c0 + j);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) y[e] += f4c(b4, e);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[j + e] = y[e];
           }
           if (p.res) {
             const bf16* resr = p.res + (long)row * p.ldr + nc;
@@ -269,17 +353,32 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&tempty[acc]);
+        else mbar_arrive(&tempty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
   }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_s8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const S8Params p) {
+  gemm_s8_body<BN, false>(tmA, tmB, p);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_s8_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const S8Params p) {
+  gemm_s8_body<256, true>(tmA, tmB, p);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -313,9 +412,38 @@ int make_map_s8(CUtensorMap* map, const void* base, long K, long rows, long ld, 
   return 0;
 }
 
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, S8Params p, cudaStream_t stream) {
+  using C = Cfg<256, true>;
+  static int max_pairs = 0;
+  if (!max_pairs) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_s8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      oq_set_error("oq_gemm_s8: cudaFuncSetAttribute (CTA-pair kernel) failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * oq_num_sms());
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, gemm_s8_pair_kernel, &cfg);
+    if (e != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = oq_num_sms() / 2;
+    }
+    max_pairs = std::min(n, oq_num_sms() / 2);
+  }
+  p.num_m = (p.M + 2 * BM - 1) / (2 * BM);
+  p.num_n = (p.N + 255) / 256;
+  const long tiles = (long)p.num_m * p.num_n;
+  const int pairs = (int)std::min<long>(tiles, max_pairs);
+  gemm_s8_pair_kernel<<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  return oq_check_launch("oq_gemm_s8 (CTA pair)");
+}
+
 template <int BN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, S8Params p, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, false>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_s8_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -353,8 +481,12 @@ extern "C" int oq_gemm_s8(const void* A, long lda, const void* B, long ldb, void
   p.rs = row_scale; p.cs = col_scale; p.rt = row_t; p.rbeta = row_beta; p.ct = col_t; p.cbeta = col_beta;
   const long t256 = (long)((M + BM - 1) / BM) * ((N + 255) / 256);
   const int tile_n = (N <= 128 || t256 < oq_num_sms()) ? 128 : 256;
+  static const int pair_mode = [] { const char* e = getenv("OQ_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+  const long tpair = (long)((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256);
+  const bool pair = pair_mode && M >= 2 * BM && N >= 256 && tpair >= oq_num_sms() / 2;
   CUtensorMap ta, tb;
   if (make_map_s8(&ta, A, K, M, lda, BM)) return -1;
-  if (make_map_s8(&tb, B, K, N, ldb, tile_n)) return -1;
+  if (make_map_s8(&tb, B, K, N, ldb, pair ? 128 : tile_n)) return -1;
+  if (pair) return launch_pair(ta, tb, p, stream);
   return tile_n == 256 ? launch<256>(ta, tb, p, stream) : launch<128>(ta, tb, p, stream);
 }
