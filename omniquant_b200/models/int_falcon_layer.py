@@ -8,7 +8,8 @@ from torch import nn
 
 from ..quantize.int_linear import QuantLinear
 from ..quantize.omni_norm import OmniLayerNorm
-from ._block import QuantDecoderLayerBase
+from ._attention import falcon_attention_forward
+from ._block import QuantDecoderLayerBase, rope_theta_of
 
 
 class QuantFalconMLP(nn.Module):
@@ -40,6 +41,13 @@ class QuantFalconAttention(nn.Module):
         self.inv_norm_factor = 1.0 / self.head_dim ** 0.5
         self.query_key_value = QuantLinear(org_module.query_key_value, args.weight_quant_params, args.act_quant_params)
         self.dense = QuantLinear(org_module.dense, args.weight_quant_params, args.act_quant_params)
+        self.rope_theta = rope_theta_of(config)
+
+    def forward(self, hidden_states, alibi, attention_mask, layer_past=None, head_mask=None, use_cache=False,
+                output_attentions=False):
+        """Causal rotary attention without KV cache on the fused attention kernels (models/_attention.py)."""
+        return falcon_attention_forward(self, hidden_states, alibi, attention_mask, layer_past, head_mask, use_cache,
+                                        output_attentions, rope_theta=self.rope_theta)
 
 
 class QuantFalconDecoderLayer(QuantDecoderLayerBase):

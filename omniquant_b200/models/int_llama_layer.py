@@ -9,7 +9,8 @@ from torch import nn
 from ..quantize.int_linear import QuantLinear
 from ..quantize.int_matmul import QuantMatMul
 from ..quantize.omni_norm import OmniLlamaRMSNorm
-from ._block import QuantDecoderLayerBase
+from ._attention import llama_attention_forward
+from ._block import QuantDecoderLayerBase, rope_theta_of
 from .transformation import *  # noqa: F401,F403  (the reference re-exports the folds from here)
 
 
@@ -31,7 +32,8 @@ class QuantLlamaMLP(nn.Module):
 
 
 class QuantLlamaAttention(nn.Module):
-    """Holder of the attention projections and the two QuantMatMul operators (int_llama_layer.py:48-187)."""
+    """The attention projections and the two QuantMatMul operators (int_llama_layer.py:48-187); ``forward`` for a causal
+    sequence without KV cache on the fused attention kernels (models/_attention.py)."""
 
     def __init__(self, org_module: nn.Module, config, args=None):
         super().__init__()
@@ -54,6 +56,12 @@ class QuantLlamaAttention(nn.Module):
         self.pv_matmul = QuantMatMul(args.p_quant_params, args.v_quant_params, matmul_func=torch.matmul)
         self.use_weight_quant = False
         self.use_act_quant = False
+        self.rope_theta = rope_theta_of(config)
+
+    def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None, output_attentions=False,
+                use_cache=False):
+        return llama_attention_forward(self, hidden_states, attention_mask, position_ids, past_key_value, output_attentions,
+                                       use_cache, rope_theta=self.rope_theta)
 
     def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
         self.use_weight_quant = weight_quant

@@ -8,6 +8,7 @@ from torch import nn
 from ..quantize.int_linear import QuantLinear
 from ..quantize.int_matmul import QuantMatMul
 from ..quantize.omni_norm import OmniLayerNorm
+from ._attention import opt_attention_forward
 from ._block import QuantDecoderLayerBase
 from .transformation import *  # noqa: F401,F403
 
@@ -34,6 +35,12 @@ class QuantOPTAttention(nn.Module):
         self.pv_matmul = QuantMatMul(args.p_quant_params, args.v_quant_params, matmul_func=torch.bmm)
         self.use_weight_quant = False
         self.use_act_quant = False
+
+    def forward(self, hidden_states, key_value_states=None, past_key_value=None, attention_mask=None, layer_head_mask=None,
+                output_attentions=False):
+        """Causal self-attention without KV cache on the library's kernels (models/_attention.py)."""
+        return opt_attention_forward(self, hidden_states, key_value_states, past_key_value, attention_mask, layer_head_mask,
+                                     output_attentions)
 
     def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
         self.use_weight_quant = weight_quant

@@ -322,3 +322,86 @@ def test_smooth_functions_have_no_cpu_path():
     ln = _Holder(torch.ones(8), None)
     with pytest.raises(OqError):
         TR.smooth_ln_fcs_temporary(ln, [fc], torch.ones(8), torch.zeros(8))
+
+
+def _tiny_layer(family, H, F_, heads, kv, abits):
+    """A random-init HF decoder layer of the family and its Quant* wrapper (weights raw, 8-bit or no activation quant)."""
+    torch.manual_seed(0)
+    fx = SimpleNamespace(wbits=4, abits=abits, group_size=None, lwc=True, let=False)
+    args = make_args(fx)
+    if family == "llama":
+        from transformers import LlamaConfig
+        from transformers.models.llama.modeling_llama import LlamaDecoderLayer
+        from omniquant_b200.models.int_llama_layer import QuantLlamaDecoderLayer as Q
+        cfg = LlamaConfig(hidden_size=H, intermediate_size=F_, num_attention_heads=heads, num_key_value_heads=kv,
+                          num_hidden_layers=1, vocab_size=64, max_position_embeddings=2048)
+        layer = LlamaDecoderLayer(cfg, 0)
+    elif family == "opt":
+        from transformers import OPTConfig
+        from transformers.models.opt.modeling_opt import OPTDecoderLayer
+        from omniquant_b200.models.int_opt_layer import QuantOPTDecoderLayer as Q
+        cfg = OPTConfig(hidden_size=H, ffn_dim=F_, num_attention_heads=heads, num_hidden_layers=1, vocab_size=64,
+                        max_position_embeddings=2048, word_embed_proj_dim=H)
+        try:
+            layer = OPTDecoderLayer(cfg, layer_idx=0)
+        except TypeError:
+            layer = OPTDecoderLayer(cfg)
+    else:
+        from transformers import FalconConfig
+        from transformers.models.falcon.modeling_falcon import FalconDecoderLayer
+        from omniquant_b200.models.int_falcon_layer import QuantFalconDecoderLayer as Q
+        cfg = FalconConfig(hidden_size=H, num_attention_heads=heads, num_kv_heads=kv, num_hidden_layers=1, vocab_size=64,
+                           new_decoder_architecture=True, bias=False, parallel_attn=True, ffn_hidden_size=F_)
+        layer = FalconDecoderLayer(cfg, 0)
+    return Q(cfg, layer.half().cuda(), args).cuda()
+
+
+@pytest.mark.parametrize("family,heads,kv,T", [("llama", 2, 2, 256), ("llama", 4, 2, 128), ("llama", 4, 4, 96), ("opt", 2, 2, 256),
+                                               ("opt", 4, 4, 96), ("falcon", 4, 2, 256)])
+@pytest.mark.parametrize("abits", [16, 8])
+def test_attention_module_forward_composes_to_the_block(family, heads, kv, T, abits):
+    """Quant{Llama,OPT,Falcon}Attention.forward (sub-block level, fused attention kernels when T % 128 == 0, two GEMMs and a
+    softmax otherwise) composed with the norms and the MLP reproduces the block forward of the engine."""
+    d = 128 if T != 96 else 64
+    H, F_ = heads * d, 2 * heads * d
+    q = _tiny_layer(family, H, F_, heads, kv, abits)
+    q.set_quant_state(weight_quant=False, act_quant=abits < 16)
+    x = (torch.randn(2, T, H, device="cuda") * 0.5).to(torch.bfloat16)
+    mask = torch.triu(torch.full((T, T), torch.finfo(torch.float32).min, device="cuda"), diagonal=1)[None, None]
+    pos = torch.arange(T, device="cuda")[None]
+    with torch.no_grad():
+        if family == "llama":
+            want = q(x, attention_mask=mask, position_ids=pos)[0]
+            h = x + q.self_attn(q.input_layernorm(x), attention_mask=mask, position_ids=pos)[0]
+            got = h + q.mlp(q.post_attention_layernorm(h))
+        elif family == "opt":
+            want = q(x, attention_mask=mask)[0]
+            h = x + q.self_attn(q.self_attn_layer_norm(x), attention_mask=mask)[0]
+            got = h + q.fc2(torch.relu(q.fc1(q.final_layer_norm(h))))
+        else:
+            want = q(x)[0]
+            got = x + q.self_attention(q.ln_attn(x), None, None)[0] + q.mlp(q.ln_mlp(x))
+    rel = float((got.float() - want.float()).norm() / want.float().norm())
+    print(family, heads, kv, T, abits, "composed vs engine block rel", rel)
+    assert rel < (1e-2 if abits >= 16 else 3e-2)
+
+
+def test_attention_module_backward_matches_fp32_autograd():
+    """Gradients through the fused attention operator of the module path against the fp32 autograd evaluation."""
+    from omniquant_b200.models._attention import causal_attention
+    b, h, hkv, T, d = 2, 4, 2, 256, 128
+    g = torch.Generator(device="cuda").manual_seed(3)
+    mk = lambda n: (torch.randn(b, n, T, d, device="cuda", generator=g)).to(torch.bfloat16).requires_grad_(True)
+    q, k, v = mk(h), mk(hkv), mk(hkv)
+    out = causal_attention(q, k, v, d ** -0.5)
+    dO = torch.randn(b, T, h * d, device="cuda", generator=g).to(torch.bfloat16)
+    out.backward(dO)
+    qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    kk, vv = kf.repeat_interleave(h // hkv, 1), vf.repeat_interleave(h // hkv, 1)
+    s = (qf @ kk.transpose(2, 3)) * d ** -0.5
+    s = s.masked_fill(torch.triu(torch.ones(T, T, dtype=torch.bool, device="cuda"), diagonal=1), float("-inf"))
+    ref = (torch.softmax(s, -1) @ vv).transpose(1, 2).reshape(b, T, h * d)
+    ref.backward(dO.float())
+    rel = lambda a, r: float((a.float() - r).norm() / r.norm())
+    assert rel(out, ref) < 1e-2
+    assert rel(q.grad, qf.grad) < 2e-2 and rel(k.grad, kf.grad) < 2e-2 and rel(v.grad, vf.grad) < 2e-2
