@@ -352,6 +352,7 @@ def _tiny_layer(family, H, F_, heads, kv, abits):
         from omniquant_b200.models.int_falcon_layer import QuantFalconDecoderLayer as Q
         cfg = FalconConfig(hidden_size=H, num_attention_heads=heads, num_kv_heads=kv, num_hidden_layers=1, vocab_size=64,
                            new_decoder_architecture=True, bias=False, parallel_attn=True, ffn_hidden_size=F_)
+        cfg._attn_implementation = "eager"
         layer = FalconDecoderLayer(cfg, 0)
     return Q(cfg, layer.half().cuda(), args).cuda()
 
