@@ -83,27 +83,54 @@ __device__ __forceinline__ void aq_quant_codes(float (&v)[E], float (&c)[E], con
   else aq_quant_codes_t<false, E>(v, c, q, inv);
 }
 // first backward pass over E elements: accumulates R = dL/dscale, the tie counts of the row extrema, and zeroes the
-// gradient of clipped elements (straight-through part); same codes as the forward, ties included
+// gradient of clipped elements (straight-through part); same codes as the forward, ties included.
+// The in-range test and the clamp are one operation: with t = rint(q) + zp and zp an integer, t in [0, qmax] <=>
+// qlo <= q <= qhi for the half-integers qlo = -zp - 0.5, qhi = qmax - zp + 0.5 (moved one ulp inwards when the tie
+// rounds -- to even -- out of the range), and rint(clamp(q, qlo, qhi)) = clamp(t, 0, qmax) - zp; rint of the bounded value
+// is a magic-number add.  The extrema are counted only by the threads whose 8..16 elements contain one (a 3-input max /
+// min per element pair instead of two compare-and-adds per element).  Identical values for finite inputs.
+struct AqRange { float qlo, qhi; };
+__device__ __forceinline__ AqRange aq_range(const OqQParams& q) {
+  const float lo = -q.zp, hi = q.qmax - q.zp;                   // integers (|zp| <= 1e4): exact
+  const bool lo_even = rintf(lo * 0.5f) * 2.0f == lo, hi_even = rintf(hi * 0.5f) * 2.0f == hi;
+  float qlo = lo - 0.5f, qhi = hi + 0.5f;                        // never zero
+  if (!lo_even) qlo = __int_as_float(__float_as_int(qlo) + (qlo > 0.f ? 1 : -1));     // one ulp up
+  if (!hi_even) qhi = __int_as_float(__float_as_int(qhi) + (qhi > 0.f ? -1 : 1));     // one ulp down
+  return {qlo, qhi};
+}
+// returns whether one of the E elements is a row extremum (only those need the tie correction of the last pass)
 template <bool FAST, int E>
-__device__ __forceinline__ void aq_bwd_elems_t(const float (&v)[E], float (&g)[E], const OqQParams& q, float inv, float mn,
-                                               float mx, float& R, float& nmax, float& nmin) {
+__device__ __forceinline__ bool aq_bwd_elems_t(const float (&v)[E], float (&g)[E], const OqQParams& q, float inv, AqRange rg,
+                                               float mn, float mx, float& R, float& nmax, float& nmin) {
+  const float magic = 12582912.0f;
+  float vhi = -INFINITY, vlo = INFINITY;
 #pragma unroll
   for (int j = 0; j < E; ++j) {
-    float qa;
-    const float t = aq_t<FAST>(v[j], q, inv, qa);
-    const bool inr = (t >= 0.0f) && (t <= q.qmax);
-    const float cc = oq_clampf(t, 0.0f, q.qmax);
-    R += g[j] * ((cc - q.zp) - (inr ? qa : 0.0f));
-    nmax += (v[j] == mx) ? 1.0f : 0.0f;
-    nmin += (v[j] == mn) ? 1.0f : 0.0f;
-    if (!inr) g[j] = 0.0f;
+    const float qa = __fmul_rn(v[j], inv);
+    const float q1 = FAST ? __fmaf_rn(__fmaf_rn(-qa, q.scale, v[j]), inv, qa) : OQ_DIV(v[j], q.scale);
+    const float qc = fminf(fmaxf(q1, rg.qlo), rg.qhi);
+    const bool inr = qc == q1;
+    const float rc = __fsub_rn(__fadd_rn(qc, magic), magic);       // clamp(rint(q1) + zp, 0, qmax) - zp
+    R = fmaf(g[j], rc - (inr ? qa : 0.0f), R);
+    g[j] = inr ? g[j] : 0.0f;
+    vhi = fmaxf(vhi, v[j]);
+    vlo = fminf(vlo, v[j]);
   }
+  const bool ext = vhi == mx || vlo == mn;
+  if (ext) {
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      nmax += (v[j] == mx) ? 1.0f : 0.0f;
+      nmin += (v[j] == mn) ? 1.0f : 0.0f;
+    }
+  }
+  return ext;
 }
 template <int E>
-__device__ __forceinline__ void aq_bwd_elems(const float (&v)[E], float (&g)[E], const OqQParams& q, float inv, int inv_ok,
-                                             float mn, float mx, float& R, float& nmax, float& nmin) {
-  if (inv_ok) aq_bwd_elems_t<true, E>(v, g, q, inv, mn, mx, R, nmax, nmin);
-  else aq_bwd_elems_t<false, E>(v, g, q, inv, mn, mx, R, nmax, nmin);
+__device__ __forceinline__ bool aq_bwd_elems(const float (&v)[E], float (&g)[E], const OqQParams& q, float inv, int inv_ok,
+                                             AqRange rg, float mn, float mx, float& R, float& nmax, float& nmin) {
+  if (inv_ok) return aq_bwd_elems_t<true, E>(v, g, q, inv, rg, mn, mx, R, nmax, nmin);
+  return aq_bwd_elems_t<false, E>(v, g, q, inv, rg, mn, mx, R, nmax, nmin);
 }
 
 // ---- block per row (C large, no rope) ---------------------------------------
@@ -285,7 +312,7 @@ __global__ void __launch_bounds__(256) aq_bwd_block_reg(AqArgs a) {
       load_bf8(xr + c, v[i]);
       load_bf8(gr + c, g[i]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { mn = fminf(mn, v[i][j]); mx = fmaxf(mx, v[i][j]); }
+      for (int j = 0; j < 8; j += 2) { mn = fminf(fminf(mn, v[i][j]), v[i][j + 1]); mx = fmaxf(fmaxf(mx, v[i][j]), v[i][j + 1]); }
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -299,13 +326,14 @@ __global__ void __launch_bounds__(256) aq_bwd_block_reg(AqArgs a) {
   const OqQParams q = oq_qparams(mn, mx, 1.f, 1.f, 0, a.n_bits, a.symmetric, a.recip_div);
   const float inv = OQ_DIV(1.0f, q.scale);
   const int inv_ok = oq_inv_ok(inv);
+  const AqRange rg = aq_range(q);
   float R = 0.f, nmax = 0.f, nmin = 0.f;
+  bool ext[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (threadIdx.x + i * 256) * 8;
-    if (c < a.C) {
-      aq_bwd_elems<8>(v[i], g[i], q, inv, inv_ok, mn, mx, R, nmax, nmin);
-    }
+    ext[i] = false;
+    if (c < a.C) ext[i] = aq_bwd_elems<8>(v[i], g[i], q, inv, inv_ok, rg, mn, mx, R, nmax, nmin);
   }
   R = warp_reduce(R, OpSum()); nmax = warp_reduce(nmax, OpSum()); nmin = warp_reduce(nmin, OpSum());
   if (lane == 0) { scratch[16 + warp] = R; scratch[24 + warp] = nmax; scratch[32 + warp] = nmin; }
@@ -320,10 +348,12 @@ __global__ void __launch_bounds__(256) aq_bwd_block_reg(AqArgs a) {
   for (int i = 0; i < NV; ++i) {
     const int c = (threadIdx.x + i * 256) * 8;
     if (c < a.C) {
+      if (ext[i]) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (v[i][j] == mx) g[i][j] += cmax;
-        if (v[i][j] == mn) g[i][j] += cmin;
+        for (int j = 0; j < 8; ++j) {
+          if (v[i][j] == mx) g[i][j] += cmax;
+          if (v[i][j] == mn) g[i][j] += cmin;
+        }
       }
       store_bf8(dr + c, g[i]);
     }
@@ -476,7 +506,11 @@ __global__ void __launch_bounds__(512, 2) swiglu_aq_bwd_kernel(GluArgs a) {
   const OqQParams q = oq_qparams(mn, mx, 1.f, 1.f, 0, a.n_bits, a.symmetric, a.recip_div);
   const float inv = OQ_DIV(1.0f, q.scale);
   const int inv_ok = oq_inv_ok(inv);
+  const AqRange qr = aq_range(q);
   float R = 0.f, nmax = 0.f, nmin = 0.f;
+  bool ext[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) ext[i] = false;
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -485,7 +519,7 @@ __global__ void __launch_bounds__(512, 2) swiglu_aq_bwd_kernel(GluArgs a) {
       float x[8], gy[8];
       unpack_u4(sm_m[i * 512], x);
       unpack_u4(sm_y[i * 512], gy);
-      aq_bwd_elems<8>(x, gy, q, inv, inv_ok, mn, mx, R, nmax, nmin);
+      ext[i] = aq_bwd_elems<8>(x, gy, q, inv, inv_ok, qr, mn, mx, R, nmax, nmin);
       sm_y[i * 512] = pack_u4(gy);       // exact: entries are bf16 values or zero
     }
   }
@@ -506,15 +540,21 @@ __global__ void __launch_bounds__(512, 2) swiglu_aq_bwd_kernel(GluArgs a) {
   for (int i = 0; i < NV; ++i) {
     const int c = (threadIdx.x + i * 512) * 8;
     if (c < a.F) {
-      float x[8], d[8], g[8], u[8];
-      unpack_u4(sm_m[i * 512], x);
+      float d[8], g[8], u[8];
       unpack_u4(sm_y[i * 512], d);
       unpack_u4(rg[i], g);
       unpack_u4(ru[i], u);
+      if (ext[i]) {
+        float x[8];
+        unpack_u4(sm_m[i * 512], x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (x[j] == mx) d[j] += cmax;
+          if (x[j] == mn) d[j] += cmin;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (x[j] == mx) d[j] += cmax;
-        if (x[j] == mn) d[j] += cmin;
         float dg, du;
         swiglu_grad(g[j], u[j], bf16_round(d[j]), dg, du);   // dL/dm passes through bf16 like the unfused path
         g[j] = dg;
@@ -615,17 +655,19 @@ __device__ __forceinline__ void aq_row_bwd(const float (&v)[E], float (&g)[E], c
   float R = 0.f, nmax = 0.f, nmin = 0.f;
   const float inv = OQ_DIV(1.0f, q.scale);
   const int inv_ok = oq_inv_ok(inv);
-  aq_bwd_elems<E>(v, g, q, inv, inv_ok, mn, mx, R, nmax, nmin);
+  const bool ext = aq_bwd_elems<E>(v, g, q, inv, inv_ok, aq_range(q), mn, mx, R, nmax, nmin);
   R = group8_reduce(R, OpSum());
   nmax = group8_reduce(nmax, OpSum());
   nmin = group8_reduce(nmin, OpSum());
   float gmaxp, gminp;
   oq_scale_grad(R, mn, mx, 1.f, 1.f, 0, a.n_bits, a.symmetric, a.recip_div, &gmaxp, &gminp);
   const float cmax = gmaxp / nmax, cmin = gminp / nmin;
+  if (ext) {
 #pragma unroll
-  for (int j = 0; j < E; ++j) {
-    if (v[j] == mx) g[j] += cmax;
-    if (v[j] == mn) g[j] += cmin;
+    for (int j = 0; j < E; ++j) {
+      if (v[j] == mx) g[j] += cmax;
+      if (v[j] == mn) g[j] += cmin;
+    }
   }
 }
 
