@@ -399,6 +399,19 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Tile order of the CTA-pair kernel: m fastest inside groups of PAIR_GM m-tiles, n sweeping the group, group after group.
+// A wave of 74 pair tiles then touches 8 A tiles and ~9 B tiles instead of 74 A tiles and one B tile: with plain m-fastest
+// order the wgrad of gate|up (86 x 16 tiles, A = dY^T 90 MB) re-read A for every n tile -- 675 MB of DRAM reads for 107 MB
+// of operands (ncu, profiles/r2_gemm_ncu_full_summary.csv).  Products with at most PAIR_GM m-tiles are unchanged.
+constexpr int PAIR_GM = 8;
+__device__ __forceinline__ void pair_tile(const GemmParams& p, int tile, int& mi, int& ni) {
+  const int per_group = PAIR_GM * p.num_n;
+  const int grp = tile / per_group, local = tile - grp * per_group;
+  const int gm = min(PAIR_GM, p.num_m - grp * PAIR_GM);
+  ni = local / gm;
+  mi = grp * PAIR_GM + (local - ni * gm);
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   constexpr int BN = 256;
@@ -448,8 +461,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t phase = 0;
       const int kb1 = (p.K + BK - 1) / BK;
       for (int tile = pair; tile < total_tiles; tile += num_pairs) {
-        const int m0 = (tile % p.num_m) * 256 + 128 * (int)rank;      // this CTA's 128 rows
-        const int n0 = (tile / p.num_m) * BN + 128 * (int)rank;       // this CTA's half of the B tile
+        int mi, ni;
+        pair_tile(p, tile, mi, ni);
+        const int m0 = mi * 256 + 128 * (int)rank;      // this CTA's 128 rows
+        const int n0 = ni * BN + 128 * (int)rank;       // this CTA's half of the B tile
         for (int kb = 0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE2_BYTES;
@@ -514,8 +529,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t acc_phase = 0;
     const bool vec_ok = p.c_dtype == 1 ? (p.ldc % 4 == 0) : (p.ldc % 8 == 0);
     for (int tile = pair; tile < total_tiles; tile += num_pairs) {
-      const int m0 = (tile % p.num_m) * 256 + 128 * (int)rank;
-      const int n0 = (tile / p.num_m) * BN;
+      int mi, ni;
+      pair_tile(p, tile, mi, ni);
+      const int m0 = mi * 256 + 128 * (int)rank;
+      const int n0 = ni * BN;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
