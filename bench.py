@@ -313,9 +313,10 @@ def run_ours(a):
                                              "the exact-integer kind::i8 GEMM)", "achieved": round(achieved, 1),
                 "peak": peak_burst, "unit": "TFLOP/s", "frac": round(achieved / peak_burst, 4),
                 "frac_of_sustained_peak": round(achieved / peak_sus, 4), "peak_sustained": peak_sus,
-                "traffic": None,
-                "traffic_note": "not measured live; ncu --set full captures of the same kernels are under profiles/ (r1_gemm_ncu_full_summary.csv: "
-                                "174.5 MB DRAM read+write per QuantLinear launch vs 170 MB algorithmic at LLaMA-7B shapes)",
+                # from the committed `ncu --set full` capture of the same eight launches at LLaMA-7B W4A4 shapes, not measured live
+                "traffic": 169.3e6 if (c.idx == 3 and world >= 1) else None,
+                "traffic_note": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean of the 8 QuantLinear dgrad / wgrad launches "
+                                "of one step) from profiles/r2_gemm_ncu_full_summary.csv: 169.3 MB vs 168.5 MB algorithmic; config 3 shapes only",
                 "peak_source": f"bf16_tflops (burst), {which}", "launches_timed": len(lin),
                 "timing": "CUDA events around each launch on the launching stream, 3 eager optimiser steps after the timed region, side-stream overlap off",
                 "avg_launch_ms": round(lin_ms / max(len(lin), 1), 4),
