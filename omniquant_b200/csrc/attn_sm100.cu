@@ -560,14 +560,28 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
     const int kg = j * 128 + kr;
     const int tid = threadIdx.x - 128;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    // per-query statistics of the 64 queries of an iteration, staged in the sstat ring by threads 0-63: loaded ONE ITERATION
+    // AHEAD into registers and stored after the tile work (ncu: with load -> store -> barrier at the top of the iteration the
+    // eight warps sat in the barrier for the global-load latency every 64 queries: barrier 2.8 + long scoreboard 2.1 stalled
+    // warps per issued instruction)
+    auto stat_row = [&](int it2) {
+      const int head2 = g * p.rep + it2 / nh, i64b = 2 * j + it2 % nh;
+      return ((long)b * p.heads + head2) * p.T + i64b * 64 + tid;
+    };
+    float nx0 = 0.f, nx1 = 0.f, nx2 = 0.f;
+    if (tid < 64 && nit > 0) {
+      const long sr = stat_row(0);
+      sstat[tid] = make_float4(p.row_max[sr] * LOG2E, p.row_invl[sr], p.delta[sr], 0.f);
+    }
     for (int it = 0; it < nit; ++it) {
-      const int sb = it & 1, ss = it % DKV_ST, head = g * p.rep + it / nh, i64 = 2 * j + it % nh;
+      const int sb = it & 1, ss = it % DKV_ST, i64 = 2 * j + it % nh;
       const uint32_t ph = (it >> 1) & 1;
-      if (tid < 64) {      // (slot ss was last read in iteration it - 3; every thread has passed two named barriers since)
-        const long sr = ((long)b * p.heads + head) * p.T + i64 * 64 + tid;
-        sstat[ss * 64 + tid] = make_float4(p.row_max[sr] * LOG2E, p.row_invl[sr], p.delta[sr], 0.f);
+      const bool pre = tid < 64 && it + 1 < nit;
+      if (pre) {
+        const long sr = stat_row(it + 1);
+        nx0 = p.row_max[sr]; nx1 = p.row_invl[sr]; nx2 = p.delta[sr];
       }
-      named_bar_sync(1, SM_THREADS);
+      named_bar_sync(1, SM_THREADS);     // slot ss (stored at the end of the previous iteration / above) is visible
       mbar_wait(&s_full[sb], ph);
       tc_fence_after();
       uint8_t* bPT = sPS;
@@ -605,6 +619,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
       };
       if (i64 < 2 * j + 2) tile(std::true_type{});      // the two half tiles that touch the diagonal
       else tile(std::false_type{});
+      // slot (it + 1) % DKV_ST was last read in iteration it - 2: every thread has passed the barrier of iteration it - 1 since
+      if (pre) sstat[((it + 1) % DKV_ST) * 64 + tid] = make_float4(nx0 * LOG2E, nx1, nx2, 0.f);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
