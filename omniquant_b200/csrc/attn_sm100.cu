@@ -433,7 +433,7 @@ constexpr int DKV_ST = 3;      // Q / dO stages: a stage is needed twice (S^T / 
                                // so it is held for a whole iteration; three stages keep the TMA round trip off the critical path
 template <int DH>
 constexpr int dkv_smem() {
-  return 2 * (DH / 64) * BLK128 /*K,V*/ + DKV_ST * 2 * (DH / 64) * BLK64 /*Q,dO*/ + 2 * BLK128 /*P^T,dS^T*/ + DKV_ST * 64 * 16 /*stats*/ + 1024 + 256;
+  return 2 * (DH / 64) * BLK128 /*K,V*/ + DKV_ST * 2 * (DH / 64) * BLK64 /*Q,dO*/ + 2 * BLK128 /*P^T,dS^T*/ + SM_WARPS * 2 * 32 * 16 /*stats*/ + 1024 + 256;
 }
 
 template <int DH>
@@ -447,8 +447,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
   uint8_t* sV = sK + TILE128;
   uint8_t* sQdO = sV + TILE128;               // stage s: Q at + s * 2 * TILE64, dO right behind it
   uint8_t* sPS = sQdO + DKV_ST * 2 * TILE64;  // P^T, dS^T right behind it (one buffer: the accumulate MMAs read it for ~500 cycles)
-  float4* sstat = reinterpret_cast<float4*>(sPS + 2 * BLK128);   // [DKV_ST][64]: (max*log2e, 1/l, delta, -) of the stage's queries
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sstat) + DKV_ST * 64 * 16);
+  float4* sstat = reinterpret_cast<float4*>(sPS + 2 * BLK128);   // [softmax warp][2][32]: (max*log2e, 1/l, delta, -) of the warp's 32 query columns
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sstat) + SM_WARPS * 2 * 32 * 16);
   uint64_t* kv_full = bars;          // [1]
   uint64_t* qdo_full = bars + 1;     // [DKV_ST]
   uint64_t* qdo_empty = bars + 4;    // [DKV_ST]
@@ -558,30 +558,30 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
   } else if (warp >= 4) {
     const int q = warp & 3, kr = q * 32 + lane, half = (warp - 4) >> 2;   // key row of this thread; query columns [32 half, +32)
     const int kg = j * 128 + kr;
-    const int tid = threadIdx.x - 128;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    // per-query statistics of the 64 queries of an iteration, staged in the sstat ring by threads 0-63: loaded ONE ITERATION
-    // AHEAD into registers and stored after the tile work (ncu: with load -> store -> barrier at the top of the iteration the
-    // eight warps sat in the barrier for the global-load latency every 64 queries: barrier 2.8 + long scoreboard 2.1 stalled
-    // warps per issued instruction)
+    // per-query statistics (max * log2e, 1/l, delta) of the 32 query columns this warp works on: every warp keeps its own
+    // two-slot copy in shared memory (lane l fetches column 32 half + l), loaded ONE ITERATION AHEAD into registers and
+    // stored after the tile work, so neither the global-load latency nor a CTA-wide barrier sits between two tiles (ncu on the
+    // version that staged them once per CTA behind a named barrier: barrier 2.8 + long scoreboard 2.1 stalled warps per issue)
+    float4* wstat = sstat + (warp - 4) * 64;
     auto stat_row = [&](int it2) {
       const int head2 = g * p.rep + it2 / nh, i64b = 2 * j + it2 % nh;
-      return ((long)b * p.heads + head2) * p.T + i64b * 64 + tid;
+      return ((long)b * p.heads + head2) * p.T + i64b * 64 + 32 * half + lane;
     };
     float nx0 = 0.f, nx1 = 0.f, nx2 = 0.f;
-    if (tid < 64 && nit > 0) {
+    if (nit > 0) {
       const long sr = stat_row(0);
-      sstat[tid] = make_float4(p.row_max[sr] * LOG2E, p.row_invl[sr], p.delta[sr], 0.f);
+      wstat[lane] = make_float4(p.row_max[sr] * LOG2E, p.row_invl[sr], p.delta[sr], 0.f);
     }
+    __syncwarp();
     for (int it = 0; it < nit; ++it) {
-      const int sb = it & 1, ss = it % DKV_ST, i64 = 2 * j + it % nh;
+      const int sb = it & 1, ss = it & 1, i64 = 2 * j + it % nh;
       const uint32_t ph = (it >> 1) & 1;
-      const bool pre = tid < 64 && it + 1 < nit;
+      const bool pre = it + 1 < nit;
       if (pre) {
         const long sr = stat_row(it + 1);
         nx0 = p.row_max[sr]; nx1 = p.row_invl[sr]; nx2 = p.delta[sr];
       }
-      named_bar_sync(1, SM_THREADS);     // slot ss (stored at the end of the previous iteration / above) is visible
       mbar_wait(&s_full[sb], ph);
       tc_fence_after();
       uint8_t* bPT = sPS;
@@ -601,7 +601,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int c = c0 + ch * 8 + e;
-            const float4 stt = sstat[ss * 64 + c];          // (max * log2e, 1/l, delta, -) of query column c
+            const float4 stt = wstat[ss * 32 + ch * 8 + e];   // (max * log2e, 1/l, delta, -) of query column c
             const float pe = ex2_ftz(fmaf(masked<MASK>(score16(sv[ch * 8 + e], p.alpha), c >= lo), LOG2E, -stt.x)) * stt.y;
             pr[e] = pe;
             ds[e] = pe * (__uint_as_float(dv[ch * 8 + e]) - stt.z);
@@ -619,8 +619,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
       };
       if (i64 < 2 * j + 2) tile(std::true_type{});      // the two half tiles that touch the diagonal
       else tile(std::false_type{});
-      // slot (it + 1) % DKV_ST was last read in iteration it - 2: every thread has passed the barrier of iteration it - 1 since
-      if (pre) sstat[((it + 1) % DKV_ST) * 64 + tid] = make_float4(nx0 * LOG2E, nx1, nx2, 0.f);
+      // the other slot was last read in iteration it - 1, which every lane left through the __syncwarp below
+      if (pre) wstat[((it + 1) & 1) * 32 + lane] = make_float4(nx0 * LOG2E, nx1, nx2, 0.f);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
