@@ -95,6 +95,15 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 8 columns (one 16-byte bf16 chunk of results per thread): the softmax warps read their accumulator slice in pieces so that the
+// next piece is in flight while the current one is processed -- tcgen05.ld moves 64 B/clk per SM, so the 64 KB of an S / dP pair
+// take ~1000 cycles, as long as the arithmetic on them; loading everything, waiting, then computing serialises the two
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -715,7 +724,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
     for (int k = 0; k < 2; ++k) {
       mbar_init(&v_full[k], 1);
       mbar_init(&v_empty[k], 1);
-      mbar_init(&s_full[k], 1);
+      mbar_init(&s_full[k], 2);      // one commit per MMA-issuing thread (S; dP)
       mbar_init(&s_empty[k], SM_WARPS);
       mbar_init(&p_full[k], SM_WARPS);
       mbar_init(&p_empty[k], 1);
@@ -752,34 +761,50 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
       }
     }
   } else if (warp == 1) {
+    // Two MMA-issuing threads.  A tcgen05.mma of these small shapes (N = 64: 32 cycles of tensor work) costs the issuing
+    // thread ~100+ cycles, so ONE issuer bounded the kernel (ncu: the softmax warps spent 25 % of their samples waiting for
+    // S, the tensor pipe was 30 % active): this warp issues S = Q K^T, warp 3 issues dP = dO V^T and dQ += dS K.
+    if (lane == 0) {
+      const uint32_t id_s = make_idesc(64, 0);
+      const uint32_t ql = klo(sbase), k_k0 = klo(sbase + 2 * TILE128);
+      mbar_wait(qdo_full, 0);
+      for (int it = 0; it < nit; ++it) {
+        const int st = it & 1, ks = it % DQ_KST;
+        mbar_wait(&k_full[ks], (it / DQ_KST) & 1);
+        mbar_wait(&s_empty[st], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t kk = k_k0 + ks * (TILE64 >> 4);
+        tc_mma2(st * 128, ql, kk, id_s, 0u);
+#pragma unroll
+        for (int s = 1; s < KS; ++s) tc_mma2(st * 128, ql + kstep(s, BLK128), kk + kstep(s, BLK64), id_s, 1u);
+        tc_commit(&s_full[st]);
+      }
+    }
+  } else if (warp == 3) {
     if (lane == 0) {
       const uint32_t id_s = make_idesc(64, 0), id_a = make_idesc(D, 1);
-      const uint32_t ql = klo(sbase), dol = klo(sbase + TILE128);
-      const uint32_t k_k0 = klo(sbase + 2 * TILE128), k_mn0 = mnlo(sbase + 2 * TILE128, BLK64);
+      const uint32_t dol = klo(sbase + TILE128), k_mn0 = mnlo(sbase + 2 * TILE128, BLK64);
       const uint32_t v_k0 = klo(sbase + 2 * TILE128 + DQ_KST * TILE64), ds0 = klo(sbase + 2 * TILE128 + (DQ_KST + 2) * TILE64);
       auto accumulate = [&](int u) {     // dQ += dS K   (K = the 64 keys of step u)
         const int sb = u & 1, ks = u % DQ_KST;
         const uint32_t kmn = k_mn0 + ks * (TILE64 >> 4), dsl = ds0 + sb * (BLK128 >> 4);
+        mbar_wait(&k_full[ks], (u / DQ_KST) & 1);          // (the S issuer waited for it too; this thread reads K as well)
         mbar_wait(&p_full[sb], (u >> 1) & 1);
         tc_fence_after();
         tc_mma2(256, dsl, kmn, id_a, u > 0 ? 1u : 0u);
 #pragma unroll
         for (int s = 1; s < 4; ++s) tc_mma2(256, dsl + kstep(s, BLK128), kmn + mnstep(s), id_a, 1u);
         tc_commit(&p_empty[sb]);
-        tc_commit(&k_empty[ks]);
+        tc_commit(&k_empty[ks]);     // the S MMAs on this K slot (other issuer) retired before dS existed
       };
       mbar_wait(qdo_full, 0);
       for (int it = 0; it < nit; ++it) {
-        const int st = it & 1, ks = it % DQ_KST;
+        const int st = it & 1;
         const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(&k_full[ks], (it / DQ_KST) & 1);
         mbar_wait(&v_full[st], ph);
         mbar_wait(&s_empty[st], ph ^ 1);
         tc_fence_after();
-        const uint32_t kk = k_k0 + ks * (TILE64 >> 4), vk = v_k0 + st * (TILE64 >> 4);
-        tc_mma2(st * 128, ql, kk, id_s, 0u);
-#pragma unroll
-        for (int s = 1; s < KS; ++s) tc_mma2(st * 128, ql + kstep(s, BLK128), kk + kstep(s, BLK64), id_s, 1u);
+        const uint32_t vk = v_k0 + st * (TILE64 >> 4);
         tc_mma2(st * 128 + 64, dol, vk, id_s, 0u);
 #pragma unroll
         for (int s = 1; s < KS; ++s) tc_mma2(st * 128 + 64, dol + kstep(s, BLK128), vk + kstep(s, BLK64), id_s, 1u);
@@ -808,20 +833,25 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
         constexpr bool MASK = decltype(mask_tag)::value;
         {
           const int c0 = 32 * half;
-          uint32_t sv[32], dv[32];
-          tc_ld32(lane_base + sb * 128 + c0, sv);
-          tc_ld32(lane_base + sb * 128 + 64 + c0, dv);
+          uint32_t sv[2][8], dv[2][8];
+          tc_ld8(lane_base + sb * 128 + c0, sv[0]);
+          tc_ld8(lane_base + sb * 128 + 64 + c0, dv[0]);
           tc_wait_ld();
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
+            if (ch < 3) {      // next 8 columns in flight while these are processed
+              tc_ld8(lane_base + sb * 128 + c0 + 8 * (ch + 1), sv[(ch + 1) & 1]);
+              tc_ld8(lane_base + sb * 128 + 64 + c0 + 8 * (ch + 1), dv[(ch + 1) & 1]);
+            }
             float ds[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int c = c0 + ch * 8 + e;
-              const float pe = ex2_ftz(fmaf(masked<MASK>(score16(sv[ch * 8 + e], p.alpha), c <= hi), LOG2E, -m2)) * inv;
-              ds[e] = pe * (__uint_as_float(dv[ch * 8 + e]) - dl);
+              const float pe = ex2_ftz(fmaf(masked<MASK>(score16(sv[ch & 1][e], p.alpha), c <= hi), LOG2E, -m2)) * inv;
+              ds[e] = pe * (__uint_as_float(dv[ch & 1][e]) - dl);
             }
             st_chunk(bdS, r, (c0 >> 3) + ch, ds);
+            if (ch < 3) tc_wait_ld();
           }
         }
       };
