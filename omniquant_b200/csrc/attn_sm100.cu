@@ -763,7 +763,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
   } else if (warp == 1) {
     // Two MMA-issuing threads.  A tcgen05.mma of these small shapes (N = 64: 32 cycles of tensor work) costs the issuing
     // thread ~100+ cycles, so ONE issuer bounded the kernel (ncu: the softmax warps spent 25 % of their samples waiting for
-    // S, the tensor pipe was 30 % active): this warp issues S = Q K^T, warp 3 issues dP = dO V^T and dQ += dS K.
+    // S, the tensor pipe was 30 % active): this warp issues S = Q K^T, warp 3 dP = dO V^T, warp 2 dQ += dS K.
     if (lane == 0) {
       const uint32_t id_s = make_idesc(64, 0);
       const uint32_t ql = klo(sbase), k_k0 = klo(sbase + 2 * TILE128);
@@ -781,22 +781,9 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
       }
     }
   } else if (warp == 3) {
-    if (lane == 0) {
-      const uint32_t id_s = make_idesc(64, 0), id_a = make_idesc(D, 1);
-      const uint32_t dol = klo(sbase + TILE128), k_mn0 = mnlo(sbase + 2 * TILE128, BLK64);
-      const uint32_t v_k0 = klo(sbase + 2 * TILE128 + DQ_KST * TILE64), ds0 = klo(sbase + 2 * TILE128 + (DQ_KST + 2) * TILE64);
-      auto accumulate = [&](int u) {     // dQ += dS K   (K = the 64 keys of step u)
-        const int sb = u & 1, ks = u % DQ_KST;
-        const uint32_t kmn = k_mn0 + ks * (TILE64 >> 4), dsl = ds0 + sb * (BLK128 >> 4);
-        mbar_wait(&k_full[ks], (u / DQ_KST) & 1);          // (the S issuer waited for it too; this thread reads K as well)
-        mbar_wait(&p_full[sb], (u >> 1) & 1);
-        tc_fence_after();
-        tc_mma2(256, dsl, kmn, id_a, u > 0 ? 1u : 0u);
-#pragma unroll
-        for (int s = 1; s < 4; ++s) tc_mma2(256, dsl + kstep(s, BLK128), kmn + mnstep(s), id_a, 1u);
-        tc_commit(&p_empty[sb]);
-        tc_commit(&k_empty[ks]);     // the S MMAs on this K slot (other issuer) retired before dS existed
-      };
+    if (lane == 0) {       // dP = dO V^T
+      const uint32_t id_s = make_idesc(64, 0);
+      const uint32_t dol = klo(sbase + TILE128), v_k0 = klo(sbase + 2 * TILE128 + DQ_KST * TILE64);
       mbar_wait(qdo_full, 0);
       for (int it = 0; it < nit; ++it) {
         const int st = it & 1;
@@ -810,9 +797,24 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
         for (int s = 1; s < KS; ++s) tc_mma2(st * 128 + 64, dol + kstep(s, BLK128), vk + kstep(s, BLK64), id_s, 1u);
         tc_commit(&v_empty[st]);
         tc_commit(&s_full[st]);
-        if (it > 0) accumulate(it - 1);
       }
-      accumulate(nit - 1);
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {       // dQ += dS K   (K = the 64 keys of step u); third issuer: the TMEM-allocating warp is idle in the main loop
+      const uint32_t id_a = make_idesc(D, 1);
+      const uint32_t k_mn0 = mnlo(sbase + 2 * TILE128, BLK64), ds0 = klo(sbase + 2 * TILE128 + (DQ_KST + 2) * TILE64);
+      for (int u = 0; u < nit; ++u) {
+        const int sb = u & 1, ks = u % DQ_KST;
+        const uint32_t kmn = k_mn0 + ks * (TILE64 >> 4), dsl = ds0 + sb * (BLK128 >> 4);
+        mbar_wait(&k_full[ks], (u / DQ_KST) & 1);          // (the S issuer waited for it too; this thread reads K as well)
+        mbar_wait(&p_full[sb], (u >> 1) & 1);
+        tc_fence_after();
+        tc_mma2(256, dsl, kmn, id_a, u > 0 ? 1u : 0u);
+#pragma unroll
+        for (int s = 1; s < 4; ++s) tc_mma2(256, dsl + kstep(s, BLK128), kmn + mnstep(s), id_a, 1u);
+        tc_commit(&p_empty[sb]);
+        tc_commit(&k_empty[ks]);     // the S MMAs on this K slot (other issuer) retired before dS existed
+      }
       tc_commit(acc_full);
     }
   } else if (warp >= 4) {
