@@ -491,7 +491,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
       mbar_init(&qdo_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
+      mbar_init(&s_full[i], 2);      // one commit per issuer (S^T; dP^T)
       mbar_init(&s_empty[i], SM_WARPS);
     }
     mbar_init(p_full, SM_WARPS);
@@ -525,15 +525,50 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
       }
     }
   } else if (warp == 1) {
+    // three MMA-issuing threads (see attn_dq_kernel): S^T = K Q^T here, dP^T = V dO^T in warp 3, the accumulations in warp 2
     if (lane == 0) {
-      const uint32_t id_s = make_idesc(64, 0), id_a = make_idesc(D, 1);
-      const uint32_t kl = klo(sbase), vl = klo(sbase + TILE128);
-      const uint32_t q_k0 = klo(sbase + 2 * TILE128), q_mn0 = mnlo(sbase + 2 * TILE128, BLK64);     // stage 0: Q, then dO at + TILE64
+      const uint32_t id_s = make_idesc(64, 0);
+      const uint32_t kl = klo(sbase), q_k0 = klo(sbase + 2 * TILE128);     // stage 0: Q, then dO at + TILE64
+      mbar_wait(kv_full, 0);
+      for (int it = 0; it < nit; ++it) {
+        const int st = it % DKV_ST, sb = it & 1;
+        mbar_wait(&qdo_full[st], (it / DKV_ST) & 1);
+        mbar_wait(&s_empty[sb], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t qk = q_k0 + st * (2 * TILE64 >> 4);
+        tc_mma2(sb * 128, kl, qk, id_s, 0u);
+#pragma unroll
+        for (int s = 1; s < KS; ++s) tc_mma2(sb * 128, kl + kstep(s, BLK128), qk + kstep(s, BLK64), id_s, 1u);
+        tc_commit(&s_full[sb]);
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      const uint32_t id_s = make_idesc(64, 0);
+      const uint32_t vl = klo(sbase + TILE128), q_k0 = klo(sbase + 2 * TILE128);
+      mbar_wait(kv_full, 0);
+      for (int it = 0; it < nit; ++it) {
+        const int st = it % DKV_ST, sb = it & 1;
+        mbar_wait(&qdo_full[st], (it / DKV_ST) & 1);
+        mbar_wait(&s_empty[sb], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t dok = q_k0 + st * (2 * TILE64 >> 4) + (TILE64 >> 4);
+        tc_mma2(sb * 128 + 64, vl, dok, id_s, 0u);
+#pragma unroll
+        for (int s = 1; s < KS; ++s) tc_mma2(sb * 128 + 64, vl + kstep(s, BLK128), dok + kstep(s, BLK64), id_s, 1u);
+        tc_commit(&s_full[sb]);
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {       // dV += P^T dO,  dK += dS^T Q   (K = the 64 queries of stage u)
+      const uint32_t id_a = make_idesc(D, 1);
+      const uint32_t q_mn0 = mnlo(sbase + 2 * TILE128, BLK64);
       const uint32_t ptlo = klo(sbase + 2 * TILE128 + DKV_ST * 2 * TILE64), dstlo = ptlo + (BLK128 >> 4);
-      auto accumulate = [&](int u) {     // dV += P^T dO,  dK += dS^T Q   (K = the 64 queries of stage u)
+      for (int u = 0; u < nit; ++u) {
         const int st = u % DKV_ST;
         const uint32_t qmn = q_mn0 + st * (2 * TILE64 >> 4), domn = qmn + (TILE64 >> 4);
         const uint32_t first = u > 0 ? 1u : 0u;
+        mbar_wait(&qdo_full[st], (u / DKV_ST) & 1);
         mbar_wait(p_full, u & 1);
         tc_fence_after();
         tc_mma2(256 + D, ptlo, domn, id_a, first);
@@ -543,25 +578,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
 #pragma unroll
         for (int s = 1; s < 4; ++s) tc_mma2(256, dstlo + kstep(s, BLK128), qmn + mnstep(s), id_a, 1u);
         tc_commit(p_empty);
-        tc_commit(&qdo_empty[st]);
-      };
-      mbar_wait(kv_full, 0);
-      for (int it = 0; it < nit; ++it) {
-        const int st = it % DKV_ST, sb = it & 1;
-        mbar_wait(&qdo_full[st], (it / DKV_ST) & 1);
-        mbar_wait(&s_empty[sb], ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t qk = q_k0 + st * (2 * TILE64 >> 4), dok = qk + (TILE64 >> 4);
-        tc_mma2(sb * 128, kl, qk, id_s, 0u);
-#pragma unroll
-        for (int s = 1; s < KS; ++s) tc_mma2(sb * 128, kl + kstep(s, BLK128), qk + kstep(s, BLK64), id_s, 1u);
-        tc_mma2(sb * 128 + 64, vl, dok, id_s, 0u);
-#pragma unroll
-        for (int s = 1; s < KS; ++s) tc_mma2(sb * 128 + 64, vl + kstep(s, BLK128), dok + kstep(s, BLK64), id_s, 1u);
-        tc_commit(&s_full[sb]);
-        if (it > 0) accumulate(it - 1);
+        tc_commit(&qdo_empty[st]);      // the S^T / dP^T MMAs on this stage (other issuers) retired before P^T existed
       }
-      accumulate(nit - 1);
       tc_commit(acc_full);
     }
   } else if (warp >= 4) {
