@@ -251,22 +251,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
       }
     }
   } else if (warp == 1) {
+    // two MMA-issuing threads (a tcgen05.mma costs its issuing thread ~100 cycles, see attn_dq_kernel): S = Q K^T of both
+    // passes here, O += P V in warp 3
     if (lane == 0) {
-      const uint32_t id_s = make_idesc(128, 0), id_o = make_idesc(D, 1);
-      const uint32_t qlo = klo(sbase), plo = klo(sbase + 5 * TILE128);
-      const uint32_t klo0 = klo(sbase + TILE128), vlo0 = mnlo(sbase + 3 * TILE128, BLK128);
-      auto pv = [&](int u) {        // O += P(u) V(u);  u counts from nj (pass 2), key tile j = u - nj
-        const int j = u - nj, vs = j & 1;
-        const uint32_t vlo = vlo0 + vs * (TILE128 >> 4), pl = plo + vs * (PTILE >> 4);
-        mbar_wait(&v_full[vs], (j >> 1) & 1);
-        mbar_wait(&p_full[vs], (j >> 1) & 1);
-        tc_fence_after();
-        tc_mma2(256, pl, vlo, id_o, u > nj ? 1u : 0u);
-#pragma unroll
-        for (int s = 1; s < 8; ++s) tc_mma2(256, pl + kstep(s, BLK128), vlo + mnstep(s), id_o, 1u);
-        tc_commit(&p_empty[vs]);
-        tc_commit(&v_empty[vs]);
-      };
+      const uint32_t id_s = make_idesc(128, 0);
+      const uint32_t qlo = klo(sbase), klo0 = klo(sbase + TILE128);
       mbar_wait(q_full, 0);
       for (int t = 0; t < nit; ++t) {
         const int st = t & 1;
@@ -280,9 +269,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
         for (int s = 1; s < KS; ++s) tc_mma2(st * 128, qlo + kstep(s, BLK128), kl + kstep(s, BLK128), id_s, 1u);
         tc_commit(&k_empty[st]);
         tc_commit(&s_full[st]);
-        if (t > nj) pv(t - 1);
       }
-      pv(nit - 1);
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      const uint32_t id_o = make_idesc(D, 1);
+      const uint32_t plo = klo(sbase + 5 * TILE128), vlo0 = mnlo(sbase + 3 * TILE128, BLK128);
+      for (int j = 0; j < nj; ++j) {        // O += P(j) V(j), key tile j of pass 2
+        const int vs = j & 1;
+        const uint32_t vlo = vlo0 + vs * (TILE128 >> 4), pl = plo + vs * (PTILE >> 4);
+        mbar_wait(&v_full[vs], (j >> 1) & 1);
+        mbar_wait(&p_full[vs], (j >> 1) & 1);
+        tc_fence_after();
+        tc_mma2(256, pl, vlo, id_o, j > 0 ? 1u : 0u);
+#pragma unroll
+        for (int s = 1; s < 8; ++s) tc_mma2(256, pl + kstep(s, BLK128), vlo + mnstep(s), id_o, 1u);
+        tc_commit(&p_empty[vs]);
+        tc_commit(&v_empty[vs]);
+      }
       tc_commit(o_full);
     }
   } else if (warp >= 4) {
