@@ -909,23 +909,21 @@ static bool launch_pc_fwd_lean3(const WqArgs& a, size_t smem, cudaStream_t s) {
   return a.codes8 ? launch_pc_fwd_lean4<NV, THREADS, LET, ROWMODE, true, EXACT>(a, smem, s)
                   : launch_pc_fwd_lean4<NV, THREADS, LET, ROWMODE, false, EXACT>(a, smem, s);
 }
+// Instantiations are kept few (compile time): 128 threads for K <= 4096, 256 beyond; exact row fills for the shapes of
+// the model families, a bounds-checked variant for everything else; row folds (none / multiply / divide / segment table)
+// all go through the per-row table variant (ROWMODE 2), only "no row fold at all" has its own.
 template <bool LET, int ROWMODE>
 static bool launch_pc_fwd_lean2(const WqArgs& a, size_t smem, cudaStream_t s) {
-  static const int env_threads = [] { const char* e = getenv("OQ_WQ_LEAN_THREADS"); return e ? atoi(e) : 0; }();
   const int K4 = a.K / 4;
-  const int threads = K4 > 1024 ? 256 : (env_threads ? env_threads : 128);   // measured at K = 4096 (B200): 96 us with 128 threads x 8 float4, 110 us with 256 x 4
-  const int nv = (K4 + threads - 1) / threads;
-  if (threads == 128) {
+  if (K4 <= 1024) {
+    const int nv = (K4 + 127) / 128;
     if (nv == 2) return launch_pc_fwd_lean3<2, 128, LET, ROWMODE, true>(a, smem, s);
     if (nv == 4) return launch_pc_fwd_lean3<4, 128, LET, ROWMODE, true>(a, smem, s);
     if (nv == 6) return launch_pc_fwd_lean3<6, 128, LET, ROWMODE, true>(a, smem, s);
     if (nv == 8) return launch_pc_fwd_lean3<8, 128, LET, ROWMODE, true>(a, smem, s);
     return launch_pc_fwd_lean3<8, 128, LET, ROWMODE, false>(a, smem, s);
   }
-  if (nv == 1) return launch_pc_fwd_lean3<1, 256, LET, ROWMODE, true>(a, smem, s);
-  if (nv == 2) return launch_pc_fwd_lean3<2, 256, LET, ROWMODE, true>(a, smem, s);
-  if (nv == 3) return launch_pc_fwd_lean3<3, 256, LET, ROWMODE, true>(a, smem, s);
-  if (nv == 4) return launch_pc_fwd_lean3<4, 256, LET, ROWMODE, true>(a, smem, s);
+  const int nv = (K4 + 255) / 256;
   if (nv == 8) return launch_pc_fwd_lean3<8, 256, LET, ROWMODE, true>(a, smem, s);
   if (nv == 11) return launch_pc_fwd_lean3<11, 256, LET, ROWMODE, true>(a, smem, s);
   if (nv == 16) return launch_pc_fwd_lean3<16, 256, LET, ROWMODE, true>(a, smem, s);
@@ -937,9 +935,7 @@ static bool launch_pc_fwd_lean(const WqArgs& a, bool let, size_t smem, cudaStrea
   static const bool off = [] { const char* e = getenv("OQ_WQ_LEAN"); return e && atoi(e) == 0; }();
   if (off || !a.q_bf || a.q_f32 || a.codes) return false;
   if (!let) return launch_pc_fwd_lean2<false, 3>(a, 0, s);
-  if (a.nseg) return launch_pc_fwd_lean2<true, 2>(a, smem, s);
-  if (a.row && a.row_op == 2) return launch_pc_fwd_lean2<true, 1>(a, smem, s);
-  if (a.row && a.row_op == 1) return launch_pc_fwd_lean2<true, 0>(a, smem, s);
+  if (a.nseg || (a.row && a.row_op != 0)) return launch_pc_fwd_lean2<true, 2>(a, smem, s);
   return launch_pc_fwd_lean2<true, 3>(a, smem, s);
 }
 template <bool LET>

@@ -427,9 +427,9 @@ __global__ void __launch_bounds__(288, NV <= 4 ? 2 : 1) wq_pc_bwd_ws(WqArgs a) {
 }
 
 // rows in flight per block: the kernel is bound by bytes in flight (ncu: consumers wait on the stage's barrier), measured
-// at K = 4096 (B200): 3 stages 155 us, 4 stages see profiles/
+// at K = 4096 (B200): 3 and 4 stages within 1 % once the control warp stopped being the bound; 6 stages (one block per SM) 1.7x slower
 static int ws_stages() {
-  static const int v = [] { const char* e = getenv("OQ_WQ_WS_STAGES"); const int x = e ? atoi(e) : 4; return x == 3 || x == 6 ? x : 4; }();
+  static const int v = [] { const char* e = getenv("OQ_WQ_WS_STAGES"); return (e && atoi(e) == 3) ? 3 : 4; }();
   return v;
 }
 template <int NVV, int ROWDIV, bool G32, bool EXACT, int STAGES>
@@ -445,11 +445,8 @@ static bool launch_pc_bwd_ws5(const WqArgs& a, int grid, size_t smem, cudaStream
 }
 template <int NVV, int ROWDIV, bool G32, bool EXACT>
 static bool launch_pc_bwd_ws4(const WqArgs& a, int stages, int grid, size_t smem, cudaStream_t s) {
-  switch (stages) {
-    case 3: return launch_pc_bwd_ws5<NVV, ROWDIV, G32, EXACT, 3>(a, grid, smem, s);
-    case 6: return launch_pc_bwd_ws5<NVV, ROWDIV, G32, EXACT, 6>(a, grid, smem, s);
-    default: return launch_pc_bwd_ws5<NVV, ROWDIV, G32, EXACT, 4>(a, grid, smem, s);
-  }
+  if (stages == 3) return launch_pc_bwd_ws5<NVV, ROWDIV, G32, EXACT, 3>(a, grid, smem, s);
+  return launch_pc_bwd_ws5<NVV, ROWDIV, G32, EXACT, 4>(a, grid, smem, s);
 }
 template <int NVV, int ROWDIV, bool EXACT>
 static bool launch_pc_bwd_ws3(const WqArgs& a, int stages, int grid, size_t smem, cudaStream_t s) {
@@ -462,7 +459,6 @@ static bool launch_pc_bwd_ws2(const WqArgs& a, cudaStream_t s) {
   const int nv = (K4 + 255) / 256;
   const size_t row_bytes = (size_t)a.K * (a.g_is_f32 ? 8 : 6);
   int STAGES = ws_stages();
-  if (STAGES == 6 && 6 * row_bytes > 200 * 1024) STAGES = 4;
   if (STAGES == 4 && 4 * row_bytes > 200 * 1024) STAGES = 3;
   const size_t smem = (size_t)STAGES * row_bytes;
   if (nv > 8 || smem > 200 * 1024 || a.dW) return false;
@@ -475,7 +471,8 @@ static bool launch_pc_bwd_ws2(const WqArgs& a, cudaStream_t s) {
   if (nv == 8) return launch_pc_bwd_ws3<8, ROWDIV, true>(a, STAGES, grid, smem, s);
   return launch_pc_bwd_ws3<8, ROWDIV, false>(a, STAGES, grid, smem, s);
 }
+// row folds (multiply / divide / segment table) share the per-row table variant; "no row fold" has its own (compile time)
 static bool launch_pc_bwd_ws(const WqArgs& a, cudaStream_t s) {
-  if (a.nseg) return launch_pc_bwd_ws2<2>(a, s);
-  return (a.row && a.row_op == 2) ? launch_pc_bwd_ws2<1>(a, s) : launch_pc_bwd_ws2<0>(a, s);
+  if (a.nseg || (a.row && a.row_op != 0)) return launch_pc_bwd_ws2<2>(a, s);
+  return launch_pc_bwd_ws2<0>(a, s);
 }
