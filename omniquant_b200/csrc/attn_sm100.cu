@@ -160,6 +160,37 @@ __device__ __forceinline__ void st_chunk(uint8_t* blk, int r, int c, const float
   *reinterpret_cast<uint4*>(blk + r * ROW_B + ((c ^ (r & 7)) << 4)) = u;
 }
 
+// Epilogue of a softmax warp: its [32 accumulator rows x COLS columns] slice from TMEM to global memory as bf16.  A thread owns
+// one row (TMEM lane), so storing straight from registers makes every warp-wide 16-byte store touch 32 different rows (ncu on
+// the dK / dV kernel: 17 % of the samples waited on the store queue).  The slice goes through shared memory (16-byte chunks
+// XOR-swizzled by the row: conflict-free both ways) and leaves as whole rows: 32 lanes x 16 B = 256 / COLS rows per store.
+// `stage`: 32 * COLS * 2 bytes of shared memory private to the warp and idle by now; gbase: row 0 / column 0 of the slice.
+template <int COLS>
+__device__ __forceinline__ void store_slice(uint4* stage, uint32_t taddr, float sc, bf16* gbase, long ld, int lane) {
+  constexpr int CPR = COLS / 8, RPI = 32 / CPR;     // 16-byte chunks per row, rows per store instruction
+#pragma unroll 1
+  for (int c0 = 0; c0 < COLS; c0 += 32) {
+    uint32_t v[32];
+    tc_ld32(taddr + c0, v);
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      float t8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t8[e] = __uint_as_float(v[i + e]) * sc;
+      const int ch = (c0 + i) >> 3;
+      stage[lane * CPR + (ch ^ (lane & (CPR - 1) & 7))] =
+          make_uint4(pack_bf2(t8[0], t8[1]), pack_bf2(t8[2], t8[3]), pack_bf2(t8[4], t8[5]), pack_bf2(t8[6], t8[7]));
+    }
+  }
+  __syncwarp();
+#pragma unroll 4
+  for (int r0 = 0; r0 < 32; r0 += RPI) {
+    const int r = r0 + lane / CPR, ch = lane % CPR;
+    *reinterpret_cast<uint4*>(gbase + (long)r * ld + ch * 8) = stage[r * CPR + (ch ^ (r & (CPR - 1) & 7))];
+  }
+}
+
 // ================================================================== forward
 template <int DH>
 constexpr int fwd_smem() { return 5 * (DH / 64) * BLK128 /*Q, K ring, V ring*/ + 2 * PTILE /*P x 2*/ + 1024 + 256; }
@@ -388,20 +419,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const AttnParams p) {
     // ---- epilogue
     mbar_wait(o_full, 0);
     tc_fence_after();
-    bf16* orow = p.O + (long)(row0 + qrow) * p.ldo + head * D;
-#pragma unroll 1
-    for (int c0 = (D / 2) * half; c0 < (D / 2) * half + D / 2; c0 += 32) {
-      uint32_t v[32];
-      tc_ld32(lane_base + 256 + c0, v);
-      tc_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        float t8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t8[e] = __uint_as_float(v[i + e]);
-        store_bf8(orow + c0 + i, t8);
-      }
-    }
+    // this warp: rows [32 q, +32) of the query tile, columns [D/2 half, +D/2) of the head; the Q tile is idle by now
+    store_slice<D / 2>(reinterpret_cast<uint4*>(sQ) + (warp - 4) * (32 * (D / 16)), lane_base + 256 + (D / 2) * half, 1.0f,
+                       p.O + (long)(row0 + qt * 128 + q * 32) * p.ldo + head * D + (D / 2) * half, p.ldo, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -660,43 +680,11 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant
         mbar_arrive(&s_empty[sb]);
       }
     }
-    // ---- epilogue: dK (x alpha: s = alpha q.k), dV.  A thread owns one accumulator row (TMEM lane), so storing straight
-    // from registers makes every warp-wide 16-byte store touch 32 different rows (ncu: 17 % of the kernel's samples waited
-    // here on the store queue).  The warp's [32 rows x D] slice goes through shared memory instead (the Q / dO ring is idle
-    // once acc_full has fired; 16-byte chunks XOR-swizzled by the row) and leaves as whole rows: 32 lanes x 16 B = two rows
-    // of D = 128 (four of D = 64) bf16 per store instruction.
+    // ---- epilogue: dK (x alpha: s = alpha q.k) by the warps of column half 0, dV by half 1; the Q / dO ring is idle by now
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    {
-      constexpr int CPR = D / 8;                                   // 16-byte chunks per row
-      uint4* stage = reinterpret_cast<uint4*>(sQdO) + (warp - 4) * (32 * CPR);
-      const bool is_k = half == 0;                                 // half 0 stores dK, half 1 stores dV
-      const float sc = is_k ? p.alpha : 1.0f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < D; c0 += 32) {
-        uint32_t v[32];
-        tc_ld32(lane_base + 256 + D * half + c0, v);
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          float t8[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) t8[e] = __uint_as_float(v[i + e]) * sc;
-          const int ch = (c0 + i) >> 3;
-          stage[lane * CPR + (ch ^ (lane & (CPR - 1) & 7))] =
-              make_uint4(pack_bf2(t8[0], t8[1]), pack_bf2(t8[2], t8[3]), pack_bf2(t8[4], t8[5]), pack_bf2(t8[6], t8[7]));
-        }
-      }
-      __syncwarp();
-      bf16* gbase = p.dqkv + (long)(row0 + j * 128 + q * 32) * p.ldg + (is_k ? kc : vc);
-      constexpr int RPI = 32 / CPR;                                // rows per store instruction
-#pragma unroll 4
-      for (int r0 = 0; r0 < 32; r0 += RPI) {
-        const int r = r0 + lane / CPR, ch = lane % CPR;
-        const uint4 u = stage[r * CPR + (ch ^ (r & (CPR - 1) & 7))];
-        *reinterpret_cast<uint4*>(gbase + (long)r * p.ldg + ch * 8) = u;
-      }
-    }
+    store_slice<D>(reinterpret_cast<uint4*>(sQdO) + (warp - 4) * (32 * (D / 8)), lane_base + 256 + D * half, half == 0 ? p.alpha : 1.0f,
+                   p.dqkv + (long)(row0 + j * 128 + q * 32) * p.ldg + (half == 0 ? kc : vc), p.ldg, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -908,20 +896,9 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant_
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    bf16* dst = p.dqkv + (long)(row0 + qg) * p.ldg + qc;
-#pragma unroll 1
-    for (int c0 = (D / 2) * half; c0 < (D / 2) * half + D / 2; c0 += 32) {
-      uint32_t v[32];
-      tc_ld32(lane_base + 256 + c0, v);
-      tc_wait_ld();
-#pragma unroll
-      for (int k = 0; k < 32; k += 8) {
-        float t8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t8[e] = __uint_as_float(v[k + e]) * p.alpha;
-        store_bf8(dst + c0 + k, t8);
-      }
-    }
+    // dQ (x alpha): rows [32 q, +32) of the query tile, columns [D/2 half, +D/2); the Q tile is idle by now
+    store_slice<D / 2>(reinterpret_cast<uint4*>(sQ) + (warp - 4) * (32 * (D / 16)), lane_base + 256 + (D / 2) * half, p.alpha,
+                       p.dqkv + (long)(row0 + i * 128 + q * 32) * p.ldg + qc + (D / 2) * half, p.ldg, lane);
   }
   tc_fence_before();
   __syncthreads();
